@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- bridge-bidding env-steps/sec (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--sweep]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): random-legal-action env stepping, 8192 envs per
+GPU, env only (no policy net).  One bench "step" = one pass of the hot path over one
+batch = ONE launch of the fused rollout kernel: 32 auto-reset env sub-steps
+(`num_steps`, ppo.py:120) over 8192 envs (`num_envs`, ppo.py:119) = 262,144 env-steps,
+writing the full [32, 8192, ...] trajectory (observation f32[480], legal mask, rewards,
+terminated, current player, action) = 519 MB per step, which is larger than the 126 MB
+L2, so every timed step's stores are DRAM traffic (no flush needed).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job env-steps/s with state resident in
+HBM; `e2e` = the same metric through the host-buffer C-ABI (`brl_env_step_host`):
+actions from pinned host memory in, every Env-surface output to pinned host memory
+out, copies inside the timed region; `roofline` = the rollout kernel against measured
+HBM bandwidth; `cpu_baseline` = the C oracle on this box's host cores (bounded sample).
+`--impl reference` times the CPU restatement of the reference on the same config (the
+real pgx/JAX env cannot be installed in this image -- see DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ENVS = 8192          # per GPU (ppo.py:119)
+T_STEPS = 32           # env sub-steps per launch (ppo.py:120)
+N_DEALS = 100_000      # hash_size (ppo.py:128)
+BYTES_PER_ENV_STEP = 1980  # obs 1920 + mask 38 + rewards 16 + terminated 1 + player 1 + action 4
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+SEED = 20241017
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_throughput(n_envs, t_steps, reps, n_threads, table):
+    """env-steps/s of the C oracle (all outputs written, same workload shape)."""
+    import numpy as np
+    from oracle import oracle as orc
+    env = orc.OracleEnv(table, n_envs, n_threads=n_threads)
+    env.init(orc.make_keys(SEED, n_envs))
+    k, n = t_steps, n_envs
+    out = dict(obs=np.zeros((k, n, 480), np.float32), mask=np.zeros((k, n, 38), np.uint8),
+               rew=np.zeros((k, n, 4), np.float32), term=np.zeros((k, n), np.uint8), cur=np.zeros((k, n), np.int8),
+               act=np.zeros((k, n), np.int32))
+    import ctypes as C
+
+    def run(step0):
+        return env.L.orc_rollout_random(
+            orc._p(env.buf), C.byref(env.params), C.c_int64(n), C.c_int64(0), C.c_uint64(SEED), C.c_uint32(step0),
+            C.c_int32(k), orc._p(out["obs"]), orc._p(out["mask"]), orc._p(out["rew"]), orc._p(out["term"]),
+            orc._p(out["cur"]), orc._p(out["act"]), C.c_int(n_threads))
+
+    run(0)  # warm-up (page faults of the output buffers)
+    times = []
+    for r in range(reps):
+        t0 = time.perf_counter()
+        run((r + 1) * k)
+        times.append(time.perf_counter() - t0)
+    return n * k * len(times) / sum(times), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from brl_b200.deals import synthetic_deal_table
+    cores = os.cpu_count() or 1
+    table = synthetic_deal_table(N_DEALS, seed=0)
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_oracle_throughput(N_ENVS, T_STEPS, 1, cores, table)
+    value, times = cpu_oracle_throughput(N_ENVS, T_STEPS, args.steps, cores, table)
+    ms = 1e3 * sum(times) / len(times)
+    sample = f"{args.steps} x ({N_ENVS} envs x {T_STEPS} auto-reset random-legal steps), all outputs written"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32 state, f32 0/1 observation", "data": "synthetic",
+        "config": _config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "C restatement of pgx 1.4.0 bridge_bidding semantics (oracle/brl_oracle.c), not pgx: "
+                                 "jax/pgx are not installable in this image"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def _config(n_gpus):
+    return {"workload": "configs[1]: random-legal-action bridge_bidding env step, 8192 envs per GPU, env only",
+            "n_envs_per_gpu": N_ENVS, "env_steps_per_bench_step": N_ENVS * T_STEPS, "sub_steps_per_launch": T_STEPS,
+            "n_deals": N_DEALS, "auto_reset": True, "obs_dtype": "f32", "sharding": f"env index x{n_gpus}, no collective in step",
+            "l2": "trajectory written per step = 519 MB > 126 MB L2 (no flush needed)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--sweep", action="store_true", help="also time 65,536 and 1,048,576 envs and single-step launches")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from brl_b200 import _lib, ops
+    from brl_b200.deals import synthetic_deal_table
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()  # fail loudly if the CUDA library is missing
+
+    table_np = synthetic_deal_table(N_DEALS, seed=0)
+    table = torch.as_tensor(table_np, device=dev)
+    n, k = N_ENVS, T_STEPS
+    offset = rank * n  # global env index: results do not depend on the GPU count
+    state = ops.new_state(n, dev)
+    out0 = ops.EnvOutputs(n, dev)
+    ops.init(ops.make_keys(SEED, n, dev, env_offset=offset), table, state, out0)
+    traj = ops.EnvOutputs(n, dev, rows=k)
+    actions = torch.empty((k, n), dtype=torch.int32, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    def one_step(i):
+        ops.rollout_random(state, table, k, traj, seed=SEED, step0=i * k, env_offset=offset, action_out=actions,
+                           stats=stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    stats.zero_()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    evs[0].record()
+    for i in range(args.steps):
+        one_step(args.warmup + i)
+        evs[i + 1].record()
+    # the single collective of the path: episode statistics summed over ranks
+    sums = torch.zeros(8, dtype=torch.float64, device=dev)
+    sums[:4] = stats.to(torch.float64)
+    if world > 1:
+        dist.all_reduce(sums)
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = evs[0].elapsed_time(end)
+    kernel_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    env_steps = n * k * args.steps * world
+    value = env_steps / (total_ms * 1e-3)
+    avg_kernel_ms = sum(kernel_ms) / len(kernel_ms)
+    peak, peak_src = _peaks()
+    achieved = BYTES_PER_ENV_STEP * n * k / (avg_kernel_ms * 1e-3) / 1e9
+
+    # ---- e2e: host-buffer C-ABI, copies inside the timed region (rank-local, summed over ranks) ----
+    e2e = run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps=max(20, min(200, args.steps * 4)),
+                  warmup=args.warmup)
+
+    extra = {}
+    if args.sweep and rank == 0:
+        extra["sweep"] = run_sweep(torch, ops, table, dev, peak)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, times = cpu_oracle_throughput(n, k, 3, cores, table_np)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"3 x ({n} envs x {k} auto-reset random-legal steps), all outputs written, {cores} threads",
+               "note": "C restatement of pgx semantics (oracle/brl_oracle.c); pgx/JAX not installable here"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int32 state, f32 0/1 observation", "data": "synthetic", "config": _config(world),
+            "e2e": e2e, "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "brl::k_rollout<8,f32>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * k, "avg_launch_ms": avg_kernel_ms},
+            "cpu_baseline": cpu, "clocks": clocks,
+            "episode_stats": {"finished_auctions": float(sums[0]), "sum_reward_player0": float(sums[1]),
+                              "env_steps": float(sums[2]), "collective": "1 NCCL all-reduce of f64[8]" if world > 1 else "none (1 rank)"},
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps, warmup):
+    """Public host-buffer API: per env.step, actions come from pinned host memory (H2D) and
+    every Env-surface output goes back to pinned host memory (D2H).  Observation dtype is
+    pgx's own (bool = u8, `State.observation`); the f32 cast is the consumer's
+    (src/roll_out.py:75)."""
+    import ctypes as C
+    L = _lib.load()
+    tbl = np.ascontiguousarray(table_np)
+    h = L.brl_env_create(n, offset, tbl.ctypes.data, tbl.shape[0], SEED, _lib.F_AUTORESET | _lib.F_OBS_U8)
+    if not h:
+        raise RuntimeError("brl_env_create failed: " + L.brl_last_error().decode())
+    pin = dict(act=torch.zeros(n, dtype=torch.int32).pin_memory(), obs=torch.zeros((n, 480), dtype=torch.uint8).pin_memory(),
+               mask=torch.zeros((n, 38), dtype=torch.uint8).pin_memory(), rew=torch.zeros((n, 4), dtype=torch.float32).pin_memory(),
+               term=torch.zeros(n, dtype=torch.uint8).pin_memory(), cur=torch.zeros(n, dtype=torch.int8).pin_memory())
+    p = {k: C.c_void_p(v.data_ptr()) for k, v in pin.items()}
+    rc = L.brl_env_init_host(h, p["obs"], p["mask"], p["rew"], p["term"], p["cur"])
+    assert rc == 0, L.brl_last_error()
+    mask_np, act_np = pin["mask"].numpy(), pin["act"].numpy()
+    rng = np.random.default_rng(SEED + offset)
+
+    def host_policy():
+        # cheap host-side random-legal choice from the mask that came back over PCIe
+        score = rng.random(mask_np.shape, dtype=np.float32) * mask_np
+        act_np[:] = score.argmax(axis=1)
+
+    def one():
+        host_policy()
+        rc = L.brl_env_step_host(h, p["act"], p["obs"], p["mask"], p["rew"], p["term"], p["cur"])
+        if rc != 0:
+            raise RuntimeError(L.brl_last_error().decode())
+
+    for _ in range(warmup):
+        one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    L.brl_env_destroy(h)
+    return {"value": n * steps * world / dt, "unit": UNIT, "h2d_bytes_per_step": n * 4,
+            "d2h_bytes_per_step": n * (480 + 38 + 16 + 1 + 1), "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "api": "brl_env_step_host (C ABI, host buffers): 1 env.step over 8192 envs per call; host picks the actions "
+                   "from the returned mask; observation in pgx's bool(u8) dtype", "timed_with": "host wall clock around synchronous calls"}
+
+
+def run_sweep(torch, ops, table, dev, peak):
+    """Larger env counts (footprint >> L2 per step) and the one-launch-per-env.step path."""
+    res = []
+    for n, k in ((65536, 8), (1048576, 2)):
+        state, out0 = ops.new_state(n, dev), ops.EnvOutputs(n, dev)
+        ops.init(ops.make_keys(SEED, n, dev), table, state, out0)
+        traj = ops.EnvOutputs(n, dev, rows=k)
+        for i in range(3):
+            ops.rollout_random(state, table, k, traj, seed=SEED, step0=i * k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for i in range(reps):
+            ops.rollout_random(state, table, k, traj, seed=SEED, step0=(3 + i) * k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = BYTES_PER_ENV_STEP * n * k / (ms * 1e-3) / 1e9
+        res.append({"kernel": "k_rollout", "n_envs": n, "sub_steps": k, "ms": ms, "env_steps_per_sec": n * k / (ms * 1e-3),
+                    "GBps": gbs, "frac": gbs / peak})
+        # single env.step per launch (in-kernel random action), outputs to one [n, ...] slot
+        out1 = ops.EnvOutputs(n, dev)
+        for i in range(3):
+            ops.step(state, None, table, state, out1, autoreset=True, random_action=True, seed=SEED, step_index=i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(20):
+            ops.step(state, None, table, state, out1, autoreset=True, random_action=True, seed=SEED, step_index=10 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        gbs = BYTES_PER_ENV_STEP * n / (ms * 1e-3) / 1e9
+        res.append({"kernel": "k_step", "n_envs": n, "ms": ms, "env_steps_per_sec": n / (ms * 1e-3), "GBps": gbs,
+                    "frac": gbs / peak})
+        del state, out0, traj, out1
+        torch.cuda.empty_cache()
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+"""ctypes binding of the C-ABI library (include/brl_b200.h).
+
+There is NO CPU fallback: if the CUDA library is missing or fails to load, every
+op raises.  The library is built in-tree by `python -m brl_b200.build`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+OPS = (
+    "brl_make_keys", "brl_init", "brl_reset_fields", "brl_step", "brl_duplicate_step", "brl_duplicate_init",
+    "brl_observe", "brl_legal_mask", "brl_rollout_random", "brl_imp_reward", "brl_gae", "brl_categorical",
+    "brl_match_stats", "brl_state_fields", "brl_gather_reward",
+)
+HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host")
+MISC = ("brl_last_error", "brl_abi_version")
+ALL_SYMBOLS = OPS + HOST_API + MISC
+
+# flags (include/brl_b200.h)
+F_AUTORESET = 0x0001
+F_RANDOM_ACTION = 0x0002
+F_ACCUMULATE = 0x0004
+F_OBS_U8 = 0x0010
+F_OBS_BF16 = 0x0020
+F_SAMPLE = 0x0040
+F_QUAD_LAST = 0x0100
+
+
+def tune(epw: int = 0, wpb: int = 0) -> int:
+    """flag bits selecting envs-per-warp (8/16/32) and warps-per-block (1/2/4); 0 = automatic"""
+    return ({0: 0, 8: 1, 16: 2, 32: 3}[epw] << 16) | ({0: 0, 1: 1, 2: 2, 4: 3}[wpb] << 18)
+
+
+class BrlParams(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int64), ("env_offset", C.c_int64), ("state_stride", C.c_int64), ("seed", C.c_uint64),
+        ("n_deals", C.c_int32), ("flags", C.c_int32), ("step", C.c_uint32), ("k_steps", C.c_int32),
+        ("illegal_penalty", C.c_float), ("illegal_bonus", C.c_float), ("gamma", C.c_float), ("gae_lambda", C.c_float),
+    ]
+
+
+class BrlError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if sources are newer) the CUDA C-ABI library; raises if impossible."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path) or _build._stale():
+        try:
+            path = _build.build()
+        except Exception as exc:  # no nvcc on this box and no prebuilt library
+            if not os.path.exists(_build.LIB):
+                raise BrlError(f"libbrl_b200.so is missing and cannot be built ({exc}); there is no CPU fallback") from exc
+            path = _build.LIB
+    try:
+        L = C.CDLL(path)
+    except OSError as exc:
+        raise BrlError(f"cannot load {path}: {exc}; there is no CPU fallback") from exc
+    for name in OPS:
+        fn = getattr(L, name)
+        fn.restype = C.c_int32
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t]
+    L.brl_last_error.restype = C.c_char_p
+    L.brl_abi_version.restype = C.c_int32
+    L.brl_env_create.restype = C.c_void_p
+    L.brl_env_create.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_uint64, C.c_int32]
+    L.brl_env_destroy.restype = None
+    L.brl_env_destroy.argtypes = [C.c_void_p]
+    L.brl_env_init_host.restype = C.c_int32
+    L.brl_env_init_host.argtypes = [C.c_void_p] * 6
+    L.brl_env_step_host.restype = C.c_int32
+    L.brl_env_step_host.argtypes = [C.c_void_p] * 7
+    _LIB = L
+    return L
+
+
+def call(name: str, stream: int, buffers, params: BrlParams) -> None:
+    """Invoke one stream-first op: buffers = iterable of device addresses (int) or None."""
+    L = load()
+    arr = (C.c_void_p * len(buffers))(*[C.c_void_p(b) if b else None for b in buffers])
+    rc = getattr(L, name)(C.c_void_p(stream), arr, C.byref(params), C.sizeof(params))
+    if rc != 0:
+        raise BrlError(f"{name} failed ({rc}): {L.brl_last_error().decode()}")

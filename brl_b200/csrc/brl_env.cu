@@ -1,0 +1,686 @@
+// brl_env.cu -- environment kernels (init / step / duplicate / rollout / observe /
+// legal mask) and their C-ABI entry points.  sm_100a only.
+//
+// Execution model (DESIGN.md "Kernels"): a warp owns a tile of EPW consecutive envs.
+//   phase 1  lanes 0..EPW-1: one env per lane -- load 80 B of packed state (5
+//            coalesced 128-bit plane loads), apply the call, resolve a terminal
+//            contract from the L2-resident deal table, auto-reset, and leave the
+//            observation as 15 words of bits + the 38-bit legal mask in shared
+//            memory; per-env scalars (rewards float4, terminated, current_player)
+//            are stored directly.
+//   phase 2  all 32 lanes: for every env of the tile expand the 480 observation bits
+//            into one 1920-byte row with 128-bit coalesced stores (lane l writes
+//            float4 l, l+32, l+64, l+96), and the tile's EPW*38 mask bytes as one
+//            contiguous run of 128-bit stores.
+// The HBM traffic is the outputs (1980 B per env-step) + 2 x 80 B of state; nothing
+// is re-read.  EPW (8/16/32) trades phase-1 lane utilisation for more warps in
+// flight at small env counts.
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "env_device.cuh"
+
+namespace brl {
+
+enum ObsKind { kObsF32 = 0, kObsU8 = 1, kObsBF16 = 2 };
+constexpr int kRowStride = 17;  // odd stride: conflict-free phase-1 writes
+
+template <int EPW>
+struct alignas(16) WarpTile {
+    uint32_t R[EPW * kRowStride];
+    uint64_t M[EPW + 2];
+};
+
+struct TableInfo {  // src/duplicate.py:138-144 as SoA
+    uint8_t* terminated;
+    float4* rewards;
+    int32_t* last_bid;
+    int32_t* last_bidder;
+    uint8_t* call_x;
+    uint8_t* call_xx;
+};
+
+struct EnvArgs {
+    const uint4* state_in;
+    uint4* state_out;
+    const uint8_t* table;
+    const int32_t* action;
+    // outputs (per step; rollout advances them by n rows per step)
+    void* obs;
+    uint8_t* mask;
+    float4* rewards;
+    uint8_t* terminated;
+    int8_t* current_player;
+    int32_t* action_out;
+    unsigned long long* stats;
+    // produce-kernel inputs
+    const uint64_t* keys;
+    const int32_t* in_deal;
+    const int32_t* in_dealer;
+    const uint8_t* in_vul_ns;
+    const uint8_t* in_vul_ew;
+    const int8_t* in_players;
+    const uint64_t* in_rng_key;
+    const int8_t* in_player_id;
+    TableInfo ta, tb;
+    int64_t n, stride, env_offset;
+    uint64_t seed;
+    uint32_t n_deals, step;
+    int32_t flags, k_steps, mode;
+    float illegal_penalty, illegal_bonus;
+    int mask_vec;  // mask rows may be written with 128-bit stores
+};
+
+// 4 bits -> 4 bytes of 0/1
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+__device__ __forceinline__ float4 nibble_to_float4(uint32_t nib) {
+    return make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f, (nib & 4u) ? 1.0f : 0.0f,
+                       (nib & 8u) ? 1.0f : 0.0f);
+}
+
+// 2 bits -> two bf16 (0x3F80 = 1.0) packed in one word
+__device__ __forceinline__ uint32_t pair_to_bf16x2(uint32_t two) {
+    return ((two & 1u) ? 0x00003F80u : 0u) | ((two & 2u) ? 0x3F800000u : 0u);
+}
+
+// phase 2: cooperative, fully coalesced expansion of one tile
+template <int EPW, int OBS>
+__device__ __forceinline__ void emit_tile(const WarpTile<EPW>& t, int lane, int64_t env_base, int n_valid,
+                                          void* obs, uint8_t* mask, int mask_vec) {
+    if (obs != nullptr) {
+        for (int e = 0; e < n_valid; ++e) {
+            const uint32_t* R = &t.R[e * kRowStride];
+            if (OBS == kObsF32) {
+                float4* row = reinterpret_cast<float4*>(obs) + (env_base + e) * (kObsDim / 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int j = lane + 32 * k;
+                    if (j < kObsDim / 4) row[j] = nibble_to_float4((R[j >> 3] >> ((j & 7) * 4)) & 15u);
+                }
+            } else if (OBS == kObsU8) {
+                uint4* row = reinterpret_cast<uint4*>(obs) + (env_base + e) * (kObsDim / 16);
+                if (lane < kObsDim / 16) {
+                    uint32_t h = (R[lane >> 1] >> ((lane & 1) * 16)) & 0xFFFFu;
+                    row[lane] = make_uint4(spread4(h & 15u), spread4((h >> 4) & 15u), spread4((h >> 8) & 15u),
+                                           spread4(h >> 12));
+                }
+            } else {
+                uint4* row = reinterpret_cast<uint4*>(obs) + (env_base + e) * (kObsDim / 8);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    int j = lane + 32 * k;
+                    if (j < kObsDim / 8) {
+                        uint32_t b = (R[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                        row[j] = make_uint4(pair_to_bf16x2(b), pair_to_bf16x2(b >> 2), pair_to_bf16x2(b >> 4),
+                                            pair_to_bf16x2(b >> 6));
+                    }
+                }
+            }
+        }
+    }
+    if (mask != nullptr) {
+        uint8_t* base = mask + env_base * kNumActions;
+        int nbytes = n_valid * kNumActions;
+        if (mask_vec) {
+            for (int o = lane * 16; o < nbytes; o += 32 * 16) {
+                int e0 = o / kNumActions, a0 = o - e0 * kNumActions;
+                uint64_t bits = (t.M[e0] >> a0) | (t.M[e0 + 1] << (kNumActions - a0));
+                uint32_t h = (uint32_t)bits & 0xFFFFu;
+                uint4 v = make_uint4(spread4(h & 15u), spread4((h >> 4) & 15u), spread4((h >> 8) & 15u), spread4(h >> 12));
+                if (o + 16 <= nbytes) {
+                    *reinterpret_cast<uint4*>(base + o) = v;
+                } else {  // ragged tail of the last tile
+                    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    for (int b = 0; o + b < nbytes; ++b) base[o + b] = (uint8_t)((w[b >> 2] >> ((b & 3) * 8)) & 1u);
+                }
+            }
+        } else {
+            for (int o = lane; o < nbytes; o += 32) {
+                int e0 = o / kNumActions, a0 = o - e0 * kNumActions;
+                base[o] = (uint8_t)((t.M[e0] >> a0) & 1ull);
+            }
+        }
+    }
+}
+
+template <int EPW>
+__device__ __forceinline__ void stage_env(WarpTile<EPW>& t, int lane, const Env& e, const uint8_t* table, uint32_t q,
+                                          bool want_obs) {
+    if (want_obs) {
+        uint32_t R[kObsWords];
+        env_observe_words(e, table, q, R);
+#pragma unroll
+        for (int w = 0; w < kObsWords; ++w) t.R[lane * kRowStride + w] = R[w];
+    }
+    t.M[lane] = env_legal_mask(e);
+}
+
+__device__ __forceinline__ void write_scalars(const EnvArgs& a, int64_t row, const Env& e, float4 rew, bool accumulate) {
+    uint8_t term = (uint8_t)f_terminated(e);
+    if (a.rewards) {
+        if (accumulate) {
+            float4 o = a.rewards[row];
+            rew = make_float4(o.x + rew.x, o.y + rew.y, o.z + rew.z, o.w + rew.w);
+        }
+        a.rewards[row] = rew;
+    }
+    if (a.terminated) a.terminated[row] = accumulate ? (uint8_t)(a.terminated[row] | term) : term;
+    if (a.current_player) a.current_player[row] = (int8_t)f_player_at(e, f_cur_seat(e));
+}
+
+#define BRL_TILE_PROLOGUE()                                                          \
+    extern __shared__ __align__(16) unsigned char smem_raw[];                        \
+    WarpTile<EPW>* tiles = reinterpret_cast<WarpTile<EPW>*>(smem_raw);               \
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                      \
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;             \
+    const int64_t env_base = tile * EPW;                                             \
+    if (env_base >= a.n) return;                                                     \
+    const int n_valid = (int)((a.n - env_base) < (int64_t)EPW ? (a.n - env_base) : (int64_t)EPW); \
+    WarpTile<EPW>& t = tiles[warp];                                                  \
+    if (lane < 2) t.M[EPW + lane] = 0ull;                                            \
+    const bool active = lane < n_valid;                                              \
+    const int64_t i = env_base + lane;
+
+// ---- one env.step over n envs ---------------------------------------------------------
+template <int EPW, int OBS>
+__global__ void __launch_bounds__(128) k_step(const EnvArgs a) {
+    BRL_TILE_PROLOGUE()
+    if (lane < EPW) {
+        if (active) {
+            Env e;
+            load_env(a.state_in, a.stride, i, e);
+            int32_t act;
+            if (a.flags & BRL_F_RANDOM_ACTION) act = random_legal_action(env_legal_mask(e), a.seed, (uint64_t)(a.env_offset + i), a.step);
+            else act = a.action[i];
+            float4 rew = (a.flags & BRL_F_AUTORESET)
+                             ? env_step_autoreset(e, act, a.table, a.n_deals, a.illegal_penalty, a.illegal_bonus)
+                             : env_step(e, act, a.table, a.illegal_penalty, a.illegal_bonus);
+            const bool acc = (a.flags & BRL_F_ACCUMULATE) != 0;
+            if (acc && (a.flags & BRL_F_QUAD_LAST) && a.terminated && (a.terminated[i] || f_terminated(e)))
+                e.A |= kTermBit | (f_terminated(e) ? 0u : kCarriedBit);  // src/utils.py:128 state.replace(terminated=OR)
+            write_scalars(a, i, e, rew, acc);
+            if (a.action_out) a.action_out[i] = act;
+            store_env(a.state_out, a.stride, i, e);
+            stage_env<EPW>(t, lane, e, a.table, f_cur_seat(e), a.obs != nullptr);
+        } else {
+            t.M[lane] = 0ull;
+        }
+    }
+    __syncwarp();
+    emit_tile<EPW, OBS>(t, lane, env_base, n_valid, a.obs, a.mask, a.mask_vec);
+}
+
+// ---- K auto-reset steps with in-kernel random-legal actions ----------------------------
+template <int EPW, int OBS>
+__global__ void __launch_bounds__(128) k_rollout(const EnvArgs a) {
+    BRL_TILE_PROLOGUE()
+    Env e;
+    if (active) load_env(a.state_in, a.stride, i, e);
+    const size_t obs_row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
+    unsigned long long n_term = 0;
+    long long rew0 = 0;
+    for (int s = 0; s < a.k_steps; ++s) {
+        const int64_t row0 = (int64_t)s * a.n;
+        if (lane < EPW) {
+            if (active) {
+                int32_t act = random_legal_action(env_legal_mask(e), a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)s);
+                float4 rew = env_step_autoreset(e, act, a.table, a.n_deals, a.illegal_penalty, a.illegal_bonus);
+                n_term += f_terminated(e);
+                rew0 += (long long)rew.x;
+                write_scalars(a, row0 + i, e, rew, false);
+                if (a.action_out) a.action_out[row0 + i] = act;
+                stage_env<EPW>(t, lane, e, a.table, f_cur_seat(e), a.obs != nullptr);
+            } else {
+                t.M[lane] = 0ull;
+            }
+        }
+        __syncwarp();
+        emit_tile<EPW, OBS>(t, lane, env_base, n_valid,
+                            a.obs ? static_cast<unsigned char*>(a.obs) + (size_t)row0 * obs_row_bytes : nullptr,
+                            a.mask ? a.mask + (size_t)row0 * kNumActions : nullptr, a.mask_vec);
+        __syncwarp();
+    }
+    if (active) store_env(a.state_out, a.stride, i, e);
+    if (a.stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_term += __shfl_xor_sync(0xffffffffu, n_term, o);
+            rew0 += __shfl_xor_sync(0xffffffffu, rew0, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.stats[0], n_term);
+            atomicAdd(&a.stats[1], (unsigned long long)rew0);
+            atomicAdd(&a.stats[2], (unsigned long long)n_valid * (unsigned long long)a.k_steps);
+        }
+    }
+}
+
+// ---- init / reset_fields / duplicate_init / observe / legal_mask -----------------------
+enum ProduceMode { kModeInit = 0, kModeReset = 1, kModeDupInit = 2, kModeObserve = 3, kModeMask = 4 };
+
+template <int EPW, int OBS>
+__global__ void __launch_bounds__(128) k_produce(const EnvArgs a) {
+    BRL_TILE_PROLOGUE()
+    if (lane < EPW) {
+        if (active) {
+            Env e;
+            uint32_t q;
+            if (a.mode == kModeInit) {
+                env_init(e, a.keys[i], a.n_deals);
+            } else if (a.mode == kModeReset) {
+                const int8_t* p = a.in_players + 4 * i;
+                uint32_t seating8 = (uint32_t)(p[0] & 3) | ((uint32_t)(p[1] & 3) << 2) | ((uint32_t)(p[2] & 3) << 4) |
+                                    ((uint32_t)(p[3] & 3) << 6);
+                env_reset(e, (uint32_t)a.in_deal[i], (uint32_t)a.in_dealer[i] & 3u, a.in_vul_ns[i] ? 1u : 0u,
+                          a.in_vul_ew[i] ? 1u : 0u, seating8, a.in_rng_key ? a.in_rng_key[i] : 0ull);
+            } else {
+                load_env(a.state_in, a.stride, i, e);
+                if (a.mode == kModeDupInit) env_duplicate_init(e);
+            }
+            q = f_cur_seat(e);
+            if (a.mode == kModeObserve && a.in_player_id) {  // _observe(state, player): seat of that player id
+                uint32_t pid = (uint32_t)a.in_player_id[i] & 3u;
+#pragma unroll
+                for (uint32_t s = 0; s < 4; ++s)
+                    if (f_player_at(e, s) == pid) q = s;
+            }
+            if (a.mode <= kModeDupInit) {
+                store_env(a.state_out, a.stride, i, e);
+                write_scalars(a, i, e, make_float4(0.f, 0.f, 0.f, 0.f), false);
+            }
+            stage_env<EPW>(t, lane, e, a.table, q, a.obs != nullptr);
+        } else {
+            t.M[lane] = 0ull;
+        }
+    }
+    __syncwarp();
+    emit_tile<EPW, OBS>(t, lane, env_base, n_valid, a.obs, a.mask, a.mask_vec);
+}
+
+// ---- duplicate_step -- src/duplicate.py:147-192 ----------------------------------------
+template <int EPW, int OBS>
+__global__ void __launch_bounds__(128) k_dup_step(const EnvArgs a) {
+    BRL_TILE_PROLOGUE()
+    if (lane < EPW) {
+        if (active) {
+            Env e;
+            load_env(a.state_in, a.stride, i, e);
+            float4 rew = env_step(e, a.action[i], a.table, a.illegal_penalty, a.illegal_bonus);  // :149
+            const bool term = f_terminated(e) != 0;
+            const bool a_term = a.ta.terminated[i] != 0, b_term = a.tb.terminated[i] != 0;
+            const bool a_just = !a_term && term;           // :152
+            const bool b_just = a_term && term && !b_term;  // :158
+            // snapshot of the stepped state (:165-188)
+            const uint32_t lb1 = f_lb1(e);
+            const int32_t s_last_bid = (int32_t)lb1 - 1;
+            const int32_t s_last_bidder = lb1 ? (int32_t)f_player_at(e, f_bidder_seat(e)) : -1;
+            const uint8_t s_x = (uint8_t)f_x(e), s_xx = (uint8_t)f_xx(e);
+            float4 out_rew = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b_just) {
+                float s = imp_of_difference(a.ta.rewards[i].x + rew.x);  // :159-161, _imp_reward :15-70
+                out_rew = make_float4(s, s, -s, -s);
+            } else if (a_just) {
+                env_duplicate_init(e);  // :151-155
+            }
+            if (a_just || b_just) {
+                const TableInfo& ti = b_just ? a.tb : a.ta;
+                ti.terminated[i] = 1;
+                ti.rewards[i] = rew;
+                ti.last_bid[i] = s_last_bid;
+                ti.last_bidder[i] = s_last_bidder;
+                ti.call_x[i] = s_x;
+                ti.call_xx[i] = s_xx;
+            }
+            write_scalars(a, i, e, out_rew, false);
+            store_env(a.state_out, a.stride, i, e);
+            stage_env<EPW>(t, lane, e, a.table, f_cur_seat(e), a.obs != nullptr);
+        } else {
+            t.M[lane] = 0ull;
+        }
+    }
+    __syncwarp();
+    emit_tile<EPW, OBS>(t, lane, env_base, n_valid, a.obs, a.mask, a.mask_vec);
+}
+
+// ---- private field export ----------------------------------------------------------------
+struct FieldArgs {
+    const uint4* state;
+    int32_t* deal;
+    int32_t* dealer;
+    int8_t* shuffled;
+    uint8_t* vul;
+    int32_t* last_bid;
+    int32_t* last_bidder;
+    uint8_t* call_x;
+    uint8_t* call_xx;
+    int32_t* pass_num;
+    int32_t* step_count;
+    uint64_t* rng_key;
+    int64_t n, stride;
+};
+
+__global__ void __launch_bounds__(256) k_state_fields(const FieldArgs a) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    Env e;
+    load_env(a.state, a.stride, i, e);
+    if (a.deal) a.deal[i] = (int32_t)e.deal;
+    if (a.dealer) a.dealer[i] = (int32_t)f_dealer(e);
+    if (a.shuffled) {
+        char4 p = make_char4((char)f_player_at(e, 0), (char)f_player_at(e, 1), (char)f_player_at(e, 2), (char)f_player_at(e, 3));
+        reinterpret_cast<char4*>(a.shuffled)[i] = p;
+    }
+    if (a.vul) reinterpret_cast<uchar2*>(a.vul)[i] = make_uchar2((unsigned char)f_vul_ns(e), (unsigned char)f_vul_ew(e));
+    uint32_t lb1 = f_lb1(e);
+    if (a.last_bid) a.last_bid[i] = (int32_t)lb1 - 1;
+    if (a.last_bidder) a.last_bidder[i] = lb1 ? (int32_t)f_player_at(e, f_bidder_seat(e)) : -1;
+    if (a.call_x) a.call_x[i] = (uint8_t)f_x(e);
+    if (a.call_xx) a.call_xx[i] = (uint8_t)f_xx(e);
+    if (a.pass_num) a.pass_num[i] = (int32_t)f_pass_num(e);
+    if (a.step_count) a.step_count[i] = (int32_t)f_step_count(e);
+    if (a.rng_key) a.rng_key[i] = (uint64_t)e.key_lo | ((uint64_t)e.key_hi << 32);
+}
+
+__global__ void __launch_bounds__(256) k_make_keys(uint64_t* keys, int64_t n, uint64_t seed, int64_t env_offset) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = make_key(seed, (uint64_t)(env_offset + i));
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------
+struct Tiling {
+    int epw, wpb;
+};
+
+static Tiling choose_tiling(int64_t n, int32_t flags) {
+    // flags bits 16-17: EPW override (1->8, 2->16, 3->32); bits 18-19: warps per block (1->1, 2->2, 3->4)
+    static const int epw_of[4] = {0, 8, 16, 32};
+    static const int wpb_of[4] = {0, 1, 2, 4};
+    int epw = epw_of[(flags >> 16) & 3], wpb = wpb_of[(flags >> 18) & 3];
+    if (epw == 0) epw = n >= 262144 ? 32 : (n >= 65536 ? 16 : 8);  // >= ~8 warps per SM at every size
+    if (wpb == 0) wpb = n >= 65536 ? 4 : 2;
+    return {epw, wpb};
+}
+
+#define BRL_DEFINE_LAUNCHER(NAME, KERNEL)                                                                    \
+    template <int EPW, int OBS>                                                                              \
+    static void NAME##_inst(const EnvArgs& a, int wpb, cudaStream_t s) {                                     \
+        int64_t tiles = (a.n + EPW - 1) / EPW;                                                               \
+        unsigned grid = (unsigned)((tiles + wpb - 1) / wpb);                                                 \
+        KERNEL<EPW, OBS><<<grid, wpb * 32, wpb * sizeof(WarpTile<EPW>), s>>>(a);                             \
+    }                                                                                                        \
+    template <int OBS>                                                                                       \
+    static void NAME##_epw(const EnvArgs& a, Tiling t, cudaStream_t s) {                                     \
+        if (t.epw == 8) NAME##_inst<8, OBS>(a, t.wpb, s);                                                    \
+        else if (t.epw == 16) NAME##_inst<16, OBS>(a, t.wpb, s);                                             \
+        else NAME##_inst<32, OBS>(a, t.wpb, s);                                                              \
+    }                                                                                                        \
+    static void NAME(const EnvArgs& a, cudaStream_t s) {                                                     \
+        if (a.n == 0) return;                                                                                \
+        Tiling t = choose_tiling(a.n, a.flags);                                                              \
+        if (a.flags & BRL_F_OBS_U8) NAME##_epw<kObsU8>(a, t, s);                                             \
+        else if (a.flags & BRL_F_OBS_BF16) NAME##_epw<kObsBF16>(a, t, s);                                    \
+        else NAME##_epw<kObsF32>(a, t, s);                                                                   \
+    }
+
+BRL_DEFINE_LAUNCHER(launch_step, k_step)
+BRL_DEFINE_LAUNCHER(launch_rollout, k_rollout)
+BRL_DEFINE_LAUNCHER(launch_produce, k_produce)
+BRL_DEFINE_LAUNCHER(launch_dup_step, k_dup_step)
+
+static void fill_common(EnvArgs& a, const BrlParams* p) {
+    a.n = p->n_envs;
+    a.stride = p->state_stride > 0 ? p->state_stride : p->n_envs;
+    a.env_offset = p->env_offset;
+    a.seed = p->seed;
+    a.n_deals = (uint32_t)p->n_deals;
+    a.step = p->step;
+    a.flags = p->flags;
+    a.k_steps = p->k_steps;
+    a.illegal_penalty = p->illegal_penalty;
+    a.illegal_bonus = p->illegal_bonus;
+}
+
+static int mask_vec_ok(const void* mask, int64_t n, int rows) {
+    if (mask == nullptr) return 0;
+    if (reinterpret_cast<uintptr_t>(mask) & 15u) return 0;
+    return rows <= 1 || ((n * kNumActions) % 16 == 0);
+}
+
+static void set_outputs(EnvArgs& a, void** b, int first, int rows) {
+    a.obs = b[first];
+    a.mask = static_cast<uint8_t*>(b[first + 1]);
+    a.rewards = static_cast<float4*>(b[first + 2]);
+    a.terminated = static_cast<uint8_t*>(b[first + 3]);
+    a.current_player = static_cast<int8_t*>(b[first + 4]);
+    a.mask_vec = mask_vec_ok(a.mask, a.n, rows);
+}
+
+static int32_t check_outputs(const EnvArgs& a, const char* fn) {
+    if (a.obs && (reinterpret_cast<uintptr_t>(a.obs) & 15u)) return fail(BRL_E_BUFFER, "%s: obs is not 16-byte aligned", fn);
+    if (a.rewards && (reinterpret_cast<uintptr_t>(a.rewards) & 15u)) return fail(BRL_E_BUFFER, "%s: rewards is not 16-byte aligned", fn);
+    return BRL_OK;
+}
+
+static TableInfo table_info(void** b, int first) {
+    TableInfo t;
+    t.terminated = static_cast<uint8_t*>(b[first]);
+    t.rewards = static_cast<float4*>(b[first + 1]);
+    t.last_bid = static_cast<int32_t*>(b[first + 2]);
+    t.last_bidder = static_cast<int32_t*>(b[first + 3]);
+    t.call_x = static_cast<uint8_t*>(b[first + 4]);
+    t.call_xx = static_cast<uint8_t*>(b[first + 5]);
+    return t;
+}
+
+}  // namespace brl
+
+using namespace brl;
+
+extern "C" {
+
+int32_t brl_make_keys(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "keys");
+    if (p->n_envs == 0) return BRL_OK;
+    k_make_keys<<<(unsigned)((p->n_envs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<uint64_t*>(b[0]), p->n_envs, p->seed, p->env_offset);
+    return check_launch("brl_make_keys");
+}
+
+int32_t brl_init(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "keys");
+    BRL_REQUIRE(b[1], "deal_table");
+    BRL_REQUIRE(b[2], "state_out");
+    if (p->n_deals <= 0) return fail(BRL_E_OPAQUE, "brl_init: n_deals must be > 0");
+    EnvArgs a = {};
+    fill_common(a, p);
+    a.mode = kModeInit;
+    a.keys = static_cast<const uint64_t*>(b[0]);
+    a.table = static_cast<const uint8_t*>(b[1]);
+    a.state_out = static_cast<uint4*>(b[2]);
+    set_outputs(a, b, 3, 1);
+    if ((rc = check_outputs(a, "brl_init")) != BRL_OK) return rc;
+    launch_produce(a, (cudaStream_t)stream);
+    return check_launch("brl_init");
+}
+
+int32_t brl_reset_fields(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    static const char* names[] = {"deal", "dealer", "vul_ns", "vul_ew", "shuffled_players"};
+    for (int k = 0; k < 5; ++k)
+        if (b[k] == nullptr) return fail(BRL_E_BUFFER, "brl_reset_fields: buffer '%s' is NULL", names[k]);
+    BRL_REQUIRE(b[6], "deal_table");
+    BRL_REQUIRE(b[7], "state_out");
+    EnvArgs a = {};
+    fill_common(a, p);
+    a.mode = kModeReset;
+    a.in_deal = static_cast<const int32_t*>(b[0]);
+    a.in_dealer = static_cast<const int32_t*>(b[1]);
+    a.in_vul_ns = static_cast<const uint8_t*>(b[2]);
+    a.in_vul_ew = static_cast<const uint8_t*>(b[3]);
+    a.in_players = static_cast<const int8_t*>(b[4]);
+    a.in_rng_key = static_cast<const uint64_t*>(b[5]);
+    a.table = static_cast<const uint8_t*>(b[6]);
+    a.state_out = static_cast<uint4*>(b[7]);
+    set_outputs(a, b, 8, 1);
+    if ((rc = check_outputs(a, "brl_reset_fields")) != BRL_OK) return rc;
+    launch_produce(a, (cudaStream_t)stream);
+    return check_launch("brl_reset_fields");
+}
+
+int32_t brl_step(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "state_in");
+    if (!(p->flags & BRL_F_RANDOM_ACTION) && b[1] == nullptr) return fail(BRL_E_BUFFER, "brl_step: buffer 'action' is NULL");
+    BRL_REQUIRE(b[2], "deal_table");
+    BRL_REQUIRE(b[3], "state_out");
+    if ((p->flags & BRL_F_AUTORESET) && p->n_deals <= 0) return fail(BRL_E_OPAQUE, "brl_step: n_deals must be > 0 with BRL_F_AUTORESET");
+    EnvArgs a = {};
+    fill_common(a, p);
+    a.state_in = static_cast<const uint4*>(b[0]);
+    a.action = static_cast<const int32_t*>(b[1]);
+    a.table = static_cast<const uint8_t*>(b[2]);
+    a.state_out = static_cast<uint4*>(b[3]);
+    set_outputs(a, b, 4, 1);
+    a.action_out = static_cast<int32_t*>(b[9]);
+    if ((rc = check_outputs(a, "brl_step")) != BRL_OK) return rc;
+    launch_step(a, (cudaStream_t)stream);
+    return check_launch("brl_step");
+}
+
+int32_t brl_duplicate_step(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "state_in");
+    if (b[1] == nullptr) return fail(BRL_E_BUFFER, "brl_duplicate_step: buffer 'action' is NULL");
+    BRL_REQUIRE(b[2], "deal_table");
+    for (int k = 3; k < 15; ++k)
+        if (b[k] == nullptr) return fail(BRL_E_BUFFER, "brl_duplicate_step: table-info buffer %d is NULL", k);
+    BRL_REQUIRE(b[4], "table_a.rewards");
+    BRL_REQUIRE(b[10], "table_b.rewards");
+    BRL_REQUIRE(b[15], "state_out");
+    EnvArgs a = {};
+    fill_common(a, p);
+    a.state_in = static_cast<const uint4*>(b[0]);
+    a.action = static_cast<const int32_t*>(b[1]);
+    a.table = static_cast<const uint8_t*>(b[2]);
+    a.ta = table_info(b, 3);
+    a.tb = table_info(b, 9);
+    a.state_out = static_cast<uint4*>(b[15]);
+    set_outputs(a, b, 16, 1);
+    if ((rc = check_outputs(a, "brl_duplicate_step")) != BRL_OK) return rc;
+    launch_dup_step(a, (cudaStream_t)stream);
+    return check_launch("brl_duplicate_step");
+}
+
+int32_t brl_duplicate_init(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "state_in");
+    BRL_REQUIRE(b[1], "deal_table");
+    BRL_REQUIRE(b[2], "state_out");
+    EnvArgs a = {};
+    fill_common(a, p);
+    a.mode = kModeDupInit;
+    a.state_in = static_cast<const uint4*>(b[0]);
+    a.table = static_cast<const uint8_t*>(b[1]);
+    a.state_out = static_cast<uint4*>(b[2]);
+    set_outputs(a, b, 3, 1);
+    if ((rc = check_outputs(a, "brl_duplicate_init")) != BRL_OK) return rc;
+    launch_produce(a, (cudaStream_t)stream);
+    return check_launch("brl_duplicate_init");
+}
+
+int32_t brl_observe(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "state");
+    BRL_REQUIRE(b[2], "deal_table");
+    BRL_REQUIRE(b[3], "obs");
+    EnvArgs a = {};
+    fill_common(a, p);
+    a.mode = kModeObserve;
+    a.state_in = static_cast<const uint4*>(b[0]);
+    a.in_player_id = static_cast<const int8_t*>(b[1]);
+    a.table = static_cast<const uint8_t*>(b[2]);
+    a.obs = b[3];
+    launch_produce(a, (cudaStream_t)stream);
+    return check_launch("brl_observe");
+}
+
+int32_t brl_legal_mask(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "state");
+    if (b[1] == nullptr) return fail(BRL_E_BUFFER, "brl_legal_mask: buffer 'mask' is NULL");
+    EnvArgs a = {};
+    fill_common(a, p);
+    a.mode = kModeMask;
+    a.state_in = static_cast<const uint4*>(b[0]);
+    a.mask = static_cast<uint8_t*>(b[1]);
+    a.mask_vec = mask_vec_ok(a.mask, a.n, 1);
+    launch_produce(a, (cudaStream_t)stream);
+    return check_launch("brl_legal_mask");
+}
+
+int32_t brl_rollout_random(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "state");
+    BRL_REQUIRE(b[1], "deal_table");
+    if (p->k_steps <= 0) return fail(BRL_E_OPAQUE, "brl_rollout_random: k_steps must be > 0");
+    if (p->n_deals <= 0) return fail(BRL_E_OPAQUE, "brl_rollout_random: n_deals must be > 0");
+    EnvArgs a = {};
+    fill_common(a, p);
+    a.state_in = static_cast<const uint4*>(b[0]);
+    a.state_out = static_cast<uint4*>(b[0]);
+    a.table = static_cast<const uint8_t*>(b[1]);
+    set_outputs(a, b, 2, p->k_steps);
+    a.action_out = static_cast<int32_t*>(b[7]);
+    a.stats = static_cast<unsigned long long*>(b[8]);
+    if ((rc = check_outputs(a, "brl_rollout_random")) != BRL_OK) return rc;
+    launch_rollout(a, (cudaStream_t)stream);
+    return check_launch("brl_rollout_random");
+}
+
+int32_t brl_state_fields(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "state");
+    if (p->n_envs == 0) return BRL_OK;
+    FieldArgs a;
+    a.state = static_cast<const uint4*>(b[0]);
+    a.deal = static_cast<int32_t*>(b[1]);
+    a.dealer = static_cast<int32_t*>(b[2]);
+    a.shuffled = static_cast<int8_t*>(b[3]);
+    a.vul = static_cast<uint8_t*>(b[4]);
+    a.last_bid = static_cast<int32_t*>(b[5]);
+    a.last_bidder = static_cast<int32_t*>(b[6]);
+    a.call_x = static_cast<uint8_t*>(b[7]);
+    a.call_xx = static_cast<uint8_t*>(b[8]);
+    a.pass_num = static_cast<int32_t*>(b[9]);
+    a.step_count = static_cast<int32_t*>(b[10]);
+    a.rng_key = static_cast<uint64_t*>(b[11]);
+    a.n = p->n_envs;
+    a.stride = p->state_stride > 0 ? p->state_stride : p->n_envs;
+    k_state_fields<<<(unsigned)((a.n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("brl_state_fields");
+}
+
+}  // extern "C"

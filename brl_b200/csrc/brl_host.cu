@@ -1,0 +1,144 @@
+// brl_host.cu -- host-buffer convenience layer over the stream-first ops: the
+// library owns the device-resident packed state, the deal table replica and the
+// output staging; callers pass HOST pointers and the copies are part of the call.
+// This is what a non-JAX host (or bench.py's `e2e` leg) calls.
+#include <new>
+
+#include "common.h"
+
+struct BrlEnv {
+    uint32_t magic;
+    int64_t n, env_offset;
+    int32_t n_deals, flags;
+    uint64_t seed;
+    uint32_t step;
+    cudaStream_t stream;
+    uint8_t* d_table;
+    void* d_state;
+    int32_t* d_action;
+    uint64_t* d_keys;
+    void* d_obs;
+    uint8_t* d_mask;
+    float* d_rewards;
+    uint8_t* d_term;
+    int8_t* d_cur;
+    size_t obs_row_bytes;
+};
+
+namespace {
+constexpr uint32_t kMagic = 0x42524C45u;  // "BRLE"
+
+bool ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    brl::fail(BRL_E_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
+    return false;
+}
+
+BrlParams params_of(const BrlEnv* env, int32_t extra_flags) {
+    BrlParams p = {};
+    p.n_envs = env->n;
+    p.env_offset = env->env_offset;
+    p.state_stride = env->n;
+    p.seed = env->seed;
+    p.n_deals = env->n_deals;
+    p.flags = env->flags | extra_flags;
+    p.step = env->step;
+    p.illegal_penalty = -1.0f;
+    p.illegal_bonus = 1.0f;
+    return p;
+}
+
+int32_t copy_out(BrlEnv* env, void* obs, uint8_t* mask, float* rewards, uint8_t* terminated, int8_t* current_player) {
+    cudaStream_t s = env->stream;
+    const size_t n = (size_t)env->n;
+    if (obs && !ok(cudaMemcpyAsync(obs, env->d_obs, n * env->obs_row_bytes, cudaMemcpyDeviceToHost, s), "D2H obs")) return BRL_E_LAUNCH;
+    if (mask && !ok(cudaMemcpyAsync(mask, env->d_mask, n * BRL_NUM_ACTIONS, cudaMemcpyDeviceToHost, s), "D2H mask")) return BRL_E_LAUNCH;
+    if (rewards && !ok(cudaMemcpyAsync(rewards, env->d_rewards, n * 16, cudaMemcpyDeviceToHost, s), "D2H rewards")) return BRL_E_LAUNCH;
+    if (terminated && !ok(cudaMemcpyAsync(terminated, env->d_term, n, cudaMemcpyDeviceToHost, s), "D2H terminated")) return BRL_E_LAUNCH;
+    if (current_player && !ok(cudaMemcpyAsync(current_player, env->d_cur, n, cudaMemcpyDeviceToHost, s), "D2H current_player")) return BRL_E_LAUNCH;
+    if (!ok(cudaStreamSynchronize(s), "stream sync")) return BRL_E_LAUNCH;
+    return BRL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+BrlEnv* brl_env_create(int64_t n_envs, int64_t env_offset, const uint8_t* deal_table_host, int32_t n_deals,
+                       uint64_t seed, int32_t flags) {
+    if (n_envs <= 0 || n_deals <= 0 || deal_table_host == nullptr) {
+        brl::fail(BRL_E_OPAQUE, "brl_env_create: n_envs, n_deals must be > 0 and the deal table non-NULL");
+        return nullptr;
+    }
+    BrlEnv* env = new (std::nothrow) BrlEnv();
+    if (!env) return nullptr;
+    env->magic = kMagic;
+    env->n = n_envs;
+    env->env_offset = env_offset;
+    env->n_deals = n_deals;
+    env->flags = flags;
+    env->seed = seed;
+    env->step = 0;
+    env->obs_row_bytes = (flags & BRL_F_OBS_U8) ? BRL_OBS_DIM : ((flags & BRL_F_OBS_BF16) ? BRL_OBS_DIM * 2 : BRL_OBS_DIM * 4);
+    const size_t n = (size_t)n_envs;
+    bool good = ok(cudaStreamCreateWithFlags(&env->stream, cudaStreamNonBlocking), "stream create") &&
+                ok(cudaMalloc(&env->d_table, (size_t)n_deals * BRL_DEAL_ROW_BYTES), "malloc table") &&
+                ok(cudaMalloc(&env->d_state, n * BRL_STATE_BYTES_PER_ENV), "malloc state") &&
+                ok(cudaMalloc(&env->d_action, n * 4), "malloc action") &&
+                ok(cudaMalloc(&env->d_keys, n * 8), "malloc keys") &&
+                ok(cudaMalloc(&env->d_obs, n * env->obs_row_bytes), "malloc obs") &&
+                ok(cudaMalloc(&env->d_mask, n * BRL_NUM_ACTIONS), "malloc mask") &&
+                ok(cudaMalloc(&env->d_rewards, n * 16), "malloc rewards") &&
+                ok(cudaMalloc(&env->d_term, n), "malloc terminated") &&
+                ok(cudaMalloc(&env->d_cur, n), "malloc current_player") &&
+                ok(cudaMemcpyAsync(env->d_table, deal_table_host, (size_t)n_deals * BRL_DEAL_ROW_BYTES,
+                                   cudaMemcpyHostToDevice, env->stream), "H2D table") &&
+                ok(cudaStreamSynchronize(env->stream), "sync");
+    if (!good) {
+        brl_env_destroy(env);
+        return nullptr;
+    }
+    return env;
+}
+
+void brl_env_destroy(BrlEnv* env) {
+    if (!env || env->magic != kMagic) return;
+    cudaFree(env->d_table); cudaFree(env->d_state); cudaFree(env->d_action); cudaFree(env->d_keys);
+    cudaFree(env->d_obs); cudaFree(env->d_mask); cudaFree(env->d_rewards); cudaFree(env->d_term); cudaFree(env->d_cur);
+    if (env->stream) cudaStreamDestroy(env->stream);
+    env->magic = 0;
+    delete env;
+}
+
+int32_t brl_env_init_host(BrlEnv* env, void* obs, uint8_t* mask, float* rewards, uint8_t* terminated,
+                          int8_t* current_player) {
+    if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "brl_env_init_host: bad handle");
+    BrlParams p = params_of(env, 0);
+    void* kb[1] = {env->d_keys};
+    int32_t rc = brl_make_keys((brl_stream_t)env->stream, kb, &p, sizeof(p));
+    if (rc != BRL_OK) return rc;
+    void* b[8] = {env->d_keys, env->d_table, env->d_state, env->d_obs, env->d_mask, env->d_rewards, env->d_term, env->d_cur};
+    rc = brl_init((brl_stream_t)env->stream, b, &p, sizeof(p));
+    if (rc != BRL_OK) return rc;
+    env->step = 0;
+    return copy_out(env, obs, mask, rewards, terminated, current_player);
+}
+
+int32_t brl_env_step_host(BrlEnv* env, const int32_t* action, void* obs, uint8_t* mask, float* rewards,
+                          uint8_t* terminated, int8_t* current_player) {
+    if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "brl_env_step_host: bad handle");
+    const bool random = (env->flags & BRL_F_RANDOM_ACTION) != 0;
+    if (!random) {
+        if (action == nullptr) return brl::fail(BRL_E_BUFFER, "brl_env_step_host: action is NULL");
+        if (!ok(cudaMemcpyAsync(env->d_action, action, (size_t)env->n * 4, cudaMemcpyHostToDevice, env->stream), "H2D action"))
+            return BRL_E_LAUNCH;
+    }
+    BrlParams p = params_of(env, 0);
+    void* b[10] = {env->d_state, env->d_action, env->d_table, env->d_state, env->d_obs,
+                   env->d_mask,  env->d_rewards, env->d_term, env->d_cur, nullptr};
+    int32_t rc = brl_step((brl_stream_t)env->stream, b, &p, sizeof(p));
+    if (rc != BRL_OK) return rc;
+    env->step += 1;
+    return copy_out(env, obs, mask, rewards, terminated, current_player);
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// common.h -- error plumbing shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/brl_b200.h"
+
+namespace brl {
+
+char* last_error_buffer();  // thread-local, 512 bytes
+
+inline int32_t fail(int32_t code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+inline int32_t check_launch(const char* what) {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(BRL_E_LAUNCH, "%s: %s", what, cudaGetErrorString(err));
+    return BRL_OK;
+}
+
+inline const BrlParams* get_params(const void* opaque, size_t opaque_len, int32_t* rc) {
+    if (opaque == nullptr || opaque_len != sizeof(BrlParams)) {
+        *rc = fail(BRL_E_OPAQUE, "opaque must be one BrlParams (%zu bytes), got %zu", sizeof(BrlParams), opaque_len);
+        return nullptr;
+    }
+    const BrlParams* p = static_cast<const BrlParams*>(opaque);
+    if (p->n_envs < 0) {
+        *rc = fail(BRL_E_OPAQUE, "n_envs < 0");
+        return nullptr;
+    }
+    *rc = BRL_OK;
+    return p;
+}
+
+#define BRL_REQUIRE(ptr, name)                                                            \
+    do {                                                                                  \
+        if ((ptr) == nullptr) return brl::fail(BRL_E_BUFFER, "%s: buffer '%s' is NULL", __func__, name); \
+        if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0)                                \
+            return brl::fail(BRL_E_BUFFER, "%s: buffer '%s' is not 16-byte aligned", __func__, name);    \
+    } while (0)
+
+}  // namespace brl

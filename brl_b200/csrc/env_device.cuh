@@ -1,0 +1,343 @@
+// env_device.cuh -- per-env device logic of the bridge-bidding environment (sm_100a).
+//
+// One env = 20 x u32 of packed state (5 uint4 planes in HBM, plane-major so that
+// thread-per-env loads/stores are perfectly coalesced 128-bit accesses):
+//
+//   H[0..13]  the 424 auction-history bits of the observation, already at their
+//             observation bit positions (bit i of the 480-bit observation lives in
+//             word i/32, bit i%32), but indexed by ABSOLUTE seat instead of by seat
+//             relative to the observer.  Every observation field is a 4-bit one-hot
+//             nibble over seats (wb5/utils.py:28-46), so the observation for any
+//             observer is a nibble-rotate of H -- O(15 words), no history loop.
+//             nibble 0 (vulnerability) and bits >= 428 (hand) are kept zero.
+//   A         dealer(2) vul_ns(1) vul_ew(1) seating(8) last_bid+1(6) bidder_seat(2)
+//             call_x(1) call_xx(1) pass_num(3) terminated(1) carried(1) cur_seat(2)
+//   B         turn(9) step_count(9)
+//   D         first-namer table for the declarer rule (bidding_phase.py:156-159):
+//             bit i = pair*5+strain named; bit 10+i = which partner (seat>>1)
+//   K0,K1     `_rng_key` (src/utils.py:49)
+//   deal      row of the deal / double-dummy table
+//
+// Semantics follow the files cited in include/brl_b200.h; pgx-only conventions are
+// in conventions.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "conventions.h"
+
+namespace brl {
+
+constexpr int kNumActions = 38;
+constexpr int kObsDim = 480;
+constexpr int kObsWords = 15;
+constexpr int kDealRowBytes = 48;
+constexpr uint64_t kAllActions = (1ull << kNumActions) - 1ull;
+
+struct Env {
+    uint32_t H[14];
+    uint32_t A, B, D;
+    uint32_t key_lo, key_hi, deal;
+};
+
+// ---- field accessors --------------------------------------------------------
+__device__ __forceinline__ uint32_t f_dealer(const Env& e) { return e.A & 3u; }
+__device__ __forceinline__ uint32_t f_vul_ns(const Env& e) { return (e.A >> 2) & 1u; }
+__device__ __forceinline__ uint32_t f_vul_ew(const Env& e) { return (e.A >> 3) & 1u; }
+__device__ __forceinline__ uint32_t f_seating(const Env& e) { return (e.A >> 4) & 0xFFu; }
+__device__ __forceinline__ uint32_t f_player_at(const Env& e, uint32_t seat) { return (e.A >> (4 + 2 * seat)) & 3u; }
+__device__ __forceinline__ uint32_t f_lb1(const Env& e) { return (e.A >> 12) & 63u; }  // last_bid + 1
+__device__ __forceinline__ uint32_t f_bidder_seat(const Env& e) { return (e.A >> 18) & 3u; }
+__device__ __forceinline__ uint32_t f_x(const Env& e) { return (e.A >> 20) & 1u; }
+__device__ __forceinline__ uint32_t f_xx(const Env& e) { return (e.A >> 21) & 1u; }
+__device__ __forceinline__ uint32_t f_pass_num(const Env& e) { return (e.A >> 22) & 7u; }
+__device__ __forceinline__ uint32_t f_terminated(const Env& e) { return (e.A >> 25) & 1u; }
+__device__ __forceinline__ uint32_t f_cur_seat(const Env& e) { return (e.A >> 27) & 3u; }
+__device__ __forceinline__ uint32_t f_turn(const Env& e) { return e.B & 511u; }
+__device__ __forceinline__ uint32_t f_step_count(const Env& e) { return (e.B >> 9) & 511u; }
+
+constexpr uint32_t kTermBit = 1u << 25;
+// `terminated` is CARRIED on a live state: set by auto_reset on the fresh episode that
+// replaced a finished one (src/utils.py:49-53) and by the quad step's OR
+// (src/utils.py:128).  Such a state keeps its live legal mask; the next auto-reset
+// step clears both bits (src/utils.py:33-41).
+constexpr uint32_t kCarriedBit = 1u << 26;
+
+__device__ __forceinline__ uint32_t bitfield_set(uint32_t w, uint32_t pos, uint32_t width, uint32_t v) {
+    uint32_t m = ((1u << width) - 1u) << pos;
+    return (w & ~m) | ((v << pos) & m);
+}
+
+// ---- packed state <-> HBM (plane-major uint4) --------------------------------
+__device__ __forceinline__ void load_env(const uint4* __restrict__ st, int64_t stride, int64_t i, Env& e) {
+    uint4 p0 = st[i], p1 = st[stride + i], p2 = st[2 * stride + i], p3 = st[3 * stride + i], p4 = st[4 * stride + i];
+    e.H[0] = p0.x; e.H[1] = p0.y; e.H[2] = p0.z; e.H[3] = p0.w;
+    e.H[4] = p1.x; e.H[5] = p1.y; e.H[6] = p1.z; e.H[7] = p1.w;
+    e.H[8] = p2.x; e.H[9] = p2.y; e.H[10] = p2.z; e.H[11] = p2.w;
+    e.H[12] = p3.x; e.H[13] = p3.y; e.A = p3.z; e.B = p3.w;
+    e.D = p4.x; e.key_lo = p4.y; e.key_hi = p4.z; e.deal = p4.w;
+}
+
+__device__ __forceinline__ void store_env(uint4* __restrict__ st, int64_t stride, int64_t i, const Env& e) {
+    st[i] = make_uint4(e.H[0], e.H[1], e.H[2], e.H[3]);
+    st[stride + i] = make_uint4(e.H[4], e.H[5], e.H[6], e.H[7]);
+    st[2 * stride + i] = make_uint4(e.H[8], e.H[9], e.H[10], e.H[11]);
+    st[3 * stride + i] = make_uint4(e.H[12], e.H[13], e.A, e.B);
+    st[4 * stride + i] = make_uint4(e.D, e.key_lo, e.key_hi, e.deal);
+}
+
+// ---- Philox4x32-10 ------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+constexpr uint32_t kTagKey = 0x4B455930u;   // "KEY0"
+constexpr uint32_t kTagInit = 0x494E4954u;  // "INIT"
+constexpr uint32_t kTagAct = 0x41435430u;   // "ACT0"
+constexpr uint32_t kTagGum = 0x47554D30u;   // "GUM0"
+
+__device__ __forceinline__ uint64_t make_key(uint64_t seed, uint64_t g) {
+    uint4 r = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), kTagKey, 0u),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    return (uint64_t)r.x | ((uint64_t)r.y << 32);
+}
+
+// ---- reset / init ---------------------------------------------------------------
+__device__ __forceinline__ void env_reset(Env& e, uint32_t deal, uint32_t dealer, uint32_t vul_ns, uint32_t vul_ew,
+                                          uint32_t seating8, uint64_t key) {
+#pragma unroll
+    for (int w = 0; w < 14; ++w) e.H[w] = 0u;
+    e.A = dealer | (vul_ns << 2) | (vul_ew << 3) | (seating8 << 4) | (dealer << 27);
+    e.B = 0u;
+    e.D = 0u;
+    e.key_lo = (uint32_t)key;
+    e.key_hi = (uint32_t)(key >> 32);
+    e.deal = deal;
+}
+
+// one team (ids {0,1} or {2,3}) on N/S, the other on E/W
+__device__ __forceinline__ uint32_t seating_code_to_players(uint32_t code) {
+    uint32_t t = code & 1u, b1 = (code >> 1) & 1u, b2 = (code >> 2) & 1u;
+    uint32_t pn = 2u * t + b1, ps = 2u * t + (1u - b1);
+    uint32_t pe = 2u * (1u - t) + b2, pw = 2u * (1u - t) + (1u - b2);
+    return pn | (pe << 2) | (ps << 4) | (pw << 6);
+}
+
+// init(key): keep one half of the split in _rng_key, draw the episode from the other
+__device__ __forceinline__ void env_init(Env& e, uint64_t key, uint32_t n_deals) {
+    uint4 r = philox4x32(make_uint4((uint32_t)key, (uint32_t)(key >> 32), kTagInit, 0u),
+                         make_uint2(0x62726C5Fu, 0x62323030u));
+    uint64_t new_key = (uint64_t)r.x | ((uint64_t)r.y << 32);
+    uint32_t deal = __umulhi(r.z, n_deals);
+    env_reset(e, deal, r.w & 3u, (r.w >> 2) & 1u, (r.w >> 3) & 1u, seating_code_to_players((r.w >> 4) & 7u), new_key);
+}
+
+// src/duplicate.py:113-129: seats handed to the other team ([1,0,3,2]), same deal /
+// dealer / vulnerability, everything else (rng key included) back to defaults
+__device__ __forceinline__ void env_duplicate_init(Env& e) {
+    uint32_t s = f_seating(e);
+    uint32_t p0 = s & 3u, p1 = (s >> 2) & 3u, p2 = (s >> 4) & 3u, p3 = (s >> 6) & 3u;
+    uint32_t swapped = p1 | (p0 << 2) | (p3 << 4) | (p2 << 6);
+    env_reset(e, e.deal, f_dealer(e), f_vul_ns(e), f_vul_ew(e), swapped, 0ull);
+}
+
+// ---- legal actions ----------------------------------------------------------------
+// bidding_phase.py:51-52,157-178.  bit a of the result = action a is legal.
+__device__ __forceinline__ uint64_t env_legal_mask(const Env& e) {
+#if BRL_CONV_TERMINAL_MASK_ALL_TRUE
+    if (f_terminated(e) && !(e.A & kCarriedBit)) return kAllActions;
+#endif
+    uint32_t lb1 = f_lb1(e);
+    uint64_t m = kAllActions ^ ((1ull << (lb1 + 3u)) - 1ull);  // bids above the last bid
+    m |= 1ull;                                                  // Pass
+    if (lb1 != 0u) {
+        uint32_t partner = ((f_cur_seat(e) ^ f_bidder_seat(e)) & 1u) ^ 1u;  // same parity = same side
+        uint32_t x = f_x(e), xx = f_xx(e);
+        if (!x && !xx && !partner) m |= 2ull;
+        if (x && !xx && partner) m |= 4ull;
+    }
+    return m;
+}
+
+// ---- scoring -- score.py:5-106 in closed form (checked against the full table) -------
+__device__ __forceinline__ int32_t contract_score(uint32_t bid, uint32_t x, uint32_t xx, uint32_t vul, int32_t tricks) {
+    int32_t level = (int32_t)(bid / 5u) + 1;
+    uint32_t strain = bid % 5u;
+    int32_t need = level + 6;
+    if (need > tricks) {
+        int32_t n = need - tricks;
+        int32_t s;
+        if (!x && !xx) s = (vul ? 100 : 50) * n;
+        else {
+            s = vul ? 300 * n - 100 : (n <= 3 ? 200 * n - 100 : 300 * n - 400);
+            if (xx) s *= 2;
+        }
+        return -s;
+    }
+    int32_t over = tricks - need;
+    int32_t per = strain <= 1u ? 20 : 30;
+    int32_t score = per * level + (strain == 4u ? 10 : 0);
+    if (xx) score *= 4; else if (x) score *= 2;
+    if (score >= 100) {
+        score += vul ? 450 : 250;
+        if (level >= 6) {
+            score += vul ? 750 : 500;
+            if (level == 7) score += vul ? 750 : 500;
+        }
+    }
+    score += 50;
+    if (xx) { score += 100; per = vul ? 400 : 200; }
+    else if (x) { score += 50; per = vul ? 200 : 100; }
+    return score + per * over;
+}
+
+// src/duplicate.py:46-69: number of thresholds reached by |d|, signed by d >= 0
+__device__ __forceinline__ float imp_of_difference(float d) {
+    float ad = fabsf(d);
+    int imp = 0;
+    constexpr float T[24] = {20, 50, 90, 130, 170, 220, 270, 320, 370, 430, 500, 600,
+                             750, 900, 1100, 1300, 1500, 1750, 2000, 2250, 2500, 3000, 3500, 4000};
+#pragma unroll
+    for (int k = 0; k < 24; ++k) imp += ad >= T[k];
+    return d >= 0.0f ? (float)imp : -(float)imp;
+}
+
+__device__ __forceinline__ void history_set_bit(Env& e, uint32_t bit) {
+    uint32_t w = bit >> 5, m = 1u << (bit & 31u);
+#pragma unroll
+    for (int k = 0; k < 14; ++k)
+        if (w == (uint32_t)k) e.H[k] |= m;
+}
+
+// ---- step ---------------------------------------------------------------------------
+// pgx core.Env.step around bidding_phase.py:119-180; returns rewards by player id.
+__device__ __forceinline__ float4 env_step(Env& e, int32_t action, const uint8_t* __restrict__ table,
+                                           float illegal_penalty, float illegal_bonus) {
+    float4 rew = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f_terminated(e)) return rew;  // finished env: zero-reward no-op (src/evaluation.py:120-122)
+
+    uint32_t seat = f_cur_seat(e);
+    uint64_t legal = env_legal_mask(e);
+    bool illegal = action < 0 || action >= kNumActions || !((legal >> action) & 1ull);
+    e.B = bitfield_set(e.B, 9, 9, f_step_count(e) + 1u);
+    if (illegal) {  // SURVEY A.6.2 (unpinned convention)
+        uint32_t actor = f_player_at(e, seat);
+        rew = make_float4(illegal_bonus, illegal_bonus, illegal_bonus, illegal_bonus);
+        if (actor == 0u) rew.x = illegal_penalty;
+        else if (actor == 1u) rew.y = illegal_penalty;
+        else if (actor == 2u) rew.z = illegal_penalty;
+        else rew.w = illegal_penalty;
+        e.A |= kTermBit;
+        return rew;
+    }
+
+    uint32_t lb1 = f_lb1(e), pass_num = f_pass_num(e);
+    bool finished = false;
+    if (action == 0) {
+        pass_num += 1u;
+        finished = (pass_num == 4u) || (pass_num == 3u && lb1 != 0u);
+        if (lb1 == 0u) history_set_bit(e, 4u + seat);  // opening pass nibble (wb5/utils.py:39-41)
+    } else if (action == 1) {
+        e.A |= 1u << 20;
+        pass_num = 0u;
+        history_set_bit(e, 4u * (2u + 3u * (lb1 - 1u) + 1u) + seat);  // wb5/utils.py:42-43
+    } else if (action == 2) {
+        e.A |= 1u << 21;
+        pass_num = 0u;
+        history_set_bit(e, 4u * (2u + 3u * (lb1 - 1u) + 2u) + seat);  // wb5/utils.py:44-45
+    } else {
+        uint32_t bid = (uint32_t)action - 3u;
+        lb1 = bid + 1u;
+        e.A = bitfield_set(e.A, 12, 6, lb1);
+        e.A = bitfield_set(e.A, 18, 2, seat);
+        e.A &= ~(3u << 20);  // x = xx = 0
+        pass_num = 0u;
+        uint32_t i = (seat & 1u) * 5u + bid % 5u;  // bidding_phase.py:156-159
+        if (!((e.D >> i) & 1u)) e.D |= (1u << i) | ((seat >> 1) << (10u + i));
+        history_set_bit(e, 4u * (2u + 3u * bid) + seat);  // wb5/utils.py:36-38
+    }
+    e.A = bitfield_set(e.A, 22, 3, pass_num);
+    e.B = bitfield_set(e.B, 0, 9, f_turn(e) + 1u);
+
+    if (finished) {
+        e.A |= kTermBit;
+#if BRL_CONV_TERMINAL_ADVANCES_PLAYER
+        e.A = bitfield_set(e.A, 27, 2, (seat + 1u) & 3u);
+#endif
+        if (lb1 != 0u) {  // bidding_phase.py:182-206, score.py:109-125, contract.py:94-106
+            uint32_t bid = lb1 - 1u, strain = bid % 5u;
+            uint32_t pair = f_bidder_seat(e) & 1u;
+            uint32_t i = pair * 5u + strain;
+            uint32_t decl_seat = pair + 2u * ((e.D >> (10u + i)) & 1u);
+            uint32_t vul = pair ? f_vul_ew(e) : f_vul_ns(e);
+            uint32_t t = decl_seat * 5u + strain;
+            uint32_t byte = table[(size_t)e.deal * kDealRowBytes + 32u + (t >> 1)];
+            int32_t tricks = (int32_t)((t & 1u) ? (byte >> 4) : (byte & 15u));
+            float s = (float)contract_score(bid, f_x(e), f_xx(e), vul, tricks);
+            uint32_t team = f_player_at(e, decl_seat) >> 1;
+            float s01 = team == 0u ? s : -s;
+            rew = make_float4(s01, s01, -s01, -s01);
+        }
+    } else {
+        e.A = bitfield_set(e.A, 27, 2, (seat + 1u) & 3u);
+    }
+    return rew;
+}
+
+// src/utils.py:33-56 auto_reset around env_step; the terminal flag survives the reset
+__device__ __forceinline__ float4 env_step_autoreset(Env& e, int32_t action, const uint8_t* __restrict__ table,
+                                                     uint32_t n_deals, float illegal_penalty, float illegal_bonus) {
+    if (f_terminated(e)) {
+        e.A &= ~(kTermBit | kCarriedBit);
+        e.B = bitfield_set(e.B, 9, 9, 0u);
+    }
+    float4 rew = env_step(e, action, table, illegal_penalty, illegal_bonus);
+    if (f_terminated(e)) {
+        env_init(e, (uint64_t)e.key_lo | ((uint64_t)e.key_hi << 32), n_deals);
+        e.A |= kTermBit | kCarriedBit;
+    }
+    return rew;
+}
+
+// ---- observation -- wb5/utils.py:15-52 as 15 words of bits ------------------------------
+__device__ __forceinline__ uint32_t rotr_nibbles(uint32_t h, uint32_t q) {
+    // relative seat = (absolute - observer) mod 4: rotate every nibble right by q
+    uint32_t lo = 0x0F0F0F0Fu >> q;            // per-nibble mask of bits that stay after >> q
+    lo = (lo & 0x0F0F0F0Fu);                   // (0xF >> q) in the low nibble of each byte
+    lo |= lo << 4;
+    return ((h >> q) & lo) | ((h << (4u - q)) & ~lo);
+}
+
+__device__ __forceinline__ void env_observe_words(const Env& e, const uint8_t* __restrict__ table, uint32_t q,
+                                                  uint32_t R[kObsWords]) {
+#pragma unroll
+    for (int w = 0; w < 14; ++w) R[w] = rotr_nibbles(e.H[w], q);
+    uint32_t us = (q & 1u) ? f_vul_ew(e) : f_vul_ns(e);
+    uint32_t them = (q & 1u) ? f_vul_ns(e) : f_vul_ew(e);
+    R[0] |= (us ? 2u : 1u) | (them ? 8u : 4u);  // wb5/utils.py:15-16
+    const uint2 hm = *reinterpret_cast<const uint2*>(table + (size_t)e.deal * kDealRowBytes + 8u * q);
+    uint64_t hand = (uint64_t)hm.x | ((uint64_t)hm.y << 32);
+    R[13] |= (uint32_t)(hand << 12);  // observation bits 428..447
+    R[14] = (uint32_t)(hand >> 20);   // observation bits 448..479
+}
+
+// uniform random-legal action = k-th set bit of the mask, k = mulhi(r, n_legal)
+__device__ __forceinline__ int32_t random_legal_action(uint64_t mask, uint64_t seed, uint64_t g, uint32_t step) {
+    uint4 r = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), kTagAct, step),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
+    uint32_t n_lo = __popc(lo);
+    uint32_t k = __umulhi(r.x, n_lo + __popc(hi));
+    if (k < n_lo) return (int32_t)__fns(lo, 0u, (int)k + 1);
+    return 32 + (int32_t)__fns(hi, 0u, (int)(k - n_lo) + 1);
+}
+
+}  // namespace brl

@@ -1,0 +1,208 @@
+"""Torch-tensor front-end of the stream-first C-ABI ops (include/brl_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current CUDA stream; all
+arithmetic happens in the hand-written sm_100a kernels behind `_lib.call`.
+Every function enqueues on `torch.cuda.current_stream()` and never synchronises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (BrlParams, F_ACCUMULATE, F_AUTORESET, F_OBS_BF16, F_OBS_U8, F_QUAD_LAST, F_RANDOM_ACTION,
+                   F_SAMPLE)
+
+NUM_ACTIONS = 38
+OBS_DIM = 480
+STATE_PLANES = 5
+
+_OBS_FLAG = {torch.float32: 0, torch.uint8: F_OBS_U8, torch.bool: F_OBS_U8, torch.bfloat16: F_OBS_BF16}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.BrlError("brl_b200 ops need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise _lib.BrlError("brl_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _params(n, *, flags=0, env_offset=0, stride=0, seed=0, n_deals=0, step=0, k_steps=0, illegal_penalty=-1.0,
+            illegal_bonus=1.0, gamma=0.0, gae_lambda=0.0) -> BrlParams:
+    return BrlParams(int(n), int(env_offset), int(stride or n), int(seed) & 0xFFFFFFFFFFFFFFFF, int(n_deals), int(flags),
+                     int(step) & 0xFFFFFFFF, int(k_steps), float(illegal_penalty), float(illegal_bonus), float(gamma),
+                     float(gae_lambda))
+
+
+def obs_flag(dtype: torch.dtype) -> int:
+    try:
+        return _OBS_FLAG[dtype]
+    except KeyError:
+        raise _lib.BrlError(f"observation dtype {dtype} not supported (float32, uint8/bool, bfloat16)") from None
+
+
+def new_state(n: int, device) -> torch.Tensor:
+    """Packed env state: uint4[5][n] plane-major, seen from torch as int32[5, n, 4]."""
+    return torch.empty((STATE_PLANES, n, 4), dtype=torch.int32, device=device)
+
+
+class EnvOutputs:
+    """The Env surface brl consumes (src/roll_out.py:72-100): caller-owned output buffers."""
+
+    __slots__ = ("observation", "legal_action_mask", "rewards", "terminated", "current_player")
+
+    def __init__(self, n: int, device, obs_dtype=torch.float32, rows: int = 0):
+        lead = (rows, n) if rows else (n,)
+        odt = torch.uint8 if obs_dtype == torch.bool else obs_dtype
+        self.observation = torch.empty(lead + (OBS_DIM,), dtype=odt, device=device)
+        self.legal_action_mask = torch.empty(lead + (NUM_ACTIONS,), dtype=torch.uint8, device=device)
+        self.rewards = torch.empty(lead + (4,), dtype=torch.float32, device=device)
+        self.terminated = torch.empty(lead, dtype=torch.uint8, device=device)
+        self.current_player = torch.empty(lead, dtype=torch.int8, device=device)
+
+    def ptrs(self):
+        return [_ptr(self.observation), _ptr(self.legal_action_mask), _ptr(self.rewards), _ptr(self.terminated),
+                _ptr(self.current_player)]
+
+    def flag(self) -> int:
+        return obs_flag(self.observation.dtype)
+
+
+def make_keys(seed: int, n: int, device, env_offset: int = 0) -> torch.Tensor:
+    keys = torch.empty(n, dtype=torch.int64, device=device)
+    _lib.call("brl_make_keys", _stream(), [_ptr(keys)], _params(n, seed=seed, env_offset=env_offset))
+    return keys
+
+
+def init(keys: torch.Tensor, table: torch.Tensor, state: torch.Tensor, out: EnvOutputs, tune: int = 0) -> None:
+    n = keys.shape[0]
+    _lib.call("brl_init", _stream(), [_ptr(keys), _ptr(table), _ptr(state), *out.ptrs()],
+              _params(n, n_deals=table.shape[0], stride=state.shape[1], flags=out.flag() | tune))
+
+
+def reset_fields(deal, dealer, vul_ns, vul_ew, players, rng_key, table, state, out: EnvOutputs) -> None:
+    n = deal.shape[0]
+    _lib.call("brl_reset_fields", _stream(),
+              [_ptr(deal), _ptr(dealer), _ptr(vul_ns), _ptr(vul_ew), _ptr(players), _ptr(rng_key), _ptr(table),
+               _ptr(state), *out.ptrs()],
+              _params(n, n_deals=table.shape[0], stride=state.shape[1], flags=out.flag()))
+
+
+def step(state_in, action, table, state_out, out: EnvOutputs, *, autoreset=False, random_action=False,
+         accumulate=False, quad_last=False, seed=0, step_index=0, env_offset=0, action_out=None,
+         illegal_penalty=-1.0, illegal_bonus=1.0, tune: int = 0) -> None:
+    n = state_in.shape[1]
+    flags = out.flag() | tune
+    flags |= F_AUTORESET if autoreset else 0
+    flags |= F_RANDOM_ACTION if random_action else 0
+    flags |= F_ACCUMULATE if accumulate else 0
+    flags |= F_QUAD_LAST if quad_last else 0
+    _lib.call("brl_step", _stream(),
+              [_ptr(state_in), _ptr(action), _ptr(table), _ptr(state_out), *out.ptrs(), _ptr(action_out)],
+              _params(n, flags=flags, n_deals=table.shape[0], stride=state_in.shape[1], seed=seed, step=step_index,
+                      env_offset=env_offset, illegal_penalty=illegal_penalty, illegal_bonus=illegal_bonus))
+
+
+class TableInfoBuffers:
+    """src/duplicate.py:138-144 Table_info as SoA device buffers."""
+
+    __slots__ = ("terminated", "rewards", "last_bid", "last_bidder", "call_x", "call_xx")
+
+    def __init__(self, n: int, device):
+        self.terminated = torch.zeros(n, dtype=torch.uint8, device=device)
+        self.rewards = torch.zeros((n, 4), dtype=torch.float32, device=device)
+        self.last_bid = torch.full((n,), -1, dtype=torch.int32, device=device)
+        self.last_bidder = torch.full((n,), -1, dtype=torch.int32, device=device)
+        self.call_x = torch.zeros(n, dtype=torch.uint8, device=device)
+        self.call_xx = torch.zeros(n, dtype=torch.uint8, device=device)
+
+    def ptrs(self):
+        return [_ptr(getattr(self, k)) for k in self.__slots__]
+
+
+def duplicate_step(state_in, action, table, info_a: TableInfoBuffers, info_b: TableInfoBuffers, state_out,
+                   out: EnvOutputs, illegal_penalty=-1.0, illegal_bonus=1.0) -> None:
+    n = state_in.shape[1]
+    _lib.call("brl_duplicate_step", _stream(),
+              [_ptr(state_in), _ptr(action), _ptr(table), *info_a.ptrs(), *info_b.ptrs(), _ptr(state_out), *out.ptrs()],
+              _params(n, flags=out.flag(), n_deals=table.shape[0], stride=state_in.shape[1],
+                      illegal_penalty=illegal_penalty, illegal_bonus=illegal_bonus))
+
+
+def duplicate_init(state_in, table, state_out, out: EnvOutputs) -> None:
+    n = state_in.shape[1]
+    _lib.call("brl_duplicate_init", _stream(), [_ptr(state_in), _ptr(table), _ptr(state_out), *out.ptrs()],
+              _params(n, flags=out.flag(), n_deals=table.shape[0], stride=state_in.shape[1]))
+
+
+def observe(state, table, obs: torch.Tensor, player_id: Optional[torch.Tensor] = None, tune: int = 0) -> None:
+    n = state.shape[1]
+    _lib.call("brl_observe", _stream(), [_ptr(state), _ptr(player_id), _ptr(table), _ptr(obs)],
+              _params(n, flags=obs_flag(obs.dtype) | tune, n_deals=table.shape[0], stride=state.shape[1]))
+
+
+def legal_mask(state, mask: torch.Tensor, tune: int = 0) -> None:
+    n = state.shape[1]
+    _lib.call("brl_legal_mask", _stream(), [_ptr(state), _ptr(mask)], _params(n, stride=state.shape[1], flags=tune))
+
+
+def rollout_random(state, table, k_steps: int, out: Optional[EnvOutputs], *, seed=0, step0=0, env_offset=0,
+                   action_out=None, stats=None, obs_only: Optional[torch.Tensor] = None, tune: int = 0) -> None:
+    """K auto-reset random-legal steps in ONE launch; `out` holds [K, n, ...] trajectories."""
+    n = state.shape[1]
+    if out is not None:
+        ptrs, flag = out.ptrs(), out.flag()
+    else:
+        ptrs = [_ptr(obs_only), None, None, None, None]
+        flag = obs_flag(obs_only.dtype) if obs_only is not None else 0
+    _lib.call("brl_rollout_random", _stream(), [_ptr(state), _ptr(table), *ptrs, _ptr(action_out), _ptr(stats)],
+              _params(n, flags=flag | tune, n_deals=table.shape[0], stride=state.shape[1], seed=seed, step=step0,
+                      env_offset=env_offset, k_steps=k_steps))
+
+
+def imp_reward(a_rewards, b_rewards, out) -> None:
+    _lib.call("brl_imp_reward", _stream(), [_ptr(a_rewards), _ptr(b_rewards), _ptr(out)], _params(a_rewards.shape[0]))
+
+
+def gae(done, value, reward, last_val, adv, targets, gamma: float, gae_lambda: float) -> None:
+    t, n = done.shape
+    _lib.call("brl_gae", _stream(), [_ptr(done), _ptr(value), _ptr(reward), _ptr(last_val), _ptr(adv), _ptr(targets)],
+              _params(n, k_steps=t, gamma=gamma, gae_lambda=gae_lambda))
+
+
+def categorical(logits, mask, action, log_prob, *, sample=False, seed=0, env_offset=0, step_index=0) -> None:
+    n = logits.shape[0]
+    _lib.call("brl_categorical", _stream(), [_ptr(logits), _ptr(mask), _ptr(action), _ptr(log_prob)],
+              _params(n, flags=F_SAMPLE if sample else 0, seed=seed, env_offset=env_offset, step=step_index))
+
+
+def match_stats(x: torch.Tensor, sums: torch.Tensor) -> None:
+    _lib.call("brl_match_stats", _stream(), [_ptr(x), _ptr(sums)], _params(x.shape[0]))
+
+
+def gather_reward(rewards, actor, out, scale: float) -> None:
+    _lib.call("brl_gather_reward", _stream(), [_ptr(rewards), _ptr(actor), _ptr(out)],
+              _params(rewards.shape[0], gamma=scale))
+
+
+_FIELD_SPECS = (("deal", torch.int32, ()), ("dealer", torch.int32, ()), ("shuffled_players", torch.int8, (4,)),
+                ("vul", torch.uint8, (2,)), ("last_bid", torch.int32, ()), ("last_bidder", torch.int32, ()),
+                ("call_x", torch.uint8, ()), ("call_xx", torch.uint8, ()), ("pass_num", torch.int32, ()),
+                ("step_count", torch.int32, ()), ("rng_key", torch.int64, ()))
+
+
+def state_fields(state: torch.Tensor) -> dict:
+    """Unpack the private pgx-style fields brl reads (src/evaluation.py:97-112, 465-495)."""
+    n = state.shape[1]
+    out = {name: torch.empty((n,) + shape, dtype=dt, device=state.device) for name, dt, shape in _FIELD_SPECS}
+    _lib.call("brl_state_fields", _stream(), [_ptr(state)] + [_ptr(out[name]) for name, _, _ in _FIELD_SPECS],
+              _params(n, stride=state.shape[1]))
+    return out

@@ -1,0 +1,204 @@
+/*
+ * brl_b200.h -- C ABI of the B200-native bridge-bidding environment path.
+ *
+ * The reference (harukaki/brl) has NO native/FFI layer: its boundary for this
+ * path is the pgx 1.4.0 `bridge_bidding` Env Python surface used under
+ * jax.jit / vmap / lax.scan.  A jitted JAX program can only reach
+ * CUDA through an XLA custom call, so every entry point below has exactly the
+ * legacy XLA GPU custom-call shape
+ *
+ *     int32_t op(cudaStream_t stream, void **buffers,
+ *                const void *opaque, size_t opaque_len);
+ *
+ * `buffers` = device pointers, inputs first then outputs, in the order listed
+ * per op; `opaque` = one POD `BrlParams`.  The typed XLA FFI
+ * (XLA_FFI_DEFINE_HANDLER) wraps the same symbols (csrc/xla_ffi_shim.cc,
+ * INTEGRATION.md).  Rules for every op:
+ *   - the caller owns every buffer; nothing is allocated, no stream is created,
+ *     no host sync happens: the call only enqueues kernels on `stream` and is
+ *     capturable in a CUDA graph / XLA command buffer;
+ *   - optional outputs may be NULL (skipped); `state_in` may alias `state_out`
+ *     (XLA input_output_aliases) -- every env is read before it is written;
+ *   - re-entrant, no global mutable state;
+ *   - returns 0 on success, a negative BRL_E_* on a usage error (bad opaque
+ *     size, NULL required buffer, launch failure); `brl_last_error()` gives the
+ *     message (thread-local).  Illegal ACTIONS are data, not errors: they
+ *     terminate the env.
+ * There is no CPU fallback anywhere behind this ABI.
+ *
+ * Reference call sites each op replaces (paths relative to /root/reference):
+ *   brl_init              env.init(key)                src/evaluation.py:95, ppo.py:305
+ *   brl_step              env.step(state, action)      src/roll_out.py:51, src/duplicate.py:149
+ *                         (+ BRL_F_AUTORESET: auto_reset wrapper src/utils.py:9-58)
+ *   brl_duplicate_step    duplicate_step(env.step)     src/duplicate.py:147-192
+ *   brl_duplicate_init    duplicate_init(state)        src/duplicate.py:132-135
+ *   brl_observe           _observe(state, player)      src/duplicate.py:6,134
+ *   brl_legal_mask        state.legal_action_mask      src/roll_out.py:78
+ *   brl_rollout_random    act_randomly + auto_reset step, K steps per launch
+ *                                                      src/duplicate.py:7,234 ; src/utils.py:9-58
+ *   brl_imp_reward        _imp_reward                  src/duplicate.py:15-70
+ *   brl_gae               calc_gae reverse scan        src/gae.py:20-39
+ *   brl_categorical       masked distrax.Categorical   src/roll_out.py:27-30,79-81 ; src/evaluation.py:128-133
+ *   brl_match_stats       mean / SE / win-rate sums    src/evaluation.py:199-201
+ *   brl_state_fields      reads of State._dealer, ._last_bid, ... src/evaluation.py:97-112
+ *   brl_reset_fields      State(...) construction / state.replace(...) src/duplicate.py:120-128
+ */
+#ifndef BRL_B200_H
+#define BRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef BRL_CUDA_STREAM_T
+#define BRL_CUDA_STREAM_T
+typedef struct CUstream_st *brl_stream_t; /* == cudaStream_t */
+#endif
+
+#define BRL_ABI_VERSION 1
+#define BRL_NUM_ACTIONS 38      /* 0 Pass, 1 X, 2 XX, 3..37 = 1C..7NT (src/duplicate.py:9-12) */
+#define BRL_OBS_DIM 480         /* ppo.py:241, wb5/utils.py:48-52 */
+#define BRL_NUM_PLAYERS 4
+#define BRL_DEAL_ROW_BYTES 48   /* brl_b200/deals.py */
+#define BRL_STATE_PLANES 5      /* packed state = uint4[BRL_STATE_PLANES][state_stride] */
+#define BRL_STATE_BYTES_PER_ENV 80
+
+/* flags */
+#define BRL_F_AUTORESET     0x0001 /* src/utils.py:9-58 around the step */
+#define BRL_F_RANDOM_ACTION 0x0002 /* draw a uniform random-legal action in-kernel (act_randomly) */
+#define BRL_F_ACCUMULATE    0x0004 /* rewards += , terminated |= (quad step, src/utils.py:126-128) */
+#define BRL_F_OBS_U8        0x0010 /* observation as bool/u8 (pgx dtype) instead of f32 */
+#define BRL_F_OBS_BF16      0x0020 /* observation as bf16 (feeds a bf16 policy GEMM) */
+#define BRL_F_SAMPLE        0x0040 /* brl_categorical: Gumbel-argmax sample instead of mode */
+#define BRL_F_QUAD_LAST     0x0100 /* with ACCUMULATE: write the OR-ed terminated flag back into the state (src/utils.py:128) */
+#define BRL_F_OBS_STREAMING 0x0080 /* rollout: obs rows staged in shared memory and written by TMA bulk stores */
+
+/* tuning (0 = automatic): bits 16-17 envs per warp (1->8, 2->16, 3->32), bits 18-19 warps per block (1->1, 2->2, 3->4) */
+#define BRL_F_TUNE_EPW(code) ((code) << 16)
+#define BRL_F_TUNE_WPB(code) ((code) << 18)
+
+/* errors */
+#define BRL_OK 0
+#define BRL_E_OPAQUE (-1)   /* opaque_len != sizeof(BrlParams) or bad field */
+#define BRL_E_BUFFER (-2)   /* required buffer is NULL / misaligned */
+#define BRL_E_LAUNCH (-3)   /* CUDA launch error (message in brl_last_error) */
+#define BRL_E_HANDLE (-4)   /* bad BrlEnv handle */
+
+typedef struct BrlParams {
+    int64_t n_envs;        /* envs in this call (this rank's shard)                    */
+    int64_t env_offset;    /* global index of env 0 (RNG counters use global indices)  */
+    int64_t state_stride;  /* envs per plane of the packed state buffers (>= n_envs)   */
+    uint64_t seed;         /* key of the counter-based action / Gumbel RNG             */
+    int32_t n_deals;       /* rows in the deal table                                   */
+    int32_t flags;         /* BRL_F_*                                                  */
+    uint32_t step;         /* step counter of the action RNG (rollout: first step)     */
+    int32_t k_steps;       /* rollout length K / GAE horizon T                         */
+    float illegal_penalty; /* reward of a player making an illegal call (pgx: -1)      */
+    float illegal_bonus;   /* reward of the three others                               */
+    float gamma;           /* GAE                                                      */
+    float gae_lambda;      /* GAE                                                      */
+} BrlParams;
+
+typedef int32_t (*brl_op_fn)(brl_stream_t, void **, const void *, size_t);
+
+/* thread-local message of the last failing call on this thread ("" if none) */
+const char *brl_last_error(void);
+int32_t brl_abi_version(void);
+
+/* buffers: [0] out u64 keys[n]
+ * key_i = philox(seed, env_offset + i): mirrors jax.random.split(key, n). */
+int32_t brl_make_keys(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* buffers: [0] in u64 keys[n]  [1] in deal_table
+ *          [2] out state  [3] out obs[n,480]  [4] out u8 mask[n,38]  [5] out f32 rewards[n,4]
+ *          [6] out u8 terminated[n]  [7] out i8 current_player[n] */
+int32_t brl_init(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* Place envs on GIVEN episode draws.
+ * buffers: [0] in i32 deal[n]  [1] in i32 dealer[n]  [2] in u8 vul_ns[n]  [3] in u8 vul_ew[n]
+ *          [4] in i8 shuffled_players[n,4]  [5] in u64 rng_key[n] (NULL -> 0)  [6] in deal_table
+ *          [7..12] out as brl_init [2..7] */
+int32_t brl_reset_fields(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* buffers: [0] in state  [1] in i32 action[n] (ignored with BRL_F_RANDOM_ACTION)  [2] in deal_table
+ *          [3] out state  [4] out obs  [5] out mask  [6] out rewards  [7] out terminated
+ *          [8] out current_player  [9] out i32 action_taken[n] (optional) */
+int32_t brl_step(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* Table_info = SoA {u8 terminated[n], f32 rewards[n,4], i32 last_bid[n], i32 last_bidder[n],
+ *                   u8 call_x[n], u8 call_xx[n]}  (src/duplicate.py:138-144), updated in place.
+ * buffers: [0] in state  [1] in action  [2] in deal_table
+ *          [3..8] inout table A info  [9..14] inout table B info
+ *          [15] out state  [16] out obs  [17] out mask  [18] out rewards  [19] out terminated
+ *          [20] out current_player */
+int32_t brl_duplicate_step(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* buffers: [0] in state  [1] in deal_table  [2..7] out as brl_init [2..7] */
+int32_t brl_duplicate_init(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* buffers: [0] in state  [1] in i8 player_id[n] (NULL -> state.current_player)  [2] in deal_table
+ *          [3] out obs */
+int32_t brl_observe(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* buffers: [0] in state  [1] out u8 mask[n,38] */
+int32_t brl_legal_mask(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* K auto-reset steps with in-kernel random-legal actions; every output is a
+ * trajectory [K, n, ...] (any may be NULL); state updated in place.
+ * buffers: [0] inout state  [1] in deal_table
+ *          [2] out obs[K,n,480]  [3] out mask[K,n,38]  [4] out rewards[K,n,4]  [5] out terminated[K,n]
+ *          [6] out current_player[K,n]  [7] out i32 action[K,n]
+ *          [8] inout u64 stats[4] = {terminal steps, sum reward[player 0] (two's complement), calls, 0} */
+int32_t brl_rollout_random(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* buffers: [0] in f32 a_rewards[n,4]  [1] in f32 b_rewards[n,4]  [2] out f32 imp[n,4] */
+int32_t brl_imp_reward(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* T = k_steps; all arrays time-major [T, n].
+ * buffers: [0] in u8 done  [1] in f32 value  [2] in f32 reward  [3] in f32 last_val[n]
+ *          [4] out f32 advantages  [5] out f32 targets */
+int32_t brl_gae(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* buffers: [0] in f32 logits[n,38]  [1] in u8 mask[n,38] (NULL -> unmasked)
+ *          [2] out i32 action[n]  [3] out f32 log_prob[n] */
+int32_t brl_categorical(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* buffers: [0] in f32 x[n] (per-env return)  [1] inout f64 sums[8] += {n, sum x, sum x^2, #(x>0), 0,0,0,0} */
+int32_t brl_match_stats(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* Unpack private fields (any output may be NULL).
+ * buffers: [0] in state  [1] i32 deal  [2] i32 dealer  [3] i8 shuffled_players[n,4]  [4] u8 vul[n,2]
+ *          [5] i32 last_bid  [6] i32 last_bidder  [7] u8 call_x  [8] u8 call_xx  [9] i32 pass_num
+ *          [10] i32 step_count  [11] u64 rng_key */
+int32_t brl_state_fields(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* Transition bookkeeping of roll_out._env_step (src/roll_out.py:85-94):
+ * buffers: [0] in f32 rewards[n,4]  [1] in i8 actor[n]  [2] out f32 reward[n] = rewards[actor] / scale
+ * scale passed in BrlParams.gamma. */
+int32_t brl_gather_reward(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
+/* -------------------------------------------------------------------------
+ * Host-buffer convenience layer (the call a non-JAX host makes): the library
+ * owns device state + pinned staging; inputs/outputs are HOST pointers and the
+ * copies are part of the call.  Synchronous.  Used for bench.py's `e2e`.
+ * ------------------------------------------------------------------------- */
+typedef struct BrlEnv BrlEnv;
+
+BrlEnv *brl_env_create(int64_t n_envs, int64_t env_offset, const uint8_t *deal_table_host,
+                       int32_t n_deals, uint64_t seed, int32_t flags);
+void brl_env_destroy(BrlEnv *env);
+/* init from philox keys of (seed, env_offset+i); outputs as brl_env_step_host */
+int32_t brl_env_init_host(BrlEnv *env, void *obs, uint8_t *mask, float *rewards, uint8_t *terminated,
+                          int8_t *current_player);
+/* action: host i32[n] (NULL with BRL_F_RANDOM_ACTION); outputs: host buffers (any may be NULL).
+ * obs dtype follows the env's flags (f32 default, BRL_F_OBS_U8 = pgx bool). */
+int32_t brl_env_step_host(BrlEnv *env, const int32_t *action, void *obs, uint8_t *mask, float *rewards,
+                          uint8_t *terminated, int8_t *current_player);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRL_B200_H */
