@@ -201,8 +201,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_stats():
+        # the single collective of the path: episode statistics summed over ranks
+        sums = torch.zeros(8, dtype=torch.float64, device=dev)
+        sums[:4] = stats.to(torch.float64)
+        if world > 1:
+            dist.all_reduce(sums)
+        return sums
+
     for i in range(args.warmup):
         one_step(i)
+    reduce_stats()  # warm the (lazy-loaded) torch / NCCL kernels outside the timed region
     barrier()
     stats.zero_()
     sampler = ClockSampler(local)
@@ -214,11 +223,7 @@ def main():
     for i in range(args.steps):
         one_step(args.warmup + i)
         evs[i + 1].record()
-    # the single collective of the path: episode statistics summed over ranks
-    sums = torch.zeros(8, dtype=torch.float64, device=dev)
-    sums[:4] = stats.to(torch.float64)
-    if world > 1:
-        dist.all_reduce(sums)
+    sums = reduce_stats()
     end = torch.cuda.Event(enable_timing=True)
     end.record()
     barrier()
@@ -257,7 +262,7 @@ def main():
             "dtype": "u8/int32 state, f32 0/1 observation", "data": "synthetic", "config": _config(world),
             "e2e": e2e, "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "brl::k_rollout<8,f32>", "peak_source": peak_src,
+                         "traffic": None, "kernel": "brl::k_rollout_ws<f32> (1 env warp + 3 writer warps per 32 envs)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * k, "avg_launch_ms": avg_kernel_ms},
             "cpu_baseline": cpu, "clocks": clocks,
             "episode_stats": {"finished_auctions": float(sums[0]), "sum_reward_player0": float(sums[1]),
@@ -322,7 +327,29 @@ def run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps, warmu
 
 def run_sweep(torch, ops, table, dev, peak):
     """Larger env counts (footprint >> L2 per step) and the one-launch-per-env.step path."""
+    from brl_b200 import _lib
     res = []
+    n, k = N_ENVS, T_STEPS
+    state, out0 = ops.new_state(n, dev), ops.EnvOutputs(n, dev)
+    ops.init(ops.make_keys(SEED, n, dev), table, state, out0)
+    traj = ops.EnvOutputs(n, dev, rows=k)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, kw in (("ws7", {"writers": 7}), ("ws5", {"writers": 5}), ("ws3", {"writers": 3}), ("ws1", {"writers": 1}),
+                     ("tile8", {"classic_rollout": True, "epw": 8}), ("tile16", {"classic_rollout": True, "epw": 16}),
+                     ("tile32", {"classic_rollout": True, "epw": 32})):
+        tune = _lib.tune(**kw)
+        for i in range(3):
+            ops.rollout_random(state, table, k, traj, seed=SEED, step0=i * k, tune=tune)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(10):
+            ops.rollout_random(state, table, k, traj, seed=SEED, step0=(3 + i) * k, tune=tune)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        gbs = BYTES_PER_ENV_STEP * n * k / (ms * 1e-3) / 1e9
+        res.append({"kernel": "rollout:" + name, "n_envs": n, "sub_steps": k, "ms": round(ms, 4), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)})
+    del state, out0, traj
     for n, k in ((65536, 8), (1048576, 2)):
         state, out0 = ops.new_state(n, dev), ops.EnvOutputs(n, dev)
         ops.init(ops.make_keys(SEED, n, dev), table, state, out0)

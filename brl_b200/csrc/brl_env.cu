@@ -84,72 +84,75 @@ __device__ __forceinline__ uint32_t pair_to_bf16x2(uint32_t two) {
     return ((two & 1u) ? 0x00003F80u : 0u) | ((two & 2u) ? 0x3F800000u : 0u);
 }
 
-// phase 2: cooperative, fully coalesced expansion of one tile
-template <int EPW, int OBS>
-__device__ __forceinline__ void emit_tile(const WarpTile<EPW>& t, int lane, int64_t env_base, int n_valid,
-                                          void* obs, uint8_t* mask, int mask_vec) {
-    if (obs != nullptr) {
-        for (int e = 0; e < n_valid; ++e) {
-            const uint32_t* R = &t.R[e * kRowStride];
-            if (OBS == kObsF32) {
-                float4* row = reinterpret_cast<float4*>(obs) + (env_base + e) * (kObsDim / 4);
+// phase 2 building blocks: cooperative, fully coalesced expansion.
+// One warp writes one observation row (480 values) from its 15 words of bits.
+template <int OBS>
+__device__ __forceinline__ void emit_obs_row(const uint32_t* R, int lane, void* obs, int64_t env) {
+    if (OBS == kObsF32) {
+        float4* row = reinterpret_cast<float4*>(obs) + env * (kObsDim / 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int j = lane + 32 * k;
-                    if (j < kObsDim / 4) row[j] = nibble_to_float4((R[j >> 3] >> ((j & 7) * 4)) & 15u);
-                }
-            } else if (OBS == kObsU8) {
-                uint4* row = reinterpret_cast<uint4*>(obs) + (env_base + e) * (kObsDim / 16);
-                if (lane < kObsDim / 16) {
-                    uint32_t h = (R[lane >> 1] >> ((lane & 1) * 16)) & 0xFFFFu;
-                    row[lane] = make_uint4(spread4(h & 15u), spread4((h >> 4) & 15u), spread4((h >> 8) & 15u),
-                                           spread4(h >> 12));
-                }
-            } else {
-                uint4* row = reinterpret_cast<uint4*>(obs) + (env_base + e) * (kObsDim / 8);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    int j = lane + 32 * k;
-                    if (j < kObsDim / 8) {
-                        uint32_t b = (R[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
-                        row[j] = make_uint4(pair_to_bf16x2(b), pair_to_bf16x2(b >> 2), pair_to_bf16x2(b >> 4),
-                                            pair_to_bf16x2(b >> 6));
-                    }
-                }
-            }
+        for (int k = 0; k < 4; ++k) {
+            int j = lane + 32 * k;
+            if (j < kObsDim / 4) row[j] = nibble_to_float4((R[j >> 3] >> ((j & 7) * 4)) & 15u);
         }
-    }
-    if (mask != nullptr) {
-        uint8_t* base = mask + env_base * kNumActions;
-        int nbytes = n_valid * kNumActions;
-        if (mask_vec) {
-            for (int o = lane * 16; o < nbytes; o += 32 * 16) {
-                int e0 = o / kNumActions, a0 = o - e0 * kNumActions;
-                uint64_t bits = (t.M[e0] >> a0) | (t.M[e0 + 1] << (kNumActions - a0));
-                uint32_t h = (uint32_t)bits & 0xFFFFu;
-                uint4 v = make_uint4(spread4(h & 15u), spread4((h >> 4) & 15u), spread4((h >> 8) & 15u), spread4(h >> 12));
-                if (o + 16 <= nbytes) {
-                    *reinterpret_cast<uint4*>(base + o) = v;
-                } else {  // ragged tail of the last tile
-                    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                    for (int b = 0; o + b < nbytes; ++b) base[o + b] = (uint8_t)((w[b >> 2] >> ((b & 3) * 8)) & 1u);
-                }
-            }
-        } else {
-            for (int o = lane; o < nbytes; o += 32) {
-                int e0 = o / kNumActions, a0 = o - e0 * kNumActions;
-                base[o] = (uint8_t)((t.M[e0] >> a0) & 1ull);
+    } else if (OBS == kObsU8) {
+        uint4* row = reinterpret_cast<uint4*>(obs) + env * (kObsDim / 16);
+        if (lane < kObsDim / 16) {
+            uint32_t h = (R[lane >> 1] >> ((lane & 1) * 16)) & 0xFFFFu;
+            row[lane] = make_uint4(spread4(h & 15u), spread4((h >> 4) & 15u), spread4((h >> 8) & 15u), spread4(h >> 12));
+        }
+    } else {
+        uint4* row = reinterpret_cast<uint4*>(obs) + env * (kObsDim / 8);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            int j = lane + 32 * k;
+            if (j < kObsDim / 8) {
+                uint32_t b = (R[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                row[j] = make_uint4(pair_to_bf16x2(b), pair_to_bf16x2(b >> 2), pair_to_bf16x2(b >> 4), pair_to_bf16x2(b >> 6));
             }
         }
     }
 }
 
-template <int EPW>
-__device__ __forceinline__ void stage_env(WarpTile<EPW>& t, int lane, const Env& e, const uint8_t* table, uint32_t q,
+// `nthreads` threads (this one is `tid`) write the nbytes = n_valid*38 mask bytes of a
+// tile as one contiguous run; M[e] holds env e's 38 mask bits, M[n_valid] must be 0.
+__device__ __forceinline__ void emit_mask_run(const uint64_t* M, int tid, int nthreads, uint8_t* base, int nbytes,
+                                              int mask_vec) {
+    if (mask_vec) {
+        for (int o = tid * 16; o < nbytes; o += nthreads * 16) {
+            int e0 = o / kNumActions, a0 = o - e0 * kNumActions;
+            uint64_t bits = (M[e0] >> a0) | (M[e0 + 1] << (kNumActions - a0));
+            uint32_t h = (uint32_t)bits & 0xFFFFu;
+            uint4 v = make_uint4(spread4(h & 15u), spread4((h >> 4) & 15u), spread4((h >> 8) & 15u), spread4(h >> 12));
+            if (o + 16 <= nbytes) {
+                *reinterpret_cast<uint4*>(base + o) = v;
+            } else {  // ragged tail of the last tile
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                for (int b = 0; o + b < nbytes; ++b) base[o + b] = (uint8_t)((w[b >> 2] >> ((b & 3) * 8)) & 1u);
+            }
+        }
+    } else {
+        for (int o = tid; o < nbytes; o += nthreads) {
+            int e0 = o / kNumActions, a0 = o - e0 * kNumActions;
+            base[o] = (uint8_t)((M[e0] >> a0) & 1ull);
+        }
+    }
+}
+
+template <int EPW, int OBS>
+__device__ __forceinline__ void emit_tile(const WarpTile<EPW>& t, int lane, int64_t env_base, int n_valid,
+                                          void* obs, uint8_t* mask, int mask_vec) {
+    if (obs != nullptr)
+        for (int e = 0; e < n_valid; ++e) emit_obs_row<OBS>(&t.R[e * kRowStride], lane, obs, env_base + e);
+    if (mask != nullptr) emit_mask_run(t.M, lane, 32, mask + env_base * kNumActions, n_valid * kNumActions, mask_vec);
+}
+
+template <int EPW, class Rows>
+__device__ __forceinline__ void stage_env(WarpTile<EPW>& t, int lane, const Env& e, const Rows& rows, uint32_t q,
                                           bool want_obs) {
     if (want_obs) {
         uint32_t R[kObsWords];
-        env_observe_words(e, table, q, R);
+        env_observe_words(e, rows, q, R);
 #pragma unroll
         for (int w = 0; w < kObsWords; ++w) t.R[lane * kRowStride + w] = R[w];
     }
@@ -195,14 +198,14 @@ __global__ void __launch_bounds__(128) k_step(const EnvArgs a) {
             else act = a.action[i];
             float4 rew = (a.flags & BRL_F_AUTORESET)
                              ? env_step_autoreset(e, act, a.table, a.n_deals, a.illegal_penalty, a.illegal_bonus)
-                             : env_step(e, act, a.table, a.illegal_penalty, a.illegal_bonus);
+                             : env_step(e, act, TableRows{a.table}, a.illegal_penalty, a.illegal_bonus);
             const bool acc = (a.flags & BRL_F_ACCUMULATE) != 0;
             if (acc && (a.flags & BRL_F_QUAD_LAST) && a.terminated && (a.terminated[i] || f_terminated(e)))
                 e.A |= kTermBit | (f_terminated(e) ? 0u : kCarriedBit);  // src/utils.py:128 state.replace(terminated=OR)
             write_scalars(a, i, e, rew, acc);
             if (a.action_out) a.action_out[i] = act;
             store_env(a.state_out, a.stride, i, e);
-            stage_env<EPW>(t, lane, e, a.table, f_cur_seat(e), a.obs != nullptr);
+            stage_env<EPW>(t, lane, e, TableRows{a.table}, f_cur_seat(e), a.obs != nullptr);
         } else {
             t.M[lane] = 0ull;
         }
@@ -216,7 +219,11 @@ template <int EPW, int OBS>
 __global__ void __launch_bounds__(128) k_rollout(const EnvArgs a) {
     BRL_TILE_PROLOGUE()
     Env e;
-    if (active) load_env(a.state_in, a.stride, i, e);
+    EpisodeCache cache;
+    if (active) {
+        load_env(a.state_in, a.stride, i, e);
+        cache.prime(e, a.table, a.n_deals);
+    }
     const size_t obs_row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
     unsigned long long n_term = 0;
     long long rew0 = 0;
@@ -225,12 +232,12 @@ __global__ void __launch_bounds__(128) k_rollout(const EnvArgs a) {
         if (lane < EPW) {
             if (active) {
                 int32_t act = random_legal_action(env_legal_mask(e), a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)s);
-                float4 rew = env_step_autoreset(e, act, a.table, a.n_deals, a.illegal_penalty, a.illegal_bonus);
+                float4 rew = env_step_autoreset_cached(e, cache, act, a.table, a.n_deals, a.illegal_penalty, a.illegal_bonus);
                 n_term += f_terminated(e);
                 rew0 += (long long)rew.x;
                 write_scalars(a, row0 + i, e, rew, false);
                 if (a.action_out) a.action_out[row0 + i] = act;
-                stage_env<EPW>(t, lane, e, a.table, f_cur_seat(e), a.obs != nullptr);
+                stage_env<EPW>(t, lane, e, cache.cur, f_cur_seat(e), a.obs != nullptr);
             } else {
                 t.M[lane] = 0ull;
             }
@@ -252,6 +259,156 @@ __global__ void __launch_bounds__(128) k_rollout(const EnvArgs a) {
             atomicAdd(&a.stats[0], n_term);
             atomicAdd(&a.stats[1], (unsigned long long)rew0);
             atomicAdd(&a.stats[2], (unsigned long long)n_valid * (unsigned long long)a.k_steps);
+        }
+    }
+}
+
+// ---- warp-specialised rollout: 1 env warp + (blockDim/32 - 1) writer warps ---------------
+// At 8192 envs every env advances one step per "env-warp step latency" L, so throughput is
+// 8192 / L whatever the grouping: the HBM roofline needs L <= ~2.5 us.  The tile-per-warp
+// kernel spends L on phase 1 + phase 2 of one warp (ncu: issue-bound on a 36k-instruction
+// chain, 6.7 warps/SM).  Here a block owns 32 envs and splits the work by role:
+//   env warp (last warp: the issue arbiter favours high warp ids) -- keeps the 32 envs
+//     and their deal rows in registers, applies step s and leaves the RAW state words
+//     (absolute-seat history, vulnerability nibble, hand bits), the observer seat and the
+//     legal mask in one half of a double-buffered shared tile;
+//   writer warps -- expand step s-1 from the other half into HBM (nibble-rotate to the
+//     observer's seat while expanding, 128-bit coalesced stores), write the per-env
+//     scalars, and pre-compute the Philox uniforms of step s+1 for the env warp.
+// One __syncthreads per step hands the buffers over.
+struct WsTile {
+    uint32_t R[32 * kRowStride];  // 15 raw observation words per env (history not yet rotated)
+    uint64_t M[34];               // legal masks (+2 zero pads)
+    float4 rew[32];
+    uint32_t act[32];
+    uint8_t q[32], term[32], cur[32];
+};
+
+template <int OBS>
+__device__ __forceinline__ void emit_obs_row_rot(const uint32_t* R, uint32_t q, int lane, void* obs, int64_t env) {
+    // nibble j of the row: 0 = vulnerability, 1..106 = history (rotate right by q), 107..119 = hand
+    if (OBS == kObsF32) {
+        float4* row = reinterpret_cast<float4*>(obs) + env * (kObsDim / 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int j = lane + 32 * k;
+            if (j < kObsDim / 4) {
+                uint32_t nib = (R[j >> 3] >> ((j & 7) * 4)) & 15u;
+                if (j >= 1 && j <= 106) nib = ((nib | (nib << 4)) >> q) & 15u;
+                row[j] = nibble_to_float4(nib);
+            }
+        }
+    } else {
+        // u8 / bf16 rows: rotate whole words once, then reuse the generic expander
+        uint32_t W[kObsWords];
+#pragma unroll
+        for (int w = 0; w < kObsWords; ++w) W[w] = R[w];
+        uint32_t vul = W[0] & 15u, hand13 = W[13] & 0xFFFFF000u;
+#pragma unroll
+        for (int w = 0; w < 14; ++w) W[w] = rotr_nibbles(w == 0 ? (W[0] & ~15u) : (w == 13 ? (W[13] & 0xFFFu) : W[w]), q);
+        W[0] |= vul;
+        W[13] |= hand13;
+        emit_obs_row<OBS>(W, lane, obs, env);
+    }
+}
+
+template <int OBS>
+__global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
+    __shared__ WsTile tiles[2];
+    __shared__ uint32_t uniforms[2][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_writers = (int)(blockDim.x >> 5) - 1;
+    const int64_t env_base = (int64_t)blockIdx.x * 32;
+    const int n_valid = (int)((a.n - env_base) < 32 ? (a.n - env_base) : 32);
+    const bool active = lane < n_valid;
+    const int64_t i = env_base + lane;
+    const size_t obs_row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
+    const bool is_env_warp = warp == n_writers;
+    Env e;
+    EpisodeCache cache;
+    uint64_t mask = 0ull;
+    unsigned long long n_term = 0;
+    long long rew0 = 0;
+    if (is_env_warp) {
+        if (lane < 2) { tiles[0].M[32 + lane] = 0ull; tiles[1].M[32 + lane] = 0ull; }
+        if (active) {
+            load_env(a.state_in, a.stride, i, e);
+            cache.prime(e, a.table, a.n_deals);
+            mask = env_legal_mask(e);
+        }
+    } else if (warp == 0) {
+        uniforms[0][lane] = action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step);
+    }
+    __syncthreads();
+    for (int s = 0; s <= a.k_steps; ++s) {
+        if (is_env_warp) {
+            if (s < a.k_steps) {
+                WsTile& t = tiles[s & 1];
+                if (active) {
+                    int32_t act = kth_legal_action(mask, uniforms[s & 1][lane]);
+                    float4 rew = env_step_autoreset_cached(e, cache, act, a.table, a.n_deals, a.illegal_penalty, a.illegal_bonus);
+                    n_term += f_terminated(e);
+                    rew0 += (long long)rew.x;
+                    mask = env_legal_mask(e);
+                    const uint32_t q = f_cur_seat(e);
+                    uint32_t* R = &t.R[lane * kRowStride];
+                    if (a.obs) {
+                        const uint32_t us = (q & 1u) ? f_vul_ew(e) : f_vul_ns(e), them = (q & 1u) ? f_vul_ns(e) : f_vul_ew(e);
+                        const uint64_t hand = cache.cur.hand(e.deal, q);
+                        R[0] = e.H[0] | (us ? 2u : 1u) | (them ? 8u : 4u);
+#pragma unroll
+                        for (int w = 1; w < 13; ++w) R[w] = e.H[w];
+                        R[13] = e.H[13] | (uint32_t)(hand << 12);
+                        R[14] = (uint32_t)(hand >> 20);
+                    }
+                    t.M[lane] = mask;
+                    t.rew[lane] = rew;
+                    t.act[lane] = (uint32_t)act;
+                    t.q[lane] = (uint8_t)q;
+                    t.term[lane] = (uint8_t)f_terminated(e);
+                    t.cur[lane] = (uint8_t)f_player_at(e, q);
+                } else {
+                    t.M[lane] = 0ull;
+                }
+            }
+        } else {
+            if (s > 0) {
+                const WsTile& t = tiles[(s - 1) & 1];
+                const int64_t row0 = (int64_t)(s - 1) * a.n;
+                if (a.obs) {
+                    unsigned char* obs = static_cast<unsigned char*>(a.obs) + (size_t)row0 * obs_row_bytes;
+                    for (int r = warp; r < n_valid; r += n_writers)
+                        emit_obs_row_rot<OBS>(&t.R[r * kRowStride], t.q[r], lane, obs, env_base + r);
+                }
+                if (a.mask)
+                    emit_mask_run(t.M, (int)threadIdx.x, n_writers * 32, a.mask + (size_t)(row0 + env_base) * kNumActions,
+                                  n_valid * kNumActions, a.mask_vec);
+                if (warp == n_writers - 1 && active) {  // per-env scalars, coalesced over the tile
+                    const int64_t row = row0 + i;
+                    if (a.rewards) a.rewards[row] = t.rew[lane];
+                    if (a.terminated) a.terminated[row] = t.term[lane];
+                    if (a.current_player) a.current_player[row] = (int8_t)t.cur[lane];
+                    if (a.action_out) a.action_out[row] = (int32_t)t.act[lane];
+                }
+            }
+            if (warp == 0 && s + 1 < a.k_steps)
+                uniforms[(s + 1) & 1][lane] = action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)(s + 1));
+        }
+        __syncthreads();
+    }
+    if (is_env_warp) {
+        if (active) store_env(a.state_out, a.stride, i, e);
+        if (a.stats) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                n_term += __shfl_xor_sync(0xffffffffu, n_term, o);
+                rew0 += __shfl_xor_sync(0xffffffffu, rew0, o);
+            }
+            if (lane == 0) {
+                atomicAdd(&a.stats[0], n_term);
+                atomicAdd(&a.stats[1], (unsigned long long)rew0);
+                atomicAdd(&a.stats[2], (unsigned long long)n_valid * (unsigned long long)a.k_steps);
+            }
         }
     }
 }
@@ -289,7 +446,7 @@ __global__ void __launch_bounds__(128) k_produce(const EnvArgs a) {
                 store_env(a.state_out, a.stride, i, e);
                 write_scalars(a, i, e, make_float4(0.f, 0.f, 0.f, 0.f), false);
             }
-            stage_env<EPW>(t, lane, e, a.table, q, a.obs != nullptr);
+            stage_env<EPW>(t, lane, e, TableRows{a.table}, q, a.obs != nullptr);
         } else {
             t.M[lane] = 0ull;
         }
@@ -306,7 +463,7 @@ __global__ void __launch_bounds__(128) k_dup_step(const EnvArgs a) {
         if (active) {
             Env e;
             load_env(a.state_in, a.stride, i, e);
-            float4 rew = env_step(e, a.action[i], a.table, a.illegal_penalty, a.illegal_bonus);  // :149
+            float4 rew = env_step(e, a.action[i], TableRows{a.table}, a.illegal_penalty, a.illegal_bonus);  // :149
             const bool term = f_terminated(e) != 0;
             const bool a_term = a.ta.terminated[i] != 0, b_term = a.tb.terminated[i] != 0;
             const bool a_just = !a_term && term;           // :152
@@ -334,7 +491,7 @@ __global__ void __launch_bounds__(128) k_dup_step(const EnvArgs a) {
             }
             write_scalars(a, i, e, out_rew, false);
             store_env(a.state_out, a.stride, i, e);
-            stage_env<EPW>(t, lane, e, a.table, f_cur_seat(e), a.obs != nullptr);
+            stage_env<EPW>(t, lane, e, TableRows{a.table}, f_cur_seat(e), a.obs != nullptr);
         } else {
             t.M[lane] = 0ull;
         }
@@ -427,6 +584,18 @@ BRL_DEFINE_LAUNCHER(launch_step, k_step)
 BRL_DEFINE_LAUNCHER(launch_rollout, k_rollout)
 BRL_DEFINE_LAUNCHER(launch_produce, k_produce)
 BRL_DEFINE_LAUNCHER(launch_dup_step, k_dup_step)
+
+// flags bit 20: force the tile-per-warp rollout kernel; bits 21-22: writer warps of the
+// warp-specialised kernel (0 -> default 3, 1 -> 1, 2 -> 5, 3 -> 7)
+static void launch_rollout_ws(const EnvArgs& a, cudaStream_t s) {
+    if (a.n == 0) return;
+    static const int writers_of[4] = {3, 1, 5, 7};
+    int threads = 32 * (1 + writers_of[(a.flags >> 21) & 3]);
+    unsigned grid = (unsigned)((a.n + 31) / 32);
+    if (a.flags & BRL_F_OBS_U8) k_rollout_ws<kObsU8><<<grid, threads, 0, s>>>(a);
+    else if (a.flags & BRL_F_OBS_BF16) k_rollout_ws<kObsBF16><<<grid, threads, 0, s>>>(a);
+    else k_rollout_ws<kObsF32><<<grid, threads, 0, s>>>(a);
+}
 
 static void fill_common(EnvArgs& a, const BrlParams* p) {
     a.n = p->n_envs;
@@ -654,7 +823,8 @@ int32_t brl_rollout_random(brl_stream_t stream, void** b, const void* opaque, si
     a.action_out = static_cast<int32_t*>(b[7]);
     a.stats = static_cast<unsigned long long*>(b[8]);
     if ((rc = check_outputs(a, "brl_rollout_random")) != BRL_OK) return rc;
-    launch_rollout(a, (cudaStream_t)stream);
+    if (p->flags & (1 << 20)) launch_rollout(a, (cudaStream_t)stream);
+    else launch_rollout_ws(a, (cudaStream_t)stream);
     return check_launch("brl_rollout_random");
 }
 

@@ -131,13 +131,25 @@ __device__ __forceinline__ uint32_t seating_code_to_players(uint32_t code) {
     return pn | (pe << 2) | (ps << 4) | (pw << 6);
 }
 
-// init(key): keep one half of the split in _rng_key, draw the episode from the other
+// init(key): keep one half of the split in _rng_key, draw the episode from the other.
+// The draw is a pure function of the key, so a rollout can compute the NEXT episode's
+// draw (and prefetch its deal row) as soon as the current episode starts.
+struct EpisodeDraw {
+    uint32_t key_lo, key_hi, deal, bits;  // bits = philox word holding dealer / vul / seating
+};
+
+__device__ __forceinline__ EpisodeDraw draw_episode(uint32_t key_lo, uint32_t key_hi, uint32_t n_deals) {
+    uint4 r = philox4x32(make_uint4(key_lo, key_hi, kTagInit, 0u), make_uint2(0x62726C5Fu, 0x62323030u));
+    return EpisodeDraw{r.x, r.y, __umulhi(r.z, n_deals), r.w};
+}
+
+__device__ __forceinline__ void env_init_from_draw(Env& e, const EpisodeDraw& d) {
+    env_reset(e, d.deal, d.bits & 3u, (d.bits >> 2) & 1u, (d.bits >> 3) & 1u,
+              seating_code_to_players((d.bits >> 4) & 7u), (uint64_t)d.key_lo | ((uint64_t)d.key_hi << 32));
+}
+
 __device__ __forceinline__ void env_init(Env& e, uint64_t key, uint32_t n_deals) {
-    uint4 r = philox4x32(make_uint4((uint32_t)key, (uint32_t)(key >> 32), kTagInit, 0u),
-                         make_uint2(0x62726C5Fu, 0x62323030u));
-    uint64_t new_key = (uint64_t)r.x | ((uint64_t)r.y << 32);
-    uint32_t deal = __umulhi(r.z, n_deals);
-    env_reset(e, deal, r.w & 3u, (r.w >> 2) & 1u, (r.w >> 3) & 1u, seating_code_to_players((r.w >> 4) & 7u), new_key);
+    env_init_from_draw(e, draw_episode((uint32_t)key, (uint32_t)(key >> 32), n_deals));
 }
 
 // src/duplicate.py:113-129: seats handed to the other team ([1,0,3,2]), same deal /
@@ -217,9 +229,50 @@ __device__ __forceinline__ void history_set_bit(Env& e, uint32_t bit) {
         if (w == (uint32_t)k) e.H[k] |= m;
 }
 
+// ---- deal-row access ------------------------------------------------------------------
+// A step needs two facts about the deal: the observer's 52-bit hand mask and, at a
+// terminal, one double-dummy nibble.  TableRows gathers them from the (L2-resident)
+// table on demand -- right for one-launch-per-step kernels.  CachedRow holds the
+// whole 48-byte row in registers -- the rollout kernels load it once per episode and
+// prefetch the NEXT episode's row (its key is known in advance), which takes both
+// dependent gathers off the per-step critical path.
+struct TableRows {
+    const uint8_t* __restrict__ table;
+    __device__ __forceinline__ int32_t tricks(uint32_t deal, uint32_t seat, uint32_t strain) const {
+        uint32_t t = seat * 5u + strain;
+        uint32_t byte = table[(size_t)deal * kDealRowBytes + 32u + (t >> 1)];
+        return (int32_t)((t & 1u) ? (byte >> 4) : (byte & 15u));
+    }
+    __device__ __forceinline__ uint64_t hand(uint32_t deal, uint32_t seat) const {
+        const uint2 hm = *reinterpret_cast<const uint2*>(table + (size_t)deal * kDealRowBytes + 8u * seat);
+        return (uint64_t)hm.x | ((uint64_t)hm.y << 32);
+    }
+};
+
+struct CachedRow {
+    uint4 h01, h23, dd;  // hands N,E | hands S,W | 20 DD nibbles (80 bits) + pad
+    __device__ __forceinline__ void load(const uint8_t* __restrict__ table, uint32_t deal) {
+        const uint4* r = reinterpret_cast<const uint4*>(table + (size_t)deal * kDealRowBytes);
+        h01 = r[0];
+        h23 = r[1];
+        dd = r[2];
+    }
+    __device__ __forceinline__ int32_t tricks(uint32_t, uint32_t seat, uint32_t strain) const {
+        uint32_t t = seat * 5u + strain;  // nibble index 0..19
+        uint32_t w = t < 8u ? dd.x : (t < 16u ? dd.y : dd.z);
+        return (int32_t)((w >> ((t & 7u) * 4u)) & 15u);
+    }
+    __device__ __forceinline__ uint64_t hand(uint32_t, uint32_t seat) const {
+        uint32_t lo = seat == 0u ? h01.x : (seat == 1u ? h01.z : (seat == 2u ? h23.x : h23.z));
+        uint32_t hi = seat == 0u ? h01.y : (seat == 1u ? h01.w : (seat == 2u ? h23.y : h23.w));
+        return (uint64_t)lo | ((uint64_t)hi << 32);
+    }
+};
+
 // ---- step ---------------------------------------------------------------------------
 // pgx core.Env.step around bidding_phase.py:119-180; returns rewards by player id.
-__device__ __forceinline__ float4 env_step(Env& e, int32_t action, const uint8_t* __restrict__ table,
+template <class Rows>
+__device__ __forceinline__ float4 env_step(Env& e, int32_t action, const Rows& rows,
                                            float illegal_penalty, float illegal_bonus) {
     float4 rew = make_float4(0.f, 0.f, 0.f, 0.f);
     if (f_terminated(e)) return rew;  // finished env: zero-reward no-op (src/evaluation.py:120-122)
@@ -241,18 +294,19 @@ __device__ __forceinline__ float4 env_step(Env& e, int32_t action, const uint8_t
 
     uint32_t lb1 = f_lb1(e), pass_num = f_pass_num(e);
     bool finished = false;
+    uint32_t hist_nibble = 0u;  // nibble of the observation this call is recorded in (0 = not recorded)
     if (action == 0) {
         pass_num += 1u;
         finished = (pass_num == 4u) || (pass_num == 3u && lb1 != 0u);
-        if (lb1 == 0u) history_set_bit(e, 4u + seat);  // opening pass nibble (wb5/utils.py:39-41)
+        if (lb1 == 0u) hist_nibble = 1u;  // opening pass nibble (wb5/utils.py:39-41)
     } else if (action == 1) {
         e.A |= 1u << 20;
         pass_num = 0u;
-        history_set_bit(e, 4u * (2u + 3u * (lb1 - 1u) + 1u) + seat);  // wb5/utils.py:42-43
+        hist_nibble = 2u + 3u * (lb1 - 1u) + 1u;  // wb5/utils.py:42-43
     } else if (action == 2) {
         e.A |= 1u << 21;
         pass_num = 0u;
-        history_set_bit(e, 4u * (2u + 3u * (lb1 - 1u) + 2u) + seat);  // wb5/utils.py:44-45
+        hist_nibble = 2u + 3u * (lb1 - 1u) + 2u;  // wb5/utils.py:44-45
     } else {
         uint32_t bid = (uint32_t)action - 3u;
         lb1 = bid + 1u;
@@ -262,8 +316,9 @@ __device__ __forceinline__ float4 env_step(Env& e, int32_t action, const uint8_t
         pass_num = 0u;
         uint32_t i = (seat & 1u) * 5u + bid % 5u;  // bidding_phase.py:156-159
         if (!((e.D >> i) & 1u)) e.D |= (1u << i) | ((seat >> 1) << (10u + i));
-        history_set_bit(e, 4u * (2u + 3u * bid) + seat);  // wb5/utils.py:36-38
+        hist_nibble = 2u + 3u * bid;  // wb5/utils.py:36-38
     }
+    if (hist_nibble) history_set_bit(e, 4u * hist_nibble + seat);
     e.A = bitfield_set(e.A, 22, 3, pass_num);
     e.B = bitfield_set(e.B, 0, 9, f_turn(e) + 1u);
 
@@ -278,9 +333,7 @@ __device__ __forceinline__ float4 env_step(Env& e, int32_t action, const uint8_t
             uint32_t i = pair * 5u + strain;
             uint32_t decl_seat = pair + 2u * ((e.D >> (10u + i)) & 1u);
             uint32_t vul = pair ? f_vul_ew(e) : f_vul_ns(e);
-            uint32_t t = decl_seat * 5u + strain;
-            uint32_t byte = table[(size_t)e.deal * kDealRowBytes + 32u + (t >> 1)];
-            int32_t tricks = (int32_t)((t & 1u) ? (byte >> 4) : (byte & 15u));
+            int32_t tricks = rows.tricks(e.deal, decl_seat, strain);
             float s = (float)contract_score(bid, f_x(e), f_xx(e), vul, tricks);
             uint32_t team = f_player_at(e, decl_seat) >> 1;
             float s01 = team == 0u ? s : -s;
@@ -299,10 +352,40 @@ __device__ __forceinline__ float4 env_step_autoreset(Env& e, int32_t action, con
         e.A &= ~(kTermBit | kCarriedBit);
         e.B = bitfield_set(e.B, 9, 9, 0u);
     }
-    float4 rew = env_step(e, action, table, illegal_penalty, illegal_bonus);
+    float4 rew = env_step(e, action, TableRows{table}, illegal_penalty, illegal_bonus);
     if (f_terminated(e)) {
         env_init(e, (uint64_t)e.key_lo | ((uint64_t)e.key_hi << 32), n_deals);
         e.A |= kTermBit | kCarriedBit;
+    }
+    return rew;
+}
+
+// Same auto-reset step for the persistent rollout kernels: the current deal row lives in
+// registers, and the next episode (draw + row) was prefetched when this one started.
+struct EpisodeCache {
+    CachedRow cur, next;
+    EpisodeDraw next_draw;
+    __device__ __forceinline__ void prime(const Env& e, const uint8_t* __restrict__ table, uint32_t n_deals) {
+        cur.load(table, e.deal);
+        next_draw = draw_episode(e.key_lo, e.key_hi, n_deals);
+        next.load(table, next_draw.deal);
+    }
+};
+
+__device__ __forceinline__ float4 env_step_autoreset_cached(Env& e, EpisodeCache& c, int32_t action,
+                                                            const uint8_t* __restrict__ table, uint32_t n_deals,
+                                                            float illegal_penalty, float illegal_bonus) {
+    if (f_terminated(e)) {
+        e.A &= ~(kTermBit | kCarriedBit);
+        e.B = bitfield_set(e.B, 9, 9, 0u);
+    }
+    float4 rew = env_step(e, action, c.cur, illegal_penalty, illegal_bonus);
+    if (f_terminated(e)) {
+        env_init_from_draw(e, c.next_draw);
+        e.A |= kTermBit | kCarriedBit;
+        c.cur = c.next;
+        c.next_draw = draw_episode(e.key_lo, e.key_hi, n_deals);
+        c.next.load(table, c.next_draw.deal);  // consumed >= 4 calls from now: latency hidden
     }
     return rew;
 }
@@ -316,28 +399,45 @@ __device__ __forceinline__ uint32_t rotr_nibbles(uint32_t h, uint32_t q) {
     return ((h >> q) & lo) | ((h << (4u - q)) & ~lo);
 }
 
-__device__ __forceinline__ void env_observe_words(const Env& e, const uint8_t* __restrict__ table, uint32_t q,
+template <class Rows>
+__device__ __forceinline__ void env_observe_words(const Env& e, const Rows& rows, uint32_t q,
                                                   uint32_t R[kObsWords]) {
 #pragma unroll
     for (int w = 0; w < 14; ++w) R[w] = rotr_nibbles(e.H[w], q);
     uint32_t us = (q & 1u) ? f_vul_ew(e) : f_vul_ns(e);
     uint32_t them = (q & 1u) ? f_vul_ns(e) : f_vul_ew(e);
     R[0] |= (us ? 2u : 1u) | (them ? 8u : 4u);  // wb5/utils.py:15-16
-    const uint2 hm = *reinterpret_cast<const uint2*>(table + (size_t)e.deal * kDealRowBytes + 8u * q);
-    uint64_t hand = (uint64_t)hm.x | ((uint64_t)hm.y << 32);
+    uint64_t hand = rows.hand(e.deal, q);
     R[13] |= (uint32_t)(hand << 12);  // observation bits 428..447
     R[14] = (uint32_t)(hand >> 20);   // observation bits 448..479
 }
 
-// uniform random-legal action = k-th set bit of the mask, k = mulhi(r, n_legal)
+// uniform random-legal action = k-th set bit of the mask, k = mulhi(r, n_legal).
+// A legal mask is always {Pass, maybe X, maybe XX} + one contiguous run of bids up to
+// 7NT, so the k-th set bit needs no bit-scan loop.
+__device__ __forceinline__ int32_t kth_legal_action(uint64_t mask, uint32_t r) {
+    uint32_t low = (uint32_t)mask & 7u;                 // Pass / X / XX
+    uint32_t n_low = __popc(low);
+    uint32_t bids = (uint32_t)(mask >> 3);              // 35 bid bits, bit b = bid b (low 32 here)
+    uint32_t bids_hi = (uint32_t)(mask >> 35) & 7u;
+    uint32_t first = bids ? (uint32_t)__ffs(bids) - 1u : (bids_hi ? 32u + (uint32_t)__ffs(bids_hi) - 1u : 35u);
+    uint32_t n_legal = n_low + (35u - first);
+    uint32_t k = __umulhi(r, n_legal);
+    if (k >= n_low) return (int32_t)(3u + first + (k - n_low));
+    // k-th set bit of a 3-bit field
+    uint32_t b0 = low & 1u, b1 = (low >> 1) & 1u;
+    if (k == 0u) return b0 ? 0 : (b1 ? 1 : 2);
+    if (k == 1u) return (b0 && b1) ? 1 : 2;
+    return 2;
+}
+
+__device__ __forceinline__ uint32_t action_uniform(uint64_t seed, uint64_t g, uint32_t step) {
+    return philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), kTagAct, step),
+                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))).x;
+}
+
 __device__ __forceinline__ int32_t random_legal_action(uint64_t mask, uint64_t seed, uint64_t g, uint32_t step) {
-    uint4 r = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), kTagAct, step),
-                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
-    uint32_t n_lo = __popc(lo);
-    uint32_t k = __umulhi(r.x, n_lo + __popc(hi));
-    if (k < n_lo) return (int32_t)__fns(lo, 0u, (int)k + 1);
-    return 32 + (int32_t)__fns(hi, 0u, (int)(k - n_lo) + 1);
+    return kth_legal_action(mask, action_uniform(seed, g, step));
 }
 
 }  // namespace brl

@@ -79,6 +79,8 @@ typedef struct CUstream_st *brl_stream_t; /* == cudaStream_t */
 /* tuning (0 = automatic): bits 16-17 envs per warp (1->8, 2->16, 3->32), bits 18-19 warps per block (1->1, 2->2, 3->4) */
 #define BRL_F_TUNE_EPW(code) ((code) << 16)
 #define BRL_F_TUNE_WPB(code) ((code) << 18)
+#define BRL_F_TUNE_CLASSIC_ROLLOUT (1 << 20)     /* tile-per-warp rollout kernel instead of the warp-specialised one */
+#define BRL_F_TUNE_WRITERS(code) ((code) << 21) /* writer warps of the warp-specialised rollout: 0->3, 1->1, 2->5, 3->7 */
 
 /* errors */
 #define BRL_OK 0

@@ -170,8 +170,11 @@ def test_plain_step_terminal_is_absorbing_and_noop():
     assert (out.rewards == 0).all()
 
 
-@pytest.mark.parametrize("n,k,epw", [(2048, 24, 0), (100, 40, 32), (8, 7, 8)])
-def test_fused_rollout_kernel_matches_oracle(n, k, epw):
+@pytest.mark.parametrize("n,k,tune_kw", [
+    (2048, 24, {}), (100, 40, {"writers": 1}), (1000, 9, {"writers": 3}), (33, 5, {"writers": 5}), (1, 3, {}),
+    (2048, 24, {"classic_rollout": True}), (100, 40, {"classic_rollout": True, "epw": 32}),
+    (8, 7, {"classic_rollout": True, "epw": 8})])
+def test_fused_rollout_kernel_matches_oracle(n, k, tune_kw):
     """brl_rollout_random (K steps in one launch, in-kernel random-legal policy) against
     the oracle's rollout: whole [K, n, ...] trajectories bit-exact."""
     ops, orc = _ops(), _orc()
@@ -190,7 +193,7 @@ def test_fused_rollout_kernel_matches_oracle(n, k, epw):
     actions = torch.empty((k, n), dtype=torch.int32, device=DEV)
     stats = torch.zeros(4, dtype=torch.int64, device=DEV)
     ops.rollout_random(state, table_t, k, traj, seed=seed, step0=5, env_offset=offset, action_out=actions, stats=stats,
-                       tune=_lib.tune(epw=epw))
+                       tune=_lib.tune(**tune_kw))
     assert (actions.cpu().numpy() == ref["action"]).all()
     _cmp_outputs(traj, ref, tag="trajectory")
     st = stats.cpu().numpy()
