@@ -114,3 +114,65 @@ def boards_from_json(path_or_obj):
         vul_ew[i] = v in ("EW", "Both", "All")
         board_id[i] = b.get("board_id", i)
     return pack_deal_table(owners, dd), dealer, vul_ns, vul_ew, board_id
+
+
+# ---------------------------------------------------------------------------------
+# pgx DDS result files (`dds_results/{train_*,test_000}.npy`, eval.py:43, ppo.py:297-303)
+# ---------------------------------------------------------------------------------
+# Layout as the reference's own tooling writes it (wb5/vis_pgx.py:13-24 `_pbn_to_key`):
+# for every deal a key of 4 x int32, one per suit in PBN order S,H,D,C, each a 13-digit
+# base-4 number whose digits (most significant first: A,2,3,...,K -- pgx
+# `_card_str_to_int`) are the owning seat 0..3 = N,E,S,W; and a value of 4 x int32, one
+# per declarer seat, holding five 4-bit trick counts (most significant first).  The
+# array on disk is [2, n, 4] = (keys, values).  The strain order of the five nibbles
+# (C,D,H,S,NT) and the digit order are pgx-internal and NOT pinned by anything in the
+# reference tree ("parity unpinned"): they are isolated here.
+PGX_STRAIN_ORDER = (0, 1, 2, 3, 4)  # nibble k (MSB first) -> strain index C,D,H,S,NT
+
+
+def pgx_dds_to_table(keys: np.ndarray, values: np.ndarray) -> np.ndarray:
+    keys = np.asarray(keys, dtype=np.int64).reshape(-1, 4)
+    values = np.asarray(values, dtype=np.int64).reshape(-1, 4)
+    n = keys.shape[0]
+    owners = np.zeros((n, 52), dtype=np.int8)
+    for s_pgx in range(4):            # S,H,D,C
+        s_os = 3 - s_pgx              # OpenSpiel suit C=0..S=3
+        for i in range(13):           # A,2,...,K
+            rank = (i + 12) % 13      # OpenSpiel rank 2=0..A=12
+            owners[:, rank * 4 + s_os] = (keys[:, s_pgx] >> (2 * (12 - i))) & 3
+    dd = np.zeros((n, 4, 5), dtype=np.int8)
+    for seat in range(4):
+        for k in range(5):
+            dd[:, seat, PGX_STRAIN_ORDER[k]] = (values[:, seat] >> (4 * (4 - k))) & 15
+    return pack_deal_table(owners, dd)
+
+
+def table_to_pgx_dds(table: np.ndarray):
+    owners, dd = unpack_deal_table(table)
+    n = owners.shape[0]
+    keys = np.zeros((n, 4), dtype=np.int64)
+    values = np.zeros((n, 4), dtype=np.int64)
+    for s_pgx in range(4):
+        for i in range(13):
+            rank = (i + 12) % 13
+            keys[:, s_pgx] |= owners[:, rank * 4 + (3 - s_pgx)].astype(np.int64) << (2 * (12 - i))
+    for seat in range(4):
+        for k in range(5):
+            values[:, seat] |= dd[:, seat, PGX_STRAIN_ORDER[k]].astype(np.int64) << (4 * (4 - k))
+    return keys.astype(np.int32), values.astype(np.int32)
+
+
+def load_table(path: str) -> np.ndarray:
+    """Deal table from: a packed u8[n,48] .npy, an .npz with `table`, a pgx DDS .npy
+    ([2,n,4] int32 keys/values, converted ONCE here instead of pgx's per-step LUT scan),
+    or a board-log .json (wb5/dataset_for_vs_wb5.json schema)."""
+    if path.endswith(".json"):
+        return boards_from_json(path)[0]
+    if path.endswith(".npz"):
+        return np.ascontiguousarray(np.load(path)["table"], dtype=np.uint8)
+    arr = np.load(path)
+    if arr.dtype == np.uint8 and arr.ndim == 2 and arr.shape[1] == DEAL_ROW_BYTES:
+        return np.ascontiguousarray(arr)
+    if arr.ndim == 3 and arr.shape[0] == 2 and arr.shape[2] == 4:
+        return pgx_dds_to_table(arr[0], arr[1])
+    raise ValueError(f"{path}: not a packed deal table, pgx DDS table or board-log JSON (shape {arr.shape}, {arr.dtype})")
