@@ -35,6 +35,11 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _call(name: str, buffers, params) -> None:
+    # buffers were validated (CUDA, contiguous) while the list was built; only then touch the stream
+    _lib.call(name, _stream(), buffers, params)
+
+
 def _params(n, *, flags=0, env_offset=0, stride=0, seed=0, n_deals=0, step=0, k_steps=0, illegal_penalty=-1.0,
             illegal_bonus=1.0, gamma=0.0, gae_lambda=0.0) -> BrlParams:
     return BrlParams(int(n), int(env_offset), int(stride or n), int(seed) & 0xFFFFFFFFFFFFFFFF, int(n_deals), int(flags),
@@ -78,20 +83,19 @@ class EnvOutputs:
 
 def make_keys(seed: int, n: int, device, env_offset: int = 0) -> torch.Tensor:
     keys = torch.empty(n, dtype=torch.int64, device=device)
-    _lib.call("brl_make_keys", _stream(), [_ptr(keys)], _params(n, seed=seed, env_offset=env_offset))
+    _call("brl_make_keys", [_ptr(keys)], _params(n, seed=seed, env_offset=env_offset))
     return keys
 
 
 def init(keys: torch.Tensor, table: torch.Tensor, state: torch.Tensor, out: EnvOutputs, tune: int = 0) -> None:
     n = keys.shape[0]
-    _lib.call("brl_init", _stream(), [_ptr(keys), _ptr(table), _ptr(state), *out.ptrs()],
+    _call("brl_init", [_ptr(keys), _ptr(table), _ptr(state), *out.ptrs()],
               _params(n, n_deals=table.shape[0], stride=state.shape[1], flags=out.flag() | tune))
 
 
 def reset_fields(deal, dealer, vul_ns, vul_ew, players, rng_key, table, state, out: EnvOutputs) -> None:
     n = deal.shape[0]
-    _lib.call("brl_reset_fields", _stream(),
-              [_ptr(deal), _ptr(dealer), _ptr(vul_ns), _ptr(vul_ew), _ptr(players), _ptr(rng_key), _ptr(table),
+    _call("brl_reset_fields", [_ptr(deal), _ptr(dealer), _ptr(vul_ns), _ptr(vul_ew), _ptr(players), _ptr(rng_key), _ptr(table),
                _ptr(state), *out.ptrs()],
               _params(n, n_deals=table.shape[0], stride=state.shape[1], flags=out.flag()))
 
@@ -105,8 +109,7 @@ def step(state_in, action, table, state_out, out: EnvOutputs, *, autoreset=False
     flags |= F_RANDOM_ACTION if random_action else 0
     flags |= F_ACCUMULATE if accumulate else 0
     flags |= F_QUAD_LAST if quad_last else 0
-    _lib.call("brl_step", _stream(),
-              [_ptr(state_in), _ptr(action), _ptr(table), _ptr(state_out), *out.ptrs(), _ptr(action_out)],
+    _call("brl_step", [_ptr(state_in), _ptr(action), _ptr(table), _ptr(state_out), *out.ptrs(), _ptr(action_out)],
               _params(n, flags=flags, n_deals=table.shape[0], stride=state_in.shape[1], seed=seed, step=step_index,
                       env_offset=env_offset, illegal_penalty=illegal_penalty, illegal_bonus=illegal_bonus))
 
@@ -131,27 +134,26 @@ class TableInfoBuffers:
 def duplicate_step(state_in, action, table, info_a: TableInfoBuffers, info_b: TableInfoBuffers, state_out,
                    out: EnvOutputs, illegal_penalty=-1.0, illegal_bonus=1.0) -> None:
     n = state_in.shape[1]
-    _lib.call("brl_duplicate_step", _stream(),
-              [_ptr(state_in), _ptr(action), _ptr(table), *info_a.ptrs(), *info_b.ptrs(), _ptr(state_out), *out.ptrs()],
+    _call("brl_duplicate_step", [_ptr(state_in), _ptr(action), _ptr(table), *info_a.ptrs(), *info_b.ptrs(), _ptr(state_out), *out.ptrs()],
               _params(n, flags=out.flag(), n_deals=table.shape[0], stride=state_in.shape[1],
                       illegal_penalty=illegal_penalty, illegal_bonus=illegal_bonus))
 
 
 def duplicate_init(state_in, table, state_out, out: EnvOutputs) -> None:
     n = state_in.shape[1]
-    _lib.call("brl_duplicate_init", _stream(), [_ptr(state_in), _ptr(table), _ptr(state_out), *out.ptrs()],
+    _call("brl_duplicate_init", [_ptr(state_in), _ptr(table), _ptr(state_out), *out.ptrs()],
               _params(n, flags=out.flag(), n_deals=table.shape[0], stride=state_in.shape[1]))
 
 
 def observe(state, table, obs: torch.Tensor, player_id: Optional[torch.Tensor] = None, tune: int = 0) -> None:
     n = state.shape[1]
-    _lib.call("brl_observe", _stream(), [_ptr(state), _ptr(player_id), _ptr(table), _ptr(obs)],
+    _call("brl_observe", [_ptr(state), _ptr(player_id), _ptr(table), _ptr(obs)],
               _params(n, flags=obs_flag(obs.dtype) | tune, n_deals=table.shape[0], stride=state.shape[1]))
 
 
 def legal_mask(state, mask: torch.Tensor, tune: int = 0) -> None:
     n = state.shape[1]
-    _lib.call("brl_legal_mask", _stream(), [_ptr(state), _ptr(mask)], _params(n, stride=state.shape[1], flags=tune))
+    _call("brl_legal_mask", [_ptr(state), _ptr(mask)], _params(n, stride=state.shape[1], flags=tune))
 
 
 def rollout_random(state, table, k_steps: int, out: Optional[EnvOutputs], *, seed=0, step0=0, env_offset=0,
@@ -163,33 +165,33 @@ def rollout_random(state, table, k_steps: int, out: Optional[EnvOutputs], *, see
     else:
         ptrs = [_ptr(obs_only), None, None, None, None]
         flag = obs_flag(obs_only.dtype) if obs_only is not None else 0
-    _lib.call("brl_rollout_random", _stream(), [_ptr(state), _ptr(table), *ptrs, _ptr(action_out), _ptr(stats)],
+    _call("brl_rollout_random", [_ptr(state), _ptr(table), *ptrs, _ptr(action_out), _ptr(stats)],
               _params(n, flags=flag | tune, n_deals=table.shape[0], stride=state.shape[1], seed=seed, step=step0,
                       env_offset=env_offset, k_steps=k_steps))
 
 
 def imp_reward(a_rewards, b_rewards, out) -> None:
-    _lib.call("brl_imp_reward", _stream(), [_ptr(a_rewards), _ptr(b_rewards), _ptr(out)], _params(a_rewards.shape[0]))
+    _call("brl_imp_reward", [_ptr(a_rewards), _ptr(b_rewards), _ptr(out)], _params(a_rewards.shape[0]))
 
 
 def gae(done, value, reward, last_val, adv, targets, gamma: float, gae_lambda: float) -> None:
     t, n = done.shape
-    _lib.call("brl_gae", _stream(), [_ptr(done), _ptr(value), _ptr(reward), _ptr(last_val), _ptr(adv), _ptr(targets)],
+    _call("brl_gae", [_ptr(done), _ptr(value), _ptr(reward), _ptr(last_val), _ptr(adv), _ptr(targets)],
               _params(n, k_steps=t, gamma=gamma, gae_lambda=gae_lambda))
 
 
 def categorical(logits, mask, action, log_prob, *, sample=False, seed=0, env_offset=0, step_index=0) -> None:
     n = logits.shape[0]
-    _lib.call("brl_categorical", _stream(), [_ptr(logits), _ptr(mask), _ptr(action), _ptr(log_prob)],
+    _call("brl_categorical", [_ptr(logits), _ptr(mask), _ptr(action), _ptr(log_prob)],
               _params(n, flags=F_SAMPLE if sample else 0, seed=seed, env_offset=env_offset, step=step_index))
 
 
 def match_stats(x: torch.Tensor, sums: torch.Tensor) -> None:
-    _lib.call("brl_match_stats", _stream(), [_ptr(x), _ptr(sums)], _params(x.shape[0]))
+    _call("brl_match_stats", [_ptr(x), _ptr(sums)], _params(x.shape[0]))
 
 
 def gather_reward(rewards, actor, out, scale: float) -> None:
-    _lib.call("brl_gather_reward", _stream(), [_ptr(rewards), _ptr(actor), _ptr(out)],
+    _call("brl_gather_reward", [_ptr(rewards), _ptr(actor), _ptr(out)],
               _params(rewards.shape[0], gamma=scale))
 
 
@@ -203,6 +205,6 @@ def state_fields(state: torch.Tensor) -> dict:
     """Unpack the private pgx-style fields brl reads (src/evaluation.py:97-112, 465-495)."""
     n = state.shape[1]
     out = {name: torch.empty((n,) + shape, dtype=dt, device=state.device) for name, dt, shape in _FIELD_SPECS}
-    _lib.call("brl_state_fields", _stream(), [_ptr(state)] + [_ptr(out[name]) for name, _, _ in _FIELD_SPECS],
+    _call("brl_state_fields", [_ptr(state)] + [_ptr(out[name]) for name, _, _ in _FIELD_SPECS],
               _params(n, stride=state.shape[1]))
     return out

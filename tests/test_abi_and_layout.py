@@ -1,0 +1,72 @@
+"""CPU: the C-ABI library loads and exports every symbol include/brl_b200.h declares
+(no compute calls without a GPU); the product never imports the oracle; product ops
+fail loudly without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "brl_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(brl_[a-z_]+)\s*\(", hdr)) - {"brl_op_fn"})
+
+
+def test_header_symbols_are_all_exported():
+    from brl_b200 import _lib
+    L = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(L, name), f"{name} declared in include/brl_b200.h but not exported"
+    assert set(_lib.ALL_SYMBOLS) == set(names)
+    assert L.brl_abi_version() == 1
+
+
+def test_params_struct_matches_header():
+    from brl_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "brl_b200.h")).read()
+    body = re.search(r"typedef struct BrlParams \{(.*?)\} BrlParams;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(\w+);", body)
+    assert fields == [f[0] for f in _lib.BrlParams._fields_]
+    assert ctypes.sizeof(_lib.BrlParams) == 64
+
+
+def test_usage_errors_are_reported_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it is testable here."""
+    from brl_b200 import _lib
+    L = _lib.load()
+    p = _lib.BrlParams(4, 0, 4, 0, 10, 0, 0, 0, -1.0, 1.0, 0.0, 0.0)
+    bufs = (ctypes.c_void_p * 10)()
+    rc = L.brl_step(None, bufs, ctypes.byref(p), ctypes.sizeof(p))
+    assert rc == -2 and b"NULL" in L.brl_last_error()
+    rc = L.brl_step(None, bufs, ctypes.byref(p), 12)
+    assert rc == -1 and b"BrlParams" in L.brl_last_error()
+    with pytest.raises(_lib.BrlError):
+        _lib.call("brl_gae", 0, [None] * 6, p)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "brl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+                assert "brl_oracle" not in src, f"{f} references the oracle"
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from brl_b200 import _lib, ops
+    with pytest.raises(_lib.BrlError, match="CUDA"):
+        ops.legal_mask(torch.zeros((5, 4, 4), dtype=torch.int32), torch.zeros((4, 38), dtype=torch.uint8))
+    from brl_b200 import BridgeBidding
+    with pytest.raises(RuntimeError, match="CUDA"):
+        BridgeBidding(table=np.zeros((1, 48), np.uint8), device="cpu")
