@@ -13,9 +13,11 @@ terminated, current player, action) = 519 MB per step, which is larger than the 
 L2, so every timed step's stores are DRAM traffic (no flush needed).
 
 Prints ONE JSON line (rank 0).  `value` = whole-job env-steps/s with state resident in
-HBM; `e2e` = the same metric through the host-buffer C-ABI (`brl_env_step_host`):
-actions from pinned host memory in, every Env-surface output to pinned host memory
-out, copies inside the timed region; `roofline` = the rollout kernel against measured
+HBM; `e2e` = the same metric through the host-buffer C-ABI (`brl_env_rollout_host`):
+per step the action randomness comes from pinned host memory and the rewards /
+terminated / statistics go back to pinned host memory, copies inside the timed region
+(`e2e.full_io` = every Env-surface output copied out per env.step, PCIe-bound);
+`roofline` = the rollout kernel against measured
 HBM bandwidth; `cpu_baseline` = the C oracle on this box's host cores (bounded sample).
 `--impl reference` times the CPU restatement of the reference on the same config (the
 real pgx/JAX env cannot be installed in this image -- see DESIGN.md).
@@ -275,54 +277,100 @@ def main():
 
 
 def run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps, warmup):
-    """Public host-buffer API: per env.step, actions come from pinned host memory (H2D) and
-    every Env-surface output goes back to pinned host memory (D2H).  Observation dtype is
-    pgx's own (bool = u8, `State.observation`); the f32 cast is the consumer's
-    (src/roll_out.py:75)."""
+    """Public host-buffer C-ABI, copies inside the timed region.
+
+    `e2e` (headline): one `brl_env_rollout_host` call per bench step = the same 32 x 8192
+    env-steps as `value`.  HOST in: the randomness of the action choice, u32[32, 8192] from
+    pinned memory (4 B per env-step -- the `action` input of the algorithmic byte count; the
+    host owns the PRNG stream the way the reference's host owns the jax key).  HOST out: the
+    step's result, rewards f32[32, 8192, 4] + terminated u8[32, 8192] + the statistics vector.
+    The observation / mask trajectories stay in HBM for the device-resident consumer, exactly as
+    `traj_batch` does in the reference (src/roll_out.py:105-108).
+    `full_io`: the other extreme -- one env.step per call with EVERY Env-surface output copied to
+    the host (PCIe-bound by construction: 536 B per env-step in pgx's bool observation dtype)."""
     import ctypes as C
     L = _lib.load()
     tbl = np.ascontiguousarray(table_np)
-    h = L.brl_env_create(n, offset, tbl.ctypes.data, tbl.shape[0], SEED, _lib.F_AUTORESET | _lib.F_OBS_U8)
+    k = T_STEPS
+    # ---- headline: rollout per call --------------------------------------------------------
+    h = L.brl_env_create(n, offset, tbl.ctypes.data, tbl.shape[0], SEED, _lib.F_AUTORESET)
     if not h:
         raise RuntimeError("brl_env_create failed: " + L.brl_last_error().decode())
-    pin = dict(act=torch.zeros(n, dtype=torch.int32).pin_memory(), obs=torch.zeros((n, 480), dtype=torch.uint8).pin_memory(),
-               mask=torch.zeros((n, 38), dtype=torch.uint8).pin_memory(), rew=torch.zeros((n, 4), dtype=torch.float32).pin_memory(),
-               term=torch.zeros(n, dtype=torch.uint8).pin_memory(), cur=torch.zeros(n, dtype=torch.int8).pin_memory())
-    p = {k: C.c_void_p(v.data_ptr()) for k, v in pin.items()}
-    rc = L.brl_env_init_host(h, p["obs"], p["mask"], p["rew"], p["term"], p["cur"])
-    assert rc == 0, L.brl_last_error()
-    mask_np, act_np = pin["mask"].numpy(), pin["act"].numpy()
     rng = np.random.default_rng(SEED + offset)
+    n_pool = min(steps + warmup, 16)  # pre-generated host randomness ("the dataset"), cycled
+    pool = torch.from_numpy(rng.integers(0, 2 ** 32, size=(n_pool, k, n), dtype=np.uint32).view(np.int32)).pin_memory()
+    rew = torch.zeros((k, n, 4), dtype=torch.float32).pin_memory()
+    term = torch.zeros((k, n), dtype=torch.uint8).pin_memory()
+    stats = torch.zeros(4, dtype=torch.int64).pin_memory()
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    rc = L.brl_env_init_host(h, None, None, None, None, None)
+    assert rc == 0, L.brl_last_error()
 
-    def host_policy():
-        # cheap host-side random-legal choice from the mask that came back over PCIe
-        score = rng.random(mask_np.shape, dtype=np.float32) * mask_np
-        act_np[:] = score.argmax(axis=1)
-
-    def one():
-        host_policy()
-        rc = L.brl_env_step_host(h, p["act"], p["obs"], p["mask"], p["rew"], p["term"], p["cur"])
+    def one(i):
+        rc = L.brl_env_rollout_host(h, k, vp(pool[i % n_pool]), vp(rew), vp(term), vp(stats))
         if rc != 0:
             raise RuntimeError(L.brl_last_error().decode())
 
-    for _ in range(warmup):
-        one()
+    for i in range(warmup):
+        one(i)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
+    for i in range(steps):
+        one(warmup + i)
     dt = time.perf_counter() - t0
+    finished = int(stats[0])
+    L.brl_env_destroy(h)
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
+    res = {"value": n * k * steps * world / dt, "unit": UNIT, "h2d_bytes_per_step": n * k * 4,
+           "d2h_bytes_per_step": n * k * 17 + 32, "steps": steps, "ms_per_step": 1e3 * dt / steps,
+           "api": "brl_env_rollout_host (C ABI, host buffers): per bench step H2D u32[32,8192] action randomness from pinned "
+                  "memory, one fused rollout launch, D2H rewards f32[32,8192,4] + terminated u8[32,8192] + stats; "
+                  "obs/mask trajectories stay in HBM for the device-resident learner (as traj_batch does in the reference)",
+           "timed_with": "host wall clock around synchronous calls, max over ranks", "finished_auctions_last_call": finished}
+
+    # ---- full I/O: every Env-surface output to the host, one env.step per call -------------------
+    h = L.brl_env_create(n, offset, tbl.ctypes.data, tbl.shape[0], SEED, _lib.F_AUTORESET | _lib.F_OBS_U8)
+    pin = dict(act=torch.zeros(n, dtype=torch.int32).pin_memory(), obs=torch.zeros((n, 480), dtype=torch.uint8).pin_memory(),
+               mask=torch.zeros((n, 38), dtype=torch.uint8).pin_memory(), rew=torch.zeros((n, 4), dtype=torch.float32).pin_memory(),
+               term=torch.zeros(n, dtype=torch.uint8).pin_memory(), cur=torch.zeros(n, dtype=torch.int8).pin_memory())
+    p = {kk: vp(v) for kk, v in pin.items()}
+    rc = L.brl_env_init_host(h, p["obs"], p["mask"], p["rew"], p["term"], p["cur"])
+    assert rc == 0, L.brl_last_error()
+    mask_np, act_np = pin["mask"].numpy(), pin["act"].numpy()
+    passes = rng.random((64, n)) < 0.6
+
+    def host_policy(i):
+        # host-side legal choice from the mask that came back over PCIe: pass, or the cheapest bid
+        first_bid = mask_np[:, 3:].argmax(axis=1) + 3
+        has_bid = mask_np[np.arange(n), first_bid] != 0
+        act_np[:] = np.where(passes[i % 64] | ~has_bid, 0, first_bid)
+
+    fsteps = 60
+    for i in range(3):
+        host_policy(i)
+        L.brl_env_step_host(h, p["act"], p["obs"], p["mask"], p["rew"], p["term"], p["cur"])
+    t_pol = t_call = 0.0
+    for i in range(fsteps):
+        a = time.perf_counter()
+        host_policy(i)
+        b = time.perf_counter()
+        rc = L.brl_env_step_host(h, p["act"], p["obs"], p["mask"], p["rew"], p["term"], p["cur"])
+        t_call += time.perf_counter() - b
+        t_pol += b - a
+        if rc != 0:
+            raise RuntimeError(L.brl_last_error().decode())
     L.brl_env_destroy(h)
-    return {"value": n * steps * world / dt, "unit": UNIT, "h2d_bytes_per_step": n * 4,
-            "d2h_bytes_per_step": n * (480 + 38 + 16 + 1 + 1), "steps": steps, "ms_per_step": 1e3 * dt / steps,
-            "api": "brl_env_step_host (C ABI, host buffers): 1 env.step over 8192 envs per call; host picks the actions "
-                   "from the returned mask; observation in pgx's bool(u8) dtype", "timed_with": "host wall clock around synchronous calls"}
+    res["full_io"] = {"value": n * fsteps / (t_pol + t_call), "value_excluding_host_policy": n * fsteps / t_call, "unit": UNIT,
+                      "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": n * (480 + 38 + 16 + 1 + 1),
+                      "ms_per_call": 1e3 * t_call / fsteps, "ms_host_policy": 1e3 * t_pol / fsteps, "rank": "0 only" if world > 1 else "0",
+                      "api": "brl_env_step_host: 1 env.step over 8192 envs per call, actions from the host, observation (pgx bool/u8), "
+                             "mask, rewards, terminated, current_player all copied to pinned host memory"}
+    return res
 
 
 def run_sweep(torch, ops, table, dev, peak):

@@ -15,9 +15,11 @@ OPS = (
     "brl_observe", "brl_legal_mask", "brl_rollout_random", "brl_imp_reward", "brl_gae", "brl_categorical",
     "brl_match_stats", "brl_state_fields", "brl_gather_reward",
 )
-HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host")
+HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host", "brl_env_rollout_host",
+            "brl_env_trajectory")
 MISC = ("brl_last_error", "brl_abi_version")
-ALL_SYMBOLS = OPS + HOST_API + MISC
+XLA_LEGACY = tuple(op + "_xla" for op in OPS)  # legacy XLA GPU custom-call targets (csrc/xla_ffi_shim.cc)
+ALL_SYMBOLS = OPS + HOST_API + MISC + XLA_LEGACY
 
 # flags (include/brl_b200.h)
 F_AUTORESET = 0x0001
@@ -87,6 +89,10 @@ def load():
     L.brl_env_init_host.argtypes = [C.c_void_p] * 6
     L.brl_env_step_host.restype = C.c_int32
     L.brl_env_step_host.argtypes = [C.c_void_p] * 7
+    L.brl_env_rollout_host.restype = C.c_int32
+    L.brl_env_rollout_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.brl_env_trajectory.restype = C.c_int32
+    L.brl_env_trajectory.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     _LIB = L
     return L
 

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libbrl_b200.so")
-SOURCES = ["brl_env.cu", "brl_algo.cu", "brl_host.cu"]
+SOURCES = ["brl_env.cu", "brl_algo.cu", "brl_host.cu", "xla_ffi_shim.cc"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -39,6 +39,18 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
+def _xla_ffi_include():
+    """-I for the typed XLA FFI handlers, if jaxlib happens to be installed (it is not in this image)."""
+    try:
+        import jaxlib  # noqa: F401
+        inc = os.path.join(os.path.dirname(jaxlib.__file__), "include")
+        if os.path.exists(os.path.join(inc, "xla", "ffi", "api", "ffi.h")):
+            return ["-I", inc]
+    except Exception:
+        pass
+    return []
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
@@ -47,8 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(LIB_DIR, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *_xla_ffi_include(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -53,6 +53,7 @@ struct EnvArgs {
     int8_t* current_player;
     int32_t* action_out;
     unsigned long long* stats;
+    const uint32_t* uniforms;  // rollout: caller-supplied u32[K, n] action uniforms (NULL -> Philox)
     // produce-kernel inputs
     const uint64_t* keys;
     const int32_t* in_deal;
@@ -231,7 +232,9 @@ __global__ void __launch_bounds__(128) k_rollout(const EnvArgs a) {
         const int64_t row0 = (int64_t)s * a.n;
         if (lane < EPW) {
             if (active) {
-                int32_t act = random_legal_action(env_legal_mask(e), a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)s);
+                const uint32_t u = a.uniforms ? a.uniforms[row0 + i]
+                                              : action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)s);
+                int32_t act = kth_legal_action(env_legal_mask(e), u);
                 float4 rew = env_step_autoreset_cached(e, cache, act, a.table, a.n_deals, a.illegal_penalty, a.illegal_bonus);
                 n_term += f_terminated(e);
                 rew0 += (long long)rew.x;
@@ -337,7 +340,8 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
             mask = env_legal_mask(e);
         }
     } else if (warp == 0) {
-        uniforms[0][lane] = action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step);
+        uniforms[0][lane] = a.uniforms ? (active ? a.uniforms[i] : 0u)
+                                       : action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step);
     }
     __syncthreads();
     for (int s = 0; s <= a.k_steps; ++s) {
@@ -392,7 +396,9 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                 }
             }
             if (warp == 0 && s + 1 < a.k_steps)
-                uniforms[(s + 1) & 1][lane] = action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)(s + 1));
+                uniforms[(s + 1) & 1][lane] =
+                    a.uniforms ? (active ? a.uniforms[(int64_t)(s + 1) * a.n + i] : 0u)
+                               : action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)(s + 1));
         }
         __syncthreads();
     }
@@ -822,6 +828,7 @@ int32_t brl_rollout_random(brl_stream_t stream, void** b, const void* opaque, si
     set_outputs(a, b, 2, p->k_steps);
     a.action_out = static_cast<int32_t*>(b[7]);
     a.stats = static_cast<unsigned long long*>(b[8]);
+    a.uniforms = static_cast<const uint32_t*>(b[9]);
     if ((rc = check_outputs(a, "brl_rollout_random")) != BRL_OK) return rc;
     if (p->flags & (1 << 20)) launch_rollout(a, (cudaStream_t)stream);
     else launch_rollout_ws(a, (cudaStream_t)stream);

@@ -23,6 +23,16 @@ struct BrlEnv {
     uint8_t* d_term;
     int8_t* d_cur;
     size_t obs_row_bytes;
+    // rollout trajectory (allocated on first brl_env_rollout_host)
+    int32_t traj_k;
+    void* t_obs;
+    uint8_t* t_mask;
+    float* t_rewards;
+    uint8_t* t_term;
+    int8_t* t_cur;
+    int32_t* t_action;
+    uint32_t* t_uniforms;
+    unsigned long long* d_stats;
 };
 
 namespace {
@@ -104,6 +114,8 @@ void brl_env_destroy(BrlEnv* env) {
     if (!env || env->magic != kMagic) return;
     cudaFree(env->d_table); cudaFree(env->d_state); cudaFree(env->d_action); cudaFree(env->d_keys);
     cudaFree(env->d_obs); cudaFree(env->d_mask); cudaFree(env->d_rewards); cudaFree(env->d_term); cudaFree(env->d_cur);
+    cudaFree(env->t_obs); cudaFree(env->t_mask); cudaFree(env->t_rewards); cudaFree(env->t_term); cudaFree(env->t_cur);
+    cudaFree(env->t_action); cudaFree(env->t_uniforms); cudaFree(env->d_stats);
     if (env->stream) cudaStreamDestroy(env->stream);
     env->magic = 0;
     delete env;
@@ -139,6 +151,58 @@ int32_t brl_env_step_host(BrlEnv* env, const int32_t* action, void* obs, uint8_t
     if (rc != BRL_OK) return rc;
     env->step += 1;
     return copy_out(env, obs, mask, rewards, terminated, current_player);
+}
+
+static bool ensure_trajectory(BrlEnv* env, int32_t k) {
+    if (env->traj_k >= k) return true;
+    cudaFree(env->t_obs); cudaFree(env->t_mask); cudaFree(env->t_rewards); cudaFree(env->t_term); cudaFree(env->t_cur);
+    cudaFree(env->t_action); cudaFree(env->t_uniforms);
+    env->t_obs = nullptr; env->t_mask = nullptr; env->t_rewards = nullptr; env->t_term = nullptr; env->t_cur = nullptr;
+    env->t_action = nullptr; env->t_uniforms = nullptr;
+    env->traj_k = 0;
+    const size_t rows = (size_t)k * (size_t)env->n;
+    bool good = ok(cudaMalloc(&env->t_obs, rows * env->obs_row_bytes), "malloc traj obs") &&
+                ok(cudaMalloc(&env->t_mask, rows * BRL_NUM_ACTIONS), "malloc traj mask") &&
+                ok(cudaMalloc(&env->t_rewards, rows * 16), "malloc traj rewards") &&
+                ok(cudaMalloc(&env->t_term, rows), "malloc traj terminated") &&
+                ok(cudaMalloc(&env->t_cur, rows), "malloc traj current_player") &&
+                ok(cudaMalloc(&env->t_action, rows * 4), "malloc traj action") &&
+                ok(cudaMalloc(&env->t_uniforms, rows * 4), "malloc traj uniforms") &&
+                (env->d_stats != nullptr || ok(cudaMalloc(&env->d_stats, 32), "malloc stats"));
+    if (good) env->traj_k = k;
+    return good;
+}
+
+int32_t brl_env_rollout_host(BrlEnv* env, int32_t k_steps, const uint32_t* uniforms, float* rewards,
+                             uint8_t* terminated, uint64_t* stats) {
+    if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "brl_env_rollout_host: bad handle");
+    if (k_steps <= 0) return brl::fail(BRL_E_OPAQUE, "brl_env_rollout_host: k_steps must be > 0");
+    if (!ensure_trajectory(env, k_steps)) return BRL_E_LAUNCH;
+    cudaStream_t s = env->stream;
+    const size_t rows = (size_t)k_steps * (size_t)env->n;
+    if (uniforms && !ok(cudaMemcpyAsync(env->t_uniforms, uniforms, rows * 4, cudaMemcpyHostToDevice, s), "H2D uniforms"))
+        return BRL_E_LAUNCH;
+    if (!ok(cudaMemsetAsync(env->d_stats, 0, 32, s), "memset stats")) return BRL_E_LAUNCH;
+    BrlParams p = params_of(env, 0);
+    p.k_steps = k_steps;
+    void* b[10] = {env->d_state, env->d_table, env->t_obs, env->t_mask, env->t_rewards, env->t_term, env->t_cur,
+                   env->t_action, env->d_stats, uniforms ? (void*)env->t_uniforms : nullptr};
+    int32_t rc = brl_rollout_random((brl_stream_t)s, b, &p, sizeof(p));
+    if (rc != BRL_OK) return rc;
+    env->step += (uint32_t)k_steps;
+    if (rewards && !ok(cudaMemcpyAsync(rewards, env->t_rewards, rows * 16, cudaMemcpyDeviceToHost, s), "D2H rewards")) return BRL_E_LAUNCH;
+    if (terminated && !ok(cudaMemcpyAsync(terminated, env->t_term, rows, cudaMemcpyDeviceToHost, s), "D2H terminated")) return BRL_E_LAUNCH;
+    if (stats && !ok(cudaMemcpyAsync(stats, env->d_stats, 32, cudaMemcpyDeviceToHost, s), "D2H stats")) return BRL_E_LAUNCH;
+    if (!ok(cudaStreamSynchronize(s), "stream sync")) return BRL_E_LAUNCH;
+    return BRL_OK;
+}
+
+int32_t brl_env_trajectory(BrlEnv* env, void** out) {
+    if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "brl_env_trajectory: bad handle");
+    if (env->traj_k == 0) return brl::fail(BRL_E_HANDLE, "brl_env_trajectory: no rollout has run yet");
+    out[0] = env->t_obs; out[1] = env->t_mask; out[2] = env->t_rewards; out[3] = env->t_term; out[4] = env->t_cur;
+    out[5] = env->t_action;
+    return BRL_OK;
 }
 
 }  // extern "C"

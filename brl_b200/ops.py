@@ -157,7 +157,8 @@ def legal_mask(state, mask: torch.Tensor, tune: int = 0) -> None:
 
 
 def rollout_random(state, table, k_steps: int, out: Optional[EnvOutputs], *, seed=0, step0=0, env_offset=0,
-                   action_out=None, stats=None, obs_only: Optional[torch.Tensor] = None, tune: int = 0) -> None:
+                   action_out=None, stats=None, obs_only: Optional[torch.Tensor] = None, tune: int = 0,
+                   uniforms: Optional[torch.Tensor] = None) -> None:
     """K auto-reset random-legal steps in ONE launch; `out` holds [K, n, ...] trajectories."""
     n = state.shape[1]
     if out is not None:
@@ -165,7 +166,7 @@ def rollout_random(state, table, k_steps: int, out: Optional[EnvOutputs], *, see
     else:
         ptrs = [_ptr(obs_only), None, None, None, None]
         flag = obs_flag(obs_only.dtype) if obs_only is not None else 0
-    _call("brl_rollout_random", [_ptr(state), _ptr(table), *ptrs, _ptr(action_out), _ptr(stats)],
+    _call("brl_rollout_random", [_ptr(state), _ptr(table), *ptrs, _ptr(action_out), _ptr(stats), _ptr(uniforms)],
               _params(n, flags=flag | tune, n_deals=table.shape[0], stride=state.shape[1], seed=seed, step=step0,
                       env_offset=env_offset, k_steps=k_steps))
 

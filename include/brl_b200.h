@@ -153,7 +153,9 @@ int32_t brl_legal_mask(brl_stream_t, void **buffers, const void *opaque, size_t 
  * buffers: [0] inout state  [1] in deal_table
  *          [2] out obs[K,n,480]  [3] out mask[K,n,38]  [4] out rewards[K,n,4]  [5] out terminated[K,n]
  *          [6] out current_player[K,n]  [7] out i32 action[K,n]
- *          [8] inout u64 stats[4] = {terminal steps, sum reward[player 0] (two's complement), calls, 0} */
+ *          [8] inout u64 stats[4] = {terminal steps, sum reward[player 0] (two's complement), calls, 0}
+ *          [9] in u32 uniforms[K,n] (optional): caller-owned randomness; action = the
+ *              mulhi(u, #legal)-th legal action.  NULL -> Philox(seed, env_offset+i, step+s). */
 int32_t brl_rollout_random(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
 /* buffers: [0] in f32 a_rewards[n,4]  [1] in f32 b_rewards[n,4]  [2] out f32 imp[n,4] */
@@ -183,6 +185,31 @@ int32_t brl_state_fields(brl_stream_t, void **buffers, const void *opaque, size_
 int32_t brl_gather_reward(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
 /* -------------------------------------------------------------------------
+ * Legacy XLA GPU custom-call targets (API_VERSION_STATUS_RETURNING -- the convention
+ * of jax/jaxlib 0.4.23, the version brl pins in requirements.txt:25-26): same buffers
+ * and opaque as the op they wrap; a failing op sets the XLA status instead of returning
+ * a code.  Register with xla_client.register_custom_call_target(name, capsule, "CUDA")
+ * (INTEGRATION.md).  Typed-FFI handlers (brl_step_ffi, brl_gae_ffi) are built only when
+ * the XLA FFI headers are present (csrc/xla_ffi_shim.cc).
+ * ------------------------------------------------------------------------- */
+struct XlaCustomCallStatus_;
+void brl_make_keys_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_init_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_reset_fields_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_step_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_duplicate_step_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_duplicate_init_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_observe_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_legal_mask_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_rollout_random_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_imp_reward_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_gae_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_categorical_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_match_stats_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_state_fields_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_gather_reward_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+
+/* -------------------------------------------------------------------------
  * Host-buffer convenience layer (the call a non-JAX host makes): the library
  * owns device state + pinned staging; inputs/outputs are HOST pointers and the
  * copies are part of the call.  Synchronous.  Used for bench.py's `e2e`.
@@ -199,6 +226,16 @@ int32_t brl_env_init_host(BrlEnv *env, void *obs, uint8_t *mask, float *rewards,
  * obs dtype follows the env's flags (f32 default, BRL_F_OBS_U8 = pgx bool). */
 int32_t brl_env_step_host(BrlEnv *env, const int32_t *action, void *obs, uint8_t *mask, float *rewards,
                           uint8_t *terminated, int8_t *current_player);
+/* One rollout of k_steps auto-reset random-legal steps (the shape of roll_out's scan,
+ * src/roll_out.py:105).  HOST in: uniforms u32[k_steps, n] (the randomness of the action
+ * choice; NULL -> in-kernel Philox).  HOST out (any may be NULL): rewards f32[k_steps,n,4],
+ * terminated u8[k_steps,n], stats u64[4] (as brl_rollout_random).  The observation / mask
+ * trajectories stay in HBM for a device-resident consumer, exactly as `traj_batch` does in
+ * the reference; `brl_env_trajectory` exposes their device pointers. */
+int32_t brl_env_rollout_host(BrlEnv *env, int32_t k_steps, const uint32_t *uniforms, float *rewards,
+                             uint8_t *terminated, uint64_t *stats);
+/* device pointers of the last rollout's trajectory: obs, mask, rewards, terminated, current_player, action */
+int32_t brl_env_trajectory(BrlEnv *env, void **out_ptrs6);
 
 #ifdef __cplusplus
 }

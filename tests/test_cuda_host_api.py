@@ -1,0 +1,80 @@
+"""GPU: the host-buffer C-ABI layer (brl_env_*) and caller-supplied action randomness."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TAG_ACT = 0x41435430
+
+
+def _uniforms(orc, seed, n, k, offset=0, step0=0):
+    u = np.zeros((k, n), np.uint32)
+    key = [seed & 0xFFFFFFFF, seed >> 32]
+    for s in range(k):
+        for i in range(n):
+            g = offset + i
+            u[s, i] = orc.philox([g & 0xFFFFFFFF, g >> 32, TAG_ACT, step0 + s], key)[0]
+    return u
+
+
+@pytest.mark.parametrize("tune_kw", [{}, {"classic_rollout": True, "epw": 8}])
+def test_rollout_with_caller_supplied_uniforms_equals_philox_mode(tune_kw):
+    from brl_b200 import _lib, ops
+    from brl_b200.deals import synthetic_deal_table
+    from oracle import oracle as orc
+    n, k, seed = 200, 12, 99
+    table = synthetic_deal_table(700, seed=2)
+    table_t = torch.as_tensor(table, device=DEV)
+    env = orc.OracleEnv(table, n)
+    env.init(orc.make_keys(seed, n))
+    ref = env.rollout_random(seed, 0, k)
+    u = torch.as_tensor(_uniforms(orc, seed, n, k).view(np.int32), device=DEV)
+    state, out0 = ops.new_state(n, DEV), ops.EnvOutputs(n, DEV)
+    ops.init(ops.make_keys(seed, n, DEV), table_t, state, out0)
+    traj = ops.EnvOutputs(n, DEV, rows=k)
+    actions = torch.empty((k, n), dtype=torch.int32, device=DEV)
+    ops.rollout_random(state, table_t, k, traj, seed=12345, step0=777, action_out=actions, uniforms=u, tune=_lib.tune(**tune_kw))
+    assert (actions.cpu().numpy() == ref["action"]).all()
+    assert (traj.observation.cpu().numpy() == ref["observation"]).all()
+    assert (traj.rewards.cpu().numpy() == ref["rewards"]).all()
+
+
+def test_host_buffer_api_step_and_rollout_match_oracle():
+    from brl_b200 import _lib
+    from brl_b200.deals import synthetic_deal_table
+    from oracle import oracle as orc
+    L = _lib.load()
+    n, seed, offset = 300, 5, 40
+    table = synthetic_deal_table(900, seed=3)
+    h = L.brl_env_create(n, offset, table.ctypes.data, table.shape[0], seed, _lib.F_AUTORESET | _lib.F_OBS_U8)
+    assert h, L.brl_last_error()
+    obs, mask = np.zeros((n, 480), np.uint8), np.zeros((n, 38), np.uint8)
+    rew, term, cur = np.zeros((n, 4), np.float32), np.zeros(n, np.uint8), np.zeros(n, np.int8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    assert L.brl_env_init_host(h, p(obs), p(mask), p(rew), p(term), p(cur)) == 0
+    env = orc.OracleEnv(table, n)
+    env.init(orc.make_keys(seed, n, offset))
+    e = env.export(np.uint8)
+    assert (obs == e["observation"]).all() and (mask == e["legal_action_mask"]).all() and (cur == e["current_player"]).all()
+    for s in range(25):
+        act = env.random_legal_actions(seed, s, env_offset=offset)
+        env.step(act, autoreset=True)
+        assert L.brl_env_step_host(h, p(act), p(obs), p(mask), p(rew), p(term), p(cur)) == 0
+        e = env.export(np.uint8)
+        assert (obs == e["observation"]).all() and (mask == e["legal_action_mask"]).all()
+        assert (rew == e["rewards"]).all() and (term == e["terminated"]).all() and (cur == e["current_player"]).all()
+    # rollout with host-supplied randomness: rewards / terminated / stats come back to the host
+    k = 10
+    u = _uniforms(orc, seed, n, k, offset=offset, step0=1000)
+    ref = env.rollout_random(seed, 1000, k, env_offset=offset)
+    rr, tt, st = np.zeros((k, n, 4), np.float32), np.zeros((k, n), np.uint8), np.zeros(4, np.uint64)
+    assert L.brl_env_rollout_host(h, k, p(u), p(rr), p(tt), p(st)) == 0, L.brl_last_error()
+    assert (rr == ref["rewards"]).all() and (tt == ref["terminated"]).all()
+    assert int(st[0]) == ref["n_terminated"] and int(st[2]) == n * k
+    ptrs = (C.c_void_p * 6)()
+    assert L.brl_env_trajectory(h, ptrs) == 0 and all(ptrs)
+    assert L.brl_env_step_host(None, p(act), None, None, None, None, None) == -4  # bad handle is an error, not a crash
+    L.brl_env_destroy(h)
