@@ -32,11 +32,12 @@ F_QUAD_LAST = 0x0100
 
 
 def tune(epw: int = 0, wpb: int = 0, classic_rollout: bool = False, writers: int = 0) -> int:
-    """flag bits: envs-per-warp (8/16/32) and warps-per-block (1/2/4) of the tile-per-warp kernels
-    (0 = automatic); classic_rollout forces the tile-per-warp rollout kernel instead of the
-    warp-specialised one; writers = writer warps of the warp-specialised rollout (default 3; 1/5/7)."""
+    """flag bits: envs-per-warp of the tile kernels / envs-per-block of the warp-specialised
+    rollout (8/16/32), warps-per-block of the tile kernels (1/2/4), classic_rollout = the
+    tile-per-warp rollout instead of the warp-specialised one, writers = writer warps of the
+    warp-specialised rollout (1..7).  0 = automatic everywhere."""
     return (({0: 0, 8: 1, 16: 2, 32: 3}[epw] << 16) | ({0: 0, 1: 1, 2: 2, 4: 3}[wpb] << 18) |
-            ((1 << 20) if classic_rollout else 0) | ({0: 0, 3: 0, 1: 1, 5: 2, 7: 3}[writers] << 21))
+            ((1 << 20) if classic_rollout else 0) | ((writers & 7) << 21))
 
 
 class BrlParams(C.Structure):

@@ -279,12 +279,13 @@ __global__ void __launch_bounds__(128) k_rollout(const EnvArgs a) {
 //     observer's seat while expanding, 128-bit coalesced stores), write the per-env
 //     scalars, and pre-compute the Philox uniforms of step s+1 for the env warp.
 // One __syncthreads per step hands the buffers over.
+template <int EPB>
 struct WsTile {
-    uint32_t R[32 * kRowStride];  // 15 raw observation words per env (history not yet rotated)
-    uint64_t M[34];               // legal masks (+2 zero pads)
-    float4 rew[32];
-    uint32_t act[32];
-    uint8_t q[32], term[32], cur[32];
+    uint32_t R[EPB * kRowStride];  // 15 raw observation words per env (history not yet rotated)
+    uint64_t M[EPB + 2];           // legal masks (+2 zero pads)
+    float4 rew[EPB];
+    uint32_t act[EPB];
+    uint8_t q[EPB], term[EPB], cur[EPB];
 };
 
 template <int OBS>
@@ -315,28 +316,40 @@ __device__ __forceinline__ void emit_obs_row_rot(const uint32_t* R, uint32_t q, 
     }
 }
 
-template <int OBS>
+#ifdef BRL_ROLE_TIMING
+__device__ unsigned long long g_role_cycles[8];
+#define BRL_T0() long long _t0 = clock64()
+#define BRL_ACC(slot) do { long long _t1 = clock64(); if (lane == 0) atomicAdd(&g_role_cycles[slot], (unsigned long long)(_t1 - _t0)); _t0 = _t1; } while (0)
+#else
+#define BRL_T0()
+#define BRL_ACC(slot)
+#endif
+
+template <int EPB, int OBS>
 __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
-    __shared__ WsTile tiles[2];
+    __shared__ WsTile<EPB> tiles[2];
     __shared__ uint32_t uniforms[2][32];
+    __shared__ uint4 row_slots[2 * EPB * 3];
+    __shared__ unsigned long long row_bars[2 * EPB];
+    const RowSlots rs{row_slots, row_bars, EPB};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_writers = (int)(blockDim.x >> 5) - 1;
-    const int64_t env_base = (int64_t)blockIdx.x * 32;
-    const int n_valid = (int)((a.n - env_base) < 32 ? (a.n - env_base) : 32);
+    const int64_t env_base = (int64_t)blockIdx.x * EPB;
+    const int n_valid = (int)((a.n - env_base) < (int64_t)EPB ? (a.n - env_base) : (int64_t)EPB);
     const bool active = lane < n_valid;
     const int64_t i = env_base + lane;
     const size_t obs_row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
     const bool is_env_warp = warp == n_writers;
     Env e;
-    EpisodeCache cache;
+    EpisodePrefetch cache;
     uint64_t mask = 0ull;
     unsigned long long n_term = 0;
     long long rew0 = 0;
     if (is_env_warp) {
-        if (lane < 2) { tiles[0].M[32 + lane] = 0ull; tiles[1].M[32 + lane] = 0ull; }
+        if (lane < 2) { tiles[0].M[EPB + lane] = 0ull; tiles[1].M[EPB + lane] = 0ull; }
         if (active) {
             load_env(a.state_in, a.stride, i, e);
-            cache.prime(e, a.table, a.n_deals);
+            cache.prime(e, rs, lane, a.table, a.n_deals);
             mask = env_legal_mask(e);
         }
     } else if (warp == 0) {
@@ -344,13 +357,15 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                                        : action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step);
     }
     __syncthreads();
+    BRL_T0();
     for (int s = 0; s <= a.k_steps; ++s) {
         if (is_env_warp) {
             if (s < a.k_steps) {
-                WsTile& t = tiles[s & 1];
+                WsTile<EPB>& t = tiles[s & 1];
                 if (active) {
                     int32_t act = kth_legal_action(mask, uniforms[s & 1][lane]);
-                    float4 rew = env_step_autoreset_cached(e, cache, act, a.table, a.n_deals, a.illegal_penalty, a.illegal_bonus);
+                    float4 rew = env_step_autoreset_prefetch(e, cache, rs, lane, act, a.table, a.n_deals, a.illegal_penalty,
+                                                             a.illegal_bonus);
                     n_term += f_terminated(e);
                     rew0 += (long long)rew.x;
                     mask = env_legal_mask(e);
@@ -371,13 +386,13 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                     t.q[lane] = (uint8_t)q;
                     t.term[lane] = (uint8_t)f_terminated(e);
                     t.cur[lane] = (uint8_t)f_player_at(e, q);
-                } else {
+                } else if (lane < EPB) {
                     t.M[lane] = 0ull;
                 }
             }
         } else {
             if (s > 0) {
-                const WsTile& t = tiles[(s - 1) & 1];
+                const WsTile<EPB>& t = tiles[(s - 1) & 1];
                 const int64_t row0 = (int64_t)(s - 1) * a.n;
                 if (a.obs) {
                     unsigned char* obs = static_cast<unsigned char*>(a.obs) + (size_t)row0 * obs_row_bytes;
@@ -400,10 +415,13 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                     a.uniforms ? (active ? a.uniforms[(int64_t)(s + 1) * a.n + i] : 0u)
                                : action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)(s + 1));
         }
+        BRL_ACC(is_env_warp ? 0 : (warp == 0 ? 2 : 4));
         __syncthreads();
+        BRL_ACC(is_env_warp ? 1 : (warp == 0 ? 3 : 5));
     }
     if (is_env_warp) {
         if (active) store_env(a.state_out, a.stride, i, e);
+        asm volatile("cp.async.wait_all;" ::: "memory");  // the last prefetch must land before the block's smem is released
         if (a.stats) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -591,16 +609,29 @@ BRL_DEFINE_LAUNCHER(launch_rollout, k_rollout)
 BRL_DEFINE_LAUNCHER(launch_produce, k_produce)
 BRL_DEFINE_LAUNCHER(launch_dup_step, k_dup_step)
 
-// flags bit 20: force the tile-per-warp rollout kernel; bits 21-22: writer warps of the
-// warp-specialised kernel (0 -> default 3, 1 -> 1, 2 -> 5, 3 -> 7)
+// flags bit 20: force the tile-per-warp rollout kernel; bits 16-17: envs per block of the
+// warp-specialised kernel (as EPW); bits 21-23: its writer warps (0 = auto, else the count).
+template <int EPB, int OBS>
+static void launch_ws_inst(const EnvArgs& a, int writers, cudaStream_t s) {
+    unsigned grid = (unsigned)((a.n + EPB - 1) / EPB);
+    k_rollout_ws<EPB, OBS><<<grid, 32 * (1 + writers), 0, s>>>(a);
+}
+template <int OBS>
+static void launch_ws_obs(const EnvArgs& a, int epb, int writers, cudaStream_t s) {
+    if (epb == 8) launch_ws_inst<8, OBS>(a, writers, s);
+    else if (epb == 16) launch_ws_inst<16, OBS>(a, writers, s);
+    else launch_ws_inst<32, OBS>(a, writers, s);
+}
 static void launch_rollout_ws(const EnvArgs& a, cudaStream_t s) {
     if (a.n == 0) return;
-    static const int writers_of[4] = {3, 1, 5, 7};
-    int threads = 32 * (1 + writers_of[(a.flags >> 21) & 3]);
-    unsigned grid = (unsigned)((a.n + 31) / 32);
-    if (a.flags & BRL_F_OBS_U8) k_rollout_ws<kObsU8><<<grid, threads, 0, s>>>(a);
-    else if (a.flags & BRL_F_OBS_BF16) k_rollout_ws<kObsBF16><<<grid, threads, 0, s>>>(a);
-    else k_rollout_ws<kObsF32><<<grid, threads, 0, s>>>(a);
+    static const int epb_of[4] = {0, 8, 16, 32};
+    int epb = epb_of[(a.flags >> 16) & 3];
+    if (epb == 0) epb = a.n < 8192 ? 16 : 32;  // measured (scripts/exp_rollout_shapes.py)
+    int writers = (a.flags >> 21) & 7;
+    if (writers == 0) writers = epb == 8 ? 1 : (epb == 16 ? 2 : 3);
+    if (a.flags & BRL_F_OBS_U8) launch_ws_obs<kObsU8>(a, epb, writers, s);
+    else if (a.flags & BRL_F_OBS_BF16) launch_ws_obs<kObsBF16>(a, epb, writers, s);
+    else launch_ws_obs<kObsF32>(a, epb, writers, s);
 }
 
 static void fill_common(EnvArgs& a, const BrlParams* p) {
@@ -859,5 +890,14 @@ int32_t brl_state_fields(brl_stream_t stream, void** b, const void* opaque, size
     k_state_fields<<<(unsigned)((a.n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
     return check_launch("brl_state_fields");
 }
+
+#ifdef BRL_ROLE_TIMING
+// debug build only: cycles spent {env work, env barrier, writer0 work, writer0 barrier, other writers work, barrier}
+int32_t brl_debug_role_cycles(unsigned long long* out8, int reset) {
+    cudaMemcpyFromSymbol(out8, g_role_cycles, sizeof(g_role_cycles));
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_role_cycles, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 }  // extern "C"

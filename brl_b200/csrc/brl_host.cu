@@ -13,6 +13,8 @@ struct BrlEnv {
     uint64_t seed;
     uint32_t step;
     cudaStream_t stream;
+    cudaStream_t s_in, s_out;          // copy streams of the pipelined rollout
+    cudaEvent_t ev_in[8], ev_k[8];     // per-chunk: uniforms landed / kernel finished
     uint8_t* d_table;
     void* d_state;
     int32_t* d_action;
@@ -91,6 +93,8 @@ BrlEnv* brl_env_create(int64_t n_envs, int64_t env_offset, const uint8_t* deal_t
     env->obs_row_bytes = (flags & BRL_F_OBS_U8) ? BRL_OBS_DIM : ((flags & BRL_F_OBS_BF16) ? BRL_OBS_DIM * 2 : BRL_OBS_DIM * 4);
     const size_t n = (size_t)n_envs;
     bool good = ok(cudaStreamCreateWithFlags(&env->stream, cudaStreamNonBlocking), "stream create") &&
+                ok(cudaStreamCreateWithFlags(&env->s_in, cudaStreamNonBlocking), "stream create") &&
+                ok(cudaStreamCreateWithFlags(&env->s_out, cudaStreamNonBlocking), "stream create") &&
                 ok(cudaMalloc(&env->d_table, (size_t)n_deals * BRL_DEAL_ROW_BYTES), "malloc table") &&
                 ok(cudaMalloc(&env->d_state, n * BRL_STATE_BYTES_PER_ENV), "malloc state") &&
                 ok(cudaMalloc(&env->d_action, n * 4), "malloc action") &&
@@ -103,6 +107,9 @@ BrlEnv* brl_env_create(int64_t n_envs, int64_t env_offset, const uint8_t* deal_t
                 ok(cudaMemcpyAsync(env->d_table, deal_table_host, (size_t)n_deals * BRL_DEAL_ROW_BYTES,
                                    cudaMemcpyHostToDevice, env->stream), "H2D table") &&
                 ok(cudaStreamSynchronize(env->stream), "sync");
+    for (int c = 0; good && c < 8; ++c)
+        good = ok(cudaEventCreateWithFlags(&env->ev_in[c], cudaEventDisableTiming), "event create") &&
+               ok(cudaEventCreateWithFlags(&env->ev_k[c], cudaEventDisableTiming), "event create");
     if (!good) {
         brl_env_destroy(env);
         return nullptr;
@@ -116,6 +123,12 @@ void brl_env_destroy(BrlEnv* env) {
     cudaFree(env->d_obs); cudaFree(env->d_mask); cudaFree(env->d_rewards); cudaFree(env->d_term); cudaFree(env->d_cur);
     cudaFree(env->t_obs); cudaFree(env->t_mask); cudaFree(env->t_rewards); cudaFree(env->t_term); cudaFree(env->t_cur);
     cudaFree(env->t_action); cudaFree(env->t_uniforms); cudaFree(env->d_stats);
+    for (int c = 0; c < 8; ++c) {
+        if (env->ev_in[c]) cudaEventDestroy(env->ev_in[c]);
+        if (env->ev_k[c]) cudaEventDestroy(env->ev_k[c]);
+    }
+    if (env->s_in) cudaStreamDestroy(env->s_in);
+    if (env->s_out) cudaStreamDestroy(env->s_out);
     if (env->stream) cudaStreamDestroy(env->stream);
     env->magic = 0;
     delete env;
@@ -178,22 +191,45 @@ int32_t brl_env_rollout_host(BrlEnv* env, int32_t k_steps, const uint32_t* unifo
     if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "brl_env_rollout_host: bad handle");
     if (k_steps <= 0) return brl::fail(BRL_E_OPAQUE, "brl_env_rollout_host: k_steps must be > 0");
     if (!ensure_trajectory(env, k_steps)) return BRL_E_LAUNCH;
+    // Software pipeline over chunks of steps: the H2D copy of chunk c+1's randomness and the
+    // D2H copy of chunk c-1's results run on their own streams under chunk c's kernel.
+    const int chunks = (k_steps >= 16 && k_steps % 4 == 0 && (env->n * BRL_NUM_ACTIONS * (k_steps / 4)) % 16 == 0) ? 4 : 1;
+    const int kc = k_steps / chunks;
+    const size_t n = (size_t)env->n, crow = (size_t)kc * n;
     cudaStream_t s = env->stream;
-    const size_t rows = (size_t)k_steps * (size_t)env->n;
-    if (uniforms && !ok(cudaMemcpyAsync(env->t_uniforms, uniforms, rows * 4, cudaMemcpyHostToDevice, s), "H2D uniforms"))
-        return BRL_E_LAUNCH;
     if (!ok(cudaMemsetAsync(env->d_stats, 0, 32, s), "memset stats")) return BRL_E_LAUNCH;
-    BrlParams p = params_of(env, 0);
-    p.k_steps = k_steps;
-    void* b[10] = {env->d_state, env->d_table, env->t_obs, env->t_mask, env->t_rewards, env->t_term, env->t_cur,
-                   env->t_action, env->d_stats, uniforms ? (void*)env->t_uniforms : nullptr};
-    int32_t rc = brl_rollout_random((brl_stream_t)s, b, &p, sizeof(p));
-    if (rc != BRL_OK) return rc;
-    env->step += (uint32_t)k_steps;
-    if (rewards && !ok(cudaMemcpyAsync(rewards, env->t_rewards, rows * 16, cudaMemcpyDeviceToHost, s), "D2H rewards")) return BRL_E_LAUNCH;
-    if (terminated && !ok(cudaMemcpyAsync(terminated, env->t_term, rows, cudaMemcpyDeviceToHost, s), "D2H terminated")) return BRL_E_LAUNCH;
-    if (stats && !ok(cudaMemcpyAsync(stats, env->d_stats, 32, cudaMemcpyDeviceToHost, s), "D2H stats")) return BRL_E_LAUNCH;
-    if (!ok(cudaStreamSynchronize(s), "stream sync")) return BRL_E_LAUNCH;
+    if (uniforms)
+        for (int c = 0; c < chunks; ++c) {
+            if (!ok(cudaMemcpyAsync(env->t_uniforms + c * crow, uniforms + c * crow, crow * 4, cudaMemcpyHostToDevice, env->s_in), "H2D uniforms") ||
+                !ok(cudaEventRecord(env->ev_in[c], env->s_in), "event record"))
+                return BRL_E_LAUNCH;
+        }
+    for (int c = 0; c < chunks; ++c) {
+        if (uniforms && !ok(cudaStreamWaitEvent(s, env->ev_in[c], 0), "wait event")) return BRL_E_LAUNCH;
+        BrlParams p = params_of(env, 0);
+        p.k_steps = kc;
+        void* b[10] = {env->d_state,
+                       env->d_table,
+                       static_cast<char*>(env->t_obs) + c * crow * env->obs_row_bytes,
+                       env->t_mask + c * crow * BRL_NUM_ACTIONS,
+                       env->t_rewards + c * crow * 4,
+                       env->t_term + c * crow,
+                       env->t_cur + c * crow,
+                       env->t_action + c * crow,
+                       env->d_stats,
+                       uniforms ? (void*)(env->t_uniforms + c * crow) : nullptr};
+        int32_t rc = brl_rollout_random((brl_stream_t)s, b, &p, sizeof(p));
+        if (rc != BRL_OK) return rc;
+        env->step += (uint32_t)kc;
+        if (!ok(cudaEventRecord(env->ev_k[c], s), "event record") || !ok(cudaStreamWaitEvent(env->s_out, env->ev_k[c], 0), "wait event"))
+            return BRL_E_LAUNCH;
+        if (rewards && !ok(cudaMemcpyAsync(rewards + c * crow * 4, env->t_rewards + c * crow * 4, crow * 16, cudaMemcpyDeviceToHost, env->s_out), "D2H rewards"))
+            return BRL_E_LAUNCH;
+        if (terminated && !ok(cudaMemcpyAsync(terminated + c * crow, env->t_term + c * crow, crow, cudaMemcpyDeviceToHost, env->s_out), "D2H terminated"))
+            return BRL_E_LAUNCH;
+    }
+    if (stats && !ok(cudaMemcpyAsync(stats, env->d_stats, 32, cudaMemcpyDeviceToHost, env->s_out), "D2H stats")) return BRL_E_LAUNCH;
+    if (!ok(cudaStreamSynchronize(env->s_out), "stream sync") || !ok(cudaStreamSynchronize(s), "stream sync")) return BRL_E_LAUNCH;
     return BRL_OK;
 }
 

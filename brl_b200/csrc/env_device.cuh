@@ -390,6 +390,87 @@ __device__ __forceinline__ float4 env_step_autoreset_cached(Env& e, EpisodeCache
     return rew;
 }
 
+// Variant for the warp-specialised rollout, where one warp runs 32 envs for many steps.
+// Holding the prefetched row in REGISTERS creates a false dependency there: the warp's
+// scoreboard is per register, not per lane, and some lane resets in ~96 % of the steps, so
+// the reset branch of step s touches the registers that step s-1's (other lanes') row load
+// is still writing -- ncu showed 31 % of the env warp's time on that long-scoreboard wait.
+// Here the next episode's row is fetched with cp.async into a per-lane shared-memory slot and
+// its arrival is tracked by a per-lane mbarrier, so a lane only ever waits on ITS OWN copy,
+// issued at least 4 calls earlier.  Two slots per lane alternate (no WAR hazard on the slot).
+struct RowSlots {  // one per lane, in shared memory (arrays indexed [slot][lane])
+    uint4* rows;             // [2][EPB][3]
+    unsigned long long* bar;  // [2][EPB]
+    int epb;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct EpisodePrefetch {
+    CachedRow cur;
+    EpisodeDraw next_draw;
+    uint32_t slot;    // slot the NEXT episode's row is arriving in
+    uint32_t parity;  // bit k = phase parity to wait for on slot k's mbarrier
+
+    __device__ __forceinline__ void issue(const RowSlots& rs, int lane, const uint8_t* __restrict__ table) {
+        const uint8_t* g = table + (size_t)next_draw.deal * kDealRowBytes;
+        const uint32_t dst = smem_u32(rs.rows + ((size_t)slot * rs.epb + lane) * 3);
+        const uint32_t bar = smem_u32(rs.bar + (size_t)slot * rs.epb + lane);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(g + 16) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 32u), "l"(g + 32) : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+    }
+    __device__ __forceinline__ void prime(const Env& e, const RowSlots& rs, int lane, const uint8_t* __restrict__ table,
+                                          uint32_t n_deals) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(rs.bar + lane)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(rs.bar + rs.epb + lane)) : "memory");
+        cur.load(table, e.deal);
+        next_draw = draw_episode(e.key_lo, e.key_hi, n_deals);
+        slot = 0u;
+        parity = 0u;
+        issue(rs, lane, table);
+    }
+    // the episode ended: the prefetched row becomes current, start fetching the one after
+    __device__ __forceinline__ void advance(const Env& e, const RowSlots& rs, int lane, const uint8_t* __restrict__ table,
+                                            uint32_t n_deals) {
+        const uint32_t bar = smem_u32(rs.bar + (size_t)slot * rs.epb + lane);
+        const uint32_t want = (parity >> slot) & 1u;
+        uint32_t done = 0u;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done) : "r"(bar), "r"(want) : "memory");
+        }
+        const uint4* r = rs.rows + ((size_t)slot * rs.epb + lane) * 3;
+        cur.h01 = r[0];
+        cur.h23 = r[1];
+        cur.dd = r[2];
+        parity ^= 1u << slot;
+        slot ^= 1u;
+        next_draw = draw_episode(e.key_lo, e.key_hi, n_deals);
+        issue(rs, lane, table);
+    }
+};
+
+__device__ __forceinline__ float4 env_step_autoreset_prefetch(Env& e, EpisodePrefetch& c, const RowSlots& rs, int lane,
+                                                              int32_t action, const uint8_t* __restrict__ table,
+                                                              uint32_t n_deals, float illegal_penalty, float illegal_bonus) {
+    if (f_terminated(e)) {
+        e.A &= ~(kTermBit | kCarriedBit);
+        e.B = bitfield_set(e.B, 9, 9, 0u);
+    }
+    float4 rew = env_step(e, action, c.cur, illegal_penalty, illegal_bonus);
+    if (f_terminated(e)) {
+        env_init_from_draw(e, c.next_draw);
+        e.A |= kTermBit | kCarriedBit;
+        c.advance(e, rs, lane, table, n_deals);
+    }
+    return rew;
+}
+
 // ---- observation -- wb5/utils.py:15-52 as 15 words of bits ------------------------------
 __device__ __forceinline__ uint32_t rotr_nibbles(uint32_t h, uint32_t q) {
     // relative seat = (absolute - observer) mod 4: rotate every nibble right by q

@@ -80,7 +80,7 @@ typedef struct CUstream_st *brl_stream_t; /* == cudaStream_t */
 #define BRL_F_TUNE_EPW(code) ((code) << 16)
 #define BRL_F_TUNE_WPB(code) ((code) << 18)
 #define BRL_F_TUNE_CLASSIC_ROLLOUT (1 << 20)     /* tile-per-warp rollout kernel instead of the warp-specialised one */
-#define BRL_F_TUNE_WRITERS(code) ((code) << 21) /* writer warps of the warp-specialised rollout: 0->3, 1->1, 2->5, 3->7 */
+#define BRL_F_TUNE_WRITERS(n) ((n) << 21)       /* writer warps (1..7) of the warp-specialised rollout; EPW bits = its envs per block */
 
 /* errors */
 #define BRL_OK 0

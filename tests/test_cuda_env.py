@@ -171,7 +171,8 @@ def test_plain_step_terminal_is_absorbing_and_noop():
 
 
 @pytest.mark.parametrize("n,k,tune_kw", [
-    (2048, 24, {}), (100, 40, {"writers": 1}), (1000, 9, {"writers": 3}), (33, 5, {"writers": 5}), (1, 3, {}),
+    (2048, 24, {}), (100, 40, {"writers": 1}), (1000, 9, {"writers": 3, "epw": 32}), (33, 5, {"writers": 5, "epw": 16}),
+    (1, 3, {}), (70000, 3, {}), (777, 6, {"epw": 8, "writers": 2}),
     (2048, 24, {"classic_rollout": True}), (100, 40, {"classic_rollout": True, "epw": 32}),
     (8, 7, {"classic_rollout": True, "epw": 8})])
 def test_fused_rollout_kernel_matches_oracle(n, k, tune_kw):
