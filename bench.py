@@ -95,6 +95,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _traffic(kernel_key):
+    """per-launch DRAM bytes of the bench kernel from the committed `ncu --set full` capture (profiles/)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            e = json.load(fh)[kernel_key]
+        return e["traffic_bytes"], f"profiles/r01_traffic.json ({e['report']}: dram__bytes_read.sum + dram__bytes_write.sum, mean of {e['instances']} launches)"
+    except Exception:
+        return None, "no ncu capture committed for this kernel"
+
+
 def cpu_oracle_throughput(n_envs, t_steps, reps, n_threads, table):
     """env-steps/s of the C oracle (all outputs written, same workload shape)."""
     import numpy as np
@@ -241,6 +251,7 @@ def main():
     avg_kernel_ms = sum(kernel_ms) / len(kernel_ms)
     peak, peak_src = _peaks()
     achieved = BYTES_PER_ENV_STEP * n * k / (avg_kernel_ms * 1e-3) / 1e9
+    traffic, traffic_src = _traffic("void k_rollout_ws<32, 0>(EnvArgs) grid=256")
 
     # ---- e2e: host-buffer C-ABI, copies inside the timed region (rank-local, summed over ranks) ----
     e2e = run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps=max(20, min(200, args.steps * 4)),
@@ -253,9 +264,11 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, times = cpu_oracle_throughput(n, k, 3, cores, table_np)
+        reps = 100  # ~1.2 s wall x all cores = 10-30 s of CPU work
+        v, times = cpu_oracle_throughput(n, k, reps, cores, table_np)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"3 x ({n} envs x {k} auto-reset random-legal steps), all outputs written, {cores} threads",
+               "sample": f"{reps} x ({n} envs x {k} auto-reset random-legal steps), all outputs written, {cores} threads, "
+                         f"{sum(times):.2f} s wall",
                "note": "C restatement of pgx semantics (oracle/brl_oracle.c); pgx/JAX not installable here"}
     if rank == 0:
         line = {
@@ -264,7 +277,7 @@ def main():
             "dtype": "u8/int32 state, f32 0/1 observation", "data": "synthetic", "config": _config(world),
             "e2e": e2e, "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "brl::k_rollout_ws<f32> (1 env warp + 3 writer warps per 32 envs)", "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "brl::k_rollout_ws<f32> (1 env warp + 3 writer warps per 32 envs)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * k, "avg_launch_ms": avg_kernel_ms},
             "cpu_baseline": cpu, "clocks": clocks,
             "episode_stats": {"finished_auctions": float(sums[0]), "sum_reward_player0": float(sums[1]),

@@ -455,6 +455,10 @@ __global__ void __launch_bounds__(128) k_produce(const EnvArgs a) {
                                     ((uint32_t)(p[3] & 3) << 6);
                 env_reset(e, (uint32_t)a.in_deal[i], (uint32_t)a.in_dealer[i] & 3u, a.in_vul_ns[i] ? 1u : 0u,
                           a.in_vul_ew[i] ? 1u : 0u, seating8, a.in_rng_key ? a.in_rng_key[i] : 0ull);
+            } else if (a.mode == kModeMask) {
+                // the legal mask is a function of word A alone: read one 16-byte plane, not all five
+                e = Env{};
+                e.A = a.state_in[3 * a.stride + i].z;
             } else {
                 load_env(a.state_in, a.stride, i, e);
                 if (a.mode == kModeDupInit) env_duplicate_init(e);

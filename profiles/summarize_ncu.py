@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Turn an `ncu --set full` report into the short text summary committed under profiles/.
 
-    python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r01_<name>.txt
+    python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r01_<name>.txt [profiles/r01_traffic.json]
+
+With a third argument, the per-launch DRAM traffic of every kernel in the report (mean over
+its instances, keyed by kernel name + grid size) is merged into that JSON file; bench.py reads
+`roofline.traffic` from it.
 
 Reads the report on the CPU box (`ncu -i ... --page raw/source --csv`); numbers taken under
 the profiler are evidence about the kernel's behaviour, never bench values."""
@@ -22,7 +26,8 @@ WANT = [
 
 
 def page(rep, name):
-    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv", "--print-units", "base"], capture_output=True,
+                         text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
@@ -64,6 +69,24 @@ def main():
             lines.append(f"  {100 * num(r[i_s]) / tot:5.1f}%  exec={r[i_i]:>9s}  {r[i_src].strip()[:90]}")
     open(dst, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines[:40]))
+    if len(sys.argv) > 3:
+        import json
+        import os
+        acc = {}
+        for r in rows:
+            key = f"{r[hdr.index('Kernel Name')]} grid={r[hdr.index('launch__grid_size')]}"
+            a = acc.setdefault(key, {"n": 0, "rd": 0.0, "wr": 0.0, "ns": 0.0})
+            a["n"] += 1
+            a["rd"] += num(r[hdr.index("dram__bytes_read.sum")])
+            a["wr"] += num(r[hdr.index("dram__bytes_write.sum")])
+            a["ns"] += num(r[hdr.index("gpu__time_duration.sum")])
+        path = sys.argv[3]
+        doc = json.load(open(path)) if os.path.exists(path) else {}
+        for key, a in acc.items():
+            doc[key] = {"dram_bytes_read": a["rd"] / a["n"], "dram_bytes_write": a["wr"] / a["n"],
+                        "traffic_bytes": (a["rd"] + a["wr"]) / a["n"], "gpu_time_ns_under_ncu": a["ns"] / a["n"],
+                        "instances": a["n"], "report": os.path.basename(rep)}
+        json.dump(doc, open(path, "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
