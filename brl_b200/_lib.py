@@ -13,11 +13,11 @@ from . import build as _build
 OPS = (
     "brl_make_keys", "brl_init", "brl_reset_fields", "brl_step", "brl_duplicate_step", "brl_duplicate_init",
     "brl_observe", "brl_legal_mask", "brl_rollout_random", "brl_imp_reward", "brl_gae", "brl_categorical",
-    "brl_match_stats", "brl_state_fields", "brl_gather_reward",
+    "brl_match_stats", "brl_state_fields", "brl_gather_reward", "brl_mlp_pack", "brl_obs_to_bf16", "brl_mlp_forward",
 )
 HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host", "brl_env_rollout_host",
             "brl_env_trajectory")
-MISC = ("brl_last_error", "brl_abi_version")
+MISC = ("brl_last_error", "brl_abi_version", "brl_mlp_packed_bytes", "brl_mlp_scratch_bytes")
 XLA_LEGACY = tuple(op + "_xla" for op in OPS)  # legacy XLA GPU custom-call targets (csrc/xla_ffi_shim.cc)
 ALL_SYMBOLS = OPS + HOST_API + MISC + XLA_LEGACY
 
@@ -29,6 +29,7 @@ F_OBS_U8 = 0x0010
 F_OBS_BF16 = 0x0020
 F_SAMPLE = 0x0040
 F_QUAD_LAST = 0x0100
+F_MLP_BF16 = 0x0200
 
 
 def tune(epw: int = 0, wpb: int = 0, classic_rollout: bool = False, writers: int = 0) -> int:
@@ -82,6 +83,9 @@ def load():
         fn.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t]
     L.brl_last_error.restype = C.c_char_p
     L.brl_abi_version.restype = C.c_int32
+    L.brl_mlp_packed_bytes.restype = C.c_int64
+    L.brl_mlp_scratch_bytes.restype = C.c_int64
+    L.brl_mlp_scratch_bytes.argtypes = [C.c_int64]
     L.brl_env_create.restype = C.c_void_p
     L.brl_env_create.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_uint64, C.c_int32]
     L.brl_env_destroy.restype = None

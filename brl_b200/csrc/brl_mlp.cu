@@ -1,0 +1,464 @@
+// brl_mlp.cu -- the policy/value net of the rollout and evaluation loops on the 5th-gen
+// tensor cores: the "DeepMind" 480 -> 4 x 1024 ReLU -> {38 logits, 1 value} MLP
+// (src/models.py:23-33) as five TMA + tcgen05 GEMM launches.  sm_100a only.
+//
+// The reference runs this net in fp32 (haiku default).  A single bf16 product would
+// change near-tie argmax decisions, so the default mode here is a THREE-TERM bf16 split
+//     x . w  ~=  x_hi . w_hi  +  x_lo . w_hi  +  x_hi . w_lo        (hi = bf16(v), lo = bf16(v - hi))
+// accumulated in fp32 in tensor memory: ~2^-16 relative error per product, i.e. fp32-class
+// results at 1/3 of the bf16 tensor rate (still ~6x the fp32 SIMT GEMM rate).  The first
+// layer's input is the 0/1 observation, exact in bf16, so it needs only two terms.
+// BRL_F_MLP_BF16 selects the plain single-product mode.
+//
+// One layer = one launch of k_mlp_layer: C[M, N] = act(A[M, K] . Wt[N, K]^T + b).
+//   CTA tile 128 (envs) x BN (features), K in blocks of 64 bf16 = one 128-byte swizzle row.
+//   warp 0    TMA producer: per K block, bulk-tensor loads of the A / Wt (hi, lo) boxes into a
+//             ring of shared-memory stages (128B swizzle), completion on an mbarrier;
+//   warp 1    MMA issuer: one lane issues tcgen05.mma (UMMA 128 x BN x 16, kind::f16, fp32
+//             accumulate in TMEM); tcgen05.commit hands the stage back / signals the epilogue;
+//   warps 2-5 epilogue: tcgen05.ld the accumulator (thread = one env row), + bias, ReLU,
+//             split into bf16 hi / lo for the next layer (or fp32 logits + value for the head).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace brl {
+
+constexpr int kObsDimM = 480, kHidden = 1024, kHeadValid = 39, kHeadPad = 64;
+constexpr int kBM = 128, kBK = 64, kUmmaK = 16;
+constexpr int kMlpThreads = 192;
+constexpr uint32_t kSmemBudget = 200 * 1024;
+
+// ---- packed parameter blob ---------------------------------------------------------------
+struct MlpLayout {
+    size_t w_hi[5], w_lo[5], bias[5], total;
+    int n_out[5], k_in[5];
+};
+
+__host__ __device__ inline MlpLayout mlp_layout() {
+    MlpLayout L{};
+    size_t off = 0;
+    for (int l = 0; l < 5; ++l) {
+        L.k_in[l] = l == 0 ? kObsDimM : kHidden;
+        L.n_out[l] = l == 4 ? kHeadPad : kHidden;
+        size_t wbytes = (size_t)L.n_out[l] * L.k_in[l] * 2;
+        L.w_hi[l] = off; off += wbytes;
+        L.w_lo[l] = off; off += wbytes;
+        L.bias[l] = off; off += (size_t)L.n_out[l] * 4;
+        off = (off + 255) & ~(size_t)255;
+    }
+    L.total = off;
+    return L;
+}
+
+// w[in, out] fp32 (haiku layout, y = x @ w + b) -> Wt_hi / Wt_lo [out_pad, in] bf16 (K-major rows)
+__global__ void __launch_bounds__(256) k_mlp_pack(const float* __restrict__ w, const float* __restrict__ b,
+                                                  const float* __restrict__ w2, const float* __restrict__ b2,
+                                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                  float* __restrict__ bias, int k_in, int n_out, int n_src, int n_src2) {
+    // rows [0, n_src) come from w, rows [n_src, n_src + n_src2) from w2 (the value head), the rest are zero
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_out * k_in) return;
+    int n = (int)(idx / k_in), k = (int)(idx % k_in);
+    float v = 0.0f;
+    if (n < n_src) v = w[(size_t)k * n_src + n];
+    else if (n < n_src + n_src2) v = w2[(size_t)k * n_src2 + (n - n_src)];
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[idx] = h;
+    lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+    if (k == 0) bias[n] = n < n_src ? b[n] : (n < n_src + n_src2 ? b2[n - n_src] : 0.0f);
+}
+
+// observation f32 / u8 (0/1) -> bf16, for callers whose env emits the reference dtypes
+template <class T>
+__global__ void __launch_bounds__(256) k_obs_to_bf16(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i >= n) return;
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t a = (float)in[i + 2 * k] != 0.0f ? 0x3F80u : 0u, c = (float)in[i + 2 * k + 1] != 0.0f ? 0x3F80u : 0u;
+        w[k] = a | (c << 16);
+    }
+    *reinterpret_cast<uint4*>(out + i) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug becomes a trap (CUDA error), never a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t it = 0; !done; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (it > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {  // implies tcgen05.fence::before_thread_sync
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile in shared memory, rows of 64 bf16 = 128 bytes, 128B swizzle, 8-row
+// groups 1024 bytes apart (what the TMA box {64, rows} with CU_TENSOR_MAP_SWIZZLE_128B writes)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);      // start address, 16-byte units
+    d |= (uint64_t)(1024u >> 4) << 32;                     // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major, M x N tile
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---- one layer ------------------------------------------------------------------------------
+struct LayerArgs {
+    const float* bias;           // [n_pad]
+    __nv_bfloat16* out_hi;       // hidden: [M, n_total] bf16
+    __nv_bfloat16* out_lo;       // hidden, split mode: residual (may be NULL)
+    float* logits;               // head: [M, 38]
+    float* value;                // head: [M]
+    int M, n_total, k_blocks;
+};
+
+template <int BN, bool SPLIT_A, bool SPLIT_W>
+struct LayerCfg {
+    static constexpr uint32_t kABytes = kBM * kBK * 2, kWBytes = BN * kBK * 2;
+    static constexpr uint32_t kStageBytes = kABytes * (SPLIT_A ? 2 : 1) + kWBytes * (SPLIT_W ? 2 : 1);
+    static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (int)(kSmemBudget / kStageBytes);
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool SPLIT_A, bool SPLIT_W, bool HEAD>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+k_mlp_layer(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+            const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const LayerArgs a) {
+    using Cfg = LayerCfg<BN, SPLIT_A, SPLIT_W>;
+    constexpr int S = Cfg::kStages;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_addr(smem_dyn) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024-byte alignment
+    const uint32_t bar_base = base + S * Cfg::kStageBytes;         // full[S], empty[S], tmem_full, tmem slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * S);
+    __shared__ float bias_s[BN];
+    __shared__ uint32_t tmem_base_s;  // written by tcgen05.alloc
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kBM;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w_hi) : "memory");
+        for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_addr(&tmem_base_s), BN < 32 ? 32 : BN);
+    if (warp >= 2) {
+        int t = threadIdx.x - 64;
+        if (t < BN) bias_s[t] = a.bias[n0 + t];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(&tmem_base_s);
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            for (int kb = 0; kb < a.k_blocks; ++kb) {
+                const int s = kb % S;
+                const uint32_t ph = (uint32_t)(kb / S) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+                uint32_t dst = base + s * Cfg::kStageBytes;
+                tma_load_2d(dst, &tm_a_hi, full_bar(s), kb * kBK, m0);
+                dst += Cfg::kABytes;
+                if (SPLIT_A) { tma_load_2d(dst, &tm_a_lo, full_bar(s), kb * kBK, m0); dst += Cfg::kABytes; }
+                tma_load_2d(dst, &tm_w_hi, full_bar(s), kb * kBK, n0);
+                dst += Cfg::kWBytes;
+                if (SPLIT_W) tma_load_2d(dst, &tm_w_lo, full_bar(s), kb * kBK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+            for (int kb = 0; kb < a.k_blocks; ++kb) {
+                const int s = kb % S;
+                const uint32_t ph = (uint32_t)(kb / S) & 1u;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sa_hi = base + s * Cfg::kStageBytes;
+                const uint32_t sa_lo = sa_hi + Cfg::kABytes;
+                const uint32_t sw_hi = sa_hi + Cfg::kABytes * (SPLIT_A ? 2 : 1);
+                const uint32_t sw_lo = sw_hi + Cfg::kWBytes;
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k) {
+                    const uint32_t koff = (uint32_t)k * kUmmaK * 2;  // bytes along K inside the 128-byte row
+                    const uint64_t da_hi = umma_desc_sw128(sa_hi + koff), dw_hi = umma_desc_sw128(sw_hi + koff);
+                    umma_bf16(tmem_acc, da_hi, dw_hi, idesc, (kb | k) != 0);
+                    if (SPLIT_A) umma_bf16(tmem_acc, umma_desc_sw128(sa_lo + koff), dw_hi, idesc, 1u);
+                    if (SPLIT_W) umma_bf16(tmem_acc, da_hi, umma_desc_sw128(sw_lo + koff), idesc, 1u);
+                }
+                umma_commit(empty_bar(s));  // the stage is free once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {  // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        mbar_wait(tmem_full_bar, 0u);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16);
+        if (!HEAD) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_row + (uint32_t)c0, r);
+                if (row < a.M) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float x0 = fmaxf(__uint_as_float(r[2 * j]) + bias_s[c0 + 2 * j], 0.0f);
+                        float x1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias_s[c0 + 2 * j + 1], 0.0f);
+                        __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                        hi[j] = *reinterpret_cast<uint32_t*>(&h);
+                        lo[j] = pack_bf16x2(x0 - __low2float(h), x1 - __high2float(h));
+                    }
+                    const size_t o = (size_t)row * a.n_total + n0 + c0;
+                    uint4* ph = reinterpret_cast<uint4*>(a.out_hi + o);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+                    if (a.out_lo) {
+                        uint4* pl = reinterpret_cast<uint4*>(a.out_lo + o);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+                    }
+                }
+            }
+        } else {
+            // head tile: columns 0..37 = policy logits, 38 = value (src/models.py:30-32)
+            uint32_t r0[32], r1[32];
+            tmem_ld32(t_row, r0);
+            tmem_ld32(t_row + 32u, r1);
+            if (row < a.M) {
+                float2* pl = reinterpret_cast<float2*>(a.logits + (size_t)row * 38);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    pl[j] = make_float2(__uint_as_float(r0[2 * j]) + bias_s[2 * j], __uint_as_float(r0[2 * j + 1]) + bias_s[2 * j + 1]);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    pl[16 + j] = make_float2(__uint_as_float(r1[2 * j]) + bias_s[32 + 2 * j],
+                                             __uint_as_float(r1[2 * j + 1]) + bias_s[32 + 2 * j + 1]);
+                a.value[row] = __uint_as_float(r1[6]) + bias_s[38];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, BN < 32 ? 32 : BN);
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// bf16 matrix [rows, cols] row-major (row pitch `pitch` elements), box = 64 columns x box_rows, 128B swizzle;
+// out-of-bounds elements read as zero (K tail of the 480-wide first layer, M / N tails)
+static bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, bool SPLIT_A, bool SPLIT_W, bool HEAD>
+static int32_t launch_layer(cudaStream_t s, const void* a_hi, const void* a_lo, int k_in, const void* w_hi, const void* w_lo,
+                            int n_valid_rows, const LayerArgs& args) {
+    using Cfg = LayerCfg<BN, SPLIT_A, SPLIT_W>;
+    CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+    bool ok = make_map(&ta_hi, a_hi, (uint64_t)args.M, (uint64_t)k_in, (uint64_t)k_in, kBM) &&
+              make_map(&tw_hi, w_hi, (uint64_t)n_valid_rows, (uint64_t)k_in, (uint64_t)k_in, BN);
+    ta_lo = ta_hi;
+    tw_lo = tw_hi;
+    if (ok && SPLIT_A) ok = make_map(&ta_lo, a_lo, (uint64_t)args.M, (uint64_t)k_in, (uint64_t)k_in, kBM);
+    if (ok && SPLIT_W) ok = make_map(&tw_lo, w_lo, (uint64_t)n_valid_rows, (uint64_t)k_in, (uint64_t)k_in, BN);
+    if (!ok) return fail(BRL_E_LAUNCH, "brl_mlp_forward: cuTensorMapEncodeTiled failed");
+    auto kern = k_mlp_layer<BN, SPLIT_A, SPLIT_W, HEAD>;
+    static bool attr_set = false;  // idempotent; a race only repeats the call
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
+            return fail(BRL_E_LAUNCH, "brl_mlp_forward: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(n_valid_rows + BN - 1) / BN, (unsigned)((args.M + kBM - 1) / kBM));
+    kern<<<grid, kMlpThreads, Cfg::kSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, args);
+    return BRL_OK;
+}
+
+}  // namespace brl
+
+using namespace brl;
+
+extern "C" {
+
+int64_t brl_mlp_packed_bytes(void) { return (int64_t)mlp_layout().total; }
+int64_t brl_mlp_scratch_bytes(int64_t n_envs) { return n_envs * (int64_t)kHidden * 2 * 4; }
+
+int32_t brl_mlp_pack(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    for (int k = 0; k < 13; ++k)
+        if (b[k] == nullptr) return fail(BRL_E_BUFFER, "brl_mlp_pack: buffer %d is NULL", k);
+    BRL_REQUIRE(b[12], "packed");
+    const MlpLayout L = mlp_layout();
+    unsigned char* blob = static_cast<unsigned char*>(b[12]);
+    for (int l = 0; l < 5; ++l) {
+        const int64_t total = (int64_t)L.n_out[l] * L.k_in[l];
+        const bool head = l == 4;
+        k_mlp_pack<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            static_cast<const float*>(b[l]), static_cast<const float*>(b[6 + l]),
+            head ? static_cast<const float*>(b[5]) : nullptr, head ? static_cast<const float*>(b[11]) : nullptr,
+            reinterpret_cast<__nv_bfloat16*>(blob + L.w_hi[l]), reinterpret_cast<__nv_bfloat16*>(blob + L.w_lo[l]),
+            reinterpret_cast<float*>(blob + L.bias[l]), L.k_in[l], L.n_out[l], head ? 38 : kHidden, head ? 1 : 0);
+    }
+    return check_launch("brl_mlp_pack");
+}
+
+int32_t brl_obs_to_bf16(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "obs");
+    BRL_REQUIRE(b[1], "obs_bf16");
+    if (p->n_envs == 0) return BRL_OK;
+    const int64_t n = p->n_envs * kObsDimM;
+    const unsigned grid = (unsigned)((n / 8 + 255) / 256);
+    if (p->flags & BRL_F_OBS_U8)
+        k_obs_to_bf16<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const uint8_t*>(b[0]), static_cast<__nv_bfloat16*>(b[1]), n);
+    else
+        k_obs_to_bf16<float><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(b[0]), static_cast<__nv_bfloat16*>(b[1]), n);
+    return check_launch("brl_obs_to_bf16");
+}
+
+int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "obs_bf16");
+    BRL_REQUIRE(b[1], "packed");
+    BRL_REQUIRE(b[2], "scratch");
+    BRL_REQUIRE(b[3], "logits");
+    BRL_REQUIRE(b[4], "value");
+    if (p->n_envs == 0) return BRL_OK;
+    if (p->n_envs > (int64_t)1 << 30) return fail(BRL_E_OPAQUE, "brl_mlp_forward: n_envs too large");
+    if (encode_fn() == nullptr) return fail(BRL_E_LAUNCH, "brl_mlp_forward: cuTensorMapEncodeTiled not available from the driver");
+    const bool split = !(p->flags & BRL_F_MLP_BF16);
+    const int M = (int)p->n_envs;
+    const MlpLayout L = mlp_layout();
+    const unsigned char* blob = static_cast<const unsigned char*>(b[1]);
+    __nv_bfloat16* scratch = static_cast<__nv_bfloat16*>(b[2]);
+    const size_t act = (size_t)M * kHidden;
+    __nv_bfloat16* buf_hi[2] = {scratch, scratch + act};
+    __nv_bfloat16* buf_lo[2] = {scratch + 2 * act, scratch + 3 * act};
+    cudaStream_t s = (cudaStream_t)stream;
+    const void* in_hi = b[0];
+    const void* in_lo = nullptr;
+    for (int l = 0; l < 5; ++l) {
+        LayerArgs a{};
+        a.bias = reinterpret_cast<const float*>(blob + L.bias[l]);
+        a.M = M;
+        a.n_total = kHidden;
+        a.k_blocks = (L.k_in[l] + kBK - 1) / kBK;
+        const void* w_hi = blob + L.w_hi[l];
+        const void* w_lo = blob + L.w_lo[l];
+        if (l < 4) {
+            a.out_hi = buf_hi[l & 1];
+            a.out_lo = split ? buf_lo[l & 1] : nullptr;
+            if (l == 0) rc = split ? launch_layer<128, false, true, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
+                                   : launch_layer<128, false, false, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a);
+            else rc = split ? launch_layer<128, true, true, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
+                            : launch_layer<128, false, false, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a);
+            in_hi = a.out_hi;
+            in_lo = a.out_lo;
+        } else {
+            a.logits = static_cast<float*>(b[3]);
+            a.value = static_cast<float*>(b[4]);
+            rc = split ? launch_layer<kHeadPad, true, true, true>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHeadPad, a)
+                       : launch_layer<kHeadPad, false, false, true>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHeadPad, a);
+        }
+        if (rc != BRL_OK) return rc;
+    }
+    return check_launch("brl_mlp_forward");
+}
+
+}  // extern "C"

@@ -59,6 +59,9 @@ BRL_LEGACY_CUSTOM_CALL(brl_categorical)
 BRL_LEGACY_CUSTOM_CALL(brl_match_stats)
 BRL_LEGACY_CUSTOM_CALL(brl_state_fields)
 BRL_LEGACY_CUSTOM_CALL(brl_gather_reward)
+BRL_LEGACY_CUSTOM_CALL(brl_mlp_pack)
+BRL_LEGACY_CUSTOM_CALL(brl_obs_to_bf16)
+BRL_LEGACY_CUSTOM_CALL(brl_mlp_forward)
 }  // extern "C"
 
 // ---- (2) typed FFI handlers --------------------------------------------------------------

@@ -1,7 +1,13 @@
 """Policy/value net of the rollout and evaluation loops: the "DeepMind" 4x1024 ReLU
-actor-critic (src/models.py:23-33).  Not fused into the env kernels in this round,
-so per the north star it is a plain library GEMM chain (cuBLAS through torch.addmm);
-parameters keep haiku's layout (`actor_critic/linear{,_1..5}` -> {'w' [in,out], 'b'}).
+actor-critic (src/models.py:23-33); parameters keep haiku's layout
+(`actor_critic/linear{,_1..5}` -> {'w' [in,out], 'b'}).
+
+precision:
+  "tc"      hand-written TMA + tcgen05 forward (csrc/brl_mlp.cu), 3-term bf16 split with fp32
+            accumulation in tensor memory -- fp32-class results (the reference computes in fp32);
+  "tc-bf16" the same kernels with a single bf16 product per term;
+  "fp32" / "tf32" / "bf16"  library GEMM chain (cuBLAS through torch.addmm), kept as the
+            independent cross-check of the tensor-core path and for tanh nets.
 """
 from __future__ import annotations
 
@@ -11,6 +17,8 @@ from typing import Dict
 
 import numpy as np
 import torch
+
+from . import ops
 
 LAYERS = ("actor_critic/linear", "actor_critic/linear_1", "actor_critic/linear_2", "actor_critic/linear_3",
           "actor_critic/linear_4", "actor_critic/linear_5")
@@ -67,8 +75,35 @@ class ForwardPass:
             raise NotImplementedError("only the DeepMind 4x1024 net is on the hot path (SURVEY 8a a16)")
         self.act = torch.relu if activation == "relu" else torch.tanh
         self.precision = precision
+        if precision in ("tc", "tc-bf16") and activation != "relu":
+            raise NotImplementedError("the tensor-core forward fuses ReLU; use a library precision for tanh nets")
+        self._scratch = None
+
+    def _packed(self, params):
+        """bf16 hi/lo blob of `params`, re-packed when any tensor was replaced or updated in place."""
+        ws = [params[name]["w"] for name in LAYERS]
+        bs = [params[name]["b"] for name in LAYERS]
+        stamp = tuple((t.data_ptr(), t._version) for t in ws + bs)
+        cached = params.get("_brl_packed")
+        if cached is None or cached[0] != stamp:
+            cached = (stamp, ops.mlp_pack(ws, bs))
+            params["_brl_packed"] = cached
+        return cached[1]
+
+    def _apply_tc(self, params, x: torch.Tensor):
+        n = x.shape[0]
+        xb = ops.obs_to_bf16(x.contiguous())
+        if self._scratch is None or self._scratch.numel() < ops._lib.load().brl_mlp_scratch_bytes(n) or \
+                self._scratch.device != x.device:
+            self._scratch = ops.mlp_scratch(n, x.device)
+        logits = torch.empty((n, 38), dtype=torch.float32, device=x.device)
+        value = torch.empty(n, dtype=torch.float32, device=x.device)
+        ops.mlp_forward(xb, self._packed(params), self._scratch, logits, value, single_bf16=self.precision == "tc-bf16")
+        return logits, value
 
     def apply(self, params, x: torch.Tensor):
+        if self.precision in ("tc", "tc-bf16"):
+            return self._apply_tc(params, x)
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = self.precision == "tf32"
         try:

@@ -11,8 +11,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (BrlParams, F_ACCUMULATE, F_AUTORESET, F_OBS_BF16, F_OBS_U8, F_QUAD_LAST, F_RANDOM_ACTION,
-                   F_SAMPLE)
+from ._lib import (BrlParams, F_ACCUMULATE, F_AUTORESET, F_MLP_BF16, F_OBS_BF16, F_OBS_U8, F_QUAD_LAST,
+                   F_RANDOM_ACTION, F_SAMPLE)
 
 NUM_ACTIONS = 38
 OBS_DIM = 480
@@ -194,6 +194,46 @@ def match_stats(x: torch.Tensor, sums: torch.Tensor) -> None:
 def gather_reward(rewards, actor, out, scale: float) -> None:
     _call("brl_gather_reward", [_ptr(rewards), _ptr(actor), _ptr(out)],
               _params(rewards.shape[0], gamma=scale))
+
+
+def mlp_pack(weights, biases) -> torch.Tensor:
+    """Six haiku-layout fp32 (w[in,out], b[out]) pairs -> the packed bf16 hi/lo parameter blob."""
+    dev = weights[0].device
+    blob = torch.empty(_lib.load().brl_mlp_packed_bytes(), dtype=torch.uint8, device=dev)
+    ws = [w.detach().to(torch.float32).contiguous() for w in weights]
+    bs = [b.detach().to(torch.float32).contiguous() for b in biases]
+    _call("brl_mlp_pack", [_ptr(t) for t in ws] + [_ptr(t) for t in bs] + [_ptr(blob)], _params(0))
+    return blob
+
+
+def obs_to_bf16(obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """0/1 observation in a reference dtype (f32 / u8 / bool) -> bf16 for the tensor-core forward."""
+    if obs.dtype == torch.bfloat16:
+        return obs
+    n = obs.shape[0]
+    if out is None:
+        out = torch.empty((n, OBS_DIM), dtype=torch.bfloat16, device=obs.device)
+    src = obs.view(torch.uint8) if obs.dtype == torch.bool else obs
+    if src.dtype not in (torch.float32, torch.uint8):
+        raise _lib.BrlError(f"observation dtype {obs.dtype} not supported")
+    _call("brl_obs_to_bf16", [_ptr(src), _ptr(out)], _params(n, flags=F_OBS_U8 if src.dtype == torch.uint8 else 0))
+    return out
+
+
+def mlp_scratch(n: int, device) -> torch.Tensor:
+    return torch.empty(_lib.load().brl_mlp_scratch_bytes(n), dtype=torch.uint8, device=device)
+
+
+def mlp_forward(obs_bf16: torch.Tensor, packed: torch.Tensor, scratch: torch.Tensor, logits: torch.Tensor,
+                value: torch.Tensor, single_bf16: bool = False) -> None:
+    """logits f32[n,38], value f32[n] = DeepMind MLP(obs) on tcgen05 (3-term bf16 split unless single_bf16)."""
+    n = obs_bf16.shape[0]
+    if obs_bf16.dtype != torch.bfloat16:
+        raise _lib.BrlError("mlp_forward needs a bf16 observation (ops.obs_to_bf16)")
+    if scratch.numel() < _lib.load().brl_mlp_scratch_bytes(n):
+        raise _lib.BrlError("mlp_forward: scratch too small (ops.mlp_scratch)")
+    _call("brl_mlp_forward", [_ptr(obs_bf16), _ptr(packed), _ptr(scratch), _ptr(logits), _ptr(value)],
+          _params(n, flags=F_MLP_BF16 if single_bf16 else 0))
 
 
 _FIELD_SPECS = (("deal", torch.int32, ()), ("dealer", torch.int32, ()), ("shuffled_players", torch.int8, (4,)),

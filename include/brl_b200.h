@@ -42,6 +42,9 @@
  *   brl_match_stats       mean / SE / win-rate sums    src/evaluation.py:199-201
  *   brl_state_fields      reads of State._dealer, ._last_bid, ... src/evaluation.py:97-112
  *   brl_reset_fields      State(...) construction / state.replace(...) src/duplicate.py:120-128
+ *   brl_mlp_forward       forward.apply(params, obs) -> (logits, value)  src/models.py:23-33,
+ *                         src/roll_out.py:73-76, src/utils.py:78-82, src/evaluation.py:124-127
+ *   brl_mlp_pack          the params pytree (bridge_models/<name>.pkl, ppo.py:351-362) -> device layout
  */
 #ifndef BRL_B200_H
 #define BRL_B200_H
@@ -74,6 +77,7 @@ typedef struct CUstream_st *brl_stream_t; /* == cudaStream_t */
 #define BRL_F_OBS_BF16      0x0020 /* observation as bf16 (feeds a bf16 policy GEMM) */
 #define BRL_F_SAMPLE        0x0040 /* brl_categorical: Gumbel-argmax sample instead of mode */
 #define BRL_F_QUAD_LAST     0x0100 /* with ACCUMULATE: write the OR-ed terminated flag back into the state (src/utils.py:128) */
+#define BRL_F_MLP_BF16      0x0200 /* brl_mlp_forward: one bf16 product per term instead of the 3-term split */
 #define BRL_F_OBS_STREAMING 0x0080 /* rollout: obs rows staged in shared memory and written by TMA bulk stores */
 
 /* tuning (0 = automatic): bits 16-17 envs per warp (1->8, 2->16, 3->32), bits 18-19 warps per block (1->1, 2->2, 3->4) */
@@ -184,6 +188,22 @@ int32_t brl_state_fields(brl_stream_t, void **buffers, const void *opaque, size_
  * scale passed in BrlParams.gamma. */
 int32_t brl_gather_reward(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
+/* ---- policy / value net on the tensor cores (src/models.py:23-33, "DeepMind" 4x1024 ReLU) ----
+ * Weights are packed once (transposed to K-major bf16 hi/lo pairs); the forward is five
+ * TMA + tcgen05 GEMM launches with bias/ReLU/requantisation fused into the epilogues.
+ * Default arithmetic: 3-term bf16 split accumulated in fp32 (fp32-class results);
+ * BRL_F_MLP_BF16 = single bf16 product. */
+int64_t brl_mlp_packed_bytes(void);
+int64_t brl_mlp_scratch_bytes(int64_t n_envs);
+/* buffers: [0..5] in f32 w_l[in,out] (haiku `linear`, `linear_1`..`linear_5`; y = x @ w + b)
+ *          [6..11] in f32 b_l[out]   [12] out packed parameters (brl_mlp_packed_bytes()) */
+int32_t brl_mlp_pack(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+/* buffers: [0] in obs[n,480] f32 (or u8 with BRL_F_OBS_U8)  [1] out bf16 obs[n,480] */
+int32_t brl_obs_to_bf16(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+/* buffers: [0] in bf16 obs[n,480]  [1] in packed parameters  [2] scratch (brl_mlp_scratch_bytes(n))
+ *          [3] out f32 logits[n,38]  [4] out f32 value[n] */
+int32_t brl_mlp_forward(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
 /* -------------------------------------------------------------------------
  * Legacy XLA GPU custom-call targets (API_VERSION_STATUS_RETURNING -- the convention
  * of jax/jaxlib 0.4.23, the version brl pins in requirements.txt:25-26): same buffers
@@ -208,6 +228,9 @@ void brl_categorical_xla(brl_stream_t, void **buffers, const char *opaque, size_
 void brl_match_stats_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_state_fields_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_gather_reward_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_mlp_pack_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_obs_to_bf16_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_mlp_forward_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 
 /* -------------------------------------------------------------------------
  * Host-buffer convenience layer (the call a non-JAX host makes): the library

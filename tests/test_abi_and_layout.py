@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "brl_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(brl_[a-z_]+)\s*\(", hdr)) - {"brl_op_fn"})
+    return sorted(set(re.findall(r"\b(brl_[a-z0-9_]+)\s*\(", hdr)) - {"brl_op_fn"})
 
 
 def test_header_symbols_are_all_exported():
