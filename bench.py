@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--sweep", action="store_true", help="also time 65,536 and 1,048,576 envs and single-step launches")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-policy", action="store_true", help="skip the configs[2] policy-rollout leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -260,6 +261,9 @@ def main():
     extra = {}
     if args.sweep and rank == 0:
         extra["sweep"] = run_sweep(torch, ops, table, dev, peak)
+
+    if rank == 0 and not args.no_policy:
+        extra["policy_rollout"] = run_policy_rollout(torch, table_np, dev)
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -384,6 +388,68 @@ def run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps, warmu
                       "api": "brl_env_step_host: 1 env.step over 8192 envs per call, actions from the host, observation (pgx bool/u8), "
                              "mask, rewards, terminated, current_player all copied to pinned host memory"}
     return res
+
+
+def run_policy_rollout(torch, table_np, dev):
+    """BASELINE.json configs[2]: ppo.py rollout, num_envs=8192, num_steps=32, DeepMind 4x1024 ReLU policy
+    (random init) for actor and opponent, competitive quad step, + GAE.  Secondary to the headline metric:
+    reported so the tensor-core policy forward has a measured number beside the env kernels."""
+    from brl_b200 import BridgeBidding
+    from brl_b200 import random as brandom
+    from brl_b200.gae import make_calc_gae
+    from brl_b200.models import init_params, make_forward_pass
+    from brl_b200.roll_out import make_roll_out
+    n, T = N_ENVS, T_STEPS
+    env = BridgeBidding(table=table_np, device=dev)
+    config = dict(actor_illegal_action_mask=True, actor_illegal_action_penalty=False, game_mode="competitive",
+                  num_steps=T, reward_scale=7600.0, gamma=1.0, gae_lambda=0.95)
+    out = {"workload": "configs[2]: ppo.py rollout num_envs=8192 num_steps=32 + GAE, DeepMind MLP random-init; "
+                       "1 rollout = 32 x 4 env sub-steps x 8192 envs and 129 policy forwards"}
+    flops = 7354368.0 * n
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            tpeak = float(json.load(fh)["bf16_tflops"])
+    except Exception:
+        tpeak = 1590.0
+    for prec in ("tc", "tc-bf16", "fp32"):
+        fp = make_forward_pass("relu", "DeepMind", precision=prec)
+        params, opp = init_params(1, dev), init_params(2, dev)
+        state = env.init(env.make_keys(SEED, n))
+        runner = (params, None, state, state.observation, torch.zeros((), dtype=torch.int64, device=dev), brandom.PRNGKey(3))
+        roll_out, calc_gae = make_roll_out(config, env, fp, fp), make_calc_gae(config, fp)
+        reps = 3 if prec != "fp32" else 1
+        runner, traj = roll_out(runner, opp)  # warm-up
+        calc_gae(runner, traj)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            runner, traj = roll_out(runner, opp)
+            calc_gae(runner, traj)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        x = traj.obs[0]
+        for _ in range(3):
+            fp.apply(params, x)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            fp.apply(params, x)
+        e1.record()
+        torch.cuda.synchronize()
+        fms = e0.elapsed_time(e1) / 20
+        mma_factor = {"tc": (2 * 480 + 3 * (3 * 1024 + 39)) / (480 + 3 * 1024 + 39.0), "tc-bf16": 1.0}.get(prec)
+        out[prec] = {"ms_per_rollout_plus_gae": ms, "env_steps_per_sec": n * T * 4 / (ms * 1e-3),
+                     "agent_steps_per_sec": n * T / (ms * 1e-3), "forward_ms_8192": fms,
+                     "forward_model_TFLOPs": flops / (fms * 1e-3) / 1e12}
+        if mma_factor:
+            out[prec]["forward_tensor_roofline"] = {
+                "bound": "tensor", "achieved": flops * mma_factor / (fms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                "frac": flops * mma_factor / (fms * 1e-3) / 1e12 / tpeak,
+                "note": "achieved = bf16 MMA FLOPs actually issued (x%.2f of the model's FLOPs in this mode) / CUDA-event time of the "
+                        "whole forward (obs->bf16 cast + 5 layer launches); peak = measured cuBLAS bf16 burst" % mma_factor}
+    return out
 
 
 def run_sweep(torch, ops, table, dev, peak):

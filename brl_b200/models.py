@@ -70,10 +70,14 @@ def params_to_numpy(params) -> Dict[str, np.ndarray]:
 class ForwardPass:
     """`hk.without_apply_rng(hk.transform(forward_fn))` look-alike: `.apply(params, x)`."""
 
-    def __init__(self, activation: str = "relu", model_type: str = "DeepMind", precision: str = "fp32"):
+    def __init__(self, activation: str = "relu", model_type: str = "DeepMind", precision: str = None):
         if model_type != "DeepMind":
             raise NotImplementedError("only the DeepMind 4x1024 net is on the hot path (SURVEY 8a a16)")
         self.act = torch.relu if activation == "relu" else torch.tanh
+        if precision is None:  # the tensor-core kernels fuse ReLU (all five bundled models are ReLU nets)
+            precision = "tc" if activation == "relu" else "fp32"
+        if precision not in ("tc", "tc-bf16", "fp32", "tf32", "bf16"):
+            raise ValueError(f"unknown precision {precision!r}")
         self.precision = precision
         if precision in ("tc", "tc-bf16") and activation != "relu":
             raise NotImplementedError("the tensor-core forward fuses ReLU; use a library precision for tanh nets")
@@ -118,6 +122,6 @@ class ForwardPass:
         return logits, value
 
 
-def make_forward_pass(activation: str = "relu", model_type: str = "DeepMind", precision: str = "fp32") -> ForwardPass:
+def make_forward_pass(activation: str = "relu", model_type: str = "DeepMind", precision: str = None) -> ForwardPass:
     """src/models.py:73-83"""
     return ForwardPass(activation, model_type, precision)

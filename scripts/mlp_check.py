@@ -47,7 +47,11 @@ def timeit(fn, reps=20):
 
 
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [100, 1000, 8192]
+    modes = ("tc", "tc-bf16", "fp32", "tf32", "bf16")
+    args = sys.argv[1:]
+    if args and args[0].startswith("--modes="):
+        modes = tuple(args.pop(0).split("=")[1].split(","))
+    sizes = [int(a) for a in args] or [100, 1000, 8192]
     params = init_params(5, dev)
     for name in LAYERS:  # non-zero biases so the bias path is exercised
         params[name]["b"] = torch.randn_like(params[name]["b"]) * 0.1
@@ -56,7 +60,7 @@ def main():
         l64, v64 = ref64(params, x)
         scale_l, scale_v = float(l64.abs().max()), float(v64.abs().max())
         row = {"n_envs": n}
-        for prec in ("tc", "tc-bf16", "fp32", "tf32", "bf16"):
+        for prec in modes:
             fp = make_forward_pass(precision=prec)
             logits, value = fp.apply(params, x)
             torch.cuda.synchronize()
