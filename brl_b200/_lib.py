@@ -14,6 +14,7 @@ OPS = (
     "brl_make_keys", "brl_init", "brl_reset_fields", "brl_step", "brl_duplicate_step", "brl_duplicate_init",
     "brl_observe", "brl_legal_mask", "brl_rollout_random", "brl_imp_reward", "brl_gae", "brl_categorical",
     "brl_match_stats", "brl_state_fields", "brl_gather_reward", "brl_mlp_pack", "brl_obs_to_bf16", "brl_mlp_forward",
+    "brl_ppo_loss", "brl_adam_clip", "brl_gather_rows",
 )
 HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host", "brl_env_rollout_host",
             "brl_env_trajectory")
@@ -47,6 +48,19 @@ class BrlParams(C.Structure):
         ("n_deals", C.c_int32), ("flags", C.c_int32), ("step", C.c_uint32), ("k_steps", C.c_int32),
         ("illegal_penalty", C.c_float), ("illegal_bonus", C.c_float), ("gamma", C.c_float), ("gae_lambda", C.c_float),
     ]
+
+
+class BrlPpoParams(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("total", C.c_int64), ("clip_eps", C.c_float), ("ent_coef", C.c_float),
+                ("vf_coef", C.c_float), ("illegal_l2_coef", C.c_float), ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+class BrlAdamParams(C.Structure):
+    _fields_ = [("n", C.c_int64), ("step", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("max_grad_norm", C.c_float)]
+
+
+PPO_VALUE_CLIPPING, PPO_REWARD_SCALING, PPO_UNMASKED_POLICY = 1, 2, 4
 
 
 class BrlError(RuntimeError):
@@ -102,7 +116,7 @@ def load():
     return L
 
 
-def call(name: str, stream: int, buffers, params: BrlParams) -> None:
+def call(name: str, stream: int, buffers, params) -> None:
     """Invoke one stream-first op: buffers = iterable of device addresses (int) or None."""
     L = load()
     arr = (C.c_void_p * len(buffers))(*[C.c_void_p(b) if b else None for b in buffers])

@@ -1,0 +1,350 @@
+// brl_ppo.cu -- the PPO update's non-GEMM arithmetic (src/update.py:74-242,
+// ppo.py:195-211): the clipped-surrogate / clipped-value / entropy loss head fused with its
+// own backward (d loss / d logits, d loss / d value in one pass over the minibatch), and the
+// optimizer step (optax.clip_by_global_norm + optax.adam) over a flat parameter buffer.
+// The MLP forward/backward GEMMs between them are plain library GEMMs (cuBLAS via torch).
+#include <math.h>
+
+#include "common.h"
+
+namespace brl {
+
+constexpr int kA = 38;
+
+struct PpoArgs {
+    const float* logits;       // [B, 38]
+    const float* value;        // [B]
+    const int32_t* index;      // [B] rows of the flat trajectory (NULL = identity)
+    const uint8_t* mask;       // [total, 38]
+    const int32_t* action;     // [total]
+    const float* old_log_prob; // [total]
+    const float* old_value;    // [total]
+    const float* adv;          // [total]
+    const float* targets;      // [total]
+    float* dlogits;            // [B, 38]
+    float* dvalue;             // [B]
+    float* stats;              // [8]
+    double* acc;               // [16] scratch accumulators
+    int64_t B;
+    float clip_eps, ent_coef, vf_coef, ill_coef;
+    int value_clipping, reward_scaling, masked_policy;
+};
+
+// acc slots
+enum { kAccAdv = 0, kAccAdv2, kAccIll, kAccActor, kAccValue, kAccEnt, kAccKl, kAccClip };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// one warp per sample; lane owns actions lane and lane + 32
+struct Row {
+    float l[2];
+    bool in[2], legal[2];
+    __device__ __forceinline__ void load(const PpoArgs& a, int64_t b, int64_t src, int lane) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            int j = lane + 32 * k;
+            in[k] = j < kA;
+            l[k] = in[k] ? a.logits[b * kA + j] : -INFINITY;
+            legal[k] = in[k] && a.mask[src * kA + j] != 0;
+        }
+    }
+    // softmax over `sel` entries: returns log-partition; p[k] = probabilities (0 outside sel)
+    __device__ __forceinline__ float softmax(const bool sel[2], float p[2], float logp[2]) const {
+        float mx = warp_max(fmaxf(sel[0] ? l[0] : -INFINITY, sel[1] ? l[1] : -INFINITY));
+        float e0 = sel[0] ? expf(l[0] - mx) : 0.0f, e1 = sel[1] ? expf(l[1] - mx) : 0.0f;
+        float lse = mx + logf(warp_sum(e0 + e1));
+        logp[0] = sel[0] ? l[0] - lse : -INFINITY;
+        logp[1] = sel[1] ? l[1] - lse : -INFINITY;
+        p[0] = sel[0] ? expf(logp[0]) : 0.0f;
+        p[1] = sel[1] ? expf(logp[1]) : 0.0f;
+        return lse;
+    }
+};
+
+// sum over the minibatch of: advantages, advantages^2 (src/update.py:35-36) and the squared
+// unmasked probability mass on illegal actions (src/update.py:138-142)
+__global__ void __launch_bounds__(128) k_ppo_prepass(const PpoArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double s_adv = 0.0, s_adv2 = 0.0, s_ill = 0.0;
+    for (int64_t b = warp; b < a.B; b += nw) {
+        const int64_t src = a.index ? a.index[b] : b;
+        Row r;
+        r.load(a, b, src, lane);
+        float q[2], lq[2];
+        r.softmax(r.in, q, lq);
+        float ill = (r.in[0] && !r.legal[0] ? q[0] * q[0] : 0.0f) + (r.in[1] && !r.legal[1] ? q[1] * q[1] : 0.0f);
+        ill = warp_sum(ill);
+        if (lane == 0) {
+            double g = (double)a.adv[src];
+            s_adv += g;
+            s_adv2 += g * g;
+            s_ill += (double)ill;
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&a.acc[kAccAdv], s_adv);
+        atomicAdd(&a.acc[kAccAdv2], s_adv2);
+        atomicAdd(&a.acc[kAccIll], s_ill);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_ppo_loss(const PpoArgs a, int have_prepass) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float invB = 1.0f / (float)a.B;
+    float g_mean = 0.0f, g_istd = 1.0f, ill_norm = 0.0f;
+    if (have_prepass) {
+        double m = a.acc[kAccAdv] / (double)a.B;
+        double var = a.acc[kAccAdv2] / (double)a.B - m * m;
+        g_mean = (float)m;
+        g_istd = 1.0f / ((float)sqrt(var > 0.0 ? var : 0.0) + 1e-8f);
+        ill_norm = (float)sqrt(a.acc[kAccIll]);
+    }
+    double s_actor = 0.0, s_value = 0.0, s_ent = 0.0, s_kl = 0.0, s_clip = 0.0, s_ill = 0.0;
+    for (int64_t b = warp; b < a.B; b += nw) {
+        const int64_t src = a.index ? a.index[b] : b;
+        Row r;
+        r.load(a, b, src, lane);
+        // masked distribution: where(mask, logits, -inf) (src/update.py:12-16,132-137)
+        float p[2], logp[2];
+        r.softmax(r.legal, p, logp);
+        // unmasked distribution (src/update.py:139; also the policy when masking is off, :20-24)
+        float q[2], logq[2];
+        r.softmax(r.in, q, logq);
+        const int act = a.action[src];
+        const float* pol_p = a.masked_policy ? p : q;
+        const float* pol_logp = a.masked_policy ? logp : logq;
+        float lp_a = __shfl_sync(0xffffffffu, act >= 32 ? pol_logp[1] : pol_logp[0], act & 31);
+        // actor loss (src/update.py:115-131)
+        float gae = a.adv[src];
+        if (a.reward_scaling) gae = (gae - g_mean) * g_istd;
+        const float logratio = lp_a - a.old_log_prob[src];
+        const float ratio = expf(logratio);
+        const float l1 = ratio * gae, l2 = fminf(fmaxf(ratio, 1.0f - a.clip_eps), 1.0f + a.clip_eps) * gae;
+        const float loss_actor = -fminf(l1, l2);
+        const bool inside = ratio >= 1.0f - a.clip_eps && ratio <= 1.0f + a.clip_eps;
+        const float dl_dratio = (l1 < l2 || inside) ? -gae : 0.0f;  // min picks the unclipped term, or both coincide
+        const float c_ratio = dl_dratio * ratio * invB;               // d mean(loss_actor) / d log_prob
+        // entropy of the masked distribution (src/update.py:136-137)
+        float ent = -((r.legal[0] && p[0] > 0.0f ? p[0] * logp[0] : 0.0f) + (r.legal[1] && p[1] > 0.0f ? p[1] * logp[1] : 0.0f));
+        ent = warp_sum(ent);
+        // illegal-action loss (src/update.py:138-142): squared unmasked mass on illegal actions
+        float qi[2] = {r.in[0] && !r.legal[0] ? q[0] : 0.0f, r.in[1] && !r.legal[1] ? q[1] : 0.0f};
+        const float s_i = warp_sum(qi[0] * qi[0] + qi[1] * qi[1]);
+        // d total / d logits
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int j = lane + 32 * k;
+            if (!r.in[k]) continue;
+            float d = c_ratio * ((j == act ? 1.0f : 0.0f) - pol_p[k]);
+            if (r.legal[k] && p[k] > 0.0f) d += a.ent_coef * invB * p[k] * (logp[k] + ent);  // -ent_coef * dH/dl
+            if (a.ill_coef != 0.0f && ill_norm > 0.0f) d += a.ill_coef * (qi[k] * qi[k] - q[k] * s_i) / (2.0f * ill_norm);
+            a.dlogits[b * kA + j] = d;
+        }
+        if (lane == 0) {
+            // value loss (src/update.py:47-72)
+            const float v = a.value[b], t = a.targets[src];
+            float vl, dv;
+            if (a.value_clipping) {
+                const float ov = a.old_value[src];
+                const float diff = v - ov;
+                const float vc = ov + fminf(fmaxf(diff, -a.clip_eps), a.clip_eps);
+                const float e1 = (v - t) * (v - t), e2 = (vc - t) * (vc - t);
+                vl = 0.5f * fmaxf(e1, e2);
+                const bool unclipped = diff >= -a.clip_eps && diff <= a.clip_eps;
+                dv = (e1 > e2 || unclipped) ? (v - t) : 0.0f;  // the clipped branch is constant in v when it binds
+            } else {
+                vl = 0.5f * (v - t) * (v - t);
+                dv = v - t;
+            }
+            a.dvalue[b] = a.vf_coef * dv * invB;
+            s_actor += (double)loss_actor;
+            s_value += (double)vl;
+            s_ent += (double)ent;
+            s_kl += (double)((ratio - 1.0f) - logratio);
+            s_clip += fabsf(ratio - 1.0f) > a.clip_eps ? 1.0 : 0.0;
+            s_ill += (double)s_i;
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&a.acc[kAccActor], s_actor);
+        atomicAdd(&a.acc[kAccValue], s_value);
+        atomicAdd(&a.acc[kAccEnt], s_ent);
+        atomicAdd(&a.acc[kAccKl], s_kl);
+        atomicAdd(&a.acc[kAccClip], s_clip);
+        if (!have_prepass) atomicAdd(&a.acc[kAccIll], s_ill);
+    }
+}
+
+// stats = {total_loss, value_loss, loss_actor, entropy, approx_kl, clipfracs, illegal_action_loss, 0}
+// (the aux tuple of _loss_fn, src/update.py:144-162)
+__global__ void k_ppo_finalize(const PpoArgs a) {
+    const double B = (double)a.B;
+    const float value_loss = (float)(a.acc[kAccValue] / B), loss_actor = (float)(a.acc[kAccActor] / B);
+    const float entropy = (float)(a.acc[kAccEnt] / B), ill = 0.5f * (float)sqrt(a.acc[kAccIll]);
+    a.stats[0] = loss_actor + a.vf_coef * value_loss - a.ent_coef * entropy + a.ill_coef * ill;
+    a.stats[1] = value_loss;
+    a.stats[2] = loss_actor;
+    a.stats[3] = entropy;
+    a.stats[4] = (float)(a.acc[kAccKl] / B);
+    a.stats[5] = (float)(a.acc[kAccClip] / B);
+    a.stats[6] = ill;
+    a.stats[7] = 0.0f;
+}
+
+// ---- optimizer: optax.chain(clip_by_global_norm(c), adam(lr, eps=1e-5)) (ppo.py:195-211) -------
+__global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = (double)g[i];
+        s += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sh[k];
+        atomicAdd(out, t);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, int64_t n, const double* __restrict__ sumsq,
+                                              float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2) {
+    // optax.clip_by_global_norm: g * (max_norm / norm) only when norm >= max_norm
+    float scale = 1.0f;
+    if (max_norm > 0.0f) {
+        const float norm = (float)sqrt(*sumsq);
+        if (!(norm < max_norm)) scale = max_norm / norm;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * scale;
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] = p[i] - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    }
+}
+
+// rows of a [total, width] matrix selected by index -> [B, width] (minibatch of src/update.py:188-206)
+template <class T>
+__global__ void __launch_bounds__(256) k_gather_rows(const T* __restrict__ src, const int32_t* __restrict__ index,
+                                                     T* __restrict__ dst, int64_t B, int width_vec) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * width_vec) return;
+    const int64_t b = i / width_vec;
+    const int c = (int)(i - b * width_vec);
+    dst[b * width_vec + c] = src[(int64_t)index[b] * width_vec + c];
+}
+
+}  // namespace brl
+
+using namespace brl;
+
+extern "C" {
+
+int32_t brl_ppo_loss(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    if (opaque == nullptr || len != sizeof(BrlPpoParams))
+        return fail(BRL_E_OPAQUE, "brl_ppo_loss: opaque must be one BrlPpoParams (%zu bytes), got %zu", sizeof(BrlPpoParams), len);
+    const BrlPpoParams* p = static_cast<const BrlPpoParams*>(opaque);
+    if (p->batch <= 0) return fail(BRL_E_OPAQUE, "brl_ppo_loss: batch must be > 0");
+    static const char* names[] = {"logits", "value", "index", "mask", "action", "old_log_prob", "old_value", "advantages",
+                                  "targets", "dlogits", "dvalue", "stats", "scratch"};
+    for (int k = 0; k < 13; ++k)
+        if (b[k] == nullptr && k != 2) return fail(BRL_E_BUFFER, "brl_ppo_loss: buffer '%s' is NULL", names[k]);
+    PpoArgs a{};
+    a.logits = static_cast<const float*>(b[0]);
+    a.value = static_cast<const float*>(b[1]);
+    a.index = static_cast<const int32_t*>(b[2]);
+    a.mask = static_cast<const uint8_t*>(b[3]);
+    a.action = static_cast<const int32_t*>(b[4]);
+    a.old_log_prob = static_cast<const float*>(b[5]);
+    a.old_value = static_cast<const float*>(b[6]);
+    a.adv = static_cast<const float*>(b[7]);
+    a.targets = static_cast<const float*>(b[8]);
+    a.dlogits = static_cast<float*>(b[9]);
+    a.dvalue = static_cast<float*>(b[10]);
+    a.stats = static_cast<float*>(b[11]);
+    a.acc = static_cast<double*>(b[12]);
+    a.B = p->batch;
+    a.clip_eps = p->clip_eps;
+    a.ent_coef = p->ent_coef;
+    a.vf_coef = p->vf_coef;
+    a.ill_coef = p->illegal_l2_coef;
+    a.value_clipping = (p->flags & BRL_PPO_VALUE_CLIPPING) != 0;
+    a.reward_scaling = (p->flags & BRL_PPO_REWARD_SCALING) != 0;
+    a.masked_policy = (p->flags & BRL_PPO_UNMASKED_POLICY) == 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(a.acc, 0, 16 * sizeof(double), s) != cudaSuccess) return check_launch("brl_ppo_loss");
+    unsigned grid = (unsigned)((a.B + 3) / 4);
+    if (grid > 148u * 8u) grid = 148u * 8u;
+    const int prepass = a.reward_scaling || a.ill_coef != 0.0f;
+    if (prepass) k_ppo_prepass<<<grid, 128, 0, s>>>(a);
+    k_ppo_loss<<<grid, 128, 0, s>>>(a, prepass);
+    k_ppo_finalize<<<1, 1, 0, s>>>(a);
+    return check_launch("brl_ppo_loss");
+}
+
+int32_t brl_adam_clip(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    if (opaque == nullptr || len != sizeof(BrlAdamParams))
+        return fail(BRL_E_OPAQUE, "brl_adam_clip: opaque must be one BrlAdamParams (%zu bytes), got %zu", sizeof(BrlAdamParams), len);
+    const BrlAdamParams* p = static_cast<const BrlAdamParams*>(opaque);
+    static const char* names[] = {"params", "grads", "m", "v", "scratch"};
+    for (int k = 0; k < 5; ++k)
+        if (b[k] == nullptr) return fail(BRL_E_BUFFER, "brl_adam_clip: buffer '%s' is NULL", names[k]);
+    if (p->n <= 0 || p->step <= 0) return fail(BRL_E_OPAQUE, "brl_adam_clip: n and step (1-based) must be > 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* sumsq = static_cast<double*>(b[4]);
+    unsigned grid = (unsigned)((p->n + 255) / 256);
+    if (grid > 148u * 8u) grid = 148u * 8u;
+    if (cudaMemsetAsync(sumsq, 0, sizeof(double), s) != cudaSuccess) return check_launch("brl_adam_clip");
+    k_sumsq<<<grid, 256, 0, s>>>(static_cast<const float*>(b[1]), p->n, sumsq);
+    const float bc1 = 1.0f - powf(p->beta1, (float)p->step), bc2 = 1.0f - powf(p->beta2, (float)p->step);
+    k_adam<<<grid, 256, 0, s>>>(static_cast<float*>(b[0]), static_cast<const float*>(b[1]), static_cast<float*>(b[2]),
+                                static_cast<float*>(b[3]), p->n, sumsq, p->max_grad_norm, p->lr, p->beta1, p->beta2, p->eps,
+                                bc1, bc2);
+    return check_launch("brl_adam_clip");
+}
+
+int32_t brl_gather_rows(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "src");
+    if (b[1] == nullptr) return fail(BRL_E_BUFFER, "brl_gather_rows: buffer 'index' is NULL");
+    BRL_REQUIRE(b[2], "dst");
+    const int64_t B = p->n_envs;
+    const int row_bytes = p->k_steps;  // bytes per row
+    if (row_bytes <= 0) return fail(BRL_E_OPAQUE, "brl_gather_rows: k_steps (row bytes) must be > 0");
+    if (B == 0) return BRL_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (row_bytes % 16 == 0) {
+        const int w = row_bytes / 16;
+        k_gather_rows<uint4><<<(unsigned)((B * w + 255) / 256), 256, 0, s>>>(static_cast<const uint4*>(b[0]), static_cast<const int32_t*>(b[1]),
+                                                                              static_cast<uint4*>(b[2]), B, w);
+    } else if (row_bytes % 2 == 0) {
+        const int w = row_bytes / 2;
+        k_gather_rows<uint16_t><<<(unsigned)((B * w + 255) / 256), 256, 0, s>>>(static_cast<const uint16_t*>(b[0]), static_cast<const int32_t*>(b[1]),
+                                                                                 static_cast<uint16_t*>(b[2]), B, w);
+    } else {
+        k_gather_rows<uint8_t><<<(unsigned)((B * row_bytes + 255) / 256), 256, 0, s>>>(static_cast<const uint8_t*>(b[0]), static_cast<const int32_t*>(b[1]),
+                                                                                       static_cast<uint8_t*>(b[2]), B, row_bytes);
+    }
+    return check_launch("brl_gather_rows");
+}
+
+}  // extern "C"

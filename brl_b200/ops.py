@@ -236,6 +236,33 @@ def mlp_forward(obs_bf16: torch.Tensor, packed: torch.Tensor, scratch: torch.Ten
           _params(n, flags=F_MLP_BF16 if single_bf16 else 0))
 
 
+def ppo_loss(logits, value, index, mask, action, old_log_prob, old_value, adv, targets, dlogits, dvalue, stats, scratch,
+             *, clip_eps, ent_coef, vf_coef, illegal_l2_coef=0.0, value_clipping=True, reward_scaling=False,
+             masked_policy=True) -> None:
+    """_loss_fn of src/update.py:91-162 + its gradient w.r.t. (logits, value) for one minibatch."""
+    flags = (_lib.PPO_VALUE_CLIPPING if value_clipping else 0) | (_lib.PPO_REWARD_SCALING if reward_scaling else 0) | \
+            (0 if masked_policy else _lib.PPO_UNMASKED_POLICY)
+    p = _lib.BrlPpoParams(int(logits.shape[0]), int(action.numel()), float(clip_eps), float(ent_coef), float(vf_coef),
+                          float(illegal_l2_coef), flags, 0)
+    _call("brl_ppo_loss", [_ptr(logits), _ptr(value), _ptr(index), _ptr(mask), _ptr(action), _ptr(old_log_prob),
+                           _ptr(old_value), _ptr(adv), _ptr(targets), _ptr(dlogits), _ptr(dvalue), _ptr(stats),
+                           _ptr(scratch)], p)
+
+
+def adam_clip(params, grads, m, v, scratch, *, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-5,
+              max_grad_norm=0.0) -> None:
+    """optax.chain(clip_by_global_norm, adam) on flat fp32 buffers, in place (ppo.py:195-211)."""
+    p = _lib.BrlAdamParams(int(params.numel()), int(step), float(lr), float(beta1), float(beta2), float(eps),
+                           float(max_grad_norm))
+    _call("brl_adam_clip", [_ptr(params), _ptr(grads), _ptr(m), _ptr(v), _ptr(scratch)], p)
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[b] = src[index[b]] over the leading axis (minibatch take, src/update.py:194-199)."""
+    row_bytes = src[0].numel() * src.element_size()
+    _call("brl_gather_rows", [_ptr(src), _ptr(index), _ptr(dst)], _params(index.shape[0], k_steps=row_bytes))
+
+
 _FIELD_SPECS = (("deal", torch.int32, ()), ("dealer", torch.int32, ()), ("shuffled_players", torch.int8, (4,)),
                 ("vul", torch.uint8, (2,)), ("last_bid", torch.int32, ()), ("last_bidder", torch.int32, ()),
                 ("call_x", torch.uint8, ()), ("call_xx", torch.uint8, ()), ("pass_num", torch.int32, ()),

@@ -44,6 +44,9 @@
  *   brl_reset_fields      State(...) construction / state.replace(...) src/duplicate.py:120-128
  *   brl_mlp_forward       forward.apply(params, obs) -> (logits, value)  src/models.py:23-33,
  *                         src/roll_out.py:73-76, src/utils.py:78-82, src/evaluation.py:124-127
+ *   brl_ppo_loss          _loss_fn + jax.value_and_grad w.r.t. the net outputs   src/update.py:91-167
+ *   brl_adam_clip         optimizer.update + optax.apply_updates                  src/update.py:168-169, ppo.py:195-211
+ *   brl_gather_rows       minibatch take(permutation)                             src/update.py:194-199
  *   brl_mlp_pack          the params pytree (bridge_models/<name>.pkl, ppo.py:351-362) -> device layout
  */
 #ifndef BRL_B200_H
@@ -204,6 +207,47 @@ int32_t brl_obs_to_bf16(brl_stream_t, void **buffers, const void *opaque, size_t
  *          [3] out f32 logits[n,38]  [4] out f32 value[n] */
 int32_t brl_mlp_forward(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
+/* ---- PPO update, non-GEMM part (src/update.py:74-242, ppo.py:195-211) ----------------------- */
+#define BRL_PPO_VALUE_CLIPPING  0x1 /* config["value_clipping"]  (src/update.py:47-62) */
+#define BRL_PPO_REWARD_SCALING  0x2 /* config["reward_scaling"]: (gae - mean) / (std + 1e-8) per minibatch (src/update.py:31-45) */
+#define BRL_PPO_UNMASKED_POLICY 0x4 /* actor_illegal_action_penalty mode: log-prob from the unmasked softmax (src/update.py:18-24) */
+
+typedef struct BrlPpoParams {
+    int64_t batch;         /* samples in this minibatch                                  */
+    int64_t total;         /* rows of the flat [T * n_envs] trajectory the index addresses */
+    float clip_eps;        /* config["clip_eps"]                                         */
+    float ent_coef;        /* config["ent_coef"]                                         */
+    float vf_coef;         /* config["vf_coef"]                                          */
+    float illegal_l2_coef; /* config["illegal_action_l2norm_coef"]                       */
+    int32_t flags;         /* BRL_PPO_*                                                  */
+    int32_t reserved;
+} BrlPpoParams;
+
+typedef struct BrlAdamParams {
+    int64_t n;             /* elements of the flat parameter buffer                      */
+    int32_t step;          /* 1-based optimizer step count (bias correction)             */
+    float lr;              /* learning rate for THIS step (schedules are evaluated by the caller, ppo.py:186-192) */
+    float beta1, beta2, eps; /* optax.adam defaults 0.9 / 0.999, eps = 1e-5 (ppo.py:198) */
+    float max_grad_norm;   /* optax.clip_by_global_norm; <= 0 disables                   */
+} BrlAdamParams;
+
+/* _loss_fn of src/update.py:91-162 from the logits / value the net produced for one minibatch, fused
+ * with its backward: d total_loss / d logits and d total_loss / d value come out of the same pass.
+ * opaque = BrlPpoParams.
+ * buffers: [0] in f32 logits[B,38]  [1] in f32 value[B]  [2] in i32 index[B] (row of each sample in the
+ *          flat trajectory; NULL = identity)  [3] in u8 mask[total,38]  [4] in i32 action[total]
+ *          [5] in f32 old_log_prob[total]  [6] in f32 old_value[total]  [7] in f32 advantages[total]
+ *          [8] in f32 targets[total]  [9] out f32 dlogits[B,38]  [10] out f32 dvalue[B]
+ *          [11] out f32 stats[8] = {total_loss, value_loss, loss_actor, entropy, approx_kl, clipfracs,
+ *               illegal_action_loss, 0}  [12] scratch f64[16] */
+int32_t brl_ppo_loss(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+/* optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, eps)) over one flat fp32 buffer.  opaque = BrlAdamParams.
+ * buffers: [0] inout f32 params[n]  [1] in f32 grads[n]  [2] inout f32 m[n]  [3] inout f32 v[n]  [4] scratch f64[1] */
+int32_t brl_adam_clip(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+/* minibatch gather (jnp.take(x, permutation, axis=0), src/update.py:194-199): n_envs = B rows, k_steps = bytes per row.
+ * buffers: [0] in src[total, row]  [1] in i32 index[B]  [2] out dst[B, row] */
+int32_t brl_gather_rows(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
 /* -------------------------------------------------------------------------
  * Legacy XLA GPU custom-call targets (API_VERSION_STATUS_RETURNING -- the convention
  * of jax/jaxlib 0.4.23, the version brl pins in requirements.txt:25-26): same buffers
@@ -231,6 +275,9 @@ void brl_gather_reward_xla(brl_stream_t, void **buffers, const char *opaque, siz
 void brl_mlp_pack_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_obs_to_bf16_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_mlp_forward_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_ppo_loss_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_adam_clip_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_gather_rows_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 
 /* -------------------------------------------------------------------------
  * Host-buffer convenience layer (the call a non-JAX host makes): the library

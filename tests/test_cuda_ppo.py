@@ -1,0 +1,178 @@
+"""GPU parity of the PPO update kernels (csrc/brl_ppo.cu) against the float64 restatement of
+src/update.py / optax in oracle/ppo_ref.py.  Floating point: kernels compute in fp32 like the
+reference; tolerances are written at each comparison."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _case(B, total, seed):
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn((B, 38), generator=g, dtype=torch.float64) * 2
+    value = torch.randn(B, generator=g, dtype=torch.float64) * 0.3
+    index = torch.randperm(total, generator=g)[:B].to(torch.int32)
+    mask = torch.rand((total, 38), generator=g) < 0.5
+    mask[:, 0] = True
+    # recorded actions are legal; old log-probs near the current ones so ratios straddle the clip range
+    action = torch.zeros(total, dtype=torch.int32)
+    for i in range(total):
+        legal = torch.nonzero(mask[i])[:, 0]
+        action[i] = legal[torch.randint(len(legal), (1,), generator=g)]
+    old_lp = -torch.rand(total, generator=g, dtype=torch.float64) * 3
+    old_v = torch.randn(total, generator=g, dtype=torch.float64) * 0.3
+    adv = torch.randn(total, generator=g, dtype=torch.float64)
+    tgt = torch.randn(total, generator=g, dtype=torch.float64) * 0.3
+    return logits, value, index, mask, action, old_lp, old_v, adv, tgt
+
+
+@pytest.mark.parametrize("value_clipping,reward_scaling,masked,ill", [
+    (True, False, True, 0.0),      # ppo.py defaults
+    (False, True, True, 0.0),
+    (True, True, False, 0.3),      # penalty mode + illegal-action L2 term
+    (True, False, True, 0.7),
+])
+def test_ppo_loss_and_gradient_match_autograd(value_clipping, reward_scaling, masked, ill):
+    from brl_b200 import ops
+    from oracle import ppo_ref
+    B, total = 333, 1000
+    logits, value, index, mask, action, old_lp, old_v, adv, tgt = _case(B, total, 7)
+    # make the policy's log-prob of the taken action close to old_lp for a spread of ratios around 1
+    cfg = dict(clip_eps=0.2, ent_coef=0.01, vf_coef=0.5, illegal_l2_coef=ill, value_clipping=value_clipping,
+               reward_scaling=reward_scaling, masked_policy=masked)
+    idx = index.long()
+    with torch.no_grad():
+        ml = torch.where(mask[idx], logits, torch.tensor(float("-inf"), dtype=torch.float64))
+        lp_now = (torch.log_softmax(ml if masked else logits, 1)).gather(1, action[idx].long()[:, None])[:, 0]
+        old_lp[idx] = lp_now + (torch.rand(B, dtype=torch.float64) - 0.5) * 0.8
+    lr, vr = logits.clone().requires_grad_(), value.clone().requires_grad_()
+    total_ref, aux = ppo_ref.loss_fn(lr, vr, mask[idx], action[idx], old_lp[idx], old_v[idx], adv[idx], tgt[idx], **cfg)
+    total_ref.backward()
+    f32 = lambda t: t.to(torch.float32).to(DEV).contiguous()  # noqa: E731
+    dlogits = torch.empty((B, 38), dtype=torch.float32, device=DEV)
+    dvalue = torch.empty(B, dtype=torch.float32, device=DEV)
+    stats = torch.zeros(8, dtype=torch.float32, device=DEV)
+    scratch = torch.zeros(16, dtype=torch.float64, device=DEV)
+    ops.ppo_loss(f32(logits), f32(value), index.to(DEV), mask.to(torch.uint8).to(DEV).contiguous(), action.to(DEV), f32(old_lp),
+                 f32(old_v), f32(adv), f32(tgt), dlogits, dvalue, stats, scratch, **cfg)
+    got = stats.cpu().numpy()
+    want = np.array([float(total_ref.detach())] + [float(a.detach()) for a in aux])
+    np.testing.assert_allclose(got[:7], want, rtol=2e-5, atol=2e-6)       # fp32 kernel vs float64 reference
+    np.testing.assert_allclose(dlogits.cpu().numpy(), lr.grad.numpy(), rtol=2e-4, atol=2e-7)
+    np.testing.assert_allclose(dvalue.cpu().numpy(), vr.grad.numpy(), rtol=2e-4, atol=2e-7)
+    # illegal actions of a masked policy receive no actor / entropy gradient
+    if masked and ill == 0.0:
+        assert float(dlogits[~mask[idx].to(DEV)].abs().max()) == 0.0
+
+
+def test_adam_clip_matches_optax_restatement():
+    from brl_b200 import ops
+    from oracle import ppo_ref
+    rng = np.random.default_rng(0)
+    n = 100_003
+    p = rng.normal(0, 0.1, n)
+    m, v = np.zeros(n), np.zeros(n)
+    tp = torch.as_tensor(p, dtype=torch.float32, device=DEV)
+    tm, tv = torch.zeros(n, dtype=torch.float32, device=DEV), torch.zeros(n, dtype=torch.float32, device=DEV)
+    scratch = torch.zeros(1, dtype=torch.float64, device=DEV)
+    p = tp.cpu().numpy().astype(np.float64)
+    for step, gscale in enumerate([1.0, 1e-4, 0.3, 1e-3]):   # global norm above and below max_grad_norm = 0.5
+        g = (rng.normal(0, 1, n) * gscale).astype(np.float32)
+        p, m, v = ppo_ref.adam_clip_step(p, g, m, v, step, lr=1e-3, max_grad_norm=0.5)
+        ops.adam_clip(tp, torch.as_tensor(g, device=DEV), tm, tv, scratch, step=step + 1, lr=1e-3, max_grad_norm=0.5)
+        np.testing.assert_allclose(tm.cpu().numpy(), m, rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(tv.cpu().numpy(), v, rtol=1e-5, atol=1e-12)
+        np.testing.assert_allclose(tp.cpu().numpy(), p, rtol=0, atol=2e-6)  # lr = 1e-3: 2e-6 = 0.2 % of one step
+
+
+def test_gather_rows():
+    from brl_b200 import ops
+    for dtype, width in ((torch.float32, 480), (torch.uint8, 480), (torch.uint8, 38), (torch.bfloat16, 480), (torch.uint8, 7)):
+        src = (torch.rand((500, width), device=DEV) * 200).to(dtype)
+        index = torch.randperm(500, device=DEV)[:123].to(torch.int32)
+        dst = torch.empty((123, width), dtype=dtype, device=DEV)
+        ops.gather_rows(src, index, dst)
+        assert torch.equal(dst, src[index.long()])
+
+
+def test_update_step_matches_float64_reference():
+    """src/update.py:74-242 end to end on a small rollout with an injected permutation."""
+    from brl_b200.models import LAYERS, init_params, make_forward_pass, params_to_numpy
+    from brl_b200.optim import AdamWithClip
+    from brl_b200.roll_out import Transition
+    from brl_b200.update import make_update_step
+    from brl_b200 import random as brandom
+    from oracle import ppo_ref
+    T, n, mbs, epochs = 4, 64, 64, 2
+    nmb = T * n // mbs
+    config = dict(actor_illegal_action_mask=True, actor_illegal_action_penalty=False, clip_eps=0.2, ent_coef=0.001,
+                  vf_coef=0.5, illegal_action_l2norm_coef=0.0, value_clipping=True, reward_scaling=False,
+                  num_minibatches=nmb, minibatch_size=mbs, update_epochs=epochs, num_steps=T, num_envs=n)
+    g = torch.Generator().manual_seed(3)
+    obs = (torch.rand((T, n, 480), generator=g) < 0.04).to(torch.float32)
+    mask = torch.rand((T, n, 38), generator=g) < 0.5
+    mask[..., 0] = True
+    action = torch.zeros((T, n), dtype=torch.int32)
+    params = init_params(9, DEV)
+    fp = make_forward_pass("relu", "DeepMind", precision="fp32")
+    with torch.no_grad():
+        logits, value = fp.apply(params, obs.reshape(-1, 480).to(DEV))
+        ml = torch.where(mask.reshape(-1, 38).to(DEV), logits, torch.tensor(float("-inf"), device=DEV))
+        action = torch.distributions.Categorical(logits=ml).sample().to(torch.int32).reshape(T, n).cpu()
+        lp = torch.log_softmax(ml, 1).gather(1, action.reshape(-1, 1).long().to(DEV))[:, 0].reshape(T, n).cpu()
+        value = value.reshape(T, n).cpu()
+    old_lp = lp + (torch.rand((T, n), generator=g) - 0.5) * 0.6
+    adv = torch.randn((T, n), generator=g)
+    tgt = value + torch.randn((T, n), generator=g) * 0.2
+    traj = Transition(done=torch.zeros((T, n), dtype=torch.bool, device=DEV), action=action.to(DEV), value=value.to(DEV),
+                      reward=torch.zeros((T, n), device=DEV), log_prob=old_lp.to(DEV), obs=obs.to(DEV),
+                      legal_action_mask=mask.to(DEV))
+    perms = [torch.randperm(T * n, generator=g) for _ in range(epochs)]
+    it = iter(perms)
+    lr = 1e-3
+    opt = AdamWithClip(lr, eps=1e-5, max_grad_norm=0.5)
+    update_step = make_update_step(config, fp, opt, permutation_fn=lambda rng, bs: next(it))
+    before = {k: v.copy() for k, v in params_to_numpy(params).items()}
+    runner = (params, opt.init(params), None, None, 0, brandom.PRNGKey(0))
+    runner2, (total_loss, aux) = update_step(runner, traj, adv.to(DEV), tgt.to(DEV))
+    # the caller's params are untouched (ppo.py keeps them as opp_params)
+    for k, v in params_to_numpy(params).items():
+        assert (v == before[k]).all()
+    assert runner2[1].count == epochs * nmb and total_loss.shape == (epochs, nmb)
+    # float64 reference of the whole update with the same permutations
+    ref = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in before.items()}
+    order = [f"{c}{i}" for i in range(6) for c in ("w", "b")]
+    flat = lambda d: np.concatenate([d[k].detach().numpy().reshape(-1) for k in order])  # noqa: E731
+    p = flat(ref)
+    m, v, count = np.zeros_like(p), np.zeros_like(p), 0
+    fo, fm, fa, fl, fv, fadv, ftgt = (t.reshape(T * n, *t.shape[2:]) for t in (obs, mask, action, old_lp, value, adv, tgt))
+    losses = []
+    for e in range(epochs):
+        for mb in range(nmb):
+            idx = perms[e][mb * mbs:(mb + 1) * mbs]
+            for t in ref.values():
+                t.grad = None
+            lg, vl = ppo_ref.mlp_forward_torch(ref, fo[idx].double())
+            total, _ = ppo_ref.loss_fn(lg, vl, fm[idx], fa[idx], fl[idx].double(), fv[idx].double(), fadv[idx].double(),
+                                       ftgt[idx].double(), clip_eps=0.2, ent_coef=0.001, vf_coef=0.5)
+            total.backward()
+            grad = np.concatenate([ref[k].grad.numpy().reshape(-1) for k in order])
+            p, m, v = ppo_ref.adam_clip_step(p, grad, m, v, count, lr=lr, max_grad_norm=0.5)
+            count += 1
+            off = 0
+            with torch.no_grad():
+                for k in order:
+                    sz = ref[k].numel()
+                    ref[k].copy_(torch.as_tensor(p[off:off + sz]).reshape(ref[k].shape))
+                    off += sz
+            losses.append(float(total))
+    np.testing.assert_allclose(total_loss.cpu().numpy().reshape(-1), losses, rtol=5e-4, atol=5e-5)
+    got = params_to_numpy(runner2[0])
+    got_flat = np.concatenate([got[k].reshape(-1) for k in order])
+    delta_ref, delta_got = p - flat({k: torch.tensor(before[k]) for k in order}), got_flat - flat({k: torch.tensor(before[k]) for k in order})
+    # Adam's step is ~lr per element per step; fp32-vs-float64 gradient noise only matters where |g| ~ eps
+    err = np.abs(delta_got - delta_ref)
+    assert np.quantile(err, 0.999) <= 0.05 * lr * count
+    assert np.abs(delta_ref).max() > 0.5 * lr   # the update actually moved the parameters
