@@ -14,11 +14,11 @@ OPS = (
     "brl_make_keys", "brl_init", "brl_reset_fields", "brl_step", "brl_duplicate_step", "brl_duplicate_init",
     "brl_observe", "brl_legal_mask", "brl_rollout_random", "brl_imp_reward", "brl_gae", "brl_categorical",
     "brl_match_stats", "brl_state_fields", "brl_gather_reward", "brl_mlp_pack", "brl_obs_to_bf16", "brl_mlp_forward",
-    "brl_ppo_loss", "brl_adam_clip", "brl_gather_rows",
+    "brl_ppo_loss", "brl_adam_clip", "brl_gather_rows", "brl_eval_act_log", "brl_eval_summary",
 )
 HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host", "brl_env_rollout_host",
             "brl_env_trajectory")
-MISC = ("brl_last_error", "brl_abi_version", "brl_mlp_packed_bytes", "brl_mlp_scratch_bytes")
+MISC = ("brl_last_error", "brl_abi_version", "brl_mlp_packed_bytes", "brl_mlp_scratch_bytes", "brl_eval_num_sums")
 XLA_LEGACY = tuple(op + "_xla" for op in OPS)  # legacy XLA GPU custom-call targets (csrc/xla_ffi_shim.cc)
 ALL_SYMBOLS = OPS + HOST_API + MISC + XLA_LEGACY
 
@@ -31,6 +31,8 @@ F_OBS_BF16 = 0x0020
 F_SAMPLE = 0x0040
 F_QUAD_LAST = 0x0100
 F_MLP_BF16 = 0x0200
+F_EVAL_INDICATOR_BIDS = 0x0400
+EVAL_ACC_COLS = 76
 
 
 def tune(epw: int = 0, wpb: int = 0, classic_rollout: bool = False, writers: int = 0) -> int:

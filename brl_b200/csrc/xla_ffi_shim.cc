@@ -65,6 +65,8 @@ BRL_LEGACY_CUSTOM_CALL(brl_mlp_forward)
 BRL_LEGACY_CUSTOM_CALL(brl_ppo_loss)
 BRL_LEGACY_CUSTOM_CALL(brl_adam_clip)
 BRL_LEGACY_CUSTOM_CALL(brl_gather_rows)
+BRL_LEGACY_CUSTOM_CALL(brl_eval_act_log)
+BRL_LEGACY_CUSTOM_CALL(brl_eval_summary)
 }  // extern "C"
 
 // ---- (2) typed FFI handlers --------------------------------------------------------------

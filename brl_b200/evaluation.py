@@ -88,3 +88,127 @@ def make_simple_duplicate_evaluate(eval_env, team1_activation, team1_model_type,
         return log_info, table_a_info, table_b_info, cum_return
 
     return duplicate_evaluate
+
+
+# ---- full evaluation statistics (src/evaluation.py:207-1115) --------------------------------------
+_S_TABLE, _S_BIDS, _S_CONTRACTS = 11, 29, 99
+
+
+def _log_info_from_sums(sums, duplicate: bool):
+    """The `log_info` tuple of src/evaluation.py:575-596 (evaluate) / :986-1027 (duplicate_evaluate)
+    from the all-reduced partial sums of brl_eval_summary."""
+    import numpy as np
+    s = np.asarray(sums, dtype=np.float64)
+    n = s[0]
+    mean_cum = s[1] / n
+    bids = s[_S_BIDS:_S_BIDS + 70] / n
+    ca, cb = s[_S_CONTRACTS:_S_CONTRACTS + 70] / n, s[_S_CONTRACTS + 70:_S_CONTRACTS + 140] / n
+    ta, tb = s[_S_TABLE:_S_TABLE + 9] / n, s[_S_TABLE + 9:_S_TABLE + 18] / n
+    if not duplicate:
+        return (mean_cum, s[4] / n, s[5] / n, s[6] / n, bids[:35], bids[35:], ca[:35], ca[35:],
+                ca[:35].sum(), ca[35:].sum(), ta[1], ta[2], ta[3], ta[4], ta[5], ta[6], ta[7], ta[8], ta[0])
+    var = max(0.0, (s[2] - s[1] * s[1] / n) / (n - 1)) if n > 1 else float("nan")
+    std_error = np.sqrt(var) / np.sqrt(n)
+    half = lambda x, y: (x + y) / 2  # noqa: E731
+    return (mean_cum, std_error, half(s[9] / n, s[10] / n), s[4] / n, s[5] / n, s[6] / n, bids[:35] / 2, bids[35:] / 2,
+            half(ca[:35], cb[:35]), half(ca[35:], cb[35:]), half(ca[:35].sum(), cb[:35].sum()),
+            half(ca[35:].sum(), cb[35:].sum()), half(ta[1], tb[1]), half(ta[2], tb[2]), half(ta[3], tb[3]),
+            half(ta[4], tb[4]), half(ta[5], tb[5]), half(ta[6], tb[6]), half(ta[7], tb[7]), half(ta[8], tb[8]),
+            half(ta[0], tb[0]), s[7] / n, s[8] / n)
+
+
+def make_evaluate(eval_env, team1_activation, team1_model_type, team2_activation, team2_model_type, team2_model_path,
+                  num_eval_envs, game_mode, duplicate=False, team2_params=None, env_offset: int = 0):
+    """src/evaluation.py:207-1032.  Team 1 (`actor_params`, players 0/1) against a fixed team 2 (the pickle at
+    `team2_model_path`, or always-pass in "free-run"); every decision is the masked argmax.  Besides the score it
+    logs, per team, the unmasked probability mass on illegal actions, bid / contract histograms and declarer /
+    double / make / down / pass-out ratios.  `num_eval_envs` is this rank's shard; the statistics are all-reduced
+    (one collective) when torch.distributed is initialised."""
+    actor_forward_pass = make_forward_pass(activation=team1_activation, model_type=team1_model_type)
+    opp_forward_pass = make_forward_pass(activation=team2_activation, model_type=team2_model_type)
+    if game_mode == "competitive":
+        opp_params = team2_params if team2_params is not None else load_params(team2_model_path, eval_env.device)
+    elif game_mode == "free-run":
+        opp_params = None
+    else:
+        raise ValueError(game_mode)
+    n, dev = num_eval_envs, eval_env.device
+    n_sums = ops._lib.load().brl_eval_num_sums()
+
+    def _loop(actor_params, rng_key, step, state, trace):
+        acc = torch.zeros((n, ops._lib.EVAL_ACC_COLS), dtype=torch.float32, device=dev)
+        cum_return = torch.zeros(n, dtype=torch.float32, device=dev)
+        rewards = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+        action = torch.empty(n, dtype=torch.int32, device=dev)
+        count = 0
+        while True:
+            l1, _ = actor_forward_pass.apply(actor_params, state.observation)
+            l2 = opp_forward_pass.apply(opp_params, state.observation)[0] if opp_params is not None else None
+            ops.eval_act_log(l1.contiguous(), None if l2 is None else l2.contiguous(), state._mask_u8, state.current_player,
+                             state._terminated_u8, action, acc, indicator_bids=not duplicate)
+            if trace is not None:
+                trace.append((action.clone(), l1.clone(), None if l2 is None else l2.clone()))
+            state = step(state, action)
+            rewards += state.rewards
+            cum_return += state.rewards[:, 0]
+            count += 1
+            if count % _CHECK_EVERY == 0 and bool(state._terminated_u8.all()):
+                return state, acc, cum_return, rewards
+
+    def evaluate(actor_params, rng_key, trace=None):
+        rng_key, sub_key = brandom.split(rng_key)
+        state = eval_env.init(eval_env.make_keys(sub_key, n, env_offset))
+        state, acc, cum_return, rewards = _loop(actor_params, rng_key, lambda s, a: eval_env.step(s, a, inplace=True),
+                                                state, trace)
+        f = ops.state_fields(state._packed)
+        sums = torch.zeros(n_sums, dtype=torch.float64, device=dev)
+        ops.eval_summary(acc, cum_return, f["step_count"],
+                         (f["last_bid"], f["last_bidder"], f["call_x"], f["call_xx"], None, f["pass_num"]), None, sums)
+        bdist.allreduce_sums(sums)
+        state.rewards.copy_(rewards)                                                   # state.replace(rewards=rewards), :574
+        return state, _log_info_from_sums(sums.cpu().numpy(), duplicate=False)
+
+    def duplicate_evaluate(actor_params, rng_key, trace=None):
+        step_fn = duplicate_step(eval_env.step)
+        rng_key, sub_key = brandom.split(rng_key)
+        state = eval_env.init(eval_env.make_keys(sub_key, n, env_offset))
+        infos = [Table_info.from_state(state), Table_info.from_state(state)]
+
+        def step(s, a):
+            s, infos[0], infos[1] = step_fn(s, a, infos[0], infos[1])
+            return s
+
+        state, acc, cum_return, _ = _loop(actor_params, rng_key, step, state, trace)
+        f = ops.state_fields(state._packed)
+        sums = torch.zeros(n_sums, dtype=torch.float64, device=dev)
+        tv = lambda t: (t.last_bid, t.last_bidder, t.call_x.view(torch.uint8), t.call_xx.view(torch.uint8), t.rewards, None)  # noqa: E731
+        ops.eval_summary(acc, cum_return, f["step_count"], tv(infos[0]), tv(infos[1]), sums)
+        bdist.allreduce_sums(sums)
+        return _log_info_from_sums(sums.cpu().numpy(), duplicate=True), infos[0], infos[1]
+
+    return duplicate_evaluate if duplicate else evaluate
+
+
+_LOG_KEYS_DUP = ("eval/IMP_reward", "eval/IMP_SE", "eval/score_reward", "eval/actor_illegal_action_probs",
+                 "eval/opp_illegal_action_probs", "eval/step count", None, None, None, None, "eval/actor_declarer_ratio",
+                 "eval/opp_declarer_ratio", "eval/actor_doubled_ratio", "eval/actor_redoubled_ratio", "eval/opp_doubled_ratio",
+                 "eval/opp_redoubled_ratio", "eval/actor_make_contract_ratio", "eval/opp_make_contract_ratio",
+                 "eval/actor_down_contract_ratio", "eval/opp_down_contract_ratio", "eval/pass_out_ratio",
+                 "eval/actor_pass_ratio", "eval/opp_pass_ratio")
+
+
+def make_evaluate_log(log_info):
+    """src/evaluation.py:1035-1115: the wandb dict of a duplicate evaluation (same keys)."""
+    if len(log_info) != len(_LOG_KEYS_DUP):
+        raise ValueError("make_evaluate_log expects the 23-entry log_info of duplicate_evaluate")
+    log = {k: v for k, v in zip(_LOG_KEYS_DUP, log_info) if k is not None}
+    actor_bid, opp_bid, actor_contract, opp_contract = log_info[6:10]
+    groups = (("actor_bid_probs", actor_bid), ("actor_contract_probs", actor_contract), ("opp_bid_probs", opp_bid),
+              ("opp_contract_probs", opp_contract))
+    for name, vec in groups:
+        index = 0
+        for number in range(1, 8):
+            for suit in ("C", "D", "H", "S", "NT"):
+                log[f"eval/{name}/{number}{suit}"] = vec[index]
+                index += 1
+    return log

@@ -263,6 +263,22 @@ def gather_rows(src: torch.Tensor, index: torch.Tensor, dst: torch.Tensor) -> No
     _call("brl_gather_rows", [_ptr(src), _ptr(index), _ptr(dst)], _params(index.shape[0], k_steps=row_bytes))
 
 
+def eval_act_log(logits_team1, logits_team2, mask, current_player, terminated, action, acc, indicator_bids=False) -> None:
+    """masked argmax of the acting team's logits + update_log_info (src/evaluation.py:236-385, 650-745)."""
+    n = logits_team1.shape[0]
+    _call("brl_eval_act_log", [_ptr(logits_team1), _ptr(logits_team2), _ptr(mask), _ptr(current_player), _ptr(terminated),
+                               _ptr(action), _ptr(acc)],
+          _params(n, flags=_lib.F_EVAL_INDICATOR_BIDS if indicator_bids else 0))
+
+
+def eval_summary(acc, cum_return, step_count, table_a, table_b, sums) -> None:
+    """table_* = (last_bid i32, last_bidder i32, call_x u8, call_xx u8, rewards f32[n,4] | None, pass_num i32 | None);
+    table_b may be None (single-table evaluate).  sums f64[brl_eval_num_sums()] += partial sums."""
+    tb = table_b if table_b is not None else (None,) * 6
+    _call("brl_eval_summary", [_ptr(acc), _ptr(cum_return), _ptr(step_count)] + [_ptr(t) for t in table_a] +
+          [_ptr(t) for t in tb] + [_ptr(sums)], _params(cum_return.shape[0]))
+
+
 _FIELD_SPECS = (("deal", torch.int32, ()), ("dealer", torch.int32, ()), ("shuffled_players", torch.int8, (4,)),
                 ("vul", torch.uint8, (2,)), ("last_bid", torch.int32, ()), ("last_bidder", torch.int32, ()),
                 ("call_x", torch.uint8, ()), ("call_xx", torch.uint8, ()), ("pass_num", torch.int32, ()),

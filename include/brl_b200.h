@@ -47,6 +47,8 @@
  *   brl_ppo_loss          _loss_fn + jax.value_and_grad w.r.t. the net outputs   src/update.py:91-167
  *   brl_adam_clip         optimizer.update + optax.apply_updates                  src/update.py:168-169, ppo.py:195-211
  *   brl_gather_rows       minibatch take(permutation)                             src/update.py:194-199
+ *   brl_eval_act_log      make_action + make_step_log of evaluate / duplicate_evaluate   src/evaluation.py:236-385, 650-745
+ *   brl_eval_summary      make_terminated_log + the log_info means                        src/evaluation.py:448-596, 839-1027
  *   brl_mlp_pack          the params pytree (bridge_models/<name>.pkl, ppo.py:351-362) -> device layout
  */
 #ifndef BRL_B200_H
@@ -248,6 +250,27 @@ int32_t brl_adam_clip(brl_stream_t, void **buffers, const void *opaque, size_t o
  * buffers: [0] in src[total, row]  [1] in i32 index[B]  [2] out dst[B, row] */
 int32_t brl_gather_rows(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
+/* ---- full evaluation statistics (src/evaluation.py:207-1032) ---------------------------------- */
+#define BRL_F_EVAL_INDICATOR_BIDS 0x0400 /* non-duplicate `evaluate`: bid histogram is .set(1), not += 1 (src/evaluation.py:345-354) */
+#define BRL_EVAL_ACC_COLS 76    /* per-env log row: ill[2] steps[2] passes[2] actor_bid[35] opp_bid[35] (team 1 first) */
+int32_t brl_eval_num_sums(void); /* length of the partial-sum vector of brl_eval_summary (239) */
+/* One evaluation step: action = masked argmax of the ACTING team's logits (team 1 = players 0/1) and the
+ * per-env log update of update_log_info, skipped for finished envs.
+ * buffers: [0] in f32 logits_team1[n,38]  [1] in f32 logits_team2[n,38] (NULL = free-run opponent: always Pass)
+ *          [2] in u8 mask[n,38]  [3] in i8 current_player[n]  [4] in u8 terminated[n]
+ *          [5] out i32 action[n]  [6] inout f32 acc[n,76] */
+int32_t brl_eval_act_log(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+/* End of match: every mean of the log_info tuple as f64 partial sums (sums += ...; all-reduce, then divide).
+ * sums layout: [0] n [1] sum cum [2] sum cum^2 [3] #(cum>0) [4] sum ill1/steps1 [5] sum ill2/steps2 [6] sum step_count
+ *   [7] sum pass1/steps1 [8] sum pass2/steps2 [9] sum tableA rewards[0] [10] sum tableB rewards[0]
+ *   [11+9t ..] per table t: pass_out, x1, xx1, x2, xx2, make1, make2, down1, down2
+ *   [29..98] bid histograms team 1 then team 2   [99+70t ..] contract histograms of table t, team 1 then team 2
+ * buffers: [0] in f32 acc[n,76]  [1] in f32 cum_return[n]  [2] in i32 step_count[n]
+ *          [3..8] table A: i32 last_bid, i32 last_bidder, u8 call_x, u8 call_xx, f32 rewards[n,4] (NULL: sign from
+ *                 cum_return), i32 pass_num (NULL: not required for a pass-out)
+ *          [9..14] table B likewise ([9] NULL = single-table evaluate)   [15] inout f64 sums[239] */
+int32_t brl_eval_summary(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
 /* -------------------------------------------------------------------------
  * Legacy XLA GPU custom-call targets (API_VERSION_STATUS_RETURNING -- the convention
  * of jax/jaxlib 0.4.23, the version brl pins in requirements.txt:25-26): same buffers
@@ -278,6 +301,8 @@ void brl_mlp_forward_xla(brl_stream_t, void **buffers, const char *opaque, size_
 void brl_ppo_loss_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_adam_clip_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_gather_rows_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_eval_act_log_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_eval_summary_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 
 /* -------------------------------------------------------------------------
  * Host-buffer convenience layer (the call a non-JAX host makes): the library
