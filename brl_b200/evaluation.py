@@ -55,7 +55,9 @@ def make_simple_duplicate_evaluate(eval_env, team1_activation, team1_model_type,
     team1_forward_pass = make_forward_pass(activation=team1_activation, model_type=team1_model_type)
     team2_forward_pass = make_forward_pass(activation=team2_activation, model_type=team2_model_type)
 
-    def duplicate_evaluate(team1_params, team2_params, rng_key, trace=None):
+    def duplicate_evaluate(team1_params, team2_params, rng_key, trace=None, record=None):
+        """`record` (a list) receives per step (action, table_a.terminated, table_b.terminated) BEFORE the step --
+        the input of board_log.match_to_board_logs; record[0] is preceded by the initial private fields."""
         step_fn = duplicate_step(eval_env.step)
         rng_key, sub_key = brandom.split(rng_key)
         state = eval_env.init(eval_env.make_keys(sub_key, num_eval_envs, env_offset))      # :93-95
@@ -75,6 +77,9 @@ def make_simple_duplicate_evaluate(eval_env, team1_activation, team1_model_type,
             action = torch.where(state.current_player < 2, a1, a2)
             if trace is not None:  # tests replay the same action sequence on the oracle
                 trace.append((action.clone(), l1.clone(), l2.clone()))
+            if record is not None:
+                record.append((action.cpu(), table_a_info.terminated.view(torch.uint8).cpu(),
+                               table_b_info.terminated.view(torch.uint8).cpu()))
             state, table_a_info, table_b_info = step_fn(state, action, table_a_info, table_b_info)  # :164
             cum_return += state.rewards[:, 0]                                              # :167-169
             count += 1
