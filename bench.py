@@ -99,7 +99,8 @@ def _traffic(kernel_key):
     """per-launch DRAM bytes of the bench kernel from the committed `ncu --set full` capture (profiles/)"""
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            e = json.load(fh)[kernel_key]
+            doc = json.load(fh)
+            e = doc[doc.get("_alias", {}).get(kernel_key, kernel_key)]
         return e["traffic_bytes"], f"profiles/r01_traffic.json ({e['report']}: dram__bytes_read.sum + dram__bytes_write.sum, mean of {e['instances']} launches)"
     except Exception:
         return None, "no ncu capture committed for this kernel"
@@ -252,7 +253,7 @@ def main():
     avg_kernel_ms = sum(kernel_ms) / len(kernel_ms)
     peak, peak_src = _peaks()
     achieved = BYTES_PER_ENV_STEP * n * k / (avg_kernel_ms * 1e-3) / 1e9
-    traffic, traffic_src = _traffic("void k_rollout_ws<32, 0>(EnvArgs) grid=256")
+    traffic, traffic_src = _traffic("bench_rollout")
 
     # ---- e2e: host-buffer C-ABI, copies inside the timed region (rank-local, summed over ranks) ----
     e2e = run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps=max(20, min(200, args.steps * 4)),
@@ -281,7 +282,7 @@ def main():
             "dtype": "u8/int32 state, f32 0/1 observation", "data": "synthetic", "config": _config(world),
             "e2e": e2e, "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "brl::k_rollout_ws<f32> (1 env warp + 3 writer warps per 32 envs)", "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "brl::k_rollout_ws<f32> (296 blocks = 2 per SM, 27-28 envs each: 1 env warp + 4 writer warps)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * k, "avg_launch_ms": avg_kernel_ms},
             "cpu_baseline": cpu, "clocks": clocks,
             "episode_stats": {"finished_auctions": float(sums[0]), "sum_reward_player0": float(sums[1]),

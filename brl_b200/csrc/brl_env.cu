@@ -70,6 +70,7 @@ struct EnvArgs {
     int32_t flags, k_steps, mode;
     float illegal_penalty, illegal_bonus;
     int mask_vec;  // mask rows may be written with 128-bit stores
+    int balanced;  // warp-specialised rollout: envs split evenly over a grid that is a multiple of the SM count
 };
 
 // 4 bits -> 4 bytes of 0/1
@@ -119,7 +120,24 @@ __device__ __forceinline__ void emit_obs_row(const uint32_t* R, int lane, void* 
 // tile as one contiguous run; M[e] holds env e's 38 mask bits, M[n_valid] must be 0.
 __device__ __forceinline__ void emit_mask_run(const uint64_t* M, int tid, int nthreads, uint8_t* base, int nbytes,
                                               int mask_vec) {
-    if (mask_vec) {
+    if (mask_vec == 2) {
+        // run starting at an arbitrary byte address (balanced env split): byte stores up to the first
+        // 16-byte boundary, 128-bit stores for the body, byte stores for the tail
+        const int head = (int)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(base) & 15u)) & 15u);
+        const int body_end = head + ((nbytes - head) > 0 ? ((nbytes - head) & ~15) : 0);
+        for (int o = tid; o < nbytes; o += nthreads) {
+            if (o >= head && o < body_end) continue;
+            int e0 = o / kNumActions, a0 = o - e0 * kNumActions;
+            base[o] = (uint8_t)((M[e0] >> a0) & 1ull);
+        }
+        for (int o = head + tid * 16; o < body_end; o += nthreads * 16) {
+            int e0 = o / kNumActions, a0 = o - e0 * kNumActions;
+            uint64_t bits = (M[e0] >> a0) | (M[e0 + 1] << (kNumActions - a0));
+            uint32_t h = (uint32_t)bits & 0xFFFFu;
+            *reinterpret_cast<uint4*>(base + o) =
+                make_uint4(spread4(h & 15u), spread4((h >> 4) & 15u), spread4((h >> 8) & 15u), spread4(h >> 12));
+        }
+    } else if (mask_vec) {
         for (int o = tid * 16; o < nbytes; o += nthreads * 16) {
             int e0 = o / kNumActions, a0 = o - e0 * kNumActions;
             uint64_t bits = (M[e0] >> a0) | (M[e0 + 1] << (kNumActions - a0));
@@ -334,12 +352,16 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
     const RowSlots rs{row_slots, row_bars, EPB};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_writers = (int)(blockDim.x >> 5) - 1;
-    const int64_t env_base = (int64_t)blockIdx.x * EPB;
-    const int n_valid = (int)((a.n - env_base) < (int64_t)EPB ? (a.n - env_base) : (int64_t)EPB);
+    // a.balanced: the grid is a multiple of the SM count and block b owns envs [b*n/G, (b+1)*n/G) (<= EPB of
+    // them), so every SM carries the same number of envs even when n / EPB is a small non-multiple of 148
+    const int64_t env_base = a.balanced ? ((int64_t)blockIdx.x * a.n) / gridDim.x : (int64_t)blockIdx.x * EPB;
+    const int64_t env_end = a.balanced ? ((int64_t)(blockIdx.x + 1) * a.n) / gridDim.x : env_base + EPB;
+    const int n_valid = (int)((a.n < env_end ? a.n : env_end) - env_base);
     const bool active = lane < n_valid;
     const int64_t i = env_base + lane;
     const size_t obs_row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
     const bool is_env_warp = warp == n_writers;
+    const int mask_mode = a.balanced ? 2 : a.mask_vec;  // mode 2 copes with any alignment of the run
     Env e;
     EpisodePrefetch cache;
     uint64_t mask = 0ull;
@@ -401,7 +423,7 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                 }
                 if (a.mask)
                     emit_mask_run(t.M, (int)threadIdx.x, n_writers * 32, a.mask + (size_t)(row0 + env_base) * kNumActions,
-                                  n_valid * kNumActions, a.mask_vec);
+                                  n_valid * kNumActions, mask_mode);
                 if (warp == n_writers - 1 && active) {  // per-env scalars, coalesced over the tile
                     const int64_t row = row0 + i;
                     if (a.rewards) a.rewards[row] = t.rew[lane];
@@ -618,6 +640,7 @@ BRL_DEFINE_LAUNCHER(launch_dup_step, k_dup_step)
 template <int EPB, int OBS>
 static void launch_ws_inst(const EnvArgs& a, int writers, cudaStream_t s) {
     unsigned grid = (unsigned)((a.n + EPB - 1) / EPB);
+    if (a.balanced) grid = ((grid + 147u) / 148u) * 148u;  // 148 SMs: same number of blocks on every SM
     k_rollout_ws<EPB, OBS><<<grid, 32 * (1 + writers), 0, s>>>(a);
 }
 template <int OBS>
@@ -626,13 +649,22 @@ static void launch_ws_obs(const EnvArgs& a, int epb, int writers, cudaStream_t s
     else if (epb == 16) launch_ws_inst<16, OBS>(a, writers, s);
     else launch_ws_inst<32, OBS>(a, writers, s);
 }
-static void launch_rollout_ws(const EnvArgs& a, cudaStream_t s) {
-    if (a.n == 0) return;
+static void launch_rollout_ws(const EnvArgs& a_in, cudaStream_t s) {
+    if (a_in.n == 0) return;
+    EnvArgs a = a_in;
+    // flags bit 24: force the balanced split on, bit 25: force it off; auto = on when the plain grid would
+    // leave some SMs with >= 10 % more blocks than others (few blocks per SM)
+    {
+        const int64_t blocks = (a.n + 31) / 32;
+        const int64_t per_sm_hi = (blocks + 147) / 148;
+        const bool uneven = blocks % 148 != 0 && per_sm_hi <= 8 && blocks >= 148;
+        a.balanced = (a.flags & (1 << 24)) ? 1 : ((a.flags & (1 << 25)) ? 0 : (uneven ? 1 : 0));
+    }
     static const int epb_of[4] = {0, 8, 16, 32};
     int epb = epb_of[(a.flags >> 16) & 3];
     if (epb == 0) epb = a.n < 8192 ? 16 : 32;  // measured (scripts/exp_rollout_shapes.py)
     int writers = (a.flags >> 21) & 7;
-    if (writers == 0) writers = epb == 8 ? 1 : (epb == 16 ? 2 : 3);
+    if (writers == 0) writers = epb == 8 ? 1 : (epb == 16 ? 2 : (a.balanced ? 4 : 3));  // measured: scripts/exp_ab.py
     if (a.flags & BRL_F_OBS_U8) launch_ws_obs<kObsU8>(a, epb, writers, s);
     else if (a.flags & BRL_F_OBS_BF16) launch_ws_obs<kObsBF16>(a, epb, writers, s);
     else launch_ws_obs<kObsF32>(a, epb, writers, s);

@@ -86,6 +86,9 @@ def main():
             doc[key] = {"dram_bytes_read": a["rd"] / a["n"], "dram_bytes_write": a["wr"] / a["n"],
                         "traffic_bytes": (a["rd"] + a["wr"]) / a["n"], "gpu_time_ns_under_ncu": a["ns"] / a["n"],
                         "instances": a["n"], "report": os.path.basename(rep)}
+        if len(sys.argv) > 5 and sys.argv[4] == "--alias":   # e.g. --alias bench_rollout: bench.py reads this kernel's traffic
+            first = f"{rows[0][hdr.index('Kernel Name')]} grid={rows[0][hdr.index('launch__grid_size')]}"
+            doc.setdefault("_alias", {})[sys.argv[5]] = first
         json.dump(doc, open(path, "w"), indent=1, sort_keys=True)
 
 

@@ -20,6 +20,11 @@ def run(n, k, tune=0, reps=20, label="", obs_dtype=torch.float32):
     gbs = bpe * n * k / ms / 1e6
     print(f"{label:30s} n={n:8d} k={k:3d} ms={ms:.4f} us/step={1e3*ms/k:.3f} GB/s={gbs:7.1f} frac={gbs/6555.2:.3f}")
 if __name__ == "__main__":
+    for n in (8192, 16384, 4096, 12000):
+        run(n, 32, _lib.tune(balanced=False), label="ws auto, plain grid")
+        run(n, 32, _lib.tune(balanced=True), label="ws auto, balanced grid")
+        run(n, 32, _lib.tune(balanced=True, writers=4), label="ws4, balanced grid")
+        run(n, 32, _lib.tune(balanced=True, writers=5), label="ws5, balanced grid")
     for epb, ws in ((32, (3, 5, 7)), (16, (2, 3))):
         for w in ws:
             run(8192, 32, _lib.tune(epw=epb, writers=w), label=f"ws epb={epb} writers={w}")

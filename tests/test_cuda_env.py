@@ -174,7 +174,10 @@ def test_plain_step_terminal_is_absorbing_and_noop():
     (2048, 24, {}), (100, 40, {"writers": 1}), (1000, 9, {"writers": 3, "epw": 32}), (33, 5, {"writers": 5, "epw": 16}),
     (1, 3, {}), (70000, 3, {}), (777, 6, {"epw": 8, "writers": 2}),
     (2048, 24, {"classic_rollout": True}), (100, 40, {"classic_rollout": True, "epw": 32}),
-    (8, 7, {"classic_rollout": True, "epw": 8})])
+    (8, 7, {"classic_rollout": True, "epw": 8}),
+    # balanced env split (grid = multiple of 148 SMs, ragged 27/28-env blocks, unaligned mask runs)
+    (8192, 6, {}), (8192, 4, {"balanced": False}), (5000, 7, {"balanced": True}), (1001, 5, {"balanced": True, "epw": 16}),
+    (37, 4, {"balanced": True})])
 def test_fused_rollout_kernel_matches_oracle(n, k, tune_kw):
     """brl_rollout_random (K steps in one launch, in-kernel random-legal policy) against
     the oracle's rollout: whole [K, n, ...] trajectories bit-exact."""
