@@ -306,6 +306,17 @@ struct WsTile {
     uint8_t q[EPB], term[EPB], cur[EPB];
 };
 
+// observation word w for observer seat q from the env warp's RAW words: history nibbles are by absolute
+// seat (rotate), the vulnerability nibble (word 0, bits 0-3) and the hand bits (word 13 bits 12+, word 14)
+// are already relative to the observer
+__device__ __forceinline__ uint32_t obs_word_rot(const uint32_t* R, int w, uint32_t q) {
+    const uint32_t v = R[w];
+    if (w == 0) return rotr_nibbles(v & ~15u, q) | (v & 15u);
+    if (w == 13) return rotr_nibbles(v & 0xFFFu, q) | (v & 0xFFFFF000u);
+    if (w == 14) return v;
+    return rotr_nibbles(v, q);
+}
+
 template <int OBS>
 __device__ __forceinline__ void emit_obs_row_rot(const uint32_t* R, uint32_t q, int lane, void* obs, int64_t env) {
     // nibble j of the row: 0 = vulnerability, 1..106 = history (rotate right by q), 107..119 = hand
@@ -320,17 +331,24 @@ __device__ __forceinline__ void emit_obs_row_rot(const uint32_t* R, uint32_t q, 
                 row[j] = nibble_to_float4(nib);
             }
         }
+    } else if (OBS == kObsU8) {
+        // u8 row: lane l (< 30) expands 16 bits = half of word l/2; only that word is rotated
+        if (lane < kObsDim / 16) {
+            uint32_t h = (obs_word_rot(R, lane >> 1, q) >> ((lane & 1) * 16)) & 0xFFFFu;
+            reinterpret_cast<uint4*>(obs)[env * (kObsDim / 16) + lane] =
+                make_uint4(spread4(h & 15u), spread4((h >> 4) & 15u), spread4((h >> 8) & 15u), spread4(h >> 12));
+        }
     } else {
-        // u8 / bf16 rows: rotate whole words once, then reuse the generic expander
-        uint32_t W[kObsWords];
+        // bf16 row: 60 uint4 stores of 8 values = one byte of word j/4 each
+        uint4* row = reinterpret_cast<uint4*>(obs) + env * (kObsDim / 8);
 #pragma unroll
-        for (int w = 0; w < kObsWords; ++w) W[w] = R[w];
-        uint32_t vul = W[0] & 15u, hand13 = W[13] & 0xFFFFF000u;
-#pragma unroll
-        for (int w = 0; w < 14; ++w) W[w] = rotr_nibbles(w == 0 ? (W[0] & ~15u) : (w == 13 ? (W[13] & 0xFFFu) : W[w]), q);
-        W[0] |= vul;
-        W[13] |= hand13;
-        emit_obs_row<OBS>(W, lane, obs, env);
+        for (int k = 0; k < 2; ++k) {
+            int j = lane + 32 * k;
+            if (j < kObsDim / 8) {
+                uint32_t b = (obs_word_rot(R, j >> 2, q) >> ((j & 3) * 8)) & 0xFFu;
+                row[j] = make_uint4(pair_to_bf16x2(b), pair_to_bf16x2(b >> 2), pair_to_bf16x2(b >> 4), pair_to_bf16x2(b >> 6));
+            }
+        }
     }
 }
 

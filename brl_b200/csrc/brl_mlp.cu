@@ -11,7 +11,8 @@
 // BRL_F_MLP_BF16 selects the plain single-product mode.
 //
 // One layer = one launch of k_mlp_layer: C[M, N] = act(A[M, K] . Wt[N, K]^T + b).
-//   CTA tile 128 (envs) x BN (features), K in blocks of 64 bf16 = one 128-byte swizzle row.
+//   Persistent, one CTA per SM; CTA tile 128 (envs) x BN (features), K in blocks of 64 bf16 = one 128-byte
+//   swizzle row; two TMEM accumulators so the epilogue of one tile overlaps the main loop of the next.
 //   warp 0    TMA producer: per K block, bulk-tensor loads of the A / Wt (hi, lo) boxes into a
 //             ring of shared-memory stages (128B swizzle), completion on an mbarrier;
 //   warp 1    MMA issuer: one lane issues tcgen05.mma (UMMA 128 x BN x 16, kind::f16, fp32
@@ -170,6 +171,7 @@ struct LayerArgs {
     float* logits;               // head: [M, 38]
     float* value;                // head: [M]
     int M, n_total, k_blocks;
+    int n_tiles_n, n_tiles;      // tiles along N, total tiles of this layer
 };
 
 template <int BN, bool SPLIT_A, bool SPLIT_W>
@@ -184,33 +186,36 @@ template <int BN, bool SPLIT_A, bool SPLIT_W, bool HEAD>
 __global__ void __launch_bounds__(kMlpThreads, 1)
 k_mlp_layer(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const LayerArgs a) {
+    // PERSISTENT: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, so the
+    // CTAs running together share A row-blocks in L2).  The smem stage ring runs straight across tile
+    // boundaries and the accumulator is double-buffered in TMEM, so the epilogue of tile j overlaps the
+    // TMA + MMA main loop of tile j + 1.
     using Cfg = LayerCfg<BN, SPLIT_A, SPLIT_W>;
     constexpr int S = Cfg::kStages;
+    constexpr uint32_t kTmemCols = 2 * BN;  // two accumulators of BN fp32 columns (power of two >= 32)
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_addr(smem_dyn) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024-byte alignment
-    const uint32_t bar_base = base + S * Cfg::kStageBytes;         // full[S], empty[S], tmem_full, tmem slot
+    const uint32_t bar_base = base + S * Cfg::kStageBytes;         // full[S], empty[S], tmem_full[2], tmem_empty[2]
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * S);
-    __shared__ float bias_s[BN];
+    auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
+    auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
     __shared__ uint32_t tmem_base_s;  // written by tcgen05.alloc
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kBM;
+    const int n_tiles_n = a.n_tiles_n, n_tiles = a.n_tiles;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w_hi) : "memory");
+        if (SPLIT_A) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_lo) : "memory");
+        if (SPLIT_W) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w_lo) : "memory");
         for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(smem_addr(&tmem_base_s), BN < 32 ? 32 : BN);
-    if (warp >= 2) {
-        int t = threadIdx.x - 64;
-        if (t < BN) bias_s[t] = a.bias[n0 + t];
-    }
+    if (warp == 1) tmem_alloc(smem_addr(&tmem_base_s), kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -218,97 +223,118 @@ k_mlp_layer(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
-            for (int kb = 0; kb < a.k_blocks; ++kb) {
-                const int s = kb % S;
-                const uint32_t ph = (uint32_t)(kb / S) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
-                uint32_t dst = base + s * Cfg::kStageBytes;
-                tma_load_2d(dst, &tm_a_hi, full_bar(s), kb * kBK, m0);
-                dst += Cfg::kABytes;
-                if (SPLIT_A) { tma_load_2d(dst, &tm_a_lo, full_bar(s), kb * kBK, m0); dst += Cfg::kABytes; }
-                tma_load_2d(dst, &tm_w_hi, full_bar(s), kb * kBK, n0);
-                dst += Cfg::kWBytes;
-                if (SPLIT_W) tma_load_2d(dst, &tm_w_lo, full_bar(s), kb * kBK, n0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles_n) * kBM, n0 = (tile % n_tiles_n) * BN;
+                for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
+                    const int s = (int)(it % S);
+                    mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
+                    mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+                    uint32_t dst = base + s * Cfg::kStageBytes;
+                    tma_load_2d(dst, &tm_a_hi, full_bar(s), kb * kBK, m0);
+                    dst += Cfg::kABytes;
+                    if (SPLIT_A) { tma_load_2d(dst, &tm_a_lo, full_bar(s), kb * kBK, m0); dst += Cfg::kABytes; }
+                    tma_load_2d(dst, &tm_w_hi, full_bar(s), kb * kBK, n0);
+                    dst += Cfg::kWBytes;
+                    if (SPLIT_W) tma_load_2d(dst, &tm_w_lo, full_bar(s), kb * kBK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer =====
             constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
-            for (int kb = 0; kb < a.k_blocks; ++kb) {
-                const int s = kb % S;
-                const uint32_t ph = (uint32_t)(kb / S) & 1u;
-                mbar_wait(full_bar(s), ph);
+            uint32_t it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+                const uint32_t buf = j & 1u;
+                mbar_wait(tmem_empty_bar(buf), ((j >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t sa_hi = base + s * Cfg::kStageBytes;
-                const uint32_t sa_lo = sa_hi + Cfg::kABytes;
-                const uint32_t sw_hi = sa_hi + Cfg::kABytes * (SPLIT_A ? 2 : 1);
-                const uint32_t sw_lo = sw_hi + Cfg::kWBytes;
+                const uint32_t acc = tmem_acc + buf * BN;
+                for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
+                    const int s = (int)(it % S);
+                    mbar_wait(full_bar(s), (it / S) & 1u);
+                    tc_fence_after();
+                    const uint32_t sa_hi = base + s * Cfg::kStageBytes;
+                    const uint32_t sa_lo = sa_hi + Cfg::kABytes;
+                    const uint32_t sw_hi = sa_hi + Cfg::kABytes * (SPLIT_A ? 2 : 1);
+                    const uint32_t sw_lo = sw_hi + Cfg::kWBytes;
 #pragma unroll
-                for (int k = 0; k < kBK / kUmmaK; ++k) {
-                    const uint32_t koff = (uint32_t)k * kUmmaK * 2;  // bytes along K inside the 128-byte row
-                    const uint64_t da_hi = umma_desc_sw128(sa_hi + koff), dw_hi = umma_desc_sw128(sw_hi + koff);
-                    umma_bf16(tmem_acc, da_hi, dw_hi, idesc, (kb | k) != 0);
-                    if (SPLIT_A) umma_bf16(tmem_acc, umma_desc_sw128(sa_lo + koff), dw_hi, idesc, 1u);
-                    if (SPLIT_W) umma_bf16(tmem_acc, da_hi, umma_desc_sw128(sw_lo + koff), idesc, 1u);
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t koff = (uint32_t)k * kUmmaK * 2;  // bytes along K inside the 128-byte row
+                        const uint64_t da_hi = umma_desc_sw128(sa_hi + koff), dw_hi = umma_desc_sw128(sw_hi + koff);
+                        umma_bf16(acc, da_hi, dw_hi, idesc, (kb | k) != 0);
+                        if (SPLIT_A) umma_bf16(acc, umma_desc_sw128(sa_lo + koff), dw_hi, idesc, 1u);
+                        if (SPLIT_W) umma_bf16(acc, da_hi, umma_desc_sw128(sw_lo + koff), idesc, 1u);
+                    }
+                    umma_commit(empty_bar(s));  // the stage is free once these MMAs have read it
                 }
-                umma_commit(empty_bar(s));  // the stage is free once these MMAs have read it
+                umma_commit(tmem_full_bar(buf));
             }
-            umma_commit(tmem_full_bar);
         }
     } else {  // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        mbar_wait(tmem_full_bar, 0u);
-        tc_fence_after();
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
-        const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16);
-        if (!HEAD) {
+        uint32_t j = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            const int m0 = (tile / n_tiles_n) * kBM, n0 = (tile % n_tiles_n) * BN;
+            const uint32_t buf = j & 1u;
+            mbar_wait(tmem_full_bar(buf), (j >> 1) & 1u);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const uint32_t t_row = tmem_acc + buf * BN + ((uint32_t)(q * 32) << 16);
+            const float* bias = a.bias + n0;
+            if (!HEAD) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(t_row + (uint32_t)c0, r);
-                if (row < a.M) {
-                    uint32_t hi[16], lo[16];
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(t_row + (uint32_t)c0, r);
+                    if (row < a.M) {
+                        uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float x0 = fmaxf(__uint_as_float(r[2 * j]) + bias_s[c0 + 2 * j], 0.0f);
-                        float x1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias_s[c0 + 2 * j + 1], 0.0f);
-                        __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-                        hi[j] = *reinterpret_cast<uint32_t*>(&h);
-                        lo[j] = pack_bf16x2(x0 - __low2float(h), x1 - __high2float(h));
-                    }
-                    const size_t o = (size_t)row * a.n_total + n0 + c0;
-                    uint4* ph = reinterpret_cast<uint4*>(a.out_hi + o);
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + jj);  // warp-uniform
+                            float x0 = fmaxf(__uint_as_float(r[2 * jj]) + bb.x, 0.0f);
+                            float x1 = fmaxf(__uint_as_float(r[2 * jj + 1]) + bb.y, 0.0f);
+                            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                            hi[jj] = *reinterpret_cast<uint32_t*>(&h);
+                            lo[jj] = pack_bf16x2(x0 - __low2float(h), x1 - __high2float(h));
+                        }
+                        const size_t o = (size_t)row * a.n_total + n0 + c0;
+                        uint4* ph = reinterpret_cast<uint4*>(a.out_hi + o);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-                    if (a.out_lo) {
-                        uint4* pl = reinterpret_cast<uint4*>(a.out_lo + o);
+                        for (int v = 0; v < 4; ++v) ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+                        if (a.out_lo) {
+                            uint4* pl = reinterpret_cast<uint4*>(a.out_lo + o);
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+                            for (int v = 0; v < 4; ++v) pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+                        }
                     }
                 }
-            }
-        } else {
-            // head tile: columns 0..37 = policy logits, 38 = value (src/models.py:30-32)
-            uint32_t r0[32], r1[32];
-            tmem_ld32(t_row, r0);
-            tmem_ld32(t_row + 32u, r1);
-            if (row < a.M) {
-                float2* pl = reinterpret_cast<float2*>(a.logits + (size_t)row * 38);
+            } else {
+                // head tile: columns 0..37 = policy logits, 38 = value (src/models.py:30-32)
+                uint32_t r0[32], r1[32];
+                tmem_ld32(t_row, r0);
+                tmem_ld32(t_row + 32u, r1);
+                if (row < a.M) {
+                    float2* pl = reinterpret_cast<float2*>(a.logits + (size_t)row * 38);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    pl[j] = make_float2(__uint_as_float(r0[2 * j]) + bias_s[2 * j], __uint_as_float(r0[2 * j + 1]) + bias_s[2 * j + 1]);
+                    for (int jj = 0; jj < 16; ++jj)
+                        pl[jj] = make_float2(__uint_as_float(r0[2 * jj]) + __ldg(bias + 2 * jj),
+                                             __uint_as_float(r0[2 * jj + 1]) + __ldg(bias + 2 * jj + 1));
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    pl[16 + j] = make_float2(__uint_as_float(r1[2 * j]) + bias_s[32 + 2 * j],
-                                             __uint_as_float(r1[2 * j + 1]) + bias_s[32 + 2 * j + 1]);
-                a.value[row] = __uint_as_float(r1[6]) + bias_s[38];
+                    for (int jj = 0; jj < 3; ++jj)
+                        pl[16 + jj] = make_float2(__uint_as_float(r1[2 * jj]) + __ldg(bias + 32 + 2 * jj),
+                                                  __uint_as_float(r1[2 * jj + 1]) + __ldg(bias + 32 + 2 * jj + 1));
+                    a.value[row] = __uint_as_float(r1[6]) + __ldg(bias + 38);
+                }
             }
+            // all of this warp's tcgen05.ld have completed (wait::ld): hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(buf)) : "memory");
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_acc, BN < 32 ? 32 : BN);
+    if (warp == 1) tmem_dealloc(tmem_acc, kTmemCols);
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -359,8 +385,17 @@ static int32_t launch_layer(cudaStream_t s, const void* a_hi, const void* a_lo, 
             return fail(BRL_E_LAUNCH, "brl_mlp_forward: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);
         attr_set = true;
     }
-    dim3 grid((unsigned)(n_valid_rows + BN - 1) / BN, (unsigned)((args.M + kBM - 1) / kBM));
-    kern<<<grid, kMlpThreads, Cfg::kSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, args);
+    LayerArgs la = args;
+    la.n_tiles_n = (n_valid_rows + BN - 1) / BN;
+    la.n_tiles = la.n_tiles_n * ((args.M + kBM - 1) / kBM);
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    const unsigned grid = (unsigned)(la.n_tiles < n_sm ? la.n_tiles : n_sm);  // persistent: one CTA per SM
+    kern<<<grid, kMlpThreads, Cfg::kSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, la);
     return BRL_OK;
 }
 
@@ -444,7 +479,16 @@ int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_
         if (l < 4) {
             a.out_hi = buf_hi[l & 1];
             a.out_lo = split ? buf_lo[l & 1] : nullptr;
-            if (l == 0) rc = split ? launch_layer<128, false, true, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
+            // 128 x 256 tiles move fewer operand bytes per MMA (the L2 -> SM fill rate, ~64 B/clk, is what bounds
+            // these 1-CTA tiles): measured faster for the single-product mode and for large batches
+            // (scripts/exp_mlp_ab.py); flags bit 26 / 27 force wide / narrow
+            const bool wide = (p->flags & (1 << 27)) ? false : ((p->flags & (1 << 26)) != 0 || !split || M >= 32768);
+            if (wide) {
+                if (l == 0) rc = split ? launch_layer<256, false, true, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
+                                       : launch_layer<256, false, false, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a);
+                else rc = split ? launch_layer<256, true, true, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
+                                : launch_layer<256, false, false, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a);
+            } else if (l == 0) rc = split ? launch_layer<128, false, true, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
                                    : launch_layer<128, false, false, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a);
             else rc = split ? launch_layer<128, true, true, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
                             : launch_layer<128, false, false, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a);

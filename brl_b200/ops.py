@@ -225,7 +225,7 @@ def mlp_scratch(n: int, device) -> torch.Tensor:
 
 
 def mlp_forward(obs_bf16: torch.Tensor, packed: torch.Tensor, scratch: torch.Tensor, logits: torch.Tensor,
-                value: torch.Tensor, single_bf16: bool = False) -> None:
+                value: torch.Tensor, single_bf16: bool = False, tune: int = 0) -> None:
     """logits f32[n,38], value f32[n] = DeepMind MLP(obs) on tcgen05 (3-term bf16 split unless single_bf16)."""
     n = obs_bf16.shape[0]
     if obs_bf16.dtype != torch.bfloat16:
@@ -233,7 +233,7 @@ def mlp_forward(obs_bf16: torch.Tensor, packed: torch.Tensor, scratch: torch.Ten
     if scratch.numel() < _lib.load().brl_mlp_scratch_bytes(n):
         raise _lib.BrlError("mlp_forward: scratch too small (ops.mlp_scratch)")
     _call("brl_mlp_forward", [_ptr(obs_bf16), _ptr(packed), _ptr(scratch), _ptr(logits), _ptr(value)],
-          _params(n, flags=F_MLP_BF16 if single_bf16 else 0))
+          _params(n, flags=(F_MLP_BF16 if single_bf16 else 0) | tune))
 
 
 def ppo_loss(logits, value, index, mask, action, old_log_prob, old_value, adv, targets, dlogits, dvalue, stats, scratch,

@@ -277,3 +277,25 @@ def test_abi_errors_are_reported_not_swallowed():
         _lib.call("brl_step", 0, [None] * 10, ops._params(4))
     with pytest.raises(_lib.BrlError):
         ops.step(torch.zeros((5, 4, 4), dtype=torch.int32), None, None, None, ops.EnvOutputs(4, DEV))  # CPU tensor
+
+
+@pytest.mark.parametrize("obs_dtype", [torch.uint8, torch.bfloat16])
+@pytest.mark.parametrize("n,tune_kw", [(3000, {}), (8192, {}), (100, {"writers": 2})])
+def test_fused_rollout_other_observation_dtypes(obs_dtype, n, tune_kw):
+    """pgx's own bool/u8 observation dtype and the bf16 form that feeds the tensor-core policy: same bits as f32."""
+    ops, orc = _ops(), _orc()
+    from brl_b200 import _lib
+    from brl_b200.deals import synthetic_deal_table
+    table = synthetic_deal_table(1500, seed=3)
+    table_t = _t(table)
+    k, seed = 7, 99
+    env = orc.OracleEnv(table, n)
+    env.init(orc.make_keys(seed, n))
+    ref = env.rollout_random(seed, 0, k)
+    state, out0 = ops.new_state(n, DEV), ops.EnvOutputs(n, DEV, obs_dtype)
+    ops.init(ops.make_keys(seed, n, DEV), table_t, state, out0)
+    traj = ops.EnvOutputs(n, DEV, obs_dtype, rows=k)
+    ops.rollout_random(state, table_t, k, traj, seed=seed, step0=0, tune=_lib.tune(**tune_kw))
+    assert (traj.observation.float().cpu().numpy() == ref["observation"]).all()
+    assert (traj.legal_action_mask.cpu().numpy() == ref["legal_action_mask"]).all()
+    assert (traj.rewards.cpu().numpy() == ref["rewards"]).all()
