@@ -17,7 +17,7 @@ OPS = (
     "brl_ppo_loss", "brl_adam_clip", "brl_gather_rows", "brl_eval_act_log", "brl_eval_summary",
 )
 HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host", "brl_env_rollout_host",
-            "brl_env_trajectory")
+            "brl_env_rollout_host_async", "brl_env_wait", "brl_env_trajectory")
 MISC = ("brl_last_error", "brl_abi_version", "brl_mlp_packed_bytes", "brl_mlp_scratch_bytes", "brl_eval_num_sums")
 XLA_LEGACY = tuple(op + "_xla" for op in OPS)  # legacy XLA GPU custom-call targets (csrc/xla_ffi_shim.cc)
 ALL_SYMBOLS = OPS + HOST_API + MISC + XLA_LEGACY
@@ -32,6 +32,7 @@ F_SAMPLE = 0x0040
 F_QUAD_LAST = 0x0100
 F_MLP_BF16 = 0x0200
 F_EVAL_INDICATOR_BIDS = 0x0400
+F_HOST_STAGED = 0x0800
 EVAL_ACC_COLS = 76
 
 
@@ -113,6 +114,10 @@ def load():
     L.brl_env_step_host.argtypes = [C.c_void_p] * 7
     L.brl_env_rollout_host.restype = C.c_int32
     L.brl_env_rollout_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.brl_env_rollout_host_async.restype = C.c_int64
+    L.brl_env_rollout_host_async.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.brl_env_wait.restype = C.c_int32
+    L.brl_env_wait.argtypes = [C.c_void_p, C.c_int64]
     L.brl_env_trajectory.restype = C.c_int32
     L.brl_env_trajectory.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     _LIB = L

@@ -35,6 +35,14 @@ struct BrlEnv {
     int32_t* t_action;
     uint32_t* t_uniforms;
     unsigned long long* d_stats;
+    // depth-2 pipelined rollout (brl_env_rollout_host_async): double-buffered staging + events
+    int32_t a_k;
+    int64_t a_calls;
+    float* a_rewards[2];
+    uint8_t* a_term[2];
+    uint32_t* a_uniforms[2];
+    unsigned long long* a_stats[2];
+    cudaEvent_t a_in[2], a_kernel[2], a_done[2];
 };
 
 namespace {
@@ -127,6 +135,12 @@ void brl_env_destroy(BrlEnv* env) {
         if (env->ev_in[c]) cudaEventDestroy(env->ev_in[c]);
         if (env->ev_k[c]) cudaEventDestroy(env->ev_k[c]);
     }
+    for (int c = 0; c < 2; ++c) {
+        cudaFree(env->a_rewards[c]); cudaFree(env->a_term[c]); cudaFree(env->a_uniforms[c]); cudaFree(env->a_stats[c]);
+        if (env->a_in[c]) cudaEventDestroy(env->a_in[c]);
+        if (env->a_kernel[c]) cudaEventDestroy(env->a_kernel[c]);
+        if (env->a_done[c]) cudaEventDestroy(env->a_done[c]);
+    }
     if (env->s_in) cudaStreamDestroy(env->s_in);
     if (env->s_out) cudaStreamDestroy(env->s_out);
     if (env->stream) cudaStreamDestroy(env->stream);
@@ -191,7 +205,42 @@ int32_t brl_env_rollout_host(BrlEnv* env, int32_t k_steps, const uint32_t* unifo
     if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "brl_env_rollout_host: bad handle");
     if (k_steps <= 0) return brl::fail(BRL_E_OPAQUE, "brl_env_rollout_host: k_steps must be > 0");
     if (!ensure_trajectory(env, k_steps)) return BRL_E_LAUNCH;
-    // Software pipeline over chunks of steps: the H2D copy of chunk c+1's randomness and the
+    // Zero-copy results: when the caller's result buffers are PINNED host memory (cudaHostAlloc /
+    // cudaHostRegister -- torch .pin_memory()), the kernel's writer warps store rewards / terminated
+    // straight into them over PCIe (512-byte coalesced bursts per block-step, posted writes that overlap
+    // the rest of the step), so there is no device->host copy phase at all: one H2D of the randomness,
+    // ONE fused launch, 32 bytes of statistics back.
+    {
+        auto mapped = [](const void* p, void** dptr) {
+            if (p == nullptr) { *dptr = nullptr; return true; }
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+            if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return false;
+            *dptr = at.devicePointer;
+            return true;
+        };
+        void *d_rew = nullptr, *d_term = nullptr;
+        if (!(env->flags & BRL_F_HOST_STAGED) && mapped(rewards, &d_rew) && mapped(terminated, &d_term) &&
+            (rewards == nullptr || (reinterpret_cast<uintptr_t>(d_rew) & 15u) == 0)) {
+            cudaStream_t s = env->stream;
+            const size_t rows = (size_t)k_steps * (size_t)env->n;
+            if (!ok(cudaMemsetAsync(env->d_stats, 0, 32, s), "memset stats")) return BRL_E_LAUNCH;
+            if (uniforms && !ok(cudaMemcpyAsync(env->t_uniforms, uniforms, rows * 4, cudaMemcpyHostToDevice, s), "H2D uniforms"))
+                return BRL_E_LAUNCH;
+            BrlParams p = params_of(env, 0);
+            p.k_steps = k_steps;
+            void* b[10] = {env->d_state, env->d_table, env->t_obs, env->t_mask,
+                           rewards ? d_rew : (void*)env->t_rewards, terminated ? d_term : (void*)env->t_term,
+                           env->t_cur, env->t_action, env->d_stats, uniforms ? (void*)env->t_uniforms : nullptr};
+            int32_t rc = brl_rollout_random((brl_stream_t)s, b, &p, sizeof(p));
+            if (rc != BRL_OK) return rc;
+            env->step += (uint32_t)k_steps;
+            if (stats && !ok(cudaMemcpyAsync(stats, env->d_stats, 32, cudaMemcpyDeviceToHost, s), "D2H stats")) return BRL_E_LAUNCH;
+            if (!ok(cudaStreamSynchronize(s), "stream sync")) return BRL_E_LAUNCH;
+            return BRL_OK;
+        }
+    }
+    // Pageable result buffers: software pipeline over chunks of steps: the H2D copy of chunk c+1's randomness and the
     // D2H copy of chunk c-1's results run on their own streams under chunk c's kernel.
     const int chunks = (k_steps >= 16 && k_steps % 4 == 0 && (env->n * BRL_NUM_ACTIONS * (k_steps / 4)) % 16 == 0) ? 4 : 1;
     const int kc = k_steps / chunks;
@@ -230,6 +279,71 @@ int32_t brl_env_rollout_host(BrlEnv* env, int32_t k_steps, const uint32_t* unifo
     }
     if (stats && !ok(cudaMemcpyAsync(stats, env->d_stats, 32, cudaMemcpyDeviceToHost, env->s_out), "D2H stats")) return BRL_E_LAUNCH;
     if (!ok(cudaStreamSynchronize(env->s_out), "stream sync") || !ok(cudaStreamSynchronize(s), "stream sync")) return BRL_E_LAUNCH;
+    return BRL_OK;
+}
+
+// Pipelined form of brl_env_rollout_host: returns as soon as the work is enqueued; call c's H2D runs under
+// call c-1's kernel and its D2H under call c+1's kernel (double-buffered staging, three streams).  The host
+// buffers of call c are valid after brl_env_wait(env, ticket_c); at most two calls may be in flight.
+int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t* uniforms, float* rewards,
+                                   uint8_t* terminated, uint64_t* stats) {
+    if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "brl_env_rollout_host_async: bad handle");
+    if (k_steps <= 0) return brl::fail(BRL_E_OPAQUE, "brl_env_rollout_host_async: k_steps must be > 0");
+    if (!ensure_trajectory(env, k_steps)) return BRL_E_LAUNCH;
+    const size_t rows = (size_t)k_steps * (size_t)env->n;
+    if (env->a_k < k_steps) {
+        if (!ok(cudaDeviceSynchronize(), "sync before staging resize")) return BRL_E_LAUNCH;
+        for (int c = 0; c < 2; ++c) {
+            cudaFree(env->a_rewards[c]); cudaFree(env->a_term[c]); cudaFree(env->a_uniforms[c]);
+            env->a_rewards[c] = nullptr; env->a_term[c] = nullptr; env->a_uniforms[c] = nullptr;
+            bool good = ok(cudaMalloc(&env->a_rewards[c], rows * 16), "malloc staging rewards") &&
+                        ok(cudaMalloc(&env->a_term[c], rows), "malloc staging terminated") &&
+                        ok(cudaMalloc(&env->a_uniforms[c], rows * 4), "malloc staging uniforms") &&
+                        (env->a_stats[c] != nullptr || ok(cudaMalloc(&env->a_stats[c], 32), "malloc staging stats")) &&
+                        (env->a_in[c] != nullptr || ok(cudaEventCreateWithFlags(&env->a_in[c], cudaEventDisableTiming), "event")) &&
+                        (env->a_kernel[c] != nullptr || ok(cudaEventCreateWithFlags(&env->a_kernel[c], cudaEventDisableTiming), "event")) &&
+                        (env->a_done[c] != nullptr || ok(cudaEventCreateWithFlags(&env->a_done[c], cudaEventDisableTiming), "event"));
+            if (!good) return BRL_E_LAUNCH;
+        }
+        env->a_k = k_steps;
+        env->a_calls = 0;
+    }
+    const int slot = (int)(env->a_calls & 1);
+    const bool reuse = env->a_calls >= 2;
+    cudaStream_t s = env->stream;
+    if (uniforms) {
+        if (reuse && !ok(cudaStreamWaitEvent(env->s_in, env->a_kernel[slot], 0), "wait event")) return BRL_E_LAUNCH;
+        if (!ok(cudaMemcpyAsync(env->a_uniforms[slot], uniforms, rows * 4, cudaMemcpyHostToDevice, env->s_in), "H2D uniforms") ||
+            !ok(cudaEventRecord(env->a_in[slot], env->s_in), "event record") || !ok(cudaStreamWaitEvent(s, env->a_in[slot], 0), "wait event"))
+            return BRL_E_LAUNCH;
+    }
+    if (reuse && !ok(cudaStreamWaitEvent(s, env->a_done[slot], 0), "wait event")) return BRL_E_LAUNCH;
+    if (!ok(cudaMemsetAsync(env->a_stats[slot], 0, 32, s), "memset stats")) return BRL_E_LAUNCH;
+    BrlParams p = params_of(env, 0);
+    p.k_steps = k_steps;
+    void* b[10] = {env->d_state, env->d_table, env->t_obs, env->t_mask, env->a_rewards[slot], env->a_term[slot],
+                   env->t_cur, env->t_action, env->a_stats[slot], uniforms ? (void*)env->a_uniforms[slot] : nullptr};
+    int32_t rc = brl_rollout_random((brl_stream_t)s, b, &p, sizeof(p));
+    if (rc != BRL_OK) return rc;
+    env->step += (uint32_t)k_steps;
+    if (!ok(cudaEventRecord(env->a_kernel[slot], s), "event record") ||
+        !ok(cudaStreamWaitEvent(env->s_out, env->a_kernel[slot], 0), "wait event"))
+        return BRL_E_LAUNCH;
+    if (rewards && !ok(cudaMemcpyAsync(rewards, env->a_rewards[slot], rows * 16, cudaMemcpyDeviceToHost, env->s_out), "D2H rewards"))
+        return BRL_E_LAUNCH;
+    if (terminated && !ok(cudaMemcpyAsync(terminated, env->a_term[slot], rows, cudaMemcpyDeviceToHost, env->s_out), "D2H terminated"))
+        return BRL_E_LAUNCH;
+    if (stats && !ok(cudaMemcpyAsync(stats, env->a_stats[slot], 32, cudaMemcpyDeviceToHost, env->s_out), "D2H stats"))
+        return BRL_E_LAUNCH;
+    if (!ok(cudaEventRecord(env->a_done[slot], env->s_out), "event record")) return BRL_E_LAUNCH;
+    return ++env->a_calls;
+}
+
+int32_t brl_env_wait(BrlEnv* env, int64_t ticket) {
+    if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "brl_env_wait: bad handle");
+    if (ticket <= 0 || ticket > env->a_calls) return brl::fail(BRL_E_OPAQUE, "brl_env_wait: unknown ticket");
+    if (ticket + 2 <= env->a_calls) return BRL_OK;  // its slot was reused, which already waited for it
+    if (!ok(cudaEventSynchronize(env->a_done[(ticket - 1) & 1]), "event sync")) return BRL_E_LAUNCH;
     return BRL_OK;
 }
 

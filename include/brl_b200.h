@@ -83,6 +83,7 @@ typedef struct CUstream_st *brl_stream_t; /* == cudaStream_t */
 #define BRL_F_SAMPLE        0x0040 /* brl_categorical: Gumbel-argmax sample instead of mode */
 #define BRL_F_QUAD_LAST     0x0100 /* with ACCUMULATE: write the OR-ed terminated flag back into the state (src/utils.py:128) */
 #define BRL_F_MLP_BF16      0x0200 /* brl_mlp_forward: one bf16 product per term instead of the 3-term split */
+#define BRL_F_HOST_STAGED   0x0800 /* brl_env_create: never write results straight into pinned host buffers (always stage + copy) */
 #define BRL_F_OBS_STREAMING 0x0080 /* rollout: obs rows staged in shared memory and written by TMA bulk stores */
 
 /* tuning (0 = automatic): bits 16-17 envs per warp (1->8, 2->16, 3->32), bits 18-19 warps per block (1->1, 2->2, 3->4) */
@@ -326,9 +327,17 @@ int32_t brl_env_step_host(BrlEnv *env, const int32_t *action, void *obs, uint8_t
  * choice; NULL -> in-kernel Philox).  HOST out (any may be NULL): rewards f32[k_steps,n,4],
  * terminated u8[k_steps,n], stats u64[4] (as brl_rollout_random).  The observation / mask
  * trajectories stay in HBM for a device-resident consumer, exactly as `traj_batch` does in
- * the reference; `brl_env_trajectory` exposes their device pointers. */
+ * the reference; `brl_env_trajectory` exposes their device pointers.
+ * If `rewards` / `terminated` are pinned host memory the kernel writes them in place over PCIe
+ * (no copy phase); pageable buffers are staged in HBM and copied under the next chunk of steps. */
 int32_t brl_env_rollout_host(BrlEnv *env, int32_t k_steps, const uint32_t *uniforms, float *rewards,
                              uint8_t *terminated, uint64_t *stats);
+/* Pipelined form: enqueue and return a ticket (> 0; negative = BRL_E_*).  Call c's input copy runs under call
+ * c-1's kernel and its result copy under call c+1's kernel.  The host buffers of a call are valid after
+ * brl_env_wait(env, ticket); keep at most two calls in flight (use two sets of host buffers). */
+int64_t brl_env_rollout_host_async(BrlEnv *env, int32_t k_steps, const uint32_t *uniforms, float *rewards,
+                                   uint8_t *terminated, uint64_t *stats);
+int32_t brl_env_wait(BrlEnv *env, int64_t ticket);
 /* device pointers of the last rollout's trajectory: obs, mask, rewards, terminated, current_player, action */
 int32_t brl_env_trajectory(BrlEnv *env, void **out_ptrs6);
 

@@ -78,3 +78,85 @@ def test_host_buffer_api_step_and_rollout_match_oracle():
     assert L.brl_env_trajectory(h, ptrs) == 0 and all(ptrs)
     assert L.brl_env_step_host(None, p(act), None, None, None, None, None) == -4  # bad handle is an error, not a crash
     L.brl_env_destroy(h)
+
+
+@pytest.mark.parametrize("staged", [False, True])
+def test_host_rollout_into_pinned_buffers_zero_copy(staged):
+    """pinned result buffers are written by the kernel itself over PCIe (no copy phase); same numbers as
+    the staged path and the oracle, for a chunkable (k=32) and an odd (k=5) horizon."""
+    from brl_b200 import _lib
+    from brl_b200.deals import synthetic_deal_table
+    from oracle import oracle as orc
+    L = _lib.load()
+    n, seed = 8192, 17
+    table = synthetic_deal_table(1200, seed=4)
+    flags = _lib.F_AUTORESET | (_lib.F_HOST_STAGED if staged else 0)
+    h = L.brl_env_create(n, 0, table.ctypes.data, table.shape[0], seed, flags)
+    assert h, L.brl_last_error()
+    assert L.brl_env_init_host(h, None, None, None, None, None) == 0
+    env = orc.OracleEnv(table, n)
+    env.init(orc.make_keys(seed, n))
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    step0 = 0
+    for k in (32, 5):
+        rng = np.random.default_rng(k)
+        u_np = rng.integers(0, 2 ** 32, size=(k, n), dtype=np.uint32)
+        u = torch.from_numpy(u_np.view(np.int32)).pin_memory()
+        rew = torch.full((k, n, 4), -1.0).pin_memory()
+        term = torch.full((k, n), 7, dtype=torch.uint8).pin_memory()
+        stats = torch.zeros(4, dtype=torch.int64).pin_memory()
+        assert L.brl_env_rollout_host(h, k, vp(u), vp(rew), vp(term), vp(stats)) == 0, L.brl_last_error()
+        # oracle with the same caller-supplied uniforms: replay action by action
+        n_term = 0
+        for s in range(k):
+            e = env.export()
+            m = e["legal_action_mask"].astype(bool)
+            n_legal = m.sum(1)
+            kth = ((u_np[s].astype(np.uint64) * n_legal.astype(np.uint64)) >> np.uint64(32)).astype(np.int64)
+            act = np.array([np.nonzero(m[i])[0][kth[i]] for i in range(n)], np.int32)
+            env.step(act, autoreset=True)
+            e = env.export()
+            assert (rew[s].numpy() == e["rewards"]).all(), (k, s)
+            assert (term[s].numpy() == e["terminated"]).all(), (k, s)
+            n_term += int(e["terminated"].sum())
+        assert int(stats[0]) == n_term and int(stats[2]) == n * k
+        step0 += k
+    L.brl_env_destroy(h)
+
+
+def test_pipelined_host_rollout_equals_blocking_calls():
+    from brl_b200 import _lib
+    from brl_b200.deals import synthetic_deal_table
+    L = _lib.load()
+    n, seed, k, calls = 2048, 23, 8, 5
+    table = synthetic_deal_table(800, seed=6)
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    rng = np.random.default_rng(0)
+    us = [torch.from_numpy(rng.integers(0, 2 ** 32, size=(k, n), dtype=np.uint32).view(np.int32)).pin_memory() for _ in range(calls)]
+
+    def run(pipelined):
+        h = L.brl_env_create(n, 0, table.ctypes.data, table.shape[0], seed, _lib.F_AUTORESET)
+        assert L.brl_env_init_host(h, None, None, None, None, None) == 0
+        outs = [(torch.zeros((k, n, 4)).pin_memory(), torch.zeros((k, n), dtype=torch.uint8).pin_memory(),
+                 torch.zeros(4, dtype=torch.int64).pin_memory()) for _ in range(calls)]
+        tickets = []
+        for c in range(calls):
+            r, t, s = outs[c]
+            if pipelined:
+                tk = L.brl_env_rollout_host_async(h, k, vp(us[c]), vp(r), vp(t), vp(s))
+                assert tk == c + 1, L.brl_last_error()
+                tickets.append(tk)
+                if c >= 1:
+                    assert L.brl_env_wait(h, tickets[c - 1]) == 0
+            else:
+                assert L.brl_env_rollout_host(h, k, vp(us[c]), vp(r), vp(t), vp(s)) == 0
+        if pipelined:
+            assert L.brl_env_wait(h, tickets[-1]) == 0 and L.brl_env_wait(h, 1) == 0
+            assert L.brl_env_wait(h, calls + 1) == -1
+        L.brl_env_destroy(h)
+        return outs
+
+    a, b = run(False), run(True)
+    for (r0, t0, s0), (r1, t1, s1) in zip(a, b):
+        assert torch.equal(r0, r1) and torch.equal(t0, t1) and torch.equal(s0, s1)
+        assert int(s0[2]) == n * k and int(s0[0]) > 0
