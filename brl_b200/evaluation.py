@@ -55,9 +55,10 @@ def make_simple_duplicate_evaluate(eval_env, team1_activation, team1_model_type,
     team1_forward_pass = make_forward_pass(activation=team1_activation, model_type=team1_model_type)
     team2_forward_pass = make_forward_pass(activation=team2_activation, model_type=team2_model_type)
 
-    def duplicate_evaluate(team1_params, team2_params, rng_key, trace=None, record=None):
+    def duplicate_evaluate(team1_params, team2_params, rng_key, trace=None, record=None, local_sums=None):
         """`record` (a list) receives per step (action, table_a.terminated, table_b.terminated) BEFORE the step --
-        the input of board_log.match_to_board_logs; record[0] is preceded by the initial private fields."""
+        the input of board_log.match_to_board_logs.  `local_sums` (f64[8] tensor): accumulate this rank's partial
+        statistics there and skip the all-reduce (the league evaluator reduces all its matches at once)."""
         step_fn = duplicate_step(eval_env.step)
         rng_key, sub_key = brandom.split(rng_key)
         state = eval_env.init(eval_env.make_keys(sub_key, num_eval_envs, env_offset))      # :93-95
@@ -85,6 +86,9 @@ def make_simple_duplicate_evaluate(eval_env, team1_activation, team1_model_type,
             count += 1
             if count % _CHECK_EVERY == 0 and bool(state._terminated_u8.all()):
                 break
+        if local_sums is not None:
+            ops.match_stats(cum_return, local_sums)
+            return None, table_a_info, table_b_info, cum_return
         sums = torch.zeros(8, dtype=torch.float64, device=dev)
         ops.match_stats(cum_return, sums)
         bdist.allreduce_sums(sums)
@@ -93,6 +97,31 @@ def make_simple_duplicate_evaluate(eval_env, team1_activation, team1_model_type,
         return log_info, table_a_info, table_b_info, cum_return
 
     return duplicate_evaluate
+
+
+def make_league_evaluate(eval_env, activation, model_type, num_eval_envs_total: int, num_models: int):
+    """The PFSP league probe of ppo.py:412-436 as ONE sharded job (BASELINE configs[4]): the learner plays a
+    duplicate match against every model of the pool; the `num_eval_envs_total` envs are split into `num_models`
+    equal blocks by GLOBAL env index (block m plays pool model m) and every block is sharded across the ranks, so
+    the result does not depend on the rank count.  One all-reduce of f64[num_models, 8] for the whole league.
+    Returns per-model (mean IMP, SE, win rate) lists -- `imp_list` / `win_rate_list` of ppo.py:414-435."""
+    rank, world = bdist.rank_world()
+    per_model = num_eval_envs_total // num_models
+    lo, hi = bdist.shard_range(per_model, rank, world)
+    matches = [make_simple_duplicate_evaluate(eval_env, activation, model_type, activation, model_type, hi - lo,
+                                              env_offset=m * per_model + lo) for m in range(num_models)]
+
+    def league_evaluate(actor_params, pool_params, rng_key):
+        assert len(pool_params) == num_models
+        sums = torch.zeros((num_models, 8), dtype=torch.float64, device=eval_env.device)
+        for m, (match, opp) in enumerate(zip(matches, pool_params)):
+            if hi > lo:
+                match(actor_params, opp, rng_key, local_sums=sums[m])
+        bdist.allreduce_sums(sums)
+        host = sums.cpu()
+        return [bdist.stats_from_sums(host[m]) for m in range(num_models)]
+
+    return league_evaluate
 
 
 # ---- full evaluation statistics (src/evaluation.py:207-1115) --------------------------------------

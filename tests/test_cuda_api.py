@@ -231,3 +231,25 @@ def test_simple_evaluate_runs_to_completion():
     ev = make_simple_evaluate(env, "relu", "DeepMind", "relu", "DeepMind", None, 128, team2_params=init_params(3, DEV))
     r = ev(init_params(4, DEV), brandom.PRNGKey(5))
     assert np.isfinite(float(r)) and abs(float(r)) <= 7600
+
+
+def test_league_evaluate_equals_separate_matches():
+    """configs[4] host logic: block m of the global env range plays pool model m; identical to running the
+    matches one by one on the same global indices (so the result cannot depend on how ranks shard it)."""
+    from brl_b200 import BridgeBidding
+    from brl_b200.evaluation import make_league_evaluate, make_simple_duplicate_evaluate
+    from brl_b200.models import init_params
+    from brl_b200 import random as brandom
+    env, _ = _mk_env()
+    n_total, n_models = 600, 3
+    actor = init_params(41, DEV)
+    pool = [init_params(50 + m, DEV) for m in range(n_models)]
+    league = make_league_evaluate(env, "relu", "DeepMind", n_total, n_models)
+    rng = brandom.PRNGKey(2)
+    res = league(actor, pool, rng)
+    assert len(res) == n_models
+    for m in range(n_models):
+        single = make_simple_duplicate_evaluate(env, "relu", "DeepMind", "relu", "DeepMind", 200, env_offset=200 * m)
+        (mean, se, win), _, _, _ = single(actor, pool[m], rng)
+        np.testing.assert_allclose(res[m], (mean, se, win), rtol=1e-12)
+    assert len({round(r[0], 6) for r in res}) == n_models  # three different opponents, three different results
