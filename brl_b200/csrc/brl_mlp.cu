@@ -30,6 +30,7 @@ constexpr int kObsDimM = 480, kHidden = 1024, kHeadValid = 39, kHeadPad = 64;
 constexpr int kBM = 128, kBK = 64, kUmmaK = 16;
 constexpr int kMlpThreads = 192;
 constexpr uint32_t kSmemBudget = 200 * 1024;
+constexpr int kPairMinM = 4096;  // batches from this size on run the hidden layers on CTA pairs
 
 // ---- packed parameter blob ---------------------------------------------------------------
 struct MlpLayout {
@@ -337,6 +338,194 @@ k_mlp_layer(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (warp == 1) tmem_dealloc(tmem_acc, kTmemCols);
 }
 
+// ---- one hidden layer on CTA PAIRS (cta_group::2) ------------------------------------------------
+// The 1-CTA tiles above are bound by the L2 -> SM operand fill (~64 B/clk/SM against the split mode's
+// 83 B/clk demand at 128 x 128).  A CTA pair (cluster of 2 = the two SMs of a TPC) computes a 256 x BN tile
+// with ONE tcgen05.mma.cta_group::2 stream issued by the leader: each CTA stages its own 128 env rows of A and
+// only HALF of the Wt rows (the MMA reads the other half out of the peer's shared memory), and accumulates its
+// own 128 x BN block in its own TMEM.  Operand bytes per MMA clock: 42 B/clk/SM at BN = 256.
+//   full[s]        lives in the leader; both CTAs' TMA loads complete_tx on it (cta_group::2, peer bit masked);
+//   empty[s]       one per CTA, released by the leader's multicast tcgen05.commit;
+//   tmem_full[b]   one per CTA, multicast commit;   tmem_empty[b]  in the leader, 8 arrivals (4 epilogue warps x 2).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's even CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on `bar`'s offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <int BN, bool SPLIT_A, bool SPLIT_W>
+struct PairCfg {
+    static constexpr uint32_t kABytes = kBM * kBK * 2, kWBytes = (BN / 2) * kBK * 2;  // per CTA: own A rows, half of Wt
+    static constexpr uint32_t kStageBytes = kABytes * (SPLIT_A ? 2 : 1) + kWBytes * (SPLIT_W ? 2 : 1);
+    static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (int)(kSmemBudget / kStageBytes);
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool SPLIT_A, bool SPLIT_W>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
+k_mlp_layer_pair(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const LayerArgs a) {
+    using Cfg = PairCfg<BN, SPLIT_A, SPLIT_W>;
+    constexpr int S = Cfg::kStages;
+    constexpr uint32_t kTmemCols = 2 * BN;
+    static_assert(kTmemCols <= 512, "two accumulators must fit tensor memory");
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_addr(smem_dyn) + 1023u) & ~1023u;  // same offset in both CTAs of the pair
+    const uint32_t bar_base = base + S * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+    auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
+    auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_tiles_n = a.n_tiles_n, n_tiles = a.n_tiles;       // pair tiles: 256 rows x BN columns
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w_hi) : "memory");
+        if (SPLIT_A) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_lo) : "memory");
+        if (SPLIT_W) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w_lo) : "memory");
+        for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {  // the same warp of both CTAs allocates the pair's tensor memory
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(&tmem_base_s);
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs: own A rows, own half of the Wt rows) =====
+            const uint32_t lead_full0 = full_bar(0) & kPeerBitMask;
+            uint32_t it = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const int m0 = (tile / n_tiles_n) * (2 * kBM) + (int)rank * kBM;
+                const int n0 = (tile % n_tiles_n) * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
+                    const int s = (int)(it % S);
+                    mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
+                    if (leader) mbar_expect_tx(full_bar(s), 2u * Cfg::kStageBytes);  // both CTAs' bytes land on the leader's barrier
+                    const uint32_t fb = lead_full0 + 8u * s;
+                    uint32_t dst = base + s * Cfg::kStageBytes;
+                    tma_load_2d_pair(dst, &tm_a_hi, fb, kb * kBK, m0);
+                    dst += Cfg::kABytes;
+                    if (SPLIT_A) { tma_load_2d_pair(dst, &tm_a_lo, fb, kb * kBK, m0); dst += Cfg::kABytes; }
+                    tma_load_2d_pair(dst, &tm_w_hi, fb, kb * kBK, n0);
+                    dst += Cfg::kWBytes;
+                    if (SPLIT_W) tma_load_2d_pair(dst, &tm_w_lo, fb, kb * kBK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {  // ===== MMA issuer: the leader drives both SMs' tensor cores =====
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * kBM, BN);
+            uint32_t it = 0, j = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs, ++j) {
+                const uint32_t buf = j & 1u;
+                mbar_wait(tmem_empty_bar(buf), ((j >> 1) & 1u) ^ 1u);  // both CTAs' epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t acc = tmem_acc + buf * BN;
+                for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
+                    const int s = (int)(it % S);
+                    mbar_wait(full_bar(s), (it / S) & 1u);
+                    tc_fence_after();
+                    const uint32_t sa_hi = base + s * Cfg::kStageBytes;
+                    const uint32_t sa_lo = sa_hi + Cfg::kABytes;
+                    const uint32_t sw_hi = sa_hi + Cfg::kABytes * (SPLIT_A ? 2 : 1);
+                    const uint32_t sw_lo = sw_hi + Cfg::kWBytes;
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t koff = (uint32_t)k * kUmmaK * 2;
+                        const uint64_t da_hi = umma_desc_sw128(sa_hi + koff), dw_hi = umma_desc_sw128(sw_hi + koff);
+                        umma_bf16_pair(acc, da_hi, dw_hi, idesc, (kb | k) != 0);
+                        if (SPLIT_A) umma_bf16_pair(acc, umma_desc_sw128(sa_lo + koff), dw_hi, idesc, 1u);
+                        if (SPLIT_W) umma_bf16_pair(acc, da_hi, umma_desc_sw128(sw_lo + koff), idesc, 1u);
+                    }
+                    umma_commit_pair(empty_bar(s));
+                }
+                umma_commit_pair(tmem_full_bar(buf));
+            }
+        }
+    } else {  // ===== epilogue: warps 2..5 of each CTA drain that CTA's own 128 rows =====
+        const int q = warp & 3;
+        const uint32_t lead_tmem_empty0 = tmem_empty_bar(0) & kPeerBitMask;
+        uint32_t j = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs, ++j) {
+            const int m0 = (tile / n_tiles_n) * (2 * kBM) + (int)rank * kBM, n0 = (tile % n_tiles_n) * BN;
+            const uint32_t buf = j & 1u;
+            mbar_wait(tmem_full_bar(buf), (j >> 1) & 1u);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const uint32_t t_row = tmem_acc + buf * BN + ((uint32_t)(q * 32) << 16);
+            const float* bias = a.bias + n0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_row + (uint32_t)c0, r);
+                if (row < a.M) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + jj);
+                        float x0 = fmaxf(__uint_as_float(r[2 * jj]) + bb.x, 0.0f);
+                        float x1 = fmaxf(__uint_as_float(r[2 * jj + 1]) + bb.y, 0.0f);
+                        __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                        hi[jj] = *reinterpret_cast<uint32_t*>(&h);
+                        lo[jj] = pack_bf16x2(x0 - __low2float(h), x1 - __high2float(h));
+                    }
+                    const size_t o = (size_t)row * a.n_total + n0 + c0;
+                    uint4* ph = reinterpret_cast<uint4*>(a.out_hi + o);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+                    if (a.out_lo) {
+                        uint4* pl = reinterpret_cast<uint4*>(a.out_lo + o);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)  // remote arrive on the leader's barrier (local for the leader itself)
+                asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(lead_tmem_empty0 + 8u * buf) : "memory");
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();  // no CTA of the pair may exit (or free tensor memory) while the other still uses its smem / barriers
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(kTmemCols) : "memory");
+}
+
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -396,6 +585,39 @@ static int32_t launch_layer(cudaStream_t s, const void* a_hi, const void* a_lo, 
     }
     const unsigned grid = (unsigned)(la.n_tiles < n_sm ? la.n_tiles : n_sm);  // persistent: one CTA per SM
     kern<<<grid, kMlpThreads, Cfg::kSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, la);
+    return BRL_OK;
+}
+
+template <int BN, bool SPLIT_A, bool SPLIT_W>
+static int32_t launch_layer_pair(cudaStream_t s, const void* a_hi, const void* a_lo, int k_in, const void* w_hi, const void* w_lo,
+                                 int n_valid_rows, const LayerArgs& args) {
+    using Cfg = PairCfg<BN, SPLIT_A, SPLIT_W>;
+    CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+    bool ok = make_map(&ta_hi, a_hi, (uint64_t)args.M, (uint64_t)k_in, (uint64_t)k_in, kBM) &&
+              make_map(&tw_hi, w_hi, (uint64_t)n_valid_rows, (uint64_t)k_in, (uint64_t)k_in, BN / 2);
+    ta_lo = ta_hi;
+    tw_lo = tw_hi;
+    if (ok && SPLIT_A) ok = make_map(&ta_lo, a_lo, (uint64_t)args.M, (uint64_t)k_in, (uint64_t)k_in, kBM);
+    if (ok && SPLIT_W) ok = make_map(&tw_lo, w_lo, (uint64_t)n_valid_rows, (uint64_t)k_in, (uint64_t)k_in, BN / 2);
+    if (!ok) return fail(BRL_E_LAUNCH, "brl_mlp_forward: cuTensorMapEncodeTiled failed");
+    auto kern = k_mlp_layer_pair<BN, SPLIT_A, SPLIT_W>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
+            return fail(BRL_E_LAUNCH, "brl_mlp_forward: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);
+        attr_set = true;
+    }
+    LayerArgs la = args;
+    la.n_tiles_n = n_valid_rows / BN;
+    la.n_tiles = la.n_tiles_n * ((args.M + 2 * kBM - 1) / (2 * kBM));
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    const int n_pairs = la.n_tiles < n_sm / 2 ? la.n_tiles : n_sm / 2;  // persistent: one CTA pair per TPC
+    kern<<<(unsigned)(2 * n_pairs), kMlpThreads, Cfg::kSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, la);
     return BRL_OK;
 }
 
@@ -483,7 +705,14 @@ int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_
             // these 1-CTA tiles): measured faster for the single-product mode and for large batches
             // (scripts/exp_mlp_ab.py); flags bit 26 / 27 force wide / narrow
             const bool wide = (p->flags & (1 << 27)) ? false : ((p->flags & (1 << 26)) != 0 || !split || M >= 32768);
-            if (wide) {
+            // CTA pairs (256 x 256 tiles, cta_group::2) once the batch fills the machine; flags bit 28 / 29 force / forbid
+            const bool pair = (p->flags & (1 << 29)) ? false : ((p->flags & (1 << 28)) != 0 || M >= kPairMinM);
+            if (pair) {
+                if (l == 0) rc = split ? launch_layer_pair<256, false, true>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
+                                       : launch_layer_pair<256, false, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a);
+                else rc = split ? launch_layer_pair<256, true, true>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
+                                : launch_layer_pair<256, false, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a);
+            } else if (wide) {
                 if (l == 0) rc = split ? launch_layer<256, false, true, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
                                        : launch_layer<256, false, false, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a);
                 else rc = split ? launch_layer<256, true, true, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
