@@ -164,6 +164,56 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ---- epilogues: thread = one env row of the accumulator (TMEM lane), shared by all layer kernels ----------
+// hidden layer: + bias, ReLU, split into bf16 hi / lo for the next layer (128-bit stores)
+__device__ __forceinline__ void epilogue_hidden_row(uint32_t t_row, int n_cols, const float* __restrict__ bias, bool row_ok,
+                                                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < n_cols; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + (uint32_t)c0, r);
+        if (row_ok) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + jj);  // warp-uniform
+                float x0 = fmaxf(__uint_as_float(r[2 * jj]) + bb.x, 0.0f);
+                float x1 = fmaxf(__uint_as_float(r[2 * jj + 1]) + bb.y, 0.0f);
+                __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                hi[jj] = *reinterpret_cast<uint32_t*>(&h);
+                lo[jj] = pack_bf16x2(x0 - __low2float(h), x1 - __high2float(h));
+            }
+            uint4* ph = reinterpret_cast<uint4*>(out_hi + c0);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+            if (out_lo) {
+                uint4* pl = reinterpret_cast<uint4*>(out_lo + c0);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+            }
+        }
+    }
+}
+// head tile: columns 0..37 = policy logits, 38 = value (src/models.py:30-32)
+__device__ __forceinline__ void epilogue_head_row(uint32_t t_row, const float* __restrict__ bias, bool row_ok,
+                                                  float* __restrict__ logits_row, float* __restrict__ value_row) {
+    uint32_t r0[32], r1[32];
+    tmem_ld32(t_row, r0);
+    tmem_ld32(t_row + 32u, r1);
+    if (row_ok) {
+        float2* pl = reinterpret_cast<float2*>(logits_row);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj)
+            pl[jj] = make_float2(__uint_as_float(r0[2 * jj]) + __ldg(bias + 2 * jj),
+                                 __uint_as_float(r0[2 * jj + 1]) + __ldg(bias + 2 * jj + 1));
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj)
+            pl[16 + jj] = make_float2(__uint_as_float(r1[2 * jj]) + __ldg(bias + 32 + 2 * jj),
+                                      __uint_as_float(r1[2 * jj + 1]) + __ldg(bias + 32 + 2 * jj + 1));
+        *value_row = __uint_as_float(r1[6]) + __ldg(bias + 38);
+    }
+}
+
 // ---- one layer ------------------------------------------------------------------------------
 struct LayerArgs {
     const float* bias;           // [n_pad]
@@ -282,51 +332,11 @@ k_mlp_layer(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             const int row = m0 + q * 32 + lane;
             const uint32_t t_row = tmem_acc + buf * BN + ((uint32_t)(q * 32) << 16);
             const float* bias = a.bias + n0;
-            if (!HEAD) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(t_row + (uint32_t)c0, r);
-                    if (row < a.M) {
-                        uint32_t hi[16], lo[16];
-#pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + jj);  // warp-uniform
-                            float x0 = fmaxf(__uint_as_float(r[2 * jj]) + bb.x, 0.0f);
-                            float x1 = fmaxf(__uint_as_float(r[2 * jj + 1]) + bb.y, 0.0f);
-                            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-                            hi[jj] = *reinterpret_cast<uint32_t*>(&h);
-                            lo[jj] = pack_bf16x2(x0 - __low2float(h), x1 - __high2float(h));
-                        }
-                        const size_t o = (size_t)row * a.n_total + n0 + c0;
-                        uint4* ph = reinterpret_cast<uint4*>(a.out_hi + o);
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-                        if (a.out_lo) {
-                            uint4* pl = reinterpret_cast<uint4*>(a.out_lo + o);
-#pragma unroll
-                            for (int v = 0; v < 4; ++v) pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
-                        }
-                    }
-                }
-            } else {
-                // head tile: columns 0..37 = policy logits, 38 = value (src/models.py:30-32)
-                uint32_t r0[32], r1[32];
-                tmem_ld32(t_row, r0);
-                tmem_ld32(t_row + 32u, r1);
-                if (row < a.M) {
-                    float2* pl = reinterpret_cast<float2*>(a.logits + (size_t)row * 38);
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj)
-                        pl[jj] = make_float2(__uint_as_float(r0[2 * jj]) + __ldg(bias + 2 * jj),
-                                             __uint_as_float(r0[2 * jj + 1]) + __ldg(bias + 2 * jj + 1));
-#pragma unroll
-                    for (int jj = 0; jj < 3; ++jj)
-                        pl[16 + jj] = make_float2(__uint_as_float(r1[2 * jj]) + __ldg(bias + 32 + 2 * jj),
-                                                  __uint_as_float(r1[2 * jj + 1]) + __ldg(bias + 32 + 2 * jj + 1));
-                    a.value[row] = __uint_as_float(r1[6]) + __ldg(bias + 38);
-                }
-            }
+            if (!HEAD)
+                epilogue_hidden_row(t_row, BN, bias, row < a.M, a.out_hi + (size_t)row * a.n_total + n0,
+                                    a.out_lo ? a.out_lo + (size_t)row * a.n_total + n0 : nullptr);
+            else
+                epilogue_head_row(t_row, bias, row < a.M, a.logits + (size_t)row * 38, a.value + row);
             // all of this warp's tcgen05.ld have completed (wait::ld): hand the accumulator back
             tc_fence_before();
             __syncwarp();
@@ -489,32 +499,8 @@ k_mlp_layer_pair(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             const int row = m0 + q * 32 + lane;
             const uint32_t t_row = tmem_acc + buf * BN + ((uint32_t)(q * 32) << 16);
             const float* bias = a.bias + n0;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(t_row + (uint32_t)c0, r);
-                if (row < a.M) {
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + jj);
-                        float x0 = fmaxf(__uint_as_float(r[2 * jj]) + bb.x, 0.0f);
-                        float x1 = fmaxf(__uint_as_float(r[2 * jj + 1]) + bb.y, 0.0f);
-                        __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-                        hi[jj] = *reinterpret_cast<uint32_t*>(&h);
-                        lo[jj] = pack_bf16x2(x0 - __low2float(h), x1 - __high2float(h));
-                    }
-                    const size_t o = (size_t)row * a.n_total + n0 + c0;
-                    uint4* ph = reinterpret_cast<uint4*>(a.out_hi + o);
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-                    if (a.out_lo) {
-                        uint4* pl = reinterpret_cast<uint4*>(a.out_lo + o);
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
-                    }
-                }
-            }
+            epilogue_hidden_row(t_row, BN, bias, row < a.M, a.out_hi + (size_t)row * a.n_total + n0,
+                                a.out_lo ? a.out_lo + (size_t)row * a.n_total + n0 : nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0)  // remote arrive on the leader's barrier (local for the leader itself)
@@ -523,6 +509,200 @@ k_mlp_layer_pair(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     }
     tc_fence_before();
     cluster_sync_all();  // no CTA of the pair may exit (or free tensor memory) while the other still uses its smem / barriers
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(kTmemCols) : "memory");
+}
+
+// ---- the whole forward as ONE persistent launch on CTA pairs ----------------------------------------
+// Five separate launches lose (i) a wave-quantisation tail per layer (8192 envs = 128 pair tiles on 74 pairs =
+// 1.73 waves) and (ii) the drain / launch / pipeline-fill gap between layers.  Here all 4 x 128 + 32 tiles of the
+// five layers form one list, walked round-robin by the persistent pairs; a tile of layer l + 1 needs only the
+// 128-row block of layer l's output it reads, so the next layer's first tiles fill the previous layer's tail.
+// Dependency tracking: every epilogue warp publishes (st.global ... fence, red.add) into ready[l][128-row block];
+// the TMA producer acquires the count (16 = 4 n-tiles x 4 warps) and crosses into the async proxy before its
+// first A load of the tile.  Tiles are claimed in list order and depend only on earlier tiles, and the grid never
+// exceeds the co-resident cluster count, so the waits cannot deadlock (spins are bounded: a bug traps).
+struct FusedArgs {
+    CUtensorMap a_hi[5], a_lo[5], w_hi[5], w_lo[5];
+    const float* bias[5];
+    __nv_bfloat16* out_hi[4];
+    __nv_bfloat16* out_lo[4];
+    float* logits;
+    float* value;
+    uint32_t* ready;  // [4][2 * nmb], zeroed before the launch
+    int M, nmb, tiles_per_layer, n_tiles;
+};
+
+constexpr int kFusedBN = 256, kFusedTilesN = kHidden / kFusedBN;
+constexpr uint32_t kReadyPerBlock = kFusedTilesN * 4;  // n-tiles x epilogue warps
+
+template <bool SPLIT>
+struct FusedCfg {
+    static constexpr uint32_t kABytes = kBM * kBK * 2, kWBytes = (kFusedBN / 2) * kBK * 2, kWHeadBytes = (kHeadPad / 2) * kBK * 2;
+    static constexpr uint32_t kStageBytes = (kABytes + kWBytes) * (SPLIT ? 2 : 1);
+    static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (int)(kSmemBudget / kStageBytes);
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct FusedTile { int layer, mb, nt; };
+__device__ __forceinline__ FusedTile fused_tile(int t, int tiles_per_layer) {
+    FusedTile f;
+    f.layer = t / tiles_per_layer;
+    if (f.layer < 4) {
+        const int r = t - f.layer * tiles_per_layer;
+        f.mb = r / kFusedTilesN;
+        f.nt = r % kFusedTilesN;
+    } else {
+        f.layer = 4;
+        f.mb = t - 4 * tiles_per_layer;
+        f.nt = 0;
+    }
+    return f;
+}
+
+template <bool SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_mlp_fused(const __grid_constant__ FusedArgs a) {
+    using Cfg = FusedCfg<SPLIT>;
+    constexpr int S = Cfg::kStages;
+    constexpr uint32_t kTmemCols = 2 * kFusedBN;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_addr(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + S * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+    auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
+    auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_tiles = a.n_tiles, tpl = a.tiles_per_layer;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(&tmem_base_s);
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs) =====
+            const uint32_t lead_full0 = full_bar(0) & kPeerBitMask;
+            uint32_t it = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const FusedTile f = fused_tile(tile, tpl);
+                const bool split_a = SPLIT && f.layer > 0;  // the 0/1 observation is exact in bf16
+                const int k_blocks = f.layer == 0 ? (kObsDimM + kBK - 1) / kBK : kHidden / kBK;
+                const uint32_t w_bytes = f.layer == 4 ? Cfg::kWHeadBytes : Cfg::kWBytes;
+                const uint32_t tx = Cfg::kABytes * (split_a ? 2u : 1u) + w_bytes * (SPLIT ? 2u : 1u);
+                const int m0 = f.mb * (2 * kBM) + (int)rank * kBM;
+                const int n0 = f.layer == 4 ? (int)rank * (kHeadPad / 2) : f.nt * kFusedBN + (int)rank * (kFusedBN / 2);
+                const CUtensorMap* ma_hi = &a.a_hi[f.layer];
+                const CUtensorMap* ma_lo = &a.a_lo[f.layer];
+                const CUtensorMap* mw_hi = &a.w_hi[f.layer];
+                const CUtensorMap* mw_lo = &a.w_lo[f.layer];
+                if (f.layer > 0) {  // the previous layer's rows [m0, m0 + 128) must be complete (all 4 n-tiles)
+                    const uint32_t* flag = a.ready + (size_t)(f.layer - 1) * 2 * a.nmb + 2 * f.mb + rank;
+                    uint32_t v = 0;
+                    for (uint32_t spin = 0;; ++spin) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                        if (v >= kReadyPerBlock) break;
+                        if (spin > (1u << 24)) __trap();
+                        __nanosleep(64);
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> async-proxy (TMA) reads
+                }
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = (int)(it % S);
+                    mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
+                    if (leader) mbar_expect_tx(full_bar(s), 2u * tx);
+                    const uint32_t fb = lead_full0 + 8u * s;
+                    const uint32_t sa = base + s * Cfg::kStageBytes;
+                    const uint32_t sw = sa + Cfg::kABytes * (SPLIT ? 2 : 1);
+                    tma_load_2d_pair(sa, ma_hi, fb, kb * kBK, m0);
+                    if (split_a) tma_load_2d_pair(sa + Cfg::kABytes, ma_lo, fb, kb * kBK, m0);
+                    tma_load_2d_pair(sw, mw_hi, fb, kb * kBK, n0);
+                    if (SPLIT) tma_load_2d_pair(sw + Cfg::kWBytes, mw_lo, fb, kb * kBK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {  // ===== MMA issuer =====
+            uint32_t it = 0, j = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs, ++j) {
+                const FusedTile f = fused_tile(tile, tpl);
+                const bool split_a = SPLIT && f.layer > 0;
+                const int k_blocks = f.layer == 0 ? (kObsDimM + kBK - 1) / kBK : kHidden / kBK;
+                const uint32_t idesc = f.layer == 4 ? umma_idesc_bf16(2 * kBM, kHeadPad) : umma_idesc_bf16(2 * kBM, kFusedBN);
+                const uint32_t buf = j & 1u;
+                mbar_wait(tmem_empty_bar(buf), ((j >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t acc = tmem_acc + buf * kFusedBN;
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = (int)(it % S);
+                    mbar_wait(full_bar(s), (it / S) & 1u);
+                    tc_fence_after();
+                    const uint32_t sa_hi = base + s * Cfg::kStageBytes;
+                    const uint32_t sa_lo = sa_hi + Cfg::kABytes;
+                    const uint32_t sw_hi = sa_hi + Cfg::kABytes * (SPLIT ? 2 : 1);
+                    const uint32_t sw_lo = sw_hi + Cfg::kWBytes;
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t koff = (uint32_t)k * kUmmaK * 2;
+                        const uint64_t da_hi = umma_desc_sw128(sa_hi + koff), dw_hi = umma_desc_sw128(sw_hi + koff);
+                        umma_bf16_pair(acc, da_hi, dw_hi, idesc, (kb | k) != 0);
+                        if (split_a) umma_bf16_pair(acc, umma_desc_sw128(sa_lo + koff), dw_hi, idesc, 1u);
+                        if (SPLIT) umma_bf16_pair(acc, da_hi, umma_desc_sw128(sw_lo + koff), idesc, 1u);
+                    }
+                    umma_commit_pair(empty_bar(s));
+                }
+                umma_commit_pair(tmem_full_bar(buf));
+            }
+        }
+    } else {  // ===== epilogue =====
+        const int q = warp & 3;
+        const uint32_t lead_tmem_empty0 = tmem_empty_bar(0) & kPeerBitMask;
+        uint32_t j = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs, ++j) {
+            const FusedTile f = fused_tile(tile, tpl);
+            const int m0 = f.mb * (2 * kBM) + (int)rank * kBM;
+            const uint32_t buf = j & 1u;
+            mbar_wait(tmem_full_bar(buf), (j >> 1) & 1u);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const uint32_t t_row = tmem_acc + buf * kFusedBN + ((uint32_t)(q * 32) << 16);
+            if (f.layer < 4) {
+                const int n0 = f.nt * kFusedBN;
+                __nv_bfloat16* oh = a.out_hi[f.layer];
+                __nv_bfloat16* ol = a.out_lo[f.layer];
+                epilogue_hidden_row(t_row, kFusedBN, a.bias[f.layer] + n0, row < a.M, oh + (size_t)row * kHidden + n0,
+                                    ol ? ol + (size_t)row * kHidden + n0 : nullptr);
+            } else {
+                epilogue_head_row(t_row, a.bias[4], row < a.M, a.logits + (size_t)row * 38, a.value + row);
+            }
+            tc_fence_before();
+            __threadfence();  // this lane's activation stores are visible GPU-wide before the count below
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(lead_tmem_empty0 + 8u * buf) : "memory");
+                if (f.layer < 4) {
+                    __threadfence();
+                    atomicAdd(a.ready + (size_t)f.layer * 2 * a.nmb + 2 * f.mb + rank, 1u);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(kTmemCols) : "memory");
 }
 
@@ -621,6 +801,71 @@ static int32_t launch_layer_pair(cudaStream_t s, const void* a_hi, const void* a
     return BRL_OK;
 }
 
+// counters of the fused forward live behind the four activation buffers of the scratch
+static inline size_t fused_ready_bytes(int64_t n_envs) { return (size_t)(4 * 2 * ((n_envs + 2 * kBM - 1) / (2 * kBM))) * sizeof(uint32_t); }
+
+template <bool SPLIT>
+static int32_t launch_fused(cudaStream_t s, const void* obs, const unsigned char* blob, const MlpLayout& L, __nv_bfloat16* const buf_hi[2],
+                            __nv_bfloat16* const buf_lo[2], uint32_t* ready, float* logits, float* value, int M) {
+    using Cfg = FusedCfg<SPLIT>;
+    FusedArgs fa{};
+    bool ok = true;
+    for (int l = 0; l < 5 && ok; ++l) {
+        const void* a_hi = l == 0 ? obs : (const void*)buf_hi[(l - 1) & 1];
+        const void* a_lo = l == 0 ? obs : (const void*)buf_lo[(l - 1) & 1];
+        const uint32_t w_box = l == 4 ? kHeadPad / 2 : kFusedBN / 2;
+        ok = make_map(&fa.a_hi[l], a_hi, (uint64_t)M, (uint64_t)L.k_in[l], (uint64_t)L.k_in[l], kBM) &&
+             make_map(&fa.w_hi[l], blob + L.w_hi[l], (uint64_t)L.n_out[l], (uint64_t)L.k_in[l], (uint64_t)L.k_in[l], w_box);
+        fa.a_lo[l] = fa.a_hi[l];
+        fa.w_lo[l] = fa.w_hi[l];
+        if (ok && SPLIT && l > 0) ok = make_map(&fa.a_lo[l], a_lo, (uint64_t)M, (uint64_t)L.k_in[l], (uint64_t)L.k_in[l], kBM);
+        if (ok && SPLIT) ok = make_map(&fa.w_lo[l], blob + L.w_lo[l], (uint64_t)L.n_out[l], (uint64_t)L.k_in[l], (uint64_t)L.k_in[l], w_box);
+        fa.bias[l] = reinterpret_cast<const float*>(blob + L.bias[l]);
+        if (l < 4) {
+            fa.out_hi[l] = buf_hi[l & 1];
+            fa.out_lo[l] = SPLIT ? buf_lo[l & 1] : nullptr;
+        }
+    }
+    if (!ok) return fail(BRL_E_LAUNCH, "brl_mlp_forward: cuTensorMapEncodeTiled failed");
+    fa.logits = logits;
+    fa.value = value;
+    fa.ready = ready;
+    fa.M = M;
+    fa.nmb = (M + 2 * kBM - 1) / (2 * kBM);
+    fa.tiles_per_layer = fa.nmb * kFusedTilesN;
+    fa.n_tiles = 4 * fa.tiles_per_layer + fa.nmb;
+    auto kern = k_mlp_fused<SPLIT>;
+    static int max_pairs = 0;  // co-resident CTA pairs: the dependency waits need every launched pair to be running
+    if (max_pairs == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
+            return fail(BRL_E_LAUNCH, "brl_mlp_forward: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);
+        int dev = 0, n_sm = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(n_sm & ~1));
+        cfg.blockDim = dim3(kMlpThreads);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2;
+        at.val.clusterDim.y = 1;
+        at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) != cudaSuccess || n_clusters <= 0) {
+            cudaGetLastError();
+            n_clusters = n_sm / 2;
+        }
+        max_pairs = n_clusters < n_sm / 2 ? n_clusters : n_sm / 2;
+    }
+    if (cudaMemsetAsync(ready, 0, fused_ready_bytes(M), s) != cudaSuccess) return check_launch("brl_mlp_forward (memset)");
+    const int n_pairs = fa.n_tiles < max_pairs ? fa.n_tiles : max_pairs;
+    kern<<<(unsigned)(2 * n_pairs), kMlpThreads, Cfg::kSmemBytes, s>>>(fa);
+    return BRL_OK;
+}
+
 }  // namespace brl
 
 using namespace brl;
@@ -628,7 +873,9 @@ using namespace brl;
 extern "C" {
 
 int64_t brl_mlp_packed_bytes(void) { return (int64_t)mlp_layout().total; }
-int64_t brl_mlp_scratch_bytes(int64_t n_envs) { return n_envs * (int64_t)kHidden * 2 * 4; }
+int64_t brl_mlp_scratch_bytes(int64_t n_envs) {  // 4 activation buffers bf16[n, 1024] + the fused forward's tile counters
+    return n_envs * (int64_t)kHidden * 2 * 4 + (int64_t)((fused_ready_bytes(n_envs) + 255) & ~(size_t)255);
+}
 
 int32_t brl_mlp_pack(brl_stream_t stream, void** b, const void* opaque, size_t len) {
     int32_t rc;
@@ -688,6 +935,18 @@ int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_
     __nv_bfloat16* buf_hi[2] = {scratch, scratch + act};
     __nv_bfloat16* buf_lo[2] = {scratch + 2 * act, scratch + 3 * act};
     cudaStream_t s = (cudaStream_t)stream;
+    // one persistent launch for the whole net once the batch fills the machine; flags bit 30 forces it,
+    // bit 28 forces per-layer CTA-pair launches, bit 29 forbids both (1-CTA tiles)
+    const bool fused = (p->flags & ((1 << 29) | (1 << 28))) ? false : ((p->flags & (1 << 30)) != 0 || M >= kPairMinM);
+    if (fused) {
+        uint32_t* ready = reinterpret_cast<uint32_t*>(scratch + 4 * act);
+        float* lg = static_cast<float*>(b[3]);
+        float* vl = static_cast<float*>(b[4]);
+        rc = split ? launch_fused<true>(s, b[0], blob, L, buf_hi, buf_lo, ready, lg, vl, M)
+                   : launch_fused<false>(s, b[0], blob, L, buf_hi, buf_lo, ready, lg, vl, M);
+        if (rc != BRL_OK) return rc;
+        return check_launch("brl_mlp_forward");
+    }
     const void* in_hi = b[0];
     const void* in_lo = nullptr;
     for (int l = 0; l < 5; ++l) {

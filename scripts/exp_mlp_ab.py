@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from brl_b200 import ops
 from brl_b200.models import LAYERS, init_params
 dev = "cuda:0"
-NO_PAIR, PAIR, WIDE, NARROW = 1 << 29, 1 << 28, 1 << 26, 1 << 27
+NO_PAIR, PAIR, WIDE, NARROW, FUSED = 1 << 29, 1 << 28, 1 << 26, 1 << 27, 1 << 30
 sizes = [int(a) for a in sys.argv[1:]] or [8192, 8192 + 100, 300, 65536]
 for n in sizes:
     params = init_params(1, dev)
@@ -16,9 +16,9 @@ for n in sizes:
     lg, v = torch.empty((n, 38), device=dev), torch.empty(n, device=dev)
     ref = ref_bf = None
     res = {}
-    variants = (("bn128 x3", {"tune": NO_PAIR | NARROW}), ("bn256 x3", {"tune": NO_PAIR | WIDE}), ("pair256 x3", {"tune": PAIR}),
+    variants = (("bn128 x3", {"tune": NO_PAIR | NARROW}), ("bn256 x3", {"tune": NO_PAIR | WIDE}), ("pair256 x3", {"tune": PAIR}), ("fused x3", {"tune": FUSED}),
                 ("bn128 bf16", {"single_bf16": True, "tune": NO_PAIR | NARROW}), ("bn256 bf16", {"single_bf16": True, "tune": NO_PAIR | WIDE}),
-                ("pair256 bf16", {"single_bf16": True, "tune": PAIR}))
+                ("pair256 bf16", {"single_bf16": True, "tune": PAIR}), ("fused bf16", {"single_bf16": True, "tune": FUSED}))
     for rnd in range(5):
         for name, kw in variants:
             lg.fill_(float("nan")); v.fill_(float("nan"))
