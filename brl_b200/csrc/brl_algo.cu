@@ -160,6 +160,15 @@ __global__ void __launch_bounds__(256) k_gather_reward(const float* __restrict__
     out[i] = rewards[4 * i + (actor[i] & 3)] / scale;
 }
 
+
+int32_t launch_categorical(cudaStream_t stream, const float* logits, const unsigned char* mask, int32_t* action, float* log_prob,
+                           int64_t n, int sample, uint64_t seed, int64_t env_offset, uint32_t step) {
+    unsigned grid = (unsigned)((n + 3) / 4);  // one warp per env row
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    k_categorical<<<grid, 128, 0, stream>>>(logits, mask, action, log_prob, n, sample, seed, env_offset, step);
+    return check_launch("brl_categorical");
+}
+
 }  // namespace brl
 
 using namespace brl;
@@ -191,13 +200,9 @@ int32_t brl_categorical(brl_stream_t stream, void** b, const void* opaque, size_
     if (!p) return rc;
     if (b[0] == nullptr) return fail(BRL_E_BUFFER, "brl_categorical: buffer 'logits' is NULL");
     if (p->n_envs == 0) return BRL_OK;
-    int64_t warps = p->n_envs;
-    unsigned grid = (unsigned)((warps + 3) / 4);
-    if (grid > 148u * 16u) grid = 148u * 16u;
-    k_categorical<<<grid, 128, 0, (cudaStream_t)stream>>>(
-        static_cast<const float*>(b[0]), static_cast<const uint8_t*>(b[1]), static_cast<int32_t*>(b[2]),
-        static_cast<float*>(b[3]), p->n_envs, (p->flags & BRL_F_SAMPLE) ? 1 : 0, p->seed, p->env_offset, p->step);
-    return check_launch("brl_categorical");
+    return launch_categorical((cudaStream_t)stream, static_cast<const float*>(b[0]), static_cast<const uint8_t*>(b[1]),
+                              static_cast<int32_t*>(b[2]), static_cast<float*>(b[3]), p->n_envs,
+                              (p->flags & BRL_F_SAMPLE) ? 1 : 0, p->seed, p->env_offset, p->step);
 }
 
 int32_t brl_imp_reward(brl_stream_t stream, void** b, const void* opaque, size_t len) {

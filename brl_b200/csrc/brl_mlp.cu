@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "env_device.cuh"
 
 namespace brl {
 
@@ -212,6 +213,83 @@ __device__ __forceinline__ void epilogue_head_row(uint32_t t_row, const float* _
                                       __uint_as_float(r1[2 * jj + 1]) + __ldg(bias + 32 + 2 * jj + 1));
         *value_row = __uint_as_float(r1[6]) + __ldg(bias + 38);
     }
+}
+
+// head tile with the masked categorical of src/roll_out.py:27-30,79-81 fused in: the thread that owns an env row
+// holds its 38 logits in registers, so where(mask, logits, -inf), the Gumbel-argmax sample (same Philox stream as
+// brl_categorical: counter (env, GUM0 + a / 4, step), key = seed) or the first-argmax mode, and
+// log_softmax(masked)[action] cost no extra launch and no logits round trip.
+struct ActArgs {
+    const uint8_t* mask;   // [n, 38] or NULL (unmasked)
+    int32_t* action;       // [n]; NULL = no categorical fused (plain forward)
+    float* log_prob;       // [n] or NULL
+    uint64_t seed;
+    int64_t env_offset;
+    uint32_t step;
+    int sample;
+};
+
+__device__ __forceinline__ void epilogue_head_act_row(uint32_t t_row, const float* __restrict__ bias, bool row_ok, int64_t row,
+                                                      float* __restrict__ logits, float* __restrict__ value, const ActArgs& act) {
+    uint32_t r0[32], r1[32];
+    tmem_ld32(t_row, r0);
+    tmem_ld32(t_row + 32u, r1);
+    if (!row_ok) return;
+    float l[40];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) l[k] = __uint_as_float(r0[k]) + __ldg(bias + k);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) l[32 + k] = __uint_as_float(r1[k]) + __ldg(bias + 32 + k);
+    l[39] = 0.0f;
+    if (logits) {
+        float2* pl = reinterpret_cast<float2*>(logits + row * 38);
+#pragma unroll
+        for (int jj = 0; jj < 19; ++jj) pl[jj] = make_float2(l[2 * jj], l[2 * jj + 1]);
+    }
+    if (value) value[row] = l[38];
+    if (act.action == nullptr) return;
+    uint64_t legal = ~0ull;
+    if (act.mask) {
+        const uint16_t* pm = reinterpret_cast<const uint16_t*>(act.mask + row * 38);  // 38 * row is even
+        legal = 0;
+#pragma unroll
+        for (int jj = 0; jj < 19; ++jj) {
+            const uint32_t m2 = pm[jj];
+            legal |= (uint64_t)((m2 & 0xFFu) != 0) << (2 * jj) | (uint64_t)((m2 >> 8) != 0) << (2 * jj + 1);
+        }
+    }
+    const uint64_t g = (uint64_t)(act.env_offset + row);
+    float best = -INFINITY, mx = -INFINITY, la = 0.0f;
+    int best_a = kNumActions;
+#pragma unroll
+    for (int grp = 0; grp < 10; ++grp) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (act.sample) {
+            const uint4 rr = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), kTagGum + (uint32_t)grp, act.step),
+                                        make_uint2((uint32_t)act.seed, (uint32_t)(act.seed >> 32)));
+            w[0] = rr.x; w[1] = rr.y; w[2] = rr.z; w[3] = rr.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int aidx = 4 * grp + e;
+            if (aidx < kNumActions && ((legal >> aidx) & 1ull)) {
+                float v = l[aidx];
+                if (act.sample) {
+                    const float u = ((float)(w[e] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                    v += -logf(-logf(u));
+                }
+                if (v > best) { best = v; best_a = aidx; la = l[aidx]; }  // ascending: ties keep the lower index
+                mx = fmaxf(mx, l[aidx]);
+            }
+        }
+    }
+    float se = 0.0f;
+#pragma unroll
+    for (int aidx = 0; aidx < kNumActions; ++aidx)
+        if ((legal >> aidx) & 1ull) se += expf(l[aidx] - mx);
+    if (best_a >= kNumActions) { best_a = 0; la = l[0]; }  // no legal action: cannot happen for a valid mask
+    act.action[row] = best_a;
+    if (act.log_prob) act.log_prob[row] = la - mx - logf(se);
 }
 
 // ---- one layer ------------------------------------------------------------------------------
@@ -530,6 +608,7 @@ struct FusedArgs {
     float* value;
     uint32_t* ready;  // [4][2 * nmb], zeroed before the launch
     int M, nmb, tiles_per_layer, n_tiles;
+    ActArgs act;
 };
 
 constexpr int kFusedBN = 256, kFusedTilesN = kHidden / kFusedBN;
@@ -687,7 +766,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_ml
                 epilogue_hidden_row(t_row, kFusedBN, a.bias[f.layer] + n0, row < a.M, oh + (size_t)row * kHidden + n0,
                                     ol ? ol + (size_t)row * kHidden + n0 : nullptr);
             } else {
-                epilogue_head_row(t_row, a.bias[4], row < a.M, a.logits + (size_t)row * 38, a.value + row);
+                epilogue_head_act_row(t_row, a.bias[4], row < a.M, row, a.logits, a.value, a.act);
             }
             tc_fence_before();
             __threadfence();  // this lane's activation stores are visible GPU-wide before the count below
@@ -806,7 +885,7 @@ static inline size_t fused_ready_bytes(int64_t n_envs) { return (size_t)(4 * 2 *
 
 template <bool SPLIT>
 static int32_t launch_fused(cudaStream_t s, const void* obs, const unsigned char* blob, const MlpLayout& L, __nv_bfloat16* const buf_hi[2],
-                            __nv_bfloat16* const buf_lo[2], uint32_t* ready, float* logits, float* value, int M) {
+                            __nv_bfloat16* const buf_lo[2], uint32_t* ready, float* logits, float* value, int M, const ActArgs& act) {
     using Cfg = FusedCfg<SPLIT>;
     FusedArgs fa{};
     bool ok = true;
@@ -829,6 +908,7 @@ static int32_t launch_fused(cudaStream_t s, const void* obs, const unsigned char
     if (!ok) return fail(BRL_E_LAUNCH, "brl_mlp_forward: cuTensorMapEncodeTiled failed");
     fa.logits = logits;
     fa.value = value;
+    fa.act = act;
     fa.ready = ready;
     fa.M = M;
     fa.nmb = (M + 2 * kBM - 1) / (2 * kBM);
@@ -914,40 +994,32 @@ int32_t brl_obs_to_bf16(brl_stream_t stream, void** b, const void* opaque, size_
     return check_launch("brl_obs_to_bf16");
 }
 
-int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_t len) {
-    int32_t rc;
-    const BrlParams* p = get_params(opaque, len, &rc);
-    if (!p) return rc;
-    BRL_REQUIRE(b[0], "obs_bf16");
-    BRL_REQUIRE(b[1], "packed");
-    BRL_REQUIRE(b[2], "scratch");
-    BRL_REQUIRE(b[3], "logits");
-    BRL_REQUIRE(b[4], "value");
-    if (p->n_envs == 0) return BRL_OK;
-    if (p->n_envs > (int64_t)1 << 30) return fail(BRL_E_OPAQUE, "brl_mlp_forward: n_envs too large");
-    if (encode_fn() == nullptr) return fail(BRL_E_LAUNCH, "brl_mlp_forward: cuTensorMapEncodeTiled not available from the driver");
+// forward (+ optional fused categorical) shared by brl_mlp_forward and brl_policy_act
+static int32_t mlp_forward_impl(const char* who, cudaStream_t s, const BrlParams* p, const void* obs, const unsigned char* blob,
+                                __nv_bfloat16* scratch, float* logits, float* value, const ActArgs& act) {
+    int32_t rc = BRL_OK;
+    if (p->n_envs > (int64_t)1 << 30) return fail(BRL_E_OPAQUE, "%s: n_envs too large", who);
+    if (encode_fn() == nullptr) return fail(BRL_E_LAUNCH, "%s: cuTensorMapEncodeTiled not available from the driver", who);
     const bool split = !(p->flags & BRL_F_MLP_BF16);
     const int M = (int)p->n_envs;
     const MlpLayout L = mlp_layout();
-    const unsigned char* blob = static_cast<const unsigned char*>(b[1]);
-    __nv_bfloat16* scratch = static_cast<__nv_bfloat16*>(b[2]);
-    const size_t act = (size_t)M * kHidden;
-    __nv_bfloat16* buf_hi[2] = {scratch, scratch + act};
-    __nv_bfloat16* buf_lo[2] = {scratch + 2 * act, scratch + 3 * act};
-    cudaStream_t s = (cudaStream_t)stream;
+    const size_t act_elems = (size_t)M * kHidden;
+    __nv_bfloat16* buf_hi[2] = {scratch, scratch + act_elems};
+    __nv_bfloat16* buf_lo[2] = {scratch + 2 * act_elems, scratch + 3 * act_elems};
     // one persistent launch for the whole net once the batch fills the machine; flags bit 30 forces it,
     // bit 28 forces per-layer CTA-pair launches, bit 29 forbids both (1-CTA tiles)
     const bool fused = (p->flags & ((1 << 29) | (1 << 28))) ? false : ((p->flags & (1 << 30)) != 0 || M >= kPairMinM);
     if (fused) {
-        uint32_t* ready = reinterpret_cast<uint32_t*>(scratch + 4 * act);
-        float* lg = static_cast<float*>(b[3]);
-        float* vl = static_cast<float*>(b[4]);
-        rc = split ? launch_fused<true>(s, b[0], blob, L, buf_hi, buf_lo, ready, lg, vl, M)
-                   : launch_fused<false>(s, b[0], blob, L, buf_hi, buf_lo, ready, lg, vl, M);
+        uint32_t* ready = reinterpret_cast<uint32_t*>(scratch + 4 * act_elems);
+        rc = split ? launch_fused<true>(s, obs, blob, L, buf_hi, buf_lo, ready, logits, value, M, act)
+                   : launch_fused<false>(s, obs, blob, L, buf_hi, buf_lo, ready, logits, value, M, act);
         if (rc != BRL_OK) return rc;
-        return check_launch("brl_mlp_forward");
+        return check_launch(who);
     }
-    const void* in_hi = b[0];
+    // per-layer launches.  The head reads buffer 1, so buffer 0 is free to hold logits / value the caller did not ask for.
+    float* lg = logits ? logits : reinterpret_cast<float*>(buf_hi[0]);
+    float* vl = value ? value : reinterpret_cast<float*>(buf_lo[0]);
+    const void* in_hi = obs;
     const void* in_lo = nullptr;
     for (int l = 0; l < 5; ++l) {
         LayerArgs a{};
@@ -964,8 +1036,7 @@ int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_
             // these 1-CTA tiles): measured faster for the single-product mode and for large batches
             // (scripts/exp_mlp_ab.py); flags bit 26 / 27 force wide / narrow
             const bool wide = (p->flags & (1 << 27)) ? false : ((p->flags & (1 << 26)) != 0 || !split || M >= 32768);
-            // CTA pairs (256 x 256 tiles, cta_group::2) once the batch fills the machine; flags bit 28 / 29 force / forbid
-            const bool pair = (p->flags & (1 << 29)) ? false : ((p->flags & (1 << 28)) != 0 || M >= kPairMinM);
+            const bool pair = (p->flags & (1 << 28)) != 0;
             if (pair) {
                 if (l == 0) rc = split ? launch_layer_pair<256, false, true>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a)
                                        : launch_layer_pair<256, false, false>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHidden, a);
@@ -983,14 +1054,54 @@ int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_
             in_hi = a.out_hi;
             in_lo = a.out_lo;
         } else {
-            a.logits = static_cast<float*>(b[3]);
-            a.value = static_cast<float*>(b[4]);
+            a.logits = lg;
+            a.value = vl;
             rc = split ? launch_layer<kHeadPad, true, true, true>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHeadPad, a)
                        : launch_layer<kHeadPad, false, false, true>(s, in_hi, in_lo, L.k_in[l], w_hi, w_lo, kHeadPad, a);
         }
         if (rc != BRL_OK) return rc;
     }
-    return check_launch("brl_mlp_forward");
+    rc = check_launch(who);
+    if (rc != BRL_OK || act.action == nullptr) return rc;
+    return launch_categorical(s, lg, act.mask, act.action, act.log_prob, M, act.sample, act.seed, act.env_offset, act.step);
+}
+
+int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "obs_bf16");
+    BRL_REQUIRE(b[1], "packed");
+    BRL_REQUIRE(b[2], "scratch");
+    BRL_REQUIRE(b[3], "logits");
+    BRL_REQUIRE(b[4], "value");
+    if (p->n_envs == 0) return BRL_OK;
+    return mlp_forward_impl("brl_mlp_forward", (cudaStream_t)stream, p, b[0], static_cast<const unsigned char*>(b[1]),
+                            static_cast<__nv_bfloat16*>(b[2]), static_cast<float*>(b[3]), static_cast<float*>(b[4]), ActArgs{});
+}
+
+int32_t brl_policy_act(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "obs_bf16");
+    BRL_REQUIRE(b[1], "packed");
+    BRL_REQUIRE(b[2], "scratch");
+    BRL_REQUIRE(b[4], "action");
+    for (int k : {3, 5, 6, 7})
+        if (b[k] != nullptr && (reinterpret_cast<uintptr_t>(b[k]) & (k == 3 ? 1u : 7u)) != 0)
+            return fail(BRL_E_BUFFER, "brl_policy_act: buffer %d is misaligned", k);
+    if (p->n_envs == 0) return BRL_OK;
+    ActArgs act{};
+    act.mask = static_cast<const uint8_t*>(b[3]);
+    act.action = static_cast<int32_t*>(b[4]);
+    act.log_prob = static_cast<float*>(b[5]);
+    act.seed = p->seed;
+    act.env_offset = p->env_offset;
+    act.step = p->step;
+    act.sample = (p->flags & BRL_F_SAMPLE) ? 1 : 0;
+    return mlp_forward_impl("brl_policy_act", (cudaStream_t)stream, p, b[0], static_cast<const unsigned char*>(b[1]),
+                            static_cast<__nv_bfloat16*>(b[2]), static_cast<float*>(b[7]), static_cast<float*>(b[6]), act);
 }
 
 }  // extern "C"

@@ -38,6 +38,10 @@ inline const BrlParams* get_params(const void* opaque, size_t opaque_len, int32_
     return p;
 }
 
+// masked categorical over f32 logits[n,38] (brl_algo.cu); shared by brl_categorical and the unfused brl_policy_act path
+int32_t launch_categorical(cudaStream_t stream, const float* logits, const unsigned char* mask, int32_t* action, float* log_prob,
+                           int64_t n, int sample, uint64_t seed, int64_t env_offset, uint32_t step);
+
 #define BRL_REQUIRE(ptr, name)                                                            \
     do {                                                                                  \
         if ((ptr) == nullptr) return brl::fail(BRL_E_BUFFER, "%s: buffer '%s' is NULL", __func__, name); \

@@ -62,6 +62,7 @@ BRL_LEGACY_CUSTOM_CALL(brl_gather_reward)
 BRL_LEGACY_CUSTOM_CALL(brl_mlp_pack)
 BRL_LEGACY_CUSTOM_CALL(brl_obs_to_bf16)
 BRL_LEGACY_CUSTOM_CALL(brl_mlp_forward)
+BRL_LEGACY_CUSTOM_CALL(brl_policy_act)
 BRL_LEGACY_CUSTOM_CALL(brl_ppo_loss)
 BRL_LEGACY_CUSTOM_CALL(brl_adam_clip)
 BRL_LEGACY_CUSTOM_CALL(brl_gather_rows)

@@ -73,7 +73,7 @@ class ForwardPass:
     def __init__(self, activation: str = "relu", model_type: str = "DeepMind", precision: str = None):
         if model_type != "DeepMind":
             raise NotImplementedError("only the DeepMind 4x1024 net is on the hot path (SURVEY 8a a16)")
-        self.act = torch.relu if activation == "relu" else torch.tanh
+        self._activation = torch.relu if activation == "relu" else torch.tanh
         if precision is None:  # the tensor-core kernels fuse ReLU (all five bundled models are ReLU nets)
             precision = "tc" if activation == "relu" else "fp32"
         if precision not in ("tc", "tc-bf16", "fp32", "tf32", "bf16"):
@@ -82,6 +82,11 @@ class ForwardPass:
         if precision in ("tc", "tc-bf16") and activation != "relu":
             raise NotImplementedError("the tensor-core forward fuses ReLU; use a library precision for tanh nets")
         self._scratch = None
+
+    @property
+    def input_dtype(self):
+        """dtype the forward consumes without a cast (env kernels can write the 0/1 observation in it directly)"""
+        return torch.bfloat16 if self.precision in ("tc", "tc-bf16") else torch.float32
 
     def _packed(self, params):
         """bf16 hi/lo blob of `params`, re-packed when any tensor was replaced or updated in place."""
@@ -97,13 +102,33 @@ class ForwardPass:
     def _apply_tc(self, params, x: torch.Tensor):
         n = x.shape[0]
         xb = ops.obs_to_bf16(x.contiguous())
-        if self._scratch is None or self._scratch.numel() < ops._lib.load().brl_mlp_scratch_bytes(n) or \
-                self._scratch.device != x.device:
-            self._scratch = ops.mlp_scratch(n, x.device)
+        self._ensure_scratch(n, x.device)
         logits = torch.empty((n, 38), dtype=torch.float32, device=x.device)
         value = torch.empty(n, dtype=torch.float32, device=x.device)
         ops.mlp_forward(xb, self._packed(params), self._scratch, logits, value, single_bf16=self.precision == "tc-bf16")
         return logits, value
+
+    def act(self, params, x: torch.Tensor, mask, action: torch.Tensor, log_prob=None, value=None, *, sample: bool,
+            seed: int, env_offset: int = 0):
+        """`logits, value = apply(params, x)` followed by the masked categorical of src/roll_out.py:77-81 /
+        src/utils.py:83-88, written into caller buffers.  The tensor-core precisions do it in one call
+        (`brl_policy_act`: from 4096 envs on a single persistent launch with the sampler in the head epilogue)."""
+        if self.precision in ("tc", "tc-bf16"):
+            n = x.shape[0]
+            xb = ops.obs_to_bf16(x.contiguous())
+            self._ensure_scratch(n, x.device)
+            ops.policy_act(xb, self._packed(params), self._scratch, mask, action, log_prob, value, sample=sample, seed=seed,
+                           env_offset=env_offset, single_bf16=self.precision == "tc-bf16")
+            return
+        logits, v = self.apply(params, x)
+        ops.categorical(logits.contiguous(), mask, action, log_prob, sample=sample, seed=seed, env_offset=env_offset)
+        if value is not None:
+            value.copy_(v)
+
+    def _ensure_scratch(self, n, device):
+        if self._scratch is None or self._scratch.numel() < ops._lib.load().brl_mlp_scratch_bytes(n) or \
+                self._scratch.device != device:
+            self._scratch = ops.mlp_scratch(n, device)
 
     def apply(self, params, x: torch.Tensor):
         if self.precision in ("tc", "tc-bf16"):
@@ -114,7 +139,7 @@ class ForwardPass:
             dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
             h = x.to(dt)
             for name in LAYERS[:4]:
-                h = self.act(torch.addmm(params[name]["b"].to(dt), h, params[name]["w"].to(dt)))
+                h = self._activation(torch.addmm(params[name]["b"].to(dt), h, params[name]["w"].to(dt)))
             logits = torch.addmm(params[LAYERS[4]]["b"].to(dt), h, params[LAYERS[4]]["w"].to(dt)).float()
             value = torch.addmm(params[LAYERS[5]]["b"].to(dt), h, params[LAYERS[5]]["w"].to(dt)).float().squeeze(-1)
         finally:

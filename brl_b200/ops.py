@@ -236,6 +236,23 @@ def mlp_forward(obs_bf16: torch.Tensor, packed: torch.Tensor, scratch: torch.Ten
           _params(n, flags=(F_MLP_BF16 if single_bf16 else 0) | tune))
 
 
+def policy_act(obs_bf16: torch.Tensor, packed: torch.Tensor, scratch: torch.Tensor, mask: Optional[torch.Tensor],
+               action: torch.Tensor, log_prob: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None,
+               logits: Optional[torch.Tensor] = None, *, sample: bool = False, seed: int = 0, env_offset: int = 0,
+               step_index: int = 0, single_bf16: bool = False, tune: int = 0) -> None:
+    """forward.apply + masked Categorical sample / mode (+ log_prob, value, logits on request) in one call
+    (src/roll_out.py:73-81); same noise stream as `categorical`, so it equals mlp_forward followed by categorical."""
+    n = obs_bf16.shape[0]
+    if obs_bf16.dtype != torch.bfloat16:
+        raise _lib.BrlError("policy_act needs a bf16 observation (ops.obs_to_bf16)")
+    if scratch.numel() < _lib.load().brl_mlp_scratch_bytes(n):
+        raise _lib.BrlError("policy_act: scratch too small (ops.mlp_scratch)")
+    _call("brl_policy_act", [_ptr(obs_bf16), _ptr(packed), _ptr(scratch), _ptr(mask), _ptr(action), _ptr(log_prob), _ptr(value),
+                             _ptr(logits)],
+          _params(n, flags=(F_MLP_BF16 if single_bf16 else 0) | (F_SAMPLE if sample else 0) | tune, seed=seed,
+                  env_offset=env_offset, step=step_index))
+
+
 def ppo_loss(logits, value, index, mask, action, old_log_prob, old_value, adv, targets, dlogits, dvalue, stats, scratch,
              *, clip_eps, ent_coef, vf_coef, illegal_l2_coef=0.0, value_clipping=True, reward_scaling=False,
              masked_policy=True) -> None:

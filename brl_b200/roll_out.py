@@ -64,11 +64,10 @@ def make_roll_out(config, env, actor_forward_pass, opp_forward_pass):
         cur.observation, cur._mask_u8 = traj.obs[0], traj.legal_action_mask[0]
         cur.current_player.copy_(actor)
         for t in range(T):
-            logits, value = actor_forward_pass.apply(params, traj.obs[t])                 # :73-76
             rng, _rng = brandom.split(rng)
-            ops.categorical(logits.contiguous(), traj.legal_action_mask[t] if masked else None, traj.action[t],
-                            traj.log_prob[t], sample=True, seed=_rng, env_offset=getattr(env, "env_offset", 0))  # :77-81
-            traj.value[t].copy_(value)
+            actor_forward_pass.act(params, traj.obs[t], traj.legal_action_mask[t] if masked else None, traj.action[t],
+                                   traj.log_prob[t], traj.value[t], sample=True, seed=_rng,
+                                   env_offset=getattr(env, "env_offset", 0))               # :73-81
             actor.copy_(cur.current_player)
             rng, _rng = brandom.split(rng)
             nxt = State(env, packed, out)

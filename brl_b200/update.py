@@ -53,7 +53,7 @@ def make_update_step(config, actor_forward_pass, optimizer, permutation_fn=None)
                illegal_l2_coef=config.get("illegal_action_l2norm_coef", 0.0),
                value_clipping=bool(config.get("value_clipping", True)),
                reward_scaling=bool(config.get("reward_scaling", False)), masked_policy=masked)
-    act = getattr(actor_forward_pass, "act", torch.relu)
+    act = getattr(actor_forward_pass, "_activation", torch.relu)
 
     def default_permutation(rng, batch_size, device):
         g = torch.Generator(device="cpu").manual_seed(rng & 0x7FFFFFFFFFFFFFFF)

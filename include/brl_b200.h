@@ -44,6 +44,7 @@
  *   brl_reset_fields      State(...) construction / state.replace(...) src/duplicate.py:120-128
  *   brl_mlp_forward       forward.apply(params, obs) -> (logits, value)  src/models.py:23-33,
  *                         src/roll_out.py:73-76, src/utils.py:78-82, src/evaluation.py:124-127
+ *   brl_policy_act        forward.apply + masked Categorical sample / mode + log_prob, fused   src/roll_out.py:73-81
  *   brl_ppo_loss          _loss_fn + jax.value_and_grad w.r.t. the net outputs   src/update.py:91-167
  *   brl_adam_clip         optimizer.update + optax.apply_updates                  src/update.py:168-169, ppo.py:195-211
  *   brl_gather_rows       minibatch take(permutation)                             src/update.py:194-199
@@ -209,6 +210,15 @@ int32_t brl_obs_to_bf16(brl_stream_t, void **buffers, const void *opaque, size_t
 /* buffers: [0] in bf16 obs[n,480]  [1] in packed parameters  [2] scratch (brl_mlp_scratch_bytes(n))
  *          [3] out f32 logits[n,38]  [4] out f32 value[n] */
 int32_t brl_mlp_forward(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+/* forward + masked categorical in one call -- `logits, value = forward.apply(params, obs); pi = Categorical(where(mask,
+ * logits, -inf)); action = pi.sample(seed) | pi.mode(); log_prob = pi.log_prob(action)` (src/roll_out.py:73-81,
+ * src/utils.py:78-88,150-160, src/evaluation.py:124-133).  From 4096 envs on this is ONE persistent launch: the thread
+ * that drains a head-tile row holds its 38 logits and samples in place (same Philox noise as brl_categorical).
+ * buffers: [0] in bf16 obs[n,480]  [1] in packed parameters  [2] scratch  [3] in u8 mask[n,38] (NULL -> unmasked)
+ *          [4] out i32 action[n]  [5] out f32 log_prob[n] (NULL ok)  [6] out f32 value[n] (NULL ok)
+ *          [7] out f32 logits[n,38] (NULL ok)
+ * params: flags BRL_F_SAMPLE / BRL_F_MLP_BF16, seed, env_offset, step as for brl_categorical. */
+int32_t brl_policy_act(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
 /* ---- PPO update, non-GEMM part (src/update.py:74-242, ppo.py:195-211) ----------------------- */
 #define BRL_PPO_VALUE_CLIPPING  0x1 /* config["value_clipping"]  (src/update.py:47-62) */
@@ -299,6 +309,7 @@ void brl_gather_reward_xla(brl_stream_t, void **buffers, const char *opaque, siz
 void brl_mlp_pack_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_obs_to_bf16_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_mlp_forward_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_policy_act_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_ppo_loss_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_adam_clip_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_gather_rows_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);

@@ -94,3 +94,40 @@ def test_repack_after_in_place_update():
     params[LAYERS[4]]["b"].add_(1.0)  # optimizer-style in-place update
     l1, _ = fp.apply(params, x)
     assert torch.allclose(l1, l0 + 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("n", [100, 4096 + 33, 8192])
+@pytest.mark.parametrize("sample", [False, True])
+def test_policy_act_equals_forward_then_categorical(n, sample):
+    """brl_policy_act (one persistent launch from 4096 envs on: the head-tile epilogue samples in place) against
+    brl_mlp_forward + brl_categorical: identical logits / value bits and identical actions (same Philox noise, same
+    tie rule); log_prob within 2e-6 absolute (the fused row sums exp() sequentially, the warp kernel as a tree)."""
+    from brl_b200 import ops
+    from brl_b200.deals import synthetic_deal_table
+    params = _params(3)
+    from brl_b200.models import LAYERS
+    blob = ops.mlp_pack([params[k]["w"] for k in LAYERS], [params[k]["b"] for k in LAYERS])
+    table = torch.as_tensor(synthetic_deal_table(500, 2), device=DEV)
+    state, out = ops.new_state(n, DEV), ops.EnvOutputs(n, DEV, torch.bfloat16)
+    ops.init(ops.make_keys(5, n, DEV), table, state, out)
+    for i in range(6):
+        ops.step(state, None, table, state, out, autoreset=True, random_action=True, seed=5, step_index=i)
+    x, mask = out.observation, out.legal_action_mask
+    scratch = ops.mlp_scratch(n, DEV)
+    lg, vl = torch.empty((n, 38), device=DEV), torch.empty(n, device=DEV)
+    ops.mlp_forward(x, blob, scratch, lg, vl)
+    a_ref, lp_ref = torch.empty(n, dtype=torch.int32, device=DEV), torch.empty(n, device=DEV)
+    for use_mask in (True, False):
+        m = mask if use_mask else None
+        ops.categorical(lg, m, a_ref, lp_ref, sample=sample, seed=99, env_offset=1000)
+        a, lp, v2, lg2 = torch.full_like(a_ref, -7), torch.full_like(lp_ref, float("nan")), torch.empty_like(vl), torch.empty_like(lg)
+        ops.policy_act(x, blob, scratch, m, a, lp, v2, lg2, sample=sample, seed=99, env_offset=1000)
+        assert torch.equal(lg2, lg) and torch.equal(v2, vl)
+        assert torch.equal(a, a_ref)
+        assert float((lp - lp_ref).abs().max()) <= 2e-6
+        if use_mask:
+            assert bool(mask.gather(1, a.long()[:, None]).all()), "sampled an illegal action"
+        # optional outputs may be omitted
+        a3 = torch.full_like(a_ref, -7)
+        ops.policy_act(x, blob, scratch, m, a3, sample=sample, seed=99, env_offset=1000)
+        assert torch.equal(a3, a_ref)
