@@ -345,28 +345,31 @@ def run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps, warmu
     for i in range(warmup):
         one(i)
     dt_sync = timed(lambda: [one(warmup + i) for i in range(steps)])
-    # (b) the same calls pipelined two deep (brl_env_rollout_host_async + brl_env_wait): step i's result is read on the
-    #     host while step i+1 computes; every step still copies its own inputs in and its own results out
-    rew2 = [rew, torch.zeros_like(rew).pin_memory()]
-    term2 = [term, torch.zeros_like(term).pin_memory()]
-    stats2 = [stats, torch.zeros_like(stats).pin_memory()]
+    # (b) the same calls pipelined three deep (brl_env_rollout_host_async + brl_env_wait): step i-2's result is read on
+    #     the host while steps i-1 and i are in flight; every step still copies its own inputs in and its own results out
+    depth = max(1, min(4, int(os.environ.get("BRL_E2E_DEPTH", "3"))))  # BRL_ENV_PIPELINE_DEPTH = 4 staging slots
+    rew2 = [rew] + [torch.zeros_like(rew).pin_memory() for _ in range(depth - 1)]
+    term2 = [term] + [torch.zeros_like(term).pin_memory() for _ in range(depth - 1)]
+    stats2 = [stats] + [torch.zeros_like(stats).pin_memory() for _ in range(depth - 1)]
     seen = [0]
 
     def pipelined(count, base):
-        prev = None
+        inflight = []
         for i in range(count):
-            j = i & 1
+            j = i % depth
+            if len(inflight) == depth:  # slot j's host buffers are about to be reused: consume their result first
+                t0_, j0 = inflight.pop(0)
+                if L.brl_env_wait(h, t0_) != 0:
+                    raise RuntimeError(L.brl_last_error().decode())
+                seen[0] += int(stats2[j0][0])      # the host consumes an older step's result while newer ones run
             t = L.brl_env_rollout_host_async(h, k, vp(pool[(base + i) % n_pool]), vp(rew2[j]), vp(term2[j]), vp(stats2[j]))
             if t <= 0:
                 raise RuntimeError(L.brl_last_error().decode())
-            if prev is not None:
-                if L.brl_env_wait(h, prev[0]) != 0:
-                    raise RuntimeError(L.brl_last_error().decode())
-                seen[0] += int(stats2[prev[1]][0])      # the host consumes step i-1's result while step i runs
-            prev = (t, j)
-        if L.brl_env_wait(h, prev[0]) != 0:
-            raise RuntimeError(L.brl_last_error().decode())
-        seen[0] += int(stats2[prev[1]][0])
+            inflight.append((t, j))
+        for t0_, j0 in inflight:
+            if L.brl_env_wait(h, t0_) != 0:
+                raise RuntimeError(L.brl_last_error().decode())
+            seen[0] += int(stats2[j0][0])
 
     pipelined(warmup, 0)
     seen[0] = 0
@@ -375,9 +378,9 @@ def run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps, warmu
     L.brl_env_destroy(h)
     res = {"value": n * k * steps * world / dt, "unit": UNIT, "h2d_bytes_per_step": n * k * 4,
            "d2h_bytes_per_step": n * k * 17 + 32, "steps": steps, "ms_per_step": 1e3 * dt / steps,
-           "api": "brl_env_rollout_host_async + brl_env_wait (C ABI, host buffers), two calls in flight: per bench step H2D "
+           "api": "brl_env_rollout_host_async + brl_env_wait (C ABI, host buffers), three calls in flight: per bench step H2D "
                   "u32[32,8192] action randomness from pinned memory, one fused rollout launch, D2H rewards f32[32,8192,4] + "
-                  "terminated u8[32,8192] + stats into pinned memory, read by the host while the next step computes; obs/mask "
+                  "terminated u8[32,8192] + stats into pinned memory, read by the host while the next steps compute; obs/mask "
                   "trajectories stay in HBM for the device-resident learner (as traj_batch does in the reference)",
            "timed_with": "host wall clock around the whole loop, max over ranks", "finished_auctions_read_on_host": finished,
            "sync_per_call": {"value": n * k * steps * world / dt_sync, "ms_per_step": 1e3 * dt_sync / steps,

@@ -35,14 +35,14 @@ struct BrlEnv {
     int32_t* t_action;
     uint32_t* t_uniforms;
     unsigned long long* d_stats;
-    // depth-2 pipelined rollout (brl_env_rollout_host_async): double-buffered staging + events
+    // pipelined rollout (brl_env_rollout_host_async): BRL_ENV_PIPELINE_DEPTH staging slots + events
     int32_t a_k;
     int64_t a_calls;
-    float* a_rewards[2];
-    uint8_t* a_term[2];
-    uint32_t* a_uniforms[2];
-    unsigned long long* a_stats[2];
-    cudaEvent_t a_in[2], a_kernel[2], a_done[2];
+    float* a_rewards[BRL_ENV_PIPELINE_DEPTH];
+    uint8_t* a_term[BRL_ENV_PIPELINE_DEPTH];
+    uint32_t* a_uniforms[BRL_ENV_PIPELINE_DEPTH];
+    unsigned long long* a_stats[BRL_ENV_PIPELINE_DEPTH];
+    cudaEvent_t a_in[BRL_ENV_PIPELINE_DEPTH], a_kernel[BRL_ENV_PIPELINE_DEPTH], a_done[BRL_ENV_PIPELINE_DEPTH];
 };
 
 namespace {
@@ -135,7 +135,7 @@ void brl_env_destroy(BrlEnv* env) {
         if (env->ev_in[c]) cudaEventDestroy(env->ev_in[c]);
         if (env->ev_k[c]) cudaEventDestroy(env->ev_k[c]);
     }
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < BRL_ENV_PIPELINE_DEPTH; ++c) {
         cudaFree(env->a_rewards[c]); cudaFree(env->a_term[c]); cudaFree(env->a_uniforms[c]); cudaFree(env->a_stats[c]);
         if (env->a_in[c]) cudaEventDestroy(env->a_in[c]);
         if (env->a_kernel[c]) cudaEventDestroy(env->a_kernel[c]);
@@ -283,8 +283,10 @@ int32_t brl_env_rollout_host(BrlEnv* env, int32_t k_steps, const uint32_t* unifo
 }
 
 // Pipelined form of brl_env_rollout_host: returns as soon as the work is enqueued; call c's H2D runs under
-// call c-1's kernel and its D2H under call c+1's kernel (double-buffered staging, three streams).  The host
-// buffers of call c are valid after brl_env_wait(env, ticket_c); at most two calls may be in flight.
+// call c-1's kernel and its D2H under call c+1's kernel (BRL_ENV_PIPELINE_DEPTH staging slots, three streams).
+// The host buffers of call c are valid after brl_env_wait(env, ticket_c); at most BRL_ENV_PIPELINE_DEPTH calls
+// may be in flight (a deeper submit waits on the device for the slot it reuses).  Three in flight keep the
+// GPU fed: with two, the host learns that D2H(c-1) is done only as kernel c ends, too late to enqueue c+1.
 int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t* uniforms, float* rewards,
                                    uint8_t* terminated, uint64_t* stats) {
     if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "brl_env_rollout_host_async: bad handle");
@@ -293,13 +295,14 @@ int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t*
     const size_t rows = (size_t)k_steps * (size_t)env->n;
     if (env->a_k < k_steps) {
         if (!ok(cudaDeviceSynchronize(), "sync before staging resize")) return BRL_E_LAUNCH;
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < BRL_ENV_PIPELINE_DEPTH; ++c) {
             cudaFree(env->a_rewards[c]); cudaFree(env->a_term[c]); cudaFree(env->a_uniforms[c]);
             env->a_rewards[c] = nullptr; env->a_term[c] = nullptr; env->a_uniforms[c] = nullptr;
             bool good = ok(cudaMalloc(&env->a_rewards[c], rows * 16), "malloc staging rewards") &&
                         ok(cudaMalloc(&env->a_term[c], rows), "malloc staging terminated") &&
                         ok(cudaMalloc(&env->a_uniforms[c], rows * 4), "malloc staging uniforms") &&
-                        (env->a_stats[c] != nullptr || ok(cudaMalloc(&env->a_stats[c], 32), "malloc staging stats")) &&
+                        (env->a_stats[c] != nullptr || (ok(cudaMalloc(&env->a_stats[c], 32), "malloc staging stats") &&
+                                                        ok(cudaMemset(env->a_stats[c], 0, 32), "memset stats"))) &&
                         (env->a_in[c] != nullptr || ok(cudaEventCreateWithFlags(&env->a_in[c], cudaEventDisableTiming), "event")) &&
                         (env->a_kernel[c] != nullptr || ok(cudaEventCreateWithFlags(&env->a_kernel[c], cudaEventDisableTiming), "event")) &&
                         (env->a_done[c] != nullptr || ok(cudaEventCreateWithFlags(&env->a_done[c], cudaEventDisableTiming), "event"));
@@ -308,8 +311,8 @@ int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t*
         env->a_k = k_steps;
         env->a_calls = 0;
     }
-    const int slot = (int)(env->a_calls & 1);
-    const bool reuse = env->a_calls >= 2;
+    const int slot = (int)(env->a_calls % BRL_ENV_PIPELINE_DEPTH);
+    const bool reuse = env->a_calls >= BRL_ENV_PIPELINE_DEPTH;
     cudaStream_t s = env->stream;
     if (uniforms) {
         if (reuse && !ok(cudaStreamWaitEvent(env->s_in, env->a_kernel[slot], 0), "wait event")) return BRL_E_LAUNCH;
@@ -317,8 +320,8 @@ int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t*
             !ok(cudaEventRecord(env->a_in[slot], env->s_in), "event record") || !ok(cudaStreamWaitEvent(s, env->a_in[slot], 0), "wait event"))
             return BRL_E_LAUNCH;
     }
+    // the slot's statistics were re-zeroed on the copy-out stream right after their last D2H (off the kernel stream)
     if (reuse && !ok(cudaStreamWaitEvent(s, env->a_done[slot], 0), "wait event")) return BRL_E_LAUNCH;
-    if (!ok(cudaMemsetAsync(env->a_stats[slot], 0, 32, s), "memset stats")) return BRL_E_LAUNCH;
     BrlParams p = params_of(env, 0);
     p.k_steps = k_steps;
     void* b[10] = {env->d_state, env->d_table, env->t_obs, env->t_mask, env->a_rewards[slot], env->a_term[slot],
@@ -335,6 +338,7 @@ int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t*
         return BRL_E_LAUNCH;
     if (stats && !ok(cudaMemcpyAsync(stats, env->a_stats[slot], 32, cudaMemcpyDeviceToHost, env->s_out), "D2H stats"))
         return BRL_E_LAUNCH;
+    if (!ok(cudaMemsetAsync(env->a_stats[slot], 0, 32, env->s_out), "memset stats")) return BRL_E_LAUNCH;
     if (!ok(cudaEventRecord(env->a_done[slot], env->s_out), "event record")) return BRL_E_LAUNCH;
     return ++env->a_calls;
 }
@@ -342,8 +346,9 @@ int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t*
 int32_t brl_env_wait(BrlEnv* env, int64_t ticket) {
     if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "brl_env_wait: bad handle");
     if (ticket <= 0 || ticket > env->a_calls) return brl::fail(BRL_E_OPAQUE, "brl_env_wait: unknown ticket");
-    if (ticket + 2 <= env->a_calls) return BRL_OK;  // its slot was reused, which already waited for it
-    if (!ok(cudaEventSynchronize(env->a_done[(ticket - 1) & 1]), "event sync")) return BRL_E_LAUNCH;
+    // if the ticket's slot has been reused since, its event now marks the later call, which queued behind this one on
+    // the device: waiting for it is conservative but still correct
+    if (!ok(cudaEventSynchronize(env->a_done[(ticket - 1) % BRL_ENV_PIPELINE_DEPTH]), "event sync")) return BRL_E_LAUNCH;
     return BRL_OK;
 }
 

@@ -345,7 +345,10 @@ int32_t brl_env_rollout_host(BrlEnv *env, int32_t k_steps, const uint32_t *unifo
                              uint8_t *terminated, uint64_t *stats);
 /* Pipelined form: enqueue and return a ticket (> 0; negative = BRL_E_*).  Call c's input copy runs under call
  * c-1's kernel and its result copy under call c+1's kernel.  The host buffers of a call are valid after
- * brl_env_wait(env, ticket); keep at most two calls in flight (use two sets of host buffers). */
+ * brl_env_wait(env, ticket); keep at most BRL_ENV_PIPELINE_DEPTH calls in flight, each with its own set of host
+ * buffers.  Three in flight keep the GPU fed (with two, the host learns that D2H(c-1) finished only as kernel c
+ * ends -- too late to enqueue c+1 without a bubble). */
+#define BRL_ENV_PIPELINE_DEPTH 4
 int64_t brl_env_rollout_host_async(BrlEnv *env, int32_t k_steps, const uint32_t *uniforms, float *rewards,
                                    uint8_t *terminated, uint64_t *stats);
 int32_t brl_env_wait(BrlEnv *env, int64_t ticket);

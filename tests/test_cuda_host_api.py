@@ -128,7 +128,7 @@ def test_pipelined_host_rollout_equals_blocking_calls():
     from brl_b200 import _lib
     from brl_b200.deals import synthetic_deal_table
     L = _lib.load()
-    n, seed, k, calls = 2048, 23, 8, 5
+    n, seed, k, calls = 2048, 23, 8, 9  # 9 calls through 4 staging slots: every slot is reused at least once
     table = synthetic_deal_table(800, seed=6)
     vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
     rng = np.random.default_rng(0)
@@ -146,8 +146,8 @@ def test_pipelined_host_rollout_equals_blocking_calls():
                 tk = L.brl_env_rollout_host_async(h, k, vp(us[c]), vp(r), vp(t), vp(s))
                 assert tk == c + 1, L.brl_last_error()
                 tickets.append(tk)
-                if c >= 1:
-                    assert L.brl_env_wait(h, tickets[c - 1]) == 0
+                if c >= 3:  # BRL_ENV_PIPELINE_DEPTH - 1 older calls stay in flight
+                    assert L.brl_env_wait(h, tickets[c - 3]) == 0
             else:
                 assert L.brl_env_rollout_host(h, k, vp(us[c]), vp(r), vp(t), vp(s)) == 0
         if pipelined:
