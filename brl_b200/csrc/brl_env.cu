@@ -166,6 +166,19 @@ __device__ __forceinline__ void emit_tile(const WarpTile<EPW>& t, int lane, int6
     if (mask != nullptr) emit_mask_run(t.M, lane, 32, mask + env_base * kNumActions, n_valid * kNumActions, mask_vec);
 }
 
+// block-cooperative phase 2: the block's warps write the tile's rows interleaved (warp w: rows w, w+W, ...),
+// so the addresses a block has in flight stay within a few consecutive rows (scripts/exp_store_paths.cu: a
+// pure-write kernel gains 10-15 % when the window of rows in flight per block shrinks from 128 to <= 32)
+template <int EPW, int OBS>
+__device__ __forceinline__ void emit_block(const WarpTile<EPW>& t, int tid, int nthreads, int64_t env_base, int n_valid,
+                                           void* obs, uint8_t* mask, int mask_vec) {
+    if (obs != nullptr) {
+        const int warp = tid >> 5, lane = tid & 31, nw = nthreads >> 5;
+        for (int e = warp; e < n_valid; e += nw) emit_obs_row<OBS>(&t.R[e * kRowStride], lane, obs, env_base + e);
+    }
+    if (mask != nullptr) emit_mask_run(t.M, tid, nthreads, mask + env_base * kNumActions, n_valid * kNumActions, mask_vec);
+}
+
 template <int EPW, class Rows>
 __device__ __forceinline__ void stage_env(WarpTile<EPW>& t, int lane, const Env& e, const Rows& rows, uint32_t q,
                                           bool want_obs) {
@@ -204,10 +217,22 @@ __device__ __forceinline__ void write_scalars(const EnvArgs& a, int64_t row, con
     const bool active = lane < n_valid;                                              \
     const int64_t i = env_base + lane;
 
+// Block-tile kernels (k_step, k_produce, k_dup_step): a BLOCK owns EPW (<= 32) consecutive envs.  Phase 1 runs
+// in the first EPW threads (one env per thread), phase 2 is shared by every warp of the block.
+#define BRL_BLOCK_PROLOGUE()                                                         \
+    extern __shared__ __align__(16) unsigned char smem_raw[];                        \
+    WarpTile<EPW>& t = *reinterpret_cast<WarpTile<EPW>*>(smem_raw);                  \
+    const int lane = (int)threadIdx.x;                                               \
+    const int64_t env_base = (int64_t)blockIdx.x * EPW;                              \
+    const int n_valid = (int)((a.n - env_base) < (int64_t)EPW ? (a.n - env_base) : (int64_t)EPW); \
+    if (lane < 2) t.M[EPW + lane] = 0ull;                                            \
+    const bool active = lane < n_valid;                                              \
+    const int64_t i = env_base + lane;
+
 // ---- one env.step over n envs ---------------------------------------------------------
 template <int EPW, int OBS>
-__global__ void __launch_bounds__(128) k_step(const EnvArgs a) {
-    BRL_TILE_PROLOGUE()
+__global__ void __launch_bounds__(256) k_step(const EnvArgs a) {
+    BRL_BLOCK_PROLOGUE()
     if (lane < EPW) {
         if (active) {
             Env e;
@@ -229,8 +254,8 @@ __global__ void __launch_bounds__(128) k_step(const EnvArgs a) {
             t.M[lane] = 0ull;
         }
     }
-    __syncwarp();
-    emit_tile<EPW, OBS>(t, lane, env_base, n_valid, a.obs, a.mask, a.mask_vec);
+    __syncthreads();
+    emit_block<EPW, OBS>(t, (int)threadIdx.x, (int)blockDim.x, env_base, n_valid, a.obs, a.mask, a.mask_vec);
 }
 
 // ---- K auto-reset steps with in-kernel random-legal actions ----------------------------
@@ -478,11 +503,11 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
 }
 
 // ---- init / reset_fields / duplicate_init / observe / legal_mask -----------------------
-enum ProduceMode { kModeInit = 0, kModeReset = 1, kModeDupInit = 2, kModeObserve = 3, kModeMask = 4 };
+enum ProduceMode { kModeInit = 0, kModeReset = 1, kModeDupInit = 2, kModeObserve = 3 };
 
 template <int EPW, int OBS>
-__global__ void __launch_bounds__(128) k_produce(const EnvArgs a) {
-    BRL_TILE_PROLOGUE()
+__global__ void __launch_bounds__(256) k_produce(const EnvArgs a) {
+    BRL_BLOCK_PROLOGUE()
     if (lane < EPW) {
         if (active) {
             Env e;
@@ -495,10 +520,6 @@ __global__ void __launch_bounds__(128) k_produce(const EnvArgs a) {
                                     ((uint32_t)(p[3] & 3) << 6);
                 env_reset(e, (uint32_t)a.in_deal[i], (uint32_t)a.in_dealer[i] & 3u, a.in_vul_ns[i] ? 1u : 0u,
                           a.in_vul_ew[i] ? 1u : 0u, seating8, a.in_rng_key ? a.in_rng_key[i] : 0ull);
-            } else if (a.mode == kModeMask) {
-                // the legal mask is a function of word A alone: read one 16-byte plane, not all five
-                e = Env{};
-                e.A = a.state_in[3 * a.stride + i].z;
             } else {
                 load_env(a.state_in, a.stride, i, e);
                 if (a.mode == kModeDupInit) env_duplicate_init(e);
@@ -519,14 +540,38 @@ __global__ void __launch_bounds__(128) k_produce(const EnvArgs a) {
             t.M[lane] = 0ull;
         }
     }
-    __syncwarp();
-    emit_tile<EPW, OBS>(t, lane, env_base, n_valid, a.obs, a.mask, a.mask_vec);
+    __syncthreads();
+    emit_block<EPW, OBS>(t, (int)threadIdx.x, (int)blockDim.x, env_base, n_valid, a.obs, a.mask, a.mask_vec);
+}
+
+// ---- legal_action_mask alone -------------------------------------------------------------
+// The mask is a function of state word A alone (one 16-byte plane read per env; 38 bytes out).  A block owns 256
+// consecutive envs: every thread turns one A into 38 mask bits in shared memory, then the block writes its
+// 256 * 38 = 9728 output bytes as 608 fully coalesced 128-bit stores (each one assembled from at most two envs).
+constexpr int kMaskEnvsPerBlock = 256;
+
+__global__ void __launch_bounds__(kMaskEnvsPerBlock) k_legal_mask(const uint4* __restrict__ state, int64_t stride,
+                                                                   uint8_t* __restrict__ mask, int64_t n, int vec) {
+    __shared__ uint64_t M[kMaskEnvsPerBlock + 2];
+    const int tid = (int)threadIdx.x;
+    const int64_t env_base = (int64_t)blockIdx.x * kMaskEnvsPerBlock;
+    const int n_valid = (int)((n - env_base) < (int64_t)kMaskEnvsPerBlock ? (n - env_base) : (int64_t)kMaskEnvsPerBlock);
+    uint64_t m = 0ull;
+    if (tid < n_valid) {
+        Env e = {};
+        e.A = state[3 * stride + env_base + tid].z;
+        m = env_legal_mask(e);
+    }
+    M[tid] = m;
+    if (tid < 2) M[kMaskEnvsPerBlock + tid] = 0ull;
+    __syncthreads();
+    emit_mask_run(M, tid, kMaskEnvsPerBlock, mask + env_base * kNumActions, n_valid * kNumActions, vec);
 }
 
 // ---- duplicate_step -- src/duplicate.py:147-192 ----------------------------------------
 template <int EPW, int OBS>
-__global__ void __launch_bounds__(128) k_dup_step(const EnvArgs a) {
-    BRL_TILE_PROLOGUE()
+__global__ void __launch_bounds__(256) k_dup_step(const EnvArgs a) {
+    BRL_BLOCK_PROLOGUE()
     if (lane < EPW) {
         if (active) {
             Env e;
@@ -564,8 +609,8 @@ __global__ void __launch_bounds__(128) k_dup_step(const EnvArgs a) {
             t.M[lane] = 0ull;
         }
     }
-    __syncwarp();
-    emit_tile<EPW, OBS>(t, lane, env_base, n_valid, a.obs, a.mask, a.mask_vec);
+    __syncthreads();
+    emit_block<EPW, OBS>(t, (int)threadIdx.x, (int)blockDim.x, env_base, n_valid, a.obs, a.mask, a.mask_vec);
 }
 
 // ---- private field export ----------------------------------------------------------------
@@ -618,13 +663,26 @@ struct Tiling {
 };
 
 static Tiling choose_tiling(int64_t n, int32_t flags) {
-    // flags bits 16-17: EPW override (1->8, 2->16, 3->32); bits 18-19: warps per block (1->1, 2->2, 3->4)
+    // flags bits 16-17: EPW override (1->8, 2->16, 3->32); bits 18-19: warps per block (1->1, 2->2, 3->4; with
+    // bit 26 also set: 8)
     static const int epw_of[4] = {0, 8, 16, 32};
     static const int wpb_of[4] = {0, 1, 2, 4};
     int epw = epw_of[(flags >> 16) & 3], wpb = wpb_of[(flags >> 18) & 3];
+    if (wpb && (flags & (1 << 26))) wpb = 8;
     if (epw == 0) epw = n >= 262144 ? 32 : (n >= 65536 ? 16 : 8);  // >= ~8 warps per SM at every size
     if (wpb == 0) wpb = n >= 65536 ? 4 : 2;
     return {epw, wpb};
+}
+
+// block-tile kernels: envs per block (8/16/32) and warps per block (1..8) sharing its phase 2
+static Tiling choose_block_tiling(int64_t n, int32_t flags) {
+    Tiling t = choose_tiling(n, flags);
+    // measured at 1,048,576 envs (scripts/exp_tiling.py): the fewer rows a block has in flight, the closer the stores
+    // get to the pure-write ceiling, until phase 1 (EPW of the block's threads busy) starves it; 480-byte u8 rows
+    // need twice the envs per block for the same bytes in flight
+    if (((flags >> 16) & 3) == 0) t.epw = ((flags & BRL_F_OBS_U8) && n >= 262144) ? 32 : 16;
+    if (((flags >> 18) & 3) == 0) t.wpb = 4;
+    return t;
 }
 
 #define BRL_DEFINE_LAUNCHER(NAME, KERNEL)                                                                    \
@@ -648,10 +706,31 @@ static Tiling choose_tiling(int64_t n, int32_t flags) {
         else NAME##_epw<kObsF32>(a, t, s);                                                                   \
     }
 
-BRL_DEFINE_LAUNCHER(launch_step, k_step)
 BRL_DEFINE_LAUNCHER(launch_rollout, k_rollout)
-BRL_DEFINE_LAUNCHER(launch_produce, k_produce)
-BRL_DEFINE_LAUNCHER(launch_dup_step, k_dup_step)
+
+#define BRL_DEFINE_BLOCK_LAUNCHER(NAME, KERNEL)                                                              \
+    template <int EPW, int OBS>                                                                              \
+    static void NAME##_inst(const EnvArgs& a, int wpb, cudaStream_t s) {                                     \
+        unsigned grid = (unsigned)((a.n + EPW - 1) / EPW);                                                   \
+        KERNEL<EPW, OBS><<<grid, wpb * 32, sizeof(WarpTile<EPW>), s>>>(a);                                   \
+    }                                                                                                        \
+    template <int OBS>                                                                                       \
+    static void NAME##_epw(const EnvArgs& a, Tiling t, cudaStream_t s) {                                     \
+        if (t.epw == 8) NAME##_inst<8, OBS>(a, t.wpb, s);                                                    \
+        else if (t.epw == 16) NAME##_inst<16, OBS>(a, t.wpb, s);                                             \
+        else NAME##_inst<32, OBS>(a, t.wpb, s);                                                              \
+    }                                                                                                        \
+    static void NAME(const EnvArgs& a, cudaStream_t s) {                                                     \
+        if (a.n == 0) return;                                                                                \
+        Tiling t = choose_block_tiling(a.n, a.flags);                                                        \
+        if (a.flags & BRL_F_OBS_U8) NAME##_epw<kObsU8>(a, t, s);                                             \
+        else if (a.flags & BRL_F_OBS_BF16) NAME##_epw<kObsBF16>(a, t, s);                                    \
+        else NAME##_epw<kObsF32>(a, t, s);                                                                   \
+    }
+
+BRL_DEFINE_BLOCK_LAUNCHER(launch_step, k_step)
+BRL_DEFINE_BLOCK_LAUNCHER(launch_produce, k_produce)
+BRL_DEFINE_BLOCK_LAUNCHER(launch_dup_step, k_dup_step)
 
 // flags bit 20: force the tile-per-warp rollout kernel; bits 16-17: envs per block of the
 // warp-specialised kernel (as EPW); bits 21-23: its writer warps (0 = auto, else the count).
@@ -889,11 +968,12 @@ int32_t brl_legal_mask(brl_stream_t stream, void** b, const void* opaque, size_t
     if (b[1] == nullptr) return fail(BRL_E_BUFFER, "brl_legal_mask: buffer 'mask' is NULL");
     EnvArgs a = {};
     fill_common(a, p);
-    a.mode = kModeMask;
     a.state_in = static_cast<const uint4*>(b[0]);
     a.mask = static_cast<uint8_t*>(b[1]);
-    a.mask_vec = mask_vec_ok(a.mask, a.n, 1);
-    launch_produce(a, (cudaStream_t)stream);
+    if (a.n == 0) return BRL_OK;
+    // 256 * 38 bytes per block is a multiple of 16, so every block's run starts 16-byte aligned when the buffer is
+    k_legal_mask<<<(unsigned)((a.n + kMaskEnvsPerBlock - 1) / kMaskEnvsPerBlock), kMaskEnvsPerBlock, 0, (cudaStream_t)stream>>>(
+        a.state_in, a.stride, a.mask, a.n, mask_vec_ok(a.mask, a.n, 1));
     return check_launch("brl_legal_mask");
 }
 

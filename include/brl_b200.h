@@ -85,11 +85,12 @@ typedef struct CUstream_st *brl_stream_t; /* == cudaStream_t */
 #define BRL_F_QUAD_LAST     0x0100 /* with ACCUMULATE: write the OR-ed terminated flag back into the state (src/utils.py:128) */
 #define BRL_F_MLP_BF16      0x0200 /* brl_mlp_forward: one bf16 product per term instead of the 3-term split */
 #define BRL_F_HOST_STAGED   0x0800 /* brl_env_create: never write results straight into pinned host buffers (always stage + copy) */
-#define BRL_F_OBS_STREAMING 0x0080 /* rollout: obs rows staged in shared memory and written by TMA bulk stores */
 
-/* tuning (0 = automatic): bits 16-17 envs per warp (1->8, 2->16, 3->32), bits 18-19 warps per block (1->1, 2->2, 3->4) */
+/* tuning (0 = automatic): bits 16-17 envs per block of the one-launch kernels (1->8, 2->16, 3->32), bits 18-19 warps
+ * per block (1->1, 2->2, 3->4; 3 with bit 26: 8) */
 #define BRL_F_TUNE_EPW(code) ((code) << 16)
 #define BRL_F_TUNE_WPB(code) ((code) << 18)
+#define BRL_F_TUNE_WPB8 ((3 << 18) | (1 << 26))
 #define BRL_F_TUNE_CLASSIC_ROLLOUT (1 << 20)     /* tile-per-warp rollout kernel instead of the warp-specialised one */
 #define BRL_F_TUNE_WRITERS(n) ((n) << 21)       /* writer warps (1..7) of the warp-specialised rollout; EPW bits = its envs per block */
 

@@ -117,6 +117,7 @@ def test_update_step_matches_float64_reference():
     action = torch.zeros((T, n), dtype=torch.int32)
     params = init_params(9, DEV)
     fp = make_forward_pass("relu", "DeepMind", precision="fp32")
+    torch.manual_seed(3)  # the action sample below draws from the global CUDA generator
     with torch.no_grad():
         logits, value = fp.apply(params, obs.reshape(-1, 480).to(DEV))
         ml = torch.where(mask.reshape(-1, 38).to(DEV), logits, torch.tensor(float("-inf"), device=DEV))
@@ -168,7 +169,12 @@ def test_update_step_matches_float64_reference():
                     ref[k].copy_(torch.as_tensor(p[off:off + sz]).reshape(ref[k].shape))
                     off += sz
             losses.append(float(total))
-    np.testing.assert_allclose(total_loss.cpu().numpy().reshape(-1), losses, rtol=5e-4, atol=5e-5)
+    got_losses = total_loss.cpu().numpy().reshape(-1)
+    # first minibatch: same parameters on both sides, fp32-vs-float64 evaluation only
+    np.testing.assert_allclose(got_losses[0], losses[0], rtol=5e-4, atol=5e-5)
+    # later minibatches see parameters that went through Adam, whose normalised step turns fp32 gradient
+    # noise on near-zero gradients into O(lr) parameter differences: the loss may drift by O(lr * steps)
+    np.testing.assert_allclose(got_losses, losses, rtol=5e-4, atol=0.1 * lr * len(losses))
     got = params_to_numpy(runner2[0])
     got_flat = np.concatenate([got[k].reshape(-1) for k in order])
     delta_ref, delta_got = p - flat({k: torch.tensor(before[k]) for k in order}), got_flat - flat({k: torch.tensor(before[k]) for k in order})
