@@ -14,11 +14,12 @@ OPS = (
     "brl_make_keys", "brl_init", "brl_reset_fields", "brl_step", "brl_duplicate_step", "brl_duplicate_init",
     "brl_observe", "brl_legal_mask", "brl_rollout_random", "brl_imp_reward", "brl_gae", "brl_categorical",
     "brl_match_stats", "brl_state_fields", "brl_gather_reward", "brl_mlp_pack", "brl_obs_to_bf16", "brl_mlp_forward", "brl_policy_act",
-    "brl_ppo_loss", "brl_adam_clip", "brl_gather_rows", "brl_eval_act_log", "brl_eval_summary",
+    "brl_ppo_loss", "brl_adam_clip", "brl_gather_rows", "brl_eval_act_log", "brl_eval_summary", "brl_mlp_pack_train", "brl_ppo_grad",
 )
 HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host", "brl_env_rollout_host",
             "brl_env_rollout_host_async", "brl_env_wait", "brl_env_trajectory")
-MISC = ("brl_last_error", "brl_abi_version", "brl_mlp_packed_bytes", "brl_mlp_scratch_bytes", "brl_eval_num_sums")
+MISC = ("brl_last_error", "brl_abi_version", "brl_mlp_packed_bytes", "brl_mlp_scratch_bytes", "brl_eval_num_sums",
+        "brl_mlp_num_params", "brl_mlp_train_blob_bytes", "brl_mlp_train_scratch_bytes")
 XLA_LEGACY = tuple(op + "_xla" for op in OPS)  # legacy XLA GPU custom-call targets (csrc/xla_ffi_shim.cc)
 ALL_SYMBOLS = OPS + HOST_API + MISC + XLA_LEGACY
 
@@ -65,6 +66,7 @@ class BrlAdamParams(C.Structure):
 
 
 PPO_VALUE_CLIPPING, PPO_REWARD_SCALING, PPO_UNMASKED_POLICY = 1, 2, 4
+PPO_OBS_U8, PPO_OBS_BF16 = 0x10, 0x20
 
 
 class BrlError(RuntimeError):
@@ -104,6 +106,10 @@ def load():
     L.brl_mlp_packed_bytes.restype = C.c_int64
     L.brl_mlp_scratch_bytes.restype = C.c_int64
     L.brl_mlp_scratch_bytes.argtypes = [C.c_int64]
+    L.brl_mlp_num_params.restype = C.c_int64
+    L.brl_mlp_train_blob_bytes.restype = C.c_int64
+    L.brl_mlp_train_scratch_bytes.restype = C.c_int64
+    L.brl_mlp_train_scratch_bytes.argtypes = [C.c_int64]
     L.brl_env_create.restype = C.c_void_p
     L.brl_env_create.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_uint64, C.c_int32]
     L.brl_env_destroy.restype = None

@@ -203,11 +203,23 @@ __global__ void k_ppo_finalize(const PpoArgs a) {
 }
 
 // ---- optimizer: optax.chain(clip_by_global_norm(c), adam(lr, eps=1e-5)) (ppo.py:195-211) -------
+// VEC = 4: 128-bit accesses over the first n / 4 * 4 elements (16-byte-aligned buffers), the <= 3 tail elements by block 0
+template <int VEC>
 __global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
     double s = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double v = (double)g[i];
+    const int64_t n_items = n / VEC;
+    if (VEC == 4 && blockIdx.x == 0 && n_items * VEC + threadIdx.x < n) {
+        const double v = (double)g[n_items * VEC + threadIdx.x];
         s += v * v;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (int64_t)gridDim.x * blockDim.x) {
+        if (VEC == 4) {
+            const float4 v = reinterpret_cast<const float4*>(g)[i];
+            s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+        } else {
+            const double v = (double)g[i];
+            s += v * v;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -221,6 +233,17 @@ __global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ g, int6
     }
 }
 
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float scale, float lr, float b1, float b2, float eps,
+                                         float bc1, float bc2) {
+    const float gi = g * scale;
+    const float mi = b1 * m + (1.0f - b1) * gi;
+    const float vi = b2 * v + (1.0f - b2) * gi * gi;
+    m = mi;
+    v = vi;
+    p = p - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, int64_t n, const double* __restrict__ sumsq,
                                               float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2) {
@@ -230,13 +253,25 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
         const float norm = (float)sqrt(*sumsq);
         if (!(norm < max_norm)) scale = max_norm / norm;
     }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float gi = g[i] * scale;
-        const float mi = b1 * m[i] + (1.0f - b1) * gi;
-        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        p[i] = p[i] - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    const int64_t n_items = n / VEC;
+    if (VEC == 4 && blockIdx.x == 0 && n_items * VEC + threadIdx.x < n) {
+        const int64_t i = n_items * VEC + threadIdx.x;
+        adam_one(p[i], g[i], m[i], v[i], scale, lr, b1, b2, eps, bc1, bc2);
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (int64_t)gridDim.x * blockDim.x) {
+        if (VEC == 4) {
+            float4 pi = reinterpret_cast<float4*>(p)[i], mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
+            const float4 gi = reinterpret_cast<const float4*>(g)[i];
+            adam_one(pi.x, gi.x, mi.x, vi.x, scale, lr, b1, b2, eps, bc1, bc2);
+            adam_one(pi.y, gi.y, mi.y, vi.y, scale, lr, b1, b2, eps, bc1, bc2);
+            adam_one(pi.z, gi.z, mi.z, vi.z, scale, lr, b1, b2, eps, bc1, bc2);
+            adam_one(pi.w, gi.w, mi.w, vi.w, scale, lr, b1, b2, eps, bc1, bc2);
+            reinterpret_cast<float4*>(p)[i] = pi;
+            reinterpret_cast<float4*>(m)[i] = mi;
+            reinterpret_cast<float4*>(v)[i] = vi;
+        } else {
+            adam_one(p[i], g[i], m[i], v[i], scale, lr, b1, b2, eps, bc1, bc2);
+        }
     }
 }
 
@@ -309,14 +344,24 @@ int32_t brl_adam_clip(brl_stream_t stream, void** b, const void* opaque, size_t 
     if (p->n <= 0 || p->step <= 0) return fail(BRL_E_OPAQUE, "brl_adam_clip: n and step (1-based) must be > 0");
     cudaStream_t s = (cudaStream_t)stream;
     double* sumsq = static_cast<double*>(b[4]);
-    unsigned grid = (unsigned)((p->n + 255) / 256);
+    float* pp = static_cast<float*>(b[0]);
+    const float* gg = static_cast<const float*>(b[1]);
+    float* mm = static_cast<float*>(b[2]);
+    float* vv = static_cast<float*>(b[3]);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(gg) | reinterpret_cast<uintptr_t>(mm) |
+                           reinterpret_cast<uintptr_t>(vv)) & 15u) == 0;
+    const int64_t items = aligned ? (p->n + 3) / 4 : p->n;
+    unsigned grid = (unsigned)((items + 255) / 256);
     if (grid > 148u * 8u) grid = 148u * 8u;
     if (cudaMemsetAsync(sumsq, 0, sizeof(double), s) != cudaSuccess) return check_launch("brl_adam_clip");
-    k_sumsq<<<grid, 256, 0, s>>>(static_cast<const float*>(b[1]), p->n, sumsq);
     const float bc1 = 1.0f - powf(p->beta1, (float)p->step), bc2 = 1.0f - powf(p->beta2, (float)p->step);
-    k_adam<<<grid, 256, 0, s>>>(static_cast<float*>(b[0]), static_cast<const float*>(b[1]), static_cast<float*>(b[2]),
-                                static_cast<float*>(b[3]), p->n, sumsq, p->max_grad_norm, p->lr, p->beta1, p->beta2, p->eps,
-                                bc1, bc2);
+    if (aligned) {
+        k_sumsq<4><<<grid, 256, 0, s>>>(gg, p->n, sumsq);
+        k_adam<4><<<grid, 256, 0, s>>>(pp, gg, mm, vv, p->n, sumsq, p->max_grad_norm, p->lr, p->beta1, p->beta2, p->eps, bc1, bc2);
+    } else {
+        k_sumsq<1><<<grid, 256, 0, s>>>(gg, p->n, sumsq);
+        k_adam<1><<<grid, 256, 0, s>>>(pp, gg, mm, vv, p->n, sumsq, p->max_grad_norm, p->lr, p->beta1, p->beta2, p->eps, bc1, bc2);
+    }
     return check_launch("brl_adam_clip");
 }
 

@@ -66,6 +66,8 @@ BRL_LEGACY_CUSTOM_CALL(brl_policy_act)
 BRL_LEGACY_CUSTOM_CALL(brl_ppo_loss)
 BRL_LEGACY_CUSTOM_CALL(brl_adam_clip)
 BRL_LEGACY_CUSTOM_CALL(brl_gather_rows)
+BRL_LEGACY_CUSTOM_CALL(brl_mlp_pack_train)
+BRL_LEGACY_CUSTOM_CALL(brl_ppo_grad)
 BRL_LEGACY_CUSTOM_CALL(brl_eval_act_log)
 BRL_LEGACY_CUSTOM_CALL(brl_eval_summary)
 }  // extern "C"

@@ -274,6 +274,51 @@ def adam_clip(params, grads, m, v, scratch, *, step: int, lr: float, beta1=0.9, 
     _call("brl_adam_clip", [_ptr(params), _ptr(grads), _ptr(m), _ptr(v), _ptr(scratch)], p)
 
 
+def mlp_num_params() -> int:
+    return int(_lib.load().brl_mlp_num_params())
+
+
+def mlp_pack_train(flat_params: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Flat fp32 parameters (optim.flatten_params order) -> the training blob of `ppo_grad`; its head is a valid
+    `packed` argument of `mlp_forward` / `policy_act`.  Re-run after every optimizer step."""
+    L = _lib.load()
+    if flat_params.dtype != torch.float32 or flat_params.numel() != L.brl_mlp_num_params():
+        raise _lib.BrlError("mlp_pack_train needs the flat fp32 parameter buffer of the DeepMind MLP")
+    if out is None:
+        out = torch.empty(L.brl_mlp_train_blob_bytes(), dtype=torch.uint8, device=flat_params.device)
+    _call("brl_mlp_pack_train", [_ptr(flat_params), _ptr(out)], _params(0))
+    return out
+
+
+def mlp_train_scratch(batch: int, device) -> torch.Tensor:
+    return torch.empty(_lib.load().brl_mlp_train_scratch_bytes(batch), dtype=torch.uint8, device=device)
+
+
+def ppo_grad(obs, blob, scratch, index, mask, action, old_log_prob, old_value, adv, targets, grads, stats, acc, *, clip_eps,
+             ent_coef, vf_coef, illegal_l2_coef=0.0, value_clipping=True, reward_scaling=False, masked_policy=True,
+             tune: int = 0) -> None:
+    """One minibatch of jax.value_and_grad(_loss_fn) (src/update.py:91-167): take(index), forward, loss, backward
+    through the MLP on tcgen05 -> flat fp32 gradients (+ the loss statistics of `ppo_loss`)."""
+    L = _lib.load()
+    B = int(index.shape[0]) if index is not None else int(obs.shape[0])
+    if obs.dtype == torch.bool:
+        obs = obs.view(torch.uint8)
+    try:
+        oflag = {torch.float32: 0, torch.uint8: _lib.PPO_OBS_U8, torch.bfloat16: _lib.PPO_OBS_BF16}[obs.dtype]
+    except KeyError:
+        raise _lib.BrlError(f"ppo_grad: observation dtype {obs.dtype} not supported") from None
+    if scratch.numel() < L.brl_mlp_train_scratch_bytes(B) or blob.numel() < L.brl_mlp_train_blob_bytes():
+        raise _lib.BrlError("ppo_grad: scratch / blob too small (ops.mlp_train_scratch, ops.mlp_pack_train)")
+    if grads.dtype != torch.float32 or grads.numel() != L.brl_mlp_num_params():
+        raise _lib.BrlError("ppo_grad: grads must be the flat fp32 gradient buffer")
+    flags = (_lib.PPO_VALUE_CLIPPING if value_clipping else 0) | (_lib.PPO_REWARD_SCALING if reward_scaling else 0) | \
+            (0 if masked_policy else _lib.PPO_UNMASKED_POLICY) | oflag
+    p = _lib.BrlPpoParams(B, int(action.numel()), float(clip_eps), float(ent_coef), float(vf_coef), float(illegal_l2_coef),
+                          flags, int(tune))
+    _call("brl_ppo_grad", [_ptr(obs), _ptr(blob), _ptr(scratch), _ptr(index), _ptr(mask), _ptr(action), _ptr(old_log_prob),
+                           _ptr(old_value), _ptr(adv), _ptr(targets), _ptr(grads), _ptr(stats), _ptr(acc)], p)
+
+
 def gather_rows(src: torch.Tensor, index: torch.Tensor, dst: torch.Tensor) -> None:
     """dst[b] = src[index[b]] over the leading axis (minibatch take, src/update.py:194-199)."""
     row_bytes = src[0].numel() * src.element_size()

@@ -2,11 +2,16 @@
 fresh permutation split into `num_minibatches` minibatches; per minibatch the net is re-run,
 the PPO loss and its gradient are formed, and the optimizer steps.
 
-Division of labour: the minibatch gather, the loss head fused with its backward, and the
-clip + Adam step are hand-written kernels (csrc/brl_ppo.cu); the MLP forward / backward
-between them are plain library GEMMs (cuBLAS fp32 through torch autograd).  Functional
-semantics are kept: the caller's `params` / `opt_state` are not modified (ppo.py keeps the
-pre-update params as `opp_params`), a new flat copy is updated and returned."""
+Two back ends, selected by the forward pass's precision:
+  "tc" / "tc-bf16" (default for ReLU nets)  `brl_ppo_grad`: minibatch take, forward with kept
+      activations, loss head + its backward, and the backward GEMMs all in hand-written kernels
+      on tcgen05 (csrc/brl_mlp_train.cu, three-term bf16 split = fp32-class gradients), then
+      `brl_adam_clip` and `brl_mlp_pack_train` -- no library GEMM, no autograd tape;
+  "fp32" (and tanh nets)  the minibatch gather, loss head and clip + Adam step are the same
+      kernels (csrc/brl_ppo.cu) around plain library GEMMs (cuBLAS fp32 through torch
+      autograd) -- kept as the independent cross-check of the tensor-core path.
+Functional semantics are kept: the caller's `params` / `opt_state` are not modified (ppo.py
+keeps the pre-update params as `opp_params`), a new flat copy is updated and returned."""
 from __future__ import annotations
 
 import torch
@@ -54,6 +59,8 @@ def make_update_step(config, actor_forward_pass, optimizer, permutation_fn=None)
                value_clipping=bool(config.get("value_clipping", True)),
                reward_scaling=bool(config.get("reward_scaling", False)), masked_policy=masked)
     act = getattr(actor_forward_pass, "_activation", torch.relu)
+    tensor_core = getattr(actor_forward_pass, "precision", "fp32") in ("tc", "tc-bf16") and act is torch.relu
+    tune = int(config.get("brl_train_tune", 0))
 
     def default_permutation(rng, batch_size, device):
         g = torch.Generator(device="cpu").manual_seed(rng & 0x7FFFFFFFFFFFFFFF)
@@ -78,6 +85,37 @@ def make_update_step(config, actor_forward_pass, optimizer, permutation_fn=None)
         obs = obs.contiguous()
 
         flat_p, new_params = flatten_params(params)
+        if opt_state is None:
+            opt_state = optimizer.init(params)
+        state = OptState(opt_state.count, opt_state.mu.clone(), opt_state.nu.clone())
+        n_epochs = int(config["update_epochs"])
+        stats_all = torch.zeros((n_epochs, nmb, 8), dtype=torch.float32, device=dev)
+        acc = torch.zeros(16, dtype=torch.float64, device=dev)
+
+        def permutation(_rng):
+            return (permutation_fn(_rng, batch_size) if permutation_fn is not None
+                    else default_permutation(_rng, batch_size, dev)).to(device=dev, dtype=torch.int32).contiguous()
+
+        def finish():
+            # loss_info: (total_loss, (value_loss, loss_actor, entropy, approx_kl, clipflacs, illegal_action_loss)),
+            # each [update_epochs, num_minibatches] (src/update.py:170-173, 226-229; read at ppo.py:487-506)
+            cols = [stats_all[:, :, i] for i in range(7)]
+            return (new_params, state, env_state, last_obs, terminated_count, rng), (cols[0], tuple(cols[1:]))
+
+        if tensor_core:
+            blob = ops.mlp_pack_train(flat_p)
+            scratch = ops.mlp_train_scratch(mbs, dev)
+            flat_g = torch.empty_like(flat_p)
+            for epoch in range(n_epochs):
+                rng, _rng = brandom.split(rng)                                        # src/update.py:187
+                perm = permutation(_rng)
+                for mb in range(nmb):                                                  # src/update.py:207-209
+                    ops.ppo_grad(obs, blob, scratch, perm[mb * mbs:(mb + 1) * mbs], mask, action, old_lp, old_v, adv, tgt,
+                                 flat_g, stats_all[epoch, mb], acc, tune=tune, **cfg)  # src/update.py:164-167
+                    state = optimizer.update_(flat_p, flat_g, state)                  # src/update.py:168-169
+                    ops.mlp_pack_train(flat_p, out=blob)
+            return finish()
+
         leaves = {name: {k: new_params[name][k].detach().requires_grad_() for k in ("w", "b")} for name in LAYERS}
         flat_g = torch.zeros_like(flat_p)
         off = 0
@@ -86,21 +124,14 @@ def make_update_step(config, actor_forward_pass, optimizer, permutation_fn=None)
                 t = leaves[name][k]
                 t.grad = flat_g[off: off + t.numel()].view(t.shape)
                 off += t.numel()
-        if opt_state is None:
-            opt_state = optimizer.init(params)
-        state = OptState(opt_state.count, opt_state.mu.clone(), opt_state.nu.clone())
-        call = dict(mask=mask, action=action, old_log_prob=old_lp, old_value=old_v, adv=adv, targets=tgt, cfg=cfg,
-                    scratch=torch.zeros(16, dtype=torch.float64, device=dev))
+        call = dict(mask=mask, action=action, old_log_prob=old_lp, old_value=old_v, adv=adv, targets=tgt, cfg=cfg, scratch=acc)
         x_mb = torch.empty((mbs, obs.shape[1]), dtype=obs.dtype, device=dev)
-        n_epochs = int(config["update_epochs"])
-        stats_all = torch.zeros((n_epochs, nmb, 8), dtype=torch.float32, device=dev)
         prev_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False  # the reference computes in fp32
         try:
             for epoch in range(n_epochs):
                 rng, _rng = brandom.split(rng)                                        # src/update.py:187
-                perm = (permutation_fn(_rng, batch_size) if permutation_fn is not None
-                        else default_permutation(_rng, batch_size, dev)).to(device=dev, dtype=torch.int32).contiguous()
+                perm = permutation(_rng)
                 for mb in range(nmb):                                                  # src/update.py:207-209
                     index = perm[mb * mbs:(mb + 1) * mbs]
                     ops.gather_rows(obs, index, x_mb)
@@ -113,11 +144,6 @@ def make_update_step(config, actor_forward_pass, optimizer, permutation_fn=None)
                     state = optimizer.update_(flat_p, flat_g, state)                  # src/update.py:168-169
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32
-        # loss_info: (total_loss, (value_loss, loss_actor, entropy, approx_kl, clipflacs, illegal_action_loss)),
-        # each [update_epochs, num_minibatches] (src/update.py:170-173, 226-229; read at ppo.py:487-506)
-        cols = [stats_all[:, :, i] for i in range(7)]
-        loss_info = (cols[0], tuple(cols[1:]))
-        runner_state = (new_params, state, env_state, last_obs, terminated_count, rng)
-        return runner_state, loss_info
+        return finish()
 
     return update_step

@@ -48,6 +48,9 @@
  *   brl_ppo_loss          _loss_fn + jax.value_and_grad w.r.t. the net outputs   src/update.py:91-167
  *   brl_adam_clip         optimizer.update + optax.apply_updates                  src/update.py:168-169, ppo.py:195-211
  *   brl_gather_rows       minibatch take(permutation)                             src/update.py:194-199
+ *   brl_ppo_grad          jax.value_and_grad(_loss_fn)(params, traj, gae, targets) -> (loss_info, grads): minibatch
+ *                         take + forward + loss + backward through the MLP on tcgen05   src/update.py:91-167,194-199
+ *   brl_mlp_pack_train    flat fp32 params -> device layout for brl_ppo_grad (both weight orientations)
  *   brl_eval_act_log      make_action + make_step_log of evaluate / duplicate_evaluate   src/evaluation.py:236-385, 650-745
  *   brl_eval_summary      make_terminated_log + the log_info means                        src/evaluation.py:448-596, 839-1027
  *   brl_mlp_pack          the params pytree (bridge_models/<name>.pkl, ppo.py:351-362) -> device layout
@@ -262,6 +265,30 @@ int32_t brl_adam_clip(brl_stream_t, void **buffers, const void *opaque, size_t o
  * buffers: [0] in src[total, row]  [1] in i32 index[B]  [2] out dst[B, row] */
 int32_t brl_gather_rows(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
+/* ---- PPO update, the trip through the net (src/update.py:91-167): forward + backward on tcgen05 ---- */
+#define BRL_PPO_OBS_U8   0x10 /* brl_ppo_grad: trajectory observations are u8 / bool 0-1 (pgx dtype) */
+#define BRL_PPO_OBS_BF16 0x20 /* brl_ppo_grad: trajectory observations are bf16 (what the tensor-core rollout records) */
+/* Flat fp32 parameter / gradient buffer: haiku modules actor_critic/linear, linear_1 .. linear_5 in that order, each
+ * w[in,out] then b[out] (480x1024, 3 x 1024x1024, 1024x38, 1024x1): brl_mlp_num_params() = 3,681,319 floats. */
+int64_t brl_mlp_num_params(void);
+int64_t brl_mlp_train_blob_bytes(void);
+int64_t brl_mlp_train_scratch_bytes(int64_t batch);
+/* flat params -> training blob: the forward layout of brl_mlp_pack (the blob is also a valid `packed` argument of
+ * brl_mlp_forward / brl_policy_act) followed by W[in,out_pad] bf16 hi / lo for the input-gradient GEMMs.
+ * Run after every optimizer step.  opaque = BrlParams (fields unused).
+ * buffers: [0] in f32 params[brl_mlp_num_params()]  [1] out blob[brl_mlp_train_blob_bytes()] */
+int32_t brl_mlp_pack_train(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+/* One minibatch of `jax.value_and_grad(_loss_fn, has_aux=True)(params, traj_batch, gae, targets)` (src/update.py:164-167):
+ * take(index) of the observations, forward with the activations kept, brl_ppo_loss, backward GEMMs (input gradients with
+ * the ReLU mask fused, weight gradients contracted over the batch, bias gradients), all products as three-term bf16
+ * splits accumulated in fp32 on the tensor cores.  opaque = BrlPpoParams (flags: BRL_PPO_* incl. BRL_PPO_OBS_*).
+ * buffers: [0] in obs[total,480] (f32 unless BRL_PPO_OBS_*)  [1] in blob (brl_mlp_pack_train)
+ *          [2] scratch[brl_mlp_train_scratch_bytes(B)]  [3] in i32 index[B] (NULL = identity)  [4] in u8 mask[total,38]
+ *          [5] in i32 action[total]  [6] in f32 old_log_prob[total]  [7] in f32 old_value[total]
+ *          [8] in f32 advantages[total]  [9] in f32 targets[total]  [10] out f32 grads[brl_mlp_num_params()]
+ *          [11] out f32 stats[8] (as brl_ppo_loss)  [12] scratch f64[16] */
+int32_t brl_ppo_grad(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+
 /* ---- full evaluation statistics (src/evaluation.py:207-1032) ---------------------------------- */
 #define BRL_F_EVAL_INDICATOR_BIDS 0x0400 /* non-duplicate `evaluate`: bid histogram is .set(1), not += 1 (src/evaluation.py:345-354) */
 #define BRL_EVAL_ACC_COLS 76    /* per-env log row: ill[2] steps[2] passes[2] actor_bid[35] opp_bid[35] (team 1 first) */
@@ -314,6 +341,8 @@ void brl_policy_act_xla(brl_stream_t, void **buffers, const char *opaque, size_t
 void brl_ppo_loss_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_adam_clip_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_gather_rows_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_mlp_pack_train_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_ppo_grad_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_eval_act_log_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_eval_summary_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 
