@@ -19,7 +19,7 @@ OPS = (
 HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host", "brl_env_rollout_host",
             "brl_env_rollout_host_async", "brl_env_wait", "brl_env_trajectory")
 MISC = ("brl_last_error", "brl_abi_version", "brl_mlp_packed_bytes", "brl_mlp_scratch_bytes", "brl_eval_num_sums",
-        "brl_mlp_num_params", "brl_mlp_train_blob_bytes", "brl_mlp_train_scratch_bytes")
+        "brl_mlp_num_params", "brl_mlp_train_blob_bytes", "brl_mlp_train_scratch_bytes", "brl_mlp_train_trace_offset")
 XLA_LEGACY = tuple(op + "_xla" for op in OPS)  # legacy XLA GPU custom-call targets (csrc/xla_ffi_shim.cc)
 ALL_SYMBOLS = OPS + HOST_API + MISC + XLA_LEGACY
 
@@ -110,6 +110,8 @@ def load():
     L.brl_mlp_train_blob_bytes.restype = C.c_int64
     L.brl_mlp_train_scratch_bytes.restype = C.c_int64
     L.brl_mlp_train_scratch_bytes.argtypes = [C.c_int64]
+    L.brl_mlp_train_trace_offset.restype = C.c_int64
+    L.brl_mlp_train_trace_offset.argtypes = [C.c_int64]
     L.brl_env_create.restype = C.c_void_p
     L.brl_env_create.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_uint64, C.c_int32]
     L.brl_env_destroy.restype = None

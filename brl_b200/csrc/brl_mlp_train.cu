@@ -116,13 +116,24 @@ __global__ void __launch_bounds__(256) k_pack_train(const __grid_constant__ Pack
 }
 
 // ---- per-minibatch scratch -------------------------------------------------------------------------------
+constexpr int kMaxOps = 9;  // GEMMs of one fused launch (forward: 5, backward: 9)
+constexpr int kTraceTiles = 4096;
+// tile counters of the two fused launches: per launch, per op: one counter per 128-row block of the op's OUTPUT (batch
+// rows for forward / dgrad, input features for wgrad) + one total
+__host__ __device__ inline int ready_blocks(int64_t B) {
+    const int nb = (int)((B + kBM - 1) / kBM);
+    return nb > kHidden / kBM ? nb : kHidden / kBM;
+}
+__host__ __device__ inline size_t ready_words(int64_t B) { return (size_t)2 * kMaxOps * (size_t)(ready_blocks(B) + 1); }
 struct TrainScratch {
     size_t obs_r, obs_t;                          // bf16 [B, 480], [480, ldt]
     size_t h_r_hi[4], h_r_lo[4], h_t_hi[4], h_t_lo[4];   // activations of layers 1..4: [B, 1024], [1024, ldt]
-    size_t dz_r_hi[2], dz_r_lo[2];                // d loss / d pre-activation, row-major ping-pong [B, 1024]
+    size_t dz_r_hi[4], dz_r_lo[4];                // d loss / d pre-activation of layers 1..4, row-major [B, 1024]
     size_t dz_t_hi[4], dz_t_lo[4];                // ... batch-major [1024, ldt], kept per layer for the bias sums
     size_t dz5_r_hi, dz5_r_lo, dz5_t_hi, dz5_t_lo;  // head: [B, 64], [64, ldt]
     size_t logits, value, dlogits, dvalue;        // f32 [B, 38], [B]
+    size_t ready;                                 // u32 tile counters of the fused launches (kReadyWords)
+    size_t trace;                                 // u64 [2][kTraceTiles][8] %globaltimer stamps (tune bit 3, scripts/exp_train_trace.py)
     size_t total;
     int ldt;                                      // row pitch (elements) of the batch-major arrays
 };
@@ -142,7 +153,7 @@ __host__ inline TrainScratch train_scratch(int64_t B) {
         S.dz_t_hi[l] = take((size_t)kHidden * ldt * 2);
         S.dz_t_lo[l] = take((size_t)kHidden * ldt * 2);
     }
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 4; ++k) {
         S.dz_r_hi[k] = take((size_t)B * kHidden * 2);
         S.dz_r_lo[k] = take((size_t)B * kHidden * 2);
     }
@@ -154,6 +165,8 @@ __host__ inline TrainScratch train_scratch(int64_t B) {
     S.value = take((size_t)B * 4);
     S.dlogits = take((size_t)B * 38 * 4);
     S.dvalue = take((size_t)B * 4);
+    S.ready = take(ready_words(B) * sizeof(uint32_t));
+    S.trace = take((size_t)2 * kTraceTiles * 8 * sizeof(unsigned long long));
     S.total = off;
     return S;
 }
@@ -507,12 +520,275 @@ static int32_t launch_gemm(cudaStream_t s, const void* a_hi, const void* a_lo, i
     return BRL_OK;
 }
 
-// hidden-layer GEMMs with the tile width picked at run time (narrow tiles fill more of the 148 SMs at minibatch sizes)
-template <bool SPLIT_A, int EPI>
-static int32_t launch_hidden(bool narrow, cudaStream_t s, const void* a_hi, const void* a_lo, int m_rows, int lda, const void* w_hi,
-                             const void* w_lo, int n_rows, int ldb, int k_cols, const GemmArgs& args) {
-    return narrow ? launch_gemm<64, SPLIT_A, true, EPI>(s, a_hi, a_lo, m_rows, lda, w_hi, w_lo, n_rows, ldb, k_cols, args)
-                  : launch_gemm<128, SPLIT_A, true, EPI>(s, a_hi, a_lo, m_rows, lda, w_hi, w_lo, n_rows, ldb, k_cols, args);
+// ---- all GEMMs of the forward (or of the backward) as ONE persistent launch ----------------------------------------
+// At a 1024-sample minibatch each GEMM is ~128 tiles of ~6 us on 148 SMs: run one launch per GEMM and the fixed costs
+// (launch gap, barrier / tensor-memory set-up, pipeline fill, the un-overlapped epilogue of each CTA's single tile)
+// are as large as the main loops.  Here the tiles of up to kMaxOps GEMMs form one list walked round-robin by one CTA
+// per SM, with the same producer / MMA / epilogue pipeline as k_gemm_tc running straight across op boundaries.
+// Dependencies: a forward / dgrad tile reads only rows [m0, m0 + 128) of its producer's output, so it waits for that
+// 128-row block (producer's n-tiles x 4 epilogue warps arrivals); a wgrad tile contracts over the whole batch and
+// waits for the producer's total.  Epilogue warps publish with st.global + __threadfence + atomicAdd; the TMA producer
+// acquires the counter and crosses into the async proxy before the tile's first load.  Tiles depend only on tiles
+// earlier in the list, every CTA takes its tiles in list order and the grid never exceeds the SM count (1 CTA / SM),
+// so the waits cannot deadlock; spins are bounded (a protocol bug traps instead of hanging the GPU).
+struct FusedOp {
+    CUtensorMap a_hi, a_lo, w_hi, w_lo;
+    GemmArgs g;
+    int epi, split_a;
+    int tile0;               // index of this op's first tile in the list
+    int dep;                 // producing op of this launch, -1 = none (inputs complete before the launch)
+    int dep_all;             // 1: wait for all of the producer's tiles, 0: for its row block m0 / 128
+    uint32_t dep_count;      // arrivals that complete the awaited counter
+};
+struct FusedTrainArgs {
+    FusedOp op[kMaxOps];
+    int n_ops, n_tiles, nmb;
+    uint32_t* ready;         // [n_ops][nmb + 1]: per-row-block counters, then the op's total
+    unsigned long long* trace;  // NULL, or [n_tiles][8] time stamps: dep wait begin / end, loads issued, first MMA, last MMA issued, accumulator seen, published
+};
+
+// FBN = tile width of the fused launches: 64 keeps the most tiles in flight, 128 moves a third fewer operand bytes from
+// L2 per FLOP (the measured bound at minibatch sizes) and relies on tiles of different ops to fill the SMs.
+template <int kFBN>
+struct FusedTrainCfg {
+    static constexpr uint32_t kABytes = kBM * kBK * 2, kWBytes = kFBN * kBK * 2;
+    static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kWBytes;  // A_hi, A_lo (unused when the A operand is exact), W_hi, W_lo
+    static constexpr int kStages = (int)(kSmemBudget / kStageBytes);
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void trace_stamp(const FusedTrainArgs& a, int tile, int slot) {
+    if (a.trace != nullptr && tile < kTraceTiles) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[(size_t)tile * 8 + slot] = t;
+    }
+}
+
+__device__ __forceinline__ int fused_find_op(const FusedTrainArgs& a, int tile) {
+    int o = 0;
+#pragma unroll 1
+    for (int k = 1; k < a.n_ops; ++k)
+        if (tile >= a.op[k].tile0) o = k;
+    return o;
+}
+
+template <int kFBN>
+__global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_constant__ FusedTrainArgs a) {
+    using Cfg = FusedTrainCfg<kFBN>;
+    constexpr int S = Cfg::kStages;
+    constexpr uint32_t kTmemCols = 2 * kFBN;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_addr(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + S * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+    auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
+    auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = a.n_tiles;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_addr(&tmem_base_s), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(&tmem_base_s);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int o = fused_find_op(a, tile);
+                const FusedOp& op = a.op[o];
+                const int r = tile - op.tile0;
+                const int mb = r / op.g.n_tiles_n, m0 = mb * kBM, n0 = (r % op.g.n_tiles_n) * kFBN;
+                const bool split_a = op.split_a != 0;
+                const uint32_t tx = Cfg::kABytes * (split_a ? 2u : 1u) + 2u * Cfg::kWBytes;
+                trace_stamp(a, tile, 0);
+                if (op.dep >= 0) {
+                    const uint32_t* flag = a.ready + (size_t)op.dep * (a.nmb + 1) + (op.dep_all ? a.nmb : mb);
+                    uint32_t v = 0;
+                    for (uint32_t spin = 0;; ++spin) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                        if (v >= op.dep_count) break;
+                        if (spin > (1u << 24)) __trap();
+                        __nanosleep(64);
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> async-proxy (TMA) reads
+                }
+                trace_stamp(a, tile, 1);
+                for (int kb = 0; kb < op.g.k_blocks; ++kb, ++it) {
+                    const int s = (int)(it % S);
+                    mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
+                    mbar_expect_tx(full_bar(s), tx);
+                    const uint32_t sa = base + s * Cfg::kStageBytes;
+                    const uint32_t sw = sa + 2 * Cfg::kABytes;
+                    tma_load_2d(sa, &op.a_hi, full_bar(s), kb * kBK, m0);
+                    if (split_a) tma_load_2d(sa + Cfg::kABytes, &op.a_lo, full_bar(s), kb * kBK, m0);
+                    tma_load_2d(sw, &op.w_hi, full_bar(s), kb * kBK, n0);
+                    tma_load_2d(sw + Cfg::kWBytes, &op.w_lo, full_bar(s), kb * kBK, n0);
+                }
+                trace_stamp(a, tile, 2);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_bf16(kBM, kFBN);
+            uint32_t it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+                const FusedOp& op = a.op[fused_find_op(a, tile)];
+                const bool split_a = op.split_a != 0;
+                const int k_blocks = op.g.k_blocks;
+                const uint32_t buf = j & 1u;
+                mbar_wait(tmem_empty_bar(buf), ((j >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t acc = tmem_acc + buf * kFBN;
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = (int)(it % S);
+                    mbar_wait(full_bar(s), (it / S) & 1u);
+                    tc_fence_after();
+                    if (kb == 0) trace_stamp(a, tile, 3);
+                    const uint32_t sa_hi = base + s * Cfg::kStageBytes;
+                    const uint32_t sa_lo = sa_hi + Cfg::kABytes;
+                    const uint32_t sw_hi = sa_hi + 2 * Cfg::kABytes;
+                    const uint32_t sw_lo = sw_hi + Cfg::kWBytes;
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t koff = (uint32_t)k * kUmmaK * 2;
+                        const uint64_t da_hi = umma_desc_sw128(sa_hi + koff), dw_hi = umma_desc_sw128(sw_hi + koff);
+                        umma_bf16(acc, da_hi, dw_hi, idesc, (kb | k) != 0);
+                        if (split_a) umma_bf16(acc, umma_desc_sw128(sa_lo + koff), dw_hi, idesc, 1u);
+                        umma_bf16(acc, da_hi, umma_desc_sw128(sw_lo + koff), idesc, 1u);
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tmem_full_bar(buf));
+                trace_stamp(a, tile, 4);
+            }
+        }
+    } else {  // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        uint32_t j = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            const int o = fused_find_op(a, tile);
+            const FusedOp& op = a.op[o];
+            const int r = tile - op.tile0;
+            const int mb = r / op.g.n_tiles_n, m0 = mb * kBM, n0 = (r % op.g.n_tiles_n) * kFBN;
+            const uint32_t buf = j & 1u;
+            mbar_wait(tmem_full_bar(buf), (j >> 1) & 1u);
+            tc_fence_after();
+            if (q == 0 && lane == 0) trace_stamp(a, tile, 5);
+            const int row = m0 + q * 32 + lane;
+            const uint32_t t_row = tmem_acc + buf * kFBN + ((uint32_t)(q * 32) << 16);
+            const bool row_ok = row < op.g.M;
+            if (op.epi == kEpiFwd) epilogue_act_row<kEpiFwd>(t_row, kFBN, n0, row, row_ok, op.g);
+            else if (op.epi == kEpiDgrad) epilogue_act_row<kEpiDgrad>(t_row, kFBN, n0, row, row_ok, op.g);
+            else if (op.epi == kEpiWgrad) epilogue_wgrad_row<kFBN>(t_row, n0, row, row_ok, op.g);
+            else epilogue_head_row(t_row, op.g.bias + n0, row_ok, op.g.logits + (size_t)row * 38, op.g.value + row);
+            tc_fence_before();
+            __threadfence();  // this lane's stores are visible GPU-wide before the counts below
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(buf)) : "memory");
+                __threadfence();
+                uint32_t* cnt = a.ready + (size_t)o * (a.nmb + 1);
+                atomicAdd(cnt + mb, 1u);
+                atomicAdd(cnt + a.nmb, 1u);
+                if (q == 0) trace_stamp(a, tile, 6);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, kTmemCols);
+}
+
+// one GEMM of the update, as the host describes it to either launcher
+struct OpSpec {
+    const void *a_hi, *a_lo;
+    int m_rows, lda;
+    const void *w_hi, *w_lo;
+    int n_rows, ldb, k_cols;
+    int epi;
+    GemmArgs g;
+    int dep, dep_all;
+};
+
+static int32_t launch_op(bool narrow, cudaStream_t s, const OpSpec& o) {
+    const bool sa = o.a_lo != nullptr;
+#define BRL_GEMM(BN, SA, EPI) launch_gemm<BN, SA, true, EPI>(s, o.a_hi, o.a_lo, o.m_rows, o.lda, o.w_hi, o.w_lo, o.n_rows, o.ldb, o.k_cols, o.g)
+    if (o.epi == kEpiHead) return BRL_GEMM(kHeadPad, true, kEpiHead);
+    if (o.epi == kEpiWgrad && o.n_rows == kHeadPad) return BRL_GEMM(kHeadPad, true, kEpiWgrad);
+    if (o.epi == kEpiFwd) return narrow ? (sa ? BRL_GEMM(64, true, kEpiFwd) : BRL_GEMM(64, false, kEpiFwd))
+                                        : (sa ? BRL_GEMM(128, true, kEpiFwd) : BRL_GEMM(128, false, kEpiFwd));
+    if (o.epi == kEpiDgrad) return narrow ? BRL_GEMM(64, true, kEpiDgrad) : BRL_GEMM(128, true, kEpiDgrad);
+    return narrow ? (sa ? BRL_GEMM(64, true, kEpiWgrad) : BRL_GEMM(64, false, kEpiWgrad))
+                  : (sa ? BRL_GEMM(128, true, kEpiWgrad) : BRL_GEMM(128, false, kEpiWgrad));
+#undef BRL_GEMM
+}
+
+template <int kFBN>
+static int32_t launch_fused_ops(cudaStream_t s, const OpSpec* ops, int n_ops, int nmb, uint32_t* ready, unsigned long long* trace) {
+    using Cfg = FusedTrainCfg<kFBN>;
+    FusedTrainArgs fa{};
+    int tiles = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        const OpSpec& o = ops[i];
+        FusedOp& f = fa.op[i];
+        bool ok = make_map(&f.a_hi, o.a_hi, (uint64_t)o.m_rows, (uint64_t)o.k_cols, (uint64_t)o.lda, kBM) &&
+                  make_map(&f.w_hi, o.w_hi, (uint64_t)o.n_rows, (uint64_t)o.k_cols, (uint64_t)o.ldb, kFBN) &&
+                  make_map(&f.w_lo, o.w_lo, (uint64_t)o.n_rows, (uint64_t)o.k_cols, (uint64_t)o.ldb, kFBN);
+        f.a_lo = f.a_hi;
+        if (ok && o.a_lo) ok = make_map(&f.a_lo, o.a_lo, (uint64_t)o.m_rows, (uint64_t)o.k_cols, (uint64_t)o.lda, kBM);
+        if (!ok) return fail(BRL_E_LAUNCH, "brl_ppo_grad: cuTensorMapEncodeTiled failed");
+        f.g = o.g;
+        f.g.M = o.m_rows;
+        f.g.k_blocks = (o.k_cols + kBK - 1) / kBK;
+        f.g.n_tiles_n = (o.n_rows + kFBN - 1) / kFBN;
+        f.g.n_tiles = f.g.n_tiles_n * ((o.m_rows + kBM - 1) / kBM);
+        f.epi = o.epi;
+        f.split_a = o.a_lo != nullptr;
+        f.tile0 = tiles;
+        tiles += f.g.n_tiles;
+        f.dep = o.dep;
+        f.dep_all = o.dep_all;
+        if (o.dep >= 0) f.dep_count = 4u * (uint32_t)(o.dep_all ? fa.op[o.dep].g.n_tiles : fa.op[o.dep].g.n_tiles_n);
+    }
+    fa.n_ops = n_ops;
+    fa.n_tiles = tiles;
+    fa.nmb = nmb;
+    fa.ready = ready;
+    fa.trace = trace;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        if (cudaFuncSetAttribute(k_train_fused<kFBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
+            return fail(BRL_E_LAUNCH, "brl_ppo_grad: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(tiles < n_sm ? tiles : n_sm));  // one CTA per SM: all of them co-resident
+    cfg.blockDim = dim3(kMlpThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, k_train_fused<kFBN>, fa) != cudaSuccess) return check_launch("brl_ppo_grad (fused launch)");
+    return BRL_OK;
 }
 
 }  // namespace brl
@@ -524,6 +800,7 @@ extern "C" {
 int64_t brl_mlp_num_params(void) { return (int64_t)flat_layout().total; }
 int64_t brl_mlp_train_blob_bytes(void) { return (int64_t)train_blob().total; }
 int64_t brl_mlp_train_scratch_bytes(int64_t batch) { return batch > 0 ? (int64_t)train_scratch(batch).total : 0; }
+int64_t brl_mlp_train_trace_offset(int64_t batch) { return batch > 0 ? (int64_t)train_scratch(batch).trace : 0; }
 
 int32_t brl_mlp_pack_train(brl_stream_t stream, void** b, const void* opaque, size_t len) {
     int32_t rc;
@@ -572,25 +849,88 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         else if (p->flags & BRL_PPO_OBS_U8) k_gather_obs<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(b[0]), index, B, ldt, o_r, o_t);
         else k_gather_obs<float><<<grid, 256, 0, s>>>(static_cast<const float*>(b[0]), index, B, ldt, o_r, o_t);
     }
-    // 2. forward, activations kept (row-major for the next layer / the ReLU mask, batch-major for the wgrad)
-    for (int l = 0; l < 4 && rc == BRL_OK; ++l) {
-        GemmArgs a{};
-        a.bias = reinterpret_cast<const float*>(blob + L.bias[l]);
-        a.out_hi = bf(S.h_r_hi[l]); a.out_lo = bf(S.h_r_lo[l]);
-        a.out_t_hi = bf(S.h_t_hi[l]); a.out_t_lo = bf(S.h_t_lo[l]);
-        a.ld_out = kHidden; a.ld_t = ldt;
-        if (l == 0) rc = launch_hidden<false, kEpiFwd>(narrow, s, sc + S.obs_r, nullptr, B, kObsDimM, blob + L.w_hi[0], blob + L.w_lo[0], kHidden, kObsDimM, kObsDimM, a);
-        else rc = launch_hidden<true, kEpiFwd>(narrow, s, sc + S.h_r_hi[l - 1], sc + S.h_r_lo[l - 1], B, kHidden, blob + L.w_hi[l], blob + L.w_lo[l], kHidden, kHidden, kHidden, a);
+    // 2. the GEMMs.  Forward: layers 1..4 (activations kept row-major for the next layer / the ReLU mask and batch-major
+    //    for the wgrad) + the head.  Backward: dgrad into layer l's pre-activation, dz_l = (dz_{l+1} . W_{l+1}^T) * [h_l > 0]
+    //    (dz_r[l-1] / dz_t[l-1], l = 1..4), and the wgrads dW_l = h_{l-1}^T . dz_l.
+    OpSpec fwd[5], bwd[kMaxOps];
+    for (int l = 0; l < 4; ++l) {
+        OpSpec& o = fwd[l];
+        o = OpSpec{};
+        o.a_hi = l == 0 ? sc + S.obs_r : sc + S.h_r_hi[l - 1];
+        o.a_lo = l == 0 ? nullptr : sc + S.h_r_lo[l - 1];
+        o.m_rows = B; o.lda = L.k_in[l];
+        o.w_hi = blob + L.w_hi[l]; o.w_lo = blob + L.w_lo[l];
+        o.n_rows = kHidden; o.ldb = L.k_in[l]; o.k_cols = L.k_in[l];
+        o.epi = kEpiFwd;
+        o.g.bias = reinterpret_cast<const float*>(blob + L.bias[l]);
+        o.g.out_hi = bf(S.h_r_hi[l]); o.g.out_lo = bf(S.h_r_lo[l]);
+        o.g.out_t_hi = bf(S.h_t_hi[l]); o.g.out_t_lo = bf(S.h_t_lo[l]);
+        o.g.ld_out = kHidden; o.g.ld_t = ldt;
+        o.dep = l - 1; o.dep_all = 0;
+    }
+    {
+        OpSpec& o = fwd[4];
+        o = OpSpec{};
+        o.a_hi = sc + S.h_r_hi[3]; o.a_lo = sc + S.h_r_lo[3]; o.m_rows = B; o.lda = kHidden;
+        o.w_hi = blob + L.w_hi[4]; o.w_lo = blob + L.w_lo[4]; o.n_rows = kHeadPad; o.ldb = kHidden; o.k_cols = kHidden;
+        o.epi = kEpiHead;
+        o.g.bias = reinterpret_cast<const float*>(blob + L.bias[4]);
+        o.g.logits = reinterpret_cast<float*>(sc + S.logits);
+        o.g.value = reinterpret_cast<float*>(sc + S.value);
+        o.dep = 3; o.dep_all = 0;
+    }
+    int nb = 0;
+    int dgrad_op[5] = {-1, -1, -1, -1, -1};  // op index (in bwd) that produced dz of layer l (1..4)
+    {   // head wgrad: [1024, 39] = h4^T . dz5 -> w4 grads (38 columns) + w5 grads (the value column)
+        OpSpec& o = bwd[nb++];
+        o = OpSpec{};
+        o.a_hi = sc + S.h_t_hi[3]; o.a_lo = sc + S.h_t_lo[3]; o.m_rows = kHidden; o.lda = ldt;
+        o.w_hi = sc + S.dz5_t_hi; o.w_lo = sc + S.dz5_t_lo; o.n_rows = kHeadPad; o.ldb = ldt; o.k_cols = B;
+        o.epi = kEpiWgrad;
+        o.g.c = grads + F.w[4]; o.g.ld_c = 38; o.g.n_c = 38; o.g.c2 = grads + F.w[5];
+        o.dep = -1;
+    }
+    for (int l = 4; l >= 1; --l) {
+        {   // dgrad into layer l
+            OpSpec& o = bwd[nb];
+            o = OpSpec{};
+            const int k_out = l == 4 ? kHeadPad : kHidden;  // width of dz_{l+1}
+            o.a_hi = l == 4 ? sc + S.dz5_r_hi : sc + S.dz_r_hi[l];
+            o.a_lo = l == 4 ? sc + S.dz5_r_lo : sc + S.dz_r_lo[l];
+            o.m_rows = B; o.lda = k_out;
+            o.w_hi = blob + T.wn_hi[l]; o.w_lo = blob + T.wn_lo[l]; o.n_rows = kHidden; o.ldb = k_out; o.k_cols = k_out;
+            o.epi = kEpiDgrad;
+            o.g.out_hi = bf(S.dz_r_hi[l - 1]); o.g.out_lo = bf(S.dz_r_lo[l - 1]);
+            o.g.out_t_hi = bf(S.dz_t_hi[l - 1]); o.g.out_t_lo = bf(S.dz_t_lo[l - 1]);
+            o.g.ld_out = kHidden; o.g.ld_t = ldt;
+            o.g.relu_src = bf(S.h_r_hi[l - 1]);
+            o.dep = l == 4 ? -1 : dgrad_op[l + 1]; o.dep_all = 0;
+            dgrad_op[l] = nb++;
+        }
+        {   // wgrad of layer l (0-based parameter index l - 1): dW = h_{l-1}^T . dz_l
+            OpSpec& o = bwd[nb++];
+            o = OpSpec{};
+            o.a_hi = l == 1 ? sc + S.obs_t : sc + S.h_t_hi[l - 2];
+            o.a_lo = l == 1 ? nullptr : sc + S.h_t_lo[l - 2];
+            o.m_rows = l == 1 ? kObsDimM : kHidden; o.lda = ldt;
+            o.w_hi = sc + S.dz_t_hi[l - 1]; o.w_lo = sc + S.dz_t_lo[l - 1]; o.n_rows = kHidden; o.ldb = ldt; o.k_cols = B;
+            o.epi = kEpiWgrad;
+            o.g.c = grads + F.w[l - 1]; o.g.ld_c = kHidden; o.g.n_c = kHidden;
+            o.dep = dgrad_op[l]; o.dep_all = 1;
+        }
+    }
+    const bool fused = (p->reserved & 2) == 0;  // tune bit 1: one launch per GEMM (bit 0 then picks 128 x 64 over 128 x 128 tiles)
+    const bool wide_fused = (p->reserved & 4) != 0;  // tune bit 2: 128 x 128 tiles in the fused launches
+    unsigned long long* trace = (p->reserved & 8) ? reinterpret_cast<unsigned long long*>(sc + S.trace) : nullptr;  // tune bit 3
+    const int nmb = ready_blocks(B);
+    uint32_t* ready = reinterpret_cast<uint32_t*>(sc + S.ready);
+    if (fused) {
+        if (cudaMemsetAsync(ready, 0, ready_words(B) * sizeof(uint32_t), s) != cudaSuccess) return check_launch("brl_ppo_grad (memset)");
+        rc = wide_fused ? launch_fused_ops<128>(s, fwd, 5, nmb, ready, trace) : launch_fused_ops<64>(s, fwd, 5, nmb, ready, trace);
+    } else {
+        for (int i = 0; i < 5 && rc == BRL_OK; ++i) rc = launch_op(narrow, s, fwd[i]);
     }
     if (rc != BRL_OK) return rc;
-    {
-        GemmArgs a{};
-        a.bias = reinterpret_cast<const float*>(blob + L.bias[4]);
-        a.logits = reinterpret_cast<float*>(sc + S.logits);
-        a.value = reinterpret_cast<float*>(sc + S.value);
-        rc = launch_gemm<kHeadPad, true, true, kEpiHead>(s, sc + S.h_r_hi[3], sc + S.h_r_lo[3], B, kHidden, blob + L.w_hi[4], blob + L.w_lo[4], kHeadPad, kHidden, kHidden, a);
-        if (rc != BRL_OK) return rc;
-    }
     if ((rc = check_launch("brl_ppo_grad (forward)")) != BRL_OK) return rc;
     // 3. loss head + its backward (src/update.py:97-162)
     {
@@ -603,31 +943,11 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
             reinterpret_cast<const float*>(sc + S.dlogits), reinterpret_cast<const float*>(sc + S.dvalue), B, ldt, bf(S.dz5_r_hi), bf(S.dz5_r_lo),
             bf(S.dz5_t_hi), bf(S.dz5_t_lo));
     }
-    // 4. backward: head, then hidden layers 4..1.  dz of layer l lives in dz_r[(4 - l) & 1] / dz_t[l - 1] (l = 1..4).
-    {   // head wgrad: [1024, 39] = h4^T . dz5 -> w4 grads (38 columns) + w5 grads (the value column)
-        GemmArgs a{};
-        a.c = grads + F.w[4]; a.ld_c = 38; a.n_c = 38; a.c2 = grads + F.w[5];
-        rc = launch_gemm<kHeadPad, true, true, kEpiWgrad>(s, sc + S.h_t_hi[3], sc + S.h_t_lo[3], kHidden, ldt, sc + S.dz5_t_hi, sc + S.dz5_t_lo, kHeadPad, ldt, B, a);
-        if (rc != BRL_OK) return rc;
-    }
-    for (int l = 4; l >= 1 && rc == BRL_OK; --l) {
-        // dgrad into layer l's pre-activation: dz_l = (dz_{l+1} . W_{l+1}^T) * [h_l > 0]
-        const int k_out = l == 4 ? kHeadPad : kHidden;  // width of dz_{l+1}
-        const void* up_hi = l == 4 ? (const void*)(sc + S.dz5_r_hi) : (const void*)(sc + S.dz_r_hi[(4 - (l + 1)) & 1]);
-        const void* up_lo = l == 4 ? (const void*)(sc + S.dz5_r_lo) : (const void*)(sc + S.dz_r_lo[(4 - (l + 1)) & 1]);
-        GemmArgs a{};
-        a.out_hi = bf(S.dz_r_hi[(4 - l) & 1]); a.out_lo = bf(S.dz_r_lo[(4 - l) & 1]);
-        a.out_t_hi = bf(S.dz_t_hi[l - 1]); a.out_t_lo = bf(S.dz_t_lo[l - 1]);
-        a.ld_out = kHidden; a.ld_t = ldt;
-        a.relu_src = bf(S.h_r_hi[l - 1]);
-        rc = launch_hidden<true, kEpiDgrad>(narrow, s, up_hi, up_lo, B, k_out, blob + T.wn_hi[l], blob + T.wn_lo[l], kHidden, k_out, k_out, a);
-        if (rc != BRL_OK) break;
-        // wgrad of layer l (0-based parameter index l - 1): dW = h_{l-1}^T . dz_l
-        GemmArgs w{};
-        w.c = grads + F.w[l - 1]; w.ld_c = kHidden; w.n_c = kHidden;
-        if (l == 1) rc = launch_hidden<false, kEpiWgrad>(narrow, s, sc + S.obs_t, nullptr, kObsDimM, ldt, sc + S.dz_t_hi[0], sc + S.dz_t_lo[0], kHidden, ldt, B, w);
-        else rc = launch_hidden<true, kEpiWgrad>(narrow, s, sc + S.h_t_hi[l - 2], sc + S.h_t_lo[l - 2], kHidden, ldt, sc + S.dz_t_hi[l - 1], sc + S.dz_t_lo[l - 1], kHidden, ldt, B, w);
-    }
+    // 4. backward GEMMs
+    if (fused) rc = wide_fused ? launch_fused_ops<128>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr)
+                               : launch_fused_ops<64>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr);
+    else
+        for (int i = 0; i < nb && rc == BRL_OK; ++i) rc = launch_op(narrow, s, bwd[i]);
     if (rc != BRL_OK) return rc;
     // 5. bias gradients
     {

@@ -96,6 +96,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// MN-major operand tile: the M (or N) index is the contiguous one, as when a [K, M] row-major matrix is staged by
+// TMA boxes of {64 M-elements = 128 bytes, K rows} with 128B swizzle.  Canonical form (128-bit units):
+// Swizzle<3,4,3> o ((8, m), (8, k)) : ((1, LBO), (8, SBO)): K rows 128 bytes apart, 8-row K groups SBO = 1024 bytes apart,
+// 64-element M chunks LBO bytes apart (= the size of one staged box).  Advancing K by 16 = +2048 bytes on the start address.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;     // leading byte offset between 64-element MN chunks
+    d |= (uint64_t)(1024u >> 4) << 32;                     // stride byte offset between 8-row K groups
+    d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+// ... and the instruction descriptor with both operands MN-major (a_major, b_major = bits 15, 16)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int m, int n) { return umma_idesc_bf16(m, n) | (1u << 15) | (1u << 16); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(

@@ -273,6 +273,8 @@ int32_t brl_gather_rows(brl_stream_t, void **buffers, const void *opaque, size_t
 int64_t brl_mlp_num_params(void);
 int64_t brl_mlp_train_blob_bytes(void);
 int64_t brl_mlp_train_scratch_bytes(int64_t batch);
+int64_t brl_mlp_train_trace_offset(int64_t batch); /* debug: offset in the scratch of the u64[2][4096][8] tile time stamps written when
+                                                        BrlPpoParams.reserved bit 3 is set (scripts/exp_train_trace.py) */
 /* flat params -> training blob: the forward layout of brl_mlp_pack (the blob is also a valid `packed` argument of
  * brl_mlp_forward / brl_policy_act) followed by W[in,out_pad] bf16 hi / lo for the input-gradient GEMMs.
  * Run after every optimizer step.  opaque = BrlParams (fields unused).
