@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="also time 65,536 and 1,048,576 envs and single-step launches")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-policy", action="store_true", help="skip the configs[2] policy-rollout leg")
+    ap.add_argument("--no-update", action="store_true", help="skip the PPO-update leg (SURVEY 8f-1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -265,6 +266,8 @@ def main():
 
     if rank == 0 and not args.no_policy:
         extra["policy_rollout"] = run_policy_rollout(torch, table_np, dev)
+    if rank == 0 and not args.no_update:
+        extra["ppo_update"] = run_ppo_update(torch, dev)
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -486,6 +489,71 @@ def run_policy_rollout(torch, table_np, dev):
                 "frac": flops * mma_factor / (fms * 1e-3) / 1e12 / tpeak,
                 "note": "achieved = bf16 MMA FLOPs actually issued (x%.2f of the model's FLOPs in this mode) / CUDA-event time of the "
                         "whole forward (obs->bf16 cast + 5 layer launches); peak = measured cuBLAS bf16 burst" % mma_factor}
+    return out
+
+
+def run_ppo_update(torch, dev):
+    """the update half of a ppo.py iteration on the configs[2] rollout shape (8192 envs x 32 steps,
+    minibatch 1024 => 256 optimizer steps per epoch): minibatch take + forward + loss + backward + clip/Adam per
+    step, through `make_update_step` (the call ppo.py makes), one epoch per timed call.  "tc" = all hand-written
+    kernels (brl_ppo_grad on tcgen05); "fp32" = the same loss / Adam kernels around cuBLAS fp32 GEMMs via autograd."""
+    from brl_b200 import random as brandom
+    from brl_b200.models import init_params, make_forward_pass
+    from brl_b200.optim import AdamWithClip
+    from brl_b200.roll_out import Transition
+    from brl_b200.update import make_update_step
+    n, T, mbs = N_ENVS, T_STEPS, 1024
+    nmb = n * T // mbs
+    config = dict(actor_illegal_action_mask=True, actor_illegal_action_penalty=False, clip_eps=0.2, ent_coef=0.01, vf_coef=0.5,
+                  illegal_action_l2norm_coef=0.0, value_clipping=True, reward_scaling=False, num_minibatches=nmb,
+                  minibatch_size=mbs, update_epochs=1, num_steps=T, num_envs=n)
+    g = torch.Generator(device=dev).manual_seed(11)
+    obs = (torch.rand((T, n, 480), generator=g, device=dev) < 0.04).to(torch.bfloat16)
+    mask = torch.rand((T, n, 38), generator=g, device=dev) < 0.5
+    mask[..., 0] = True
+    traj = Transition(done=torch.zeros((T, n), dtype=torch.bool, device=dev),
+                      action=torch.zeros((T, n), dtype=torch.int32, device=dev),
+                      value=torch.randn((T, n), generator=g, device=dev) * 0.3, reward=torch.zeros((T, n), device=dev),
+                      log_prob=-torch.rand((T, n), generator=g, device=dev) * 3, obs=obs, legal_action_mask=mask)
+    adv = torch.randn((T, n), generator=g, device=dev)
+    tgt = torch.randn((T, n), generator=g, device=dev) * 0.3
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            tpeak = float(json.load(fh)["bf16_tflops"])
+    except Exception:
+        tpeak = 1590.0
+    model_flop = 3 * 7354368.0 * mbs  # forward + input gradients + weight gradients, per optimizer step
+    # bf16 MMA FLOPs the split mode issues per sample: 3 products per term, 2 where the 0/1 observation is an operand
+    H, hp = 1024, 64
+    mma_flop = 2.0 * mbs * ((480 * H * 2 + 3 * H * H * 3 + H * hp * 3) + (hp * H * 3 + 3 * H * H * 3) + (H * hp * 3 + 3 * H * H * 3 + 480 * H * 2))
+    out = {"workload": f"ppo.py update on the configs[2] rollout: {T} x {n} samples, minibatch {mbs}, 1 epoch = {nmb} optimizer steps "
+                       "(take + forward + loss + backward + clip_by_global_norm + Adam each); synthetic trajectory, random-init net"}
+    for prec, reps in (("tc", 3), ("fp32", 1)):
+        fp = make_forward_pass("relu", "DeepMind", precision=prec)
+        params = init_params(1, dev)
+        opt = AdamWithClip(1e-4, eps=1e-5, max_grad_norm=0.5)
+        update_step = make_update_step(config, fp, opt)
+        runner = (params, opt.init(params), None, None, 0, brandom.PRNGKey(5))
+        runner, info0 = update_step(runner, traj, adv, tgt)  # warm-up epoch
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            runner, info = update_step(runner, traj, adv, tgt)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps / nmb
+        out[prec] = {"ms_per_optimizer_step": ms, "ms_per_epoch": ms * nmb, "samples_per_sec": mbs / (ms * 1e-3),
+                     "model_TFLOPs": model_flop / (ms * 1e-3) / 1e12,
+                     "first_total_loss": float(info0[0][0, 0])}  # same parameters and minibatch in both back ends
+        if prec == "tc":
+            out[prec]["tensor_roofline"] = {
+                "bound": "tensor", "achieved": mma_flop / (ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                "frac": mma_flop / (ms * 1e-3) / 1e12 / tpeak,
+                "note": "achieved = bf16 MMA FLOPs issued by the 14 split GEMMs of one step / CUDA-event time of the WHOLE optimizer step "
+                        "(incl. take, loss, bias sums, Adam, re-pack); at 1024 samples the GEMMs are bound by the L2 -> SM operand "
+                        "fill (~60 B/clk/SM measured, scripts/exp_train_trace.py), not by the tensor pipe"}
+    out["speedup_tc_over_library_fp32"] = out["fp32"]["ms_per_optimizer_step"] / out["tc"]["ms_per_optimizer_step"]
     return out
 
 

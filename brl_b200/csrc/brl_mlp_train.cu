@@ -12,10 +12,10 @@
 //   forward  h_l  = relu(h_{l-1} . W_l + b_l)      A = h_{l-1} [B, in]      Bt = W_l^T [out, in]   (packed "Wt")
 //   dgrad    dz_{l-1} = (dz_l . W_l^T) * (h_{l-1} > 0)   A = dz_l [B, out]  Bt = W_l [in, out]     (packed "Wn")
 //   wgrad    dW_l = h_{l-1}^T . dz_l               A = h_{l-1}^T [in, B]    Bt = dz_l^T [out, B]
-// The wgrad contracts over the batch, so it needs batch-major ("transposed") copies of the activations
-// and of the dz's: the forward / dgrad epilogues write those next to the row-major copies (a warp's 32
-// rows of one column are 64 contiguous bytes), which costs no extra launch and no extra read.
-// Bias gradients are the row sums of the transposed dz's (one warp per output feature).
+// The wgrad contracts over the batch, i.e. over the ROW index of the row-major activations and dz's the other
+// two GEMMs read and write.  No transposed copies are made: the wgrad stages {64 features x 64 samples} TMA
+// boxes of those same arrays and hands them to tcgen05.mma as MN-major operands (feature index contiguous,
+// umma_desc_mn_sw128), so the same kernel serves it too.  Bias gradients are column sums of the dz's.
 #include "common.h"
 #include "mlp_device.cuh"
 
@@ -126,41 +126,28 @@ __host__ __device__ inline int ready_blocks(int64_t B) {
 }
 __host__ __device__ inline size_t ready_words(int64_t B) { return (size_t)2 * kMaxOps * (size_t)(ready_blocks(B) + 1); }
 struct TrainScratch {
-    size_t obs_r, obs_t;                          // bf16 [B, 480], [480, ldt]
-    size_t h_r_hi[4], h_r_lo[4], h_t_hi[4], h_t_lo[4];   // activations of layers 1..4: [B, 1024], [1024, ldt]
-    size_t dz_r_hi[4], dz_r_lo[4];                // d loss / d pre-activation of layers 1..4, row-major [B, 1024]
-    size_t dz_t_hi[4], dz_t_lo[4];                // ... batch-major [1024, ldt], kept per layer for the bias sums
-    size_t dz5_r_hi, dz5_r_lo, dz5_t_hi, dz5_t_lo;  // head: [B, 64], [64, ldt]
+    size_t obs;                                   // bf16 [B, 480]
+    size_t h_hi[4], h_lo[4];                      // activations of layers 1..4, bf16 hi / lo [B, 1024]
+    size_t dz_hi[4], dz_lo[4];                    // d loss / d pre-activation of layers 1..4, bf16 hi / lo [B, 1024]
+    size_t dz5_hi, dz5_lo;                        // head: [B, 64] (38 logits, value, zero padding)
     size_t logits, value, dlogits, dvalue;        // f32 [B, 38], [B]
-    size_t ready;                                 // u32 tile counters of the fused launches (kReadyWords)
+    size_t ready;                                 // u32 tile counters of the fused launches (ready_words)
     size_t trace;                                 // u64 [2][kTraceTiles][8] %globaltimer stamps (tune bit 3, scripts/exp_train_trace.py)
     size_t total;
-    int ldt;                                      // row pitch (elements) of the batch-major arrays
 };
 __host__ inline TrainScratch train_scratch(int64_t B) {
     TrainScratch S{};
-    const size_t ldt = (size_t)((B + 63) / 64 * 64);
-    S.ldt = (int)ldt;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-    S.obs_r = take((size_t)B * kObsDimM * 2);
-    S.obs_t = take((size_t)kObsDimM * ldt * 2);
+    S.obs = take((size_t)B * kObsDimM * 2);
     for (int l = 0; l < 4; ++l) {
-        S.h_r_hi[l] = take((size_t)B * kHidden * 2);
-        S.h_r_lo[l] = take((size_t)B * kHidden * 2);
-        S.h_t_hi[l] = take((size_t)kHidden * ldt * 2);
-        S.h_t_lo[l] = take((size_t)kHidden * ldt * 2);
-        S.dz_t_hi[l] = take((size_t)kHidden * ldt * 2);
-        S.dz_t_lo[l] = take((size_t)kHidden * ldt * 2);
+        S.h_hi[l] = take((size_t)B * kHidden * 2);
+        S.h_lo[l] = take((size_t)B * kHidden * 2);
+        S.dz_hi[l] = take((size_t)B * kHidden * 2);
+        S.dz_lo[l] = take((size_t)B * kHidden * 2);
     }
-    for (int k = 0; k < 4; ++k) {
-        S.dz_r_hi[k] = take((size_t)B * kHidden * 2);
-        S.dz_r_lo[k] = take((size_t)B * kHidden * 2);
-    }
-    S.dz5_r_hi = take((size_t)B * kHeadPad * 2);
-    S.dz5_r_lo = take((size_t)B * kHeadPad * 2);
-    S.dz5_t_hi = take((size_t)kHeadPad * ldt * 2);
-    S.dz5_t_lo = take((size_t)kHeadPad * ldt * 2);
+    S.dz5_hi = take((size_t)B * kHeadPad * 2);
+    S.dz5_lo = take((size_t)B * kHeadPad * 2);
     S.logits = take((size_t)B * 38 * 4);
     S.value = take((size_t)B * 4);
     S.dlogits = take((size_t)B * 38 * 4);
@@ -171,86 +158,88 @@ __host__ inline TrainScratch train_scratch(int64_t B) {
     return S;
 }
 
-// ---- minibatch gather of the observation: obs[index[b]] (f32 / u8 0-1, or bf16) -> bf16 [B, 480] and [480, ldt] ----
+// ---- minibatch gather of the observation: obs[index[b]] (f32 / u8 0-1, or bf16) -> bf16 [B, 480] -------------------
 template <class T>
 __device__ __forceinline__ uint16_t obs_bits(T v) { return (float)v != 0.0f ? (uint16_t)0x3F80u : (uint16_t)0u; }
 template <>
 __device__ __forceinline__ uint16_t obs_bits<__nv_bfloat16>(__nv_bfloat16 v) { return *reinterpret_cast<uint16_t*>(&v); }
 
-constexpr int kGatherCols = 120;  // observation columns per block: grid = (B / 32) x 4 blocks
 template <class T>
-__global__ void __launch_bounds__(256) k_gather_obs(const T* __restrict__ obs, const int32_t* __restrict__ index, int64_t B, int ldt,
-                                                    uint16_t* __restrict__ out_r, uint16_t* __restrict__ out_t) {
-    __shared__ uint16_t tile[32][kGatherCols + 2];  // row stride 61 words: column reads are conflict-free
-    const int64_t r0 = (int64_t)blockIdx.x * 32;
-    const int c0 = blockIdx.y * kGatherCols;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = warp; r < 32; r += 8) {
-        const int64_t b = r0 + r;
-        if (b >= B) break;
-        const int64_t src = index ? (int64_t)index[b] : b;
-        for (int c = lane; c < kGatherCols; c += 32) {
-            const uint16_t v = obs_bits<T>(obs[src * kObsDimM + c0 + c]);
-            tile[r][c] = v;
-            out_r[b * kObsDimM + c0 + c] = v;
-        }
-    }
-    __syncthreads();
-    const int64_t b = r0 + lane;
-    if (b < B)
-        for (int c = warp; c < kGatherCols; c += 8) out_t[(size_t)(c0 + c) * ldt + b] = tile[lane][c];
+__global__ void __launch_bounds__(256) k_gather_obs(const T* __restrict__ obs, const int32_t* __restrict__ index, int64_t B,
+                                                    uint16_t* __restrict__ out) {
+    // 8 consecutive observation bits per thread: one 128-bit store
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * (kObsDimM / 8)) return;
+    const int64_t b = i / (kObsDimM / 8);
+    const int c = (int)(i % (kObsDimM / 8)) * 8;
+    const T* src = obs + (index ? (int64_t)index[b] : b) * kObsDimM + c;
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = (uint32_t)obs_bits<T>(src[2 * k]) | ((uint32_t)obs_bits<T>(src[2 * k + 1]) << 16);
+    *reinterpret_cast<uint4*>(out + b * kObsDimM + c) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// d loss / d (logits, value) f32 -> dz5 hi / lo, row-major [B, 64] and batch-major [64, ldt]; columns 39..63 are zero
-__global__ void __launch_bounds__(256) k_head_grad_pack(const float* __restrict__ dlogits, const float* __restrict__ dvalue, int64_t B, int ldt,
-                                                        __nv_bfloat16* __restrict__ r_hi, __nv_bfloat16* __restrict__ r_lo,
-                                                        __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo) {
+// d loss / d (logits, value) f32 -> dz5 hi / lo [B, 64]; columns 39..63 are zero
+__global__ void __launch_bounds__(256) k_head_grad_pack(const float* __restrict__ dlogits, const float* __restrict__ dvalue, int64_t B,
+                                                        __nv_bfloat16* __restrict__ r_hi, __nv_bfloat16* __restrict__ r_lo) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * kHeadPad) return;
     const int64_t row = idx / kHeadPad;
     const int c = (int)(idx % kHeadPad);
     const float v = c < 38 ? dlogits[row * 38 + c] : (c == 38 ? dvalue[row] : 0.0f);
-    const __nv_bfloat16 h = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(h));
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
     r_hi[idx] = h;
-    r_lo[idx] = lo;
-    t_hi[(size_t)c * ldt + row] = h;
-    t_lo[(size_t)c * ldt + row] = lo;
+    r_lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-// bias gradients: db[c] = sum_b dz[b, c]; one warp per output feature.  Hidden layers: row sums of the batch-major dz
-// (hi + lo); head: column sums of the fp32 d loss / d (logits, value) themselves.
+// bias gradients: db[c] = sum_b dz[b, c].  Hidden layers: column sums of dz (hi + lo); a block owns 64 columns of one
+// layer, thread = (row group of 8, column pair), then a shared-memory reduction over the row groups.  Last block: the
+// head, column sums of the fp32 d loss / d (logits, value) themselves.
 struct BiasArgs {
-    const __nv_bfloat16* t_hi[4];
-    const __nv_bfloat16* t_lo[4];
+    const __nv_bfloat16* hi[4];
+    const __nv_bfloat16* lo[4];
     const float* dlogits;  // [B, 38]
     const float* dvalue;   // [B]
     float* grads;
     int64_t B;
-    int ldt;
     FlatLayout F;
 };
 __global__ void __launch_bounds__(256) k_bias_grad(const __grid_constant__ BiasArgs a) {
-    const int col = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (col >= 4 * kHidden + kHeadValid) return;
-    const FlatLayout& F = a.F;
-    const int l = col < 4 * kHidden ? col / kHidden : 4, c = col < 4 * kHidden ? col % kHidden : col - 4 * kHidden;
-    float s = 0.0f;
-    if (l < 4) {
-        const __nv_bfloat162* hi = reinterpret_cast<const __nv_bfloat162*>(a.t_hi[l] + (size_t)c * a.ldt);
-        const __nv_bfloat162* lo = reinterpret_cast<const __nv_bfloat162*>(a.t_lo[l] + (size_t)c * a.ldt);
-        for (int64_t i = lane; 2 * i < a.B; i += 32) {
-            const float2 h = __bfloat1622float2(hi[i]), r = __bfloat1622float2(lo[i]);
-            s += h.x + r.x;
-            if (2 * i + 1 < a.B) s += h.y + r.y;
+    __shared__ float red[8][64];
+    const int tid = threadIdx.x, rg = tid >> 5, cp = tid & 31;
+    const int blocks_per_layer = kHidden / 64;
+    float s0 = 0.0f, s1 = 0.0f;
+    if ((int)blockIdx.x < 4 * blocks_per_layer) {
+        const int l = blockIdx.x / blocks_per_layer, c0 = (blockIdx.x % blocks_per_layer) * 64;
+        const __nv_bfloat162* hi = reinterpret_cast<const __nv_bfloat162*>(a.hi[l] + c0) + cp;
+        const __nv_bfloat162* lo = reinterpret_cast<const __nv_bfloat162*>(a.lo[l] + c0) + cp;
+#pragma unroll 4
+        for (int64_t b = rg; b < a.B; b += 8) {
+            const float2 h = __bfloat1622float2(hi[b * (kHidden / 2)]), r = __bfloat1622float2(lo[b * (kHidden / 2)]);
+            s0 += h.x + r.x;
+            s1 += h.y + r.y;
         }
-    } else {
-        for (int64_t i = lane; i < a.B; i += 32) s += c < 38 ? a.dlogits[i * 38 + c] : a.dvalue[i];
-    }
+        red[rg][2 * cp] = s0;
+        red[rg][2 * cp + 1] = s1;
+        __syncthreads();
+        if (tid < 64) {
+            float s = 0.0f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-        float* out = l < 4 ? a.grads + F.b[l] + c : (c < 38 ? a.grads + F.b[4] + c : a.grads + F.b[5]);
-        *out = s;
+            for (int k = 0; k < 8; ++k) s += red[k][tid];
+            a.grads[a.F.b[l] + c0 + tid] = s;
+        }
+    } else {  // head: thread = (row group, column), 39 columns
+        const int c = tid & 63, g4 = tid >> 6;
+        float s = 0.0f;
+        if (c < kHeadValid)
+            for (int64_t b = g4; b < a.B; b += 4) s += c < 38 ? a.dlogits[b * 38 + c] : a.dvalue[b];
+        red[g4][c] = s;
+        __syncthreads();
+        if (tid < kHeadValid) {
+            const float tot = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+            if (tid < 38) a.grads[a.F.b[4] + tid] = tot;
+            else a.grads[a.F.b[5]] = tot;
+        }
     }
 }
 
@@ -259,11 +248,10 @@ enum { kEpiFwd = 0, kEpiHead = 1, kEpiDgrad = 2, kEpiWgrad = 3 };
 
 struct GemmArgs {
     int M, k_blocks, n_tiles_n, n_tiles;
-    // kEpiFwd / kEpiDgrad: bf16 hi / lo outputs, row-major [M, ld_out] and batch-major [N, ld_t]
+    // kEpiFwd / kEpiDgrad: bf16 hi / lo outputs [M, ld_out]
     const float* bias;                 // kEpiFwd, kEpiHead
     __nv_bfloat16 *out_hi, *out_lo;
-    __nv_bfloat16 *out_t_hi, *out_t_lo;
-    int ld_out, ld_t;
+    int ld_out;
     const __nv_bfloat16* relu_src;     // kEpiDgrad: the forward activation (hi part) this gradient flows through, [M, ld_out]
     // kEpiWgrad: fp32 output [M, ld_c], columns < n_c; column n_c (the value head of the fused head tile) -> c2[row]
     float* c;
@@ -273,6 +261,13 @@ struct GemmArgs {
     float *logits, *value;
 };
 
+constexpr uint32_t kMnBox = 64 * kBK * 2;  // one {64 features, 64 samples} box of an MN-major operand: 8 KB
+
+template <bool MN>
+__device__ __forceinline__ uint64_t operand_desc(uint32_t saddr) {
+    return MN ? umma_desc_mn_sw128(saddr, kMnBox) : umma_desc_sw128(saddr);
+}
+
 template <int BN, bool SPLIT_A, bool SPLIT_W>
 struct GemmCfg {
     static constexpr uint32_t kABytes = kBM * kBK * 2, kWBytes = BN * kBK * 2;
@@ -281,8 +276,7 @@ struct GemmCfg {
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// forward / dgrad rows: x -> bf16 hi / lo, 128-bit row-major stores + 16-bit batch-major stores (a warp's 32 rows of one
-// column are contiguous)
+// forward / dgrad rows: x -> bf16 hi / lo, 128-bit stores
 template <int EPI>
 __device__ __forceinline__ void epilogue_act_row(uint32_t t_row, int n_cols, int n0, int row, bool row_ok, const GemmArgs& a) {
 #pragma unroll 1
@@ -323,15 +317,6 @@ __device__ __forceinline__ void epilogue_act_row(uint32_t t_row, int n_cols, int
             ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
             pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
         }
-        uint16_t* th = reinterpret_cast<uint16_t*>(a.out_t_hi) + (size_t)(n0 + c0) * a.ld_t + row;
-        uint16_t* tl = reinterpret_cast<uint16_t*>(a.out_t_lo) + (size_t)(n0 + c0) * a.ld_t + row;
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-            th[(size_t)(2 * jj) * a.ld_t] = (uint16_t)(hi[jj] & 0xFFFFu);
-            th[(size_t)(2 * jj + 1) * a.ld_t] = (uint16_t)(hi[jj] >> 16);
-            tl[(size_t)(2 * jj) * a.ld_t] = (uint16_t)(lo[jj] & 0xFFFFu);
-            tl[(size_t)(2 * jj + 1) * a.ld_t] = (uint16_t)(lo[jj] >> 16);
-        }
     }
 }
 
@@ -369,6 +354,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     // Same pipeline as k_mlp_layer (brl_mlp.cu): persistent CTAs walk tiles blockIdx.x, + gridDim.x, ... (n-tile fastest);
     // the shared-memory stage ring runs across tile boundaries; two TMEM accumulators overlap epilogue and main loop.
     using Cfg = GemmCfg<BN, SPLIT_A, SPLIT_W>;
+    constexpr bool MN = EPI == kEpiWgrad;  // the wgrad contracts over the batch: MN-major operands
     constexpr int S = Cfg::kStages;
     constexpr uint32_t kTmemCols = 2 * BN;
     extern __shared__ unsigned char smem_dyn[];
@@ -414,18 +400,36 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
                     mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
                     uint32_t dst = base + s * Cfg::kStageBytes;
-                    tma_load_2d(dst, &tm_a_hi, full_bar(s), kb * kBK, m0);
-                    dst += Cfg::kABytes;
-                    if (SPLIT_A) { tma_load_2d(dst, &tm_a_lo, full_bar(s), kb * kBK, m0); dst += Cfg::kABytes; }
-                    tma_load_2d(dst, &tm_w_hi, full_bar(s), kb * kBK, n0);
-                    dst += Cfg::kWBytes;
-                    if (SPLIT_W) tma_load_2d(dst, &tm_w_lo, full_bar(s), kb * kBK, n0);
+                    if (!MN) {
+                        tma_load_2d(dst, &tm_a_hi, full_bar(s), kb * kBK, m0);
+                        dst += Cfg::kABytes;
+                        if (SPLIT_A) { tma_load_2d(dst, &tm_a_lo, full_bar(s), kb * kBK, m0); dst += Cfg::kABytes; }
+                        tma_load_2d(dst, &tm_w_hi, full_bar(s), kb * kBK, n0);
+                        dst += Cfg::kWBytes;
+                        if (SPLIT_W) tma_load_2d(dst, &tm_w_lo, full_bar(s), kb * kBK, n0);
+                    } else {  // operands are [batch, feature] row-major: boxes of {64 features, 64 samples}, kMnBox bytes each
+#pragma unroll
+                        for (int j = 0; j < kBM / 64; ++j) tma_load_2d(dst + j * kMnBox, &tm_a_hi, full_bar(s), m0 + 64 * j, kb * kBK);
+                        dst += Cfg::kABytes;
+                        if (SPLIT_A) {
+#pragma unroll
+                            for (int j = 0; j < kBM / 64; ++j) tma_load_2d(dst + j * kMnBox, &tm_a_lo, full_bar(s), m0 + 64 * j, kb * kBK);
+                            dst += Cfg::kABytes;
+                        }
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(dst + j * kMnBox, &tm_w_hi, full_bar(s), n0 + 64 * j, kb * kBK);
+                        dst += Cfg::kWBytes;
+                        if (SPLIT_W) {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j) tma_load_2d(dst + j * kMnBox, &tm_w_lo, full_bar(s), n0 + 64 * j, kb * kBK);
+                        }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer =====
-            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+            constexpr uint32_t idesc = MN ? umma_idesc_bf16_mn(kBM, BN) : umma_idesc_bf16(kBM, BN);
             uint32_t it = 0, j = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
                 const uint32_t buf = j & 1u;
@@ -442,11 +446,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     const uint32_t sw_lo = sw_hi + Cfg::kWBytes;
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint32_t koff = (uint32_t)k * kUmmaK * 2;
-                        const uint64_t da_hi = umma_desc_sw128(sa_hi + koff), dw_hi = umma_desc_sw128(sw_hi + koff);
+                        // K-major: 16 K elements = 32 bytes along the 128-byte row; MN-major: 16 K rows of 128 bytes
+                        const uint32_t koff = (uint32_t)k * kUmmaK * (MN ? 128u : 2u);
+                        const uint64_t da_hi = operand_desc<MN>(sa_hi + koff), dw_hi = operand_desc<MN>(sw_hi + koff);
                         umma_bf16(acc, da_hi, dw_hi, idesc, (kb | k) != 0);
-                        if (SPLIT_A) umma_bf16(acc, umma_desc_sw128(sa_lo + koff), dw_hi, idesc, 1u);
-                        if (SPLIT_W) umma_bf16(acc, da_hi, umma_desc_sw128(sw_lo + koff), idesc, 1u);
+                        if (SPLIT_A) umma_bf16(acc, operand_desc<MN>(sa_lo + koff), dw_hi, idesc, 1u);
+                        if (SPLIT_W) umma_bf16(acc, da_hi, operand_desc<MN>(sw_lo + koff), idesc, 1u);
                     }
                     umma_commit(empty_bar(s));
                 }
@@ -476,18 +481,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     if (warp == 1) tmem_dealloc(tmem_acc, kTmemCols);
 }
 
-// A [m_rows, k_cols] (pitch lda), Bt [n_rows, k_cols] (pitch ldb), both bf16 K-major; hi / lo pairs
+// A [m_rows, k_cols] (pitch lda), Bt [n_rows, k_cols] (pitch ldb), both bf16 K-major; hi / lo pairs.
+// kEpiWgrad: the same logical operands stored transposed, [k_cols, m_rows] / [k_cols, n_rows] (MN-major).
 template <int BN, bool SPLIT_A, bool SPLIT_W, int EPI>
 static int32_t launch_gemm(cudaStream_t s, const void* a_hi, const void* a_lo, int m_rows, int lda, const void* w_hi, const void* w_lo,
                            int n_rows, int ldb, int k_cols, GemmArgs args) {
     using Cfg = GemmCfg<BN, SPLIT_A, SPLIT_W>;
     CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
-    bool ok = make_map(&ta_hi, a_hi, (uint64_t)m_rows, (uint64_t)k_cols, (uint64_t)lda, kBM) &&
-              make_map(&tw_hi, w_hi, (uint64_t)n_rows, (uint64_t)k_cols, (uint64_t)ldb, BN);
+    constexpr bool MN = EPI == kEpiWgrad;  // operands given as [k_cols, m_rows] / [k_cols, n_rows] row-major
+    bool ok = MN ? make_map(&ta_hi, a_hi, (uint64_t)k_cols, (uint64_t)m_rows, (uint64_t)lda, 64) &&
+                       make_map(&tw_hi, w_hi, (uint64_t)k_cols, (uint64_t)n_rows, (uint64_t)ldb, 64)
+                 : make_map(&ta_hi, a_hi, (uint64_t)m_rows, (uint64_t)k_cols, (uint64_t)lda, kBM) &&
+                       make_map(&tw_hi, w_hi, (uint64_t)n_rows, (uint64_t)k_cols, (uint64_t)ldb, BN);
     ta_lo = ta_hi;
     tw_lo = tw_hi;
-    if (ok && SPLIT_A) ok = make_map(&ta_lo, a_lo, (uint64_t)m_rows, (uint64_t)k_cols, (uint64_t)lda, kBM);
-    if (ok && SPLIT_W) ok = make_map(&tw_lo, w_lo, (uint64_t)n_rows, (uint64_t)k_cols, (uint64_t)ldb, BN);
+    if (ok && SPLIT_A) ok = MN ? make_map(&ta_lo, a_lo, (uint64_t)k_cols, (uint64_t)m_rows, (uint64_t)lda, 64)
+                               : make_map(&ta_lo, a_lo, (uint64_t)m_rows, (uint64_t)k_cols, (uint64_t)lda, kBM);
+    if (ok && SPLIT_W) ok = MN ? make_map(&tw_lo, w_lo, (uint64_t)k_cols, (uint64_t)n_rows, (uint64_t)ldb, 64)
+                               : make_map(&tw_lo, w_lo, (uint64_t)n_rows, (uint64_t)k_cols, (uint64_t)ldb, BN);
     if (!ok) return fail(BRL_E_LAUNCH, "brl_ppo_grad: cuTensorMapEncodeTiled failed");
     auto kern = k_gemm_tc<BN, SPLIT_A, SPLIT_W, EPI>;
     static bool attr_set = false;  // idempotent; a race only repeats the call
@@ -612,7 +623,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
                 const FusedOp& op = a.op[o];
                 const int r = tile - op.tile0;
                 const int mb = r / op.g.n_tiles_n, m0 = mb * kBM, n0 = (r % op.g.n_tiles_n) * kFBN;
-                const bool split_a = op.split_a != 0;
+                const bool split_a = op.split_a != 0, mn = op.epi == kEpiWgrad;
                 const uint32_t tx = Cfg::kABytes * (split_a ? 2u : 1u) + 2u * Cfg::kWBytes;
                 trace_stamp(a, tile, 0);
                 if (op.dep >= 0) {
@@ -633,21 +644,34 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
                     mbar_expect_tx(full_bar(s), tx);
                     const uint32_t sa = base + s * Cfg::kStageBytes;
                     const uint32_t sw = sa + 2 * Cfg::kABytes;
-                    tma_load_2d(sa, &op.a_hi, full_bar(s), kb * kBK, m0);
-                    if (split_a) tma_load_2d(sa + Cfg::kABytes, &op.a_lo, full_bar(s), kb * kBK, m0);
-                    tma_load_2d(sw, &op.w_hi, full_bar(s), kb * kBK, n0);
-                    tma_load_2d(sw + Cfg::kWBytes, &op.w_lo, full_bar(s), kb * kBK, n0);
+                    if (!mn) {
+                        tma_load_2d(sa, &op.a_hi, full_bar(s), kb * kBK, m0);
+                        if (split_a) tma_load_2d(sa + Cfg::kABytes, &op.a_lo, full_bar(s), kb * kBK, m0);
+                        tma_load_2d(sw, &op.w_hi, full_bar(s), kb * kBK, n0);
+                        tma_load_2d(sw + Cfg::kWBytes, &op.w_lo, full_bar(s), kb * kBK, n0);
+                    } else {  // [batch, feature] row-major operands: boxes of {64 features, 64 samples}
+#pragma unroll
+                        for (int j = 0; j < kBM / 64; ++j) {
+                            tma_load_2d(sa + j * kMnBox, &op.a_hi, full_bar(s), m0 + 64 * j, kb * kBK);
+                            if (split_a) tma_load_2d(sa + Cfg::kABytes + j * kMnBox, &op.a_lo, full_bar(s), m0 + 64 * j, kb * kBK);
+                        }
+#pragma unroll
+                        for (int j = 0; j < kFBN / 64; ++j) {
+                            tma_load_2d(sw + j * kMnBox, &op.w_hi, full_bar(s), n0 + 64 * j, kb * kBK);
+                            tma_load_2d(sw + Cfg::kWBytes + j * kMnBox, &op.w_lo, full_bar(s), n0 + 64 * j, kb * kBK);
+                        }
+                    }
                 }
                 trace_stamp(a, tile, 2);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer =====
-            constexpr uint32_t idesc = umma_idesc_bf16(kBM, kFBN);
             uint32_t it = 0, j = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
                 const FusedOp& op = a.op[fused_find_op(a, tile)];
-                const bool split_a = op.split_a != 0;
+                const bool split_a = op.split_a != 0, mn = op.epi == kEpiWgrad;
+                const uint32_t idesc = mn ? umma_idesc_bf16_mn(kBM, kFBN) : umma_idesc_bf16(kBM, kFBN);
                 const int k_blocks = op.g.k_blocks;
                 const uint32_t buf = j & 1u;
                 mbar_wait(tmem_empty_bar(buf), ((j >> 1) & 1u) ^ 1u);
@@ -664,11 +688,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
                     const uint32_t sw_lo = sw_hi + Cfg::kWBytes;
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint32_t koff = (uint32_t)k * kUmmaK * 2;
-                        const uint64_t da_hi = umma_desc_sw128(sa_hi + koff), dw_hi = umma_desc_sw128(sw_hi + koff);
+                        const uint32_t koff = (uint32_t)k * kUmmaK * (mn ? 128u : 2u);
+                        const uint64_t da_hi = mn ? operand_desc<true>(sa_hi + koff) : operand_desc<false>(sa_hi + koff);
+                        const uint64_t dw_hi = mn ? operand_desc<true>(sw_hi + koff) : operand_desc<false>(sw_hi + koff);
                         umma_bf16(acc, da_hi, dw_hi, idesc, (kb | k) != 0);
-                        if (split_a) umma_bf16(acc, umma_desc_sw128(sa_lo + koff), dw_hi, idesc, 1u);
-                        umma_bf16(acc, da_hi, umma_desc_sw128(sw_lo + koff), idesc, 1u);
+                        if (split_a) umma_bf16(acc, mn ? operand_desc<true>(sa_lo + koff) : operand_desc<false>(sa_lo + koff), dw_hi, idesc, 1u);
+                        umma_bf16(acc, da_hi, mn ? operand_desc<true>(sw_lo + koff) : operand_desc<false>(sw_lo + koff), idesc, 1u);
                     }
                     umma_commit(empty_bar(s));
                 }
@@ -696,11 +721,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
             else if (op.epi == kEpiWgrad) epilogue_wgrad_row<kFBN>(t_row, n0, row, row_ok, op.g);
             else epilogue_head_row(t_row, op.g.bias + n0, row_ok, op.g.logits + (size_t)row * 38, op.g.value + row);
             tc_fence_before();
-            __threadfence();  // this lane's stores are visible GPU-wide before the counts below
-            __syncwarp();
+            __syncwarp();  // orders the other lanes' stores before lane 0's fence (the grid-barrier idiom: sync, one fence, one atomic)
             if (lane == 0) {
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(buf)) : "memory");
-                __threadfence();
+                __threadfence();  // cumulative: the warp's output rows are visible GPU-wide before the counts below
                 uint32_t* cnt = a.ready + (size_t)o * (a.nmb + 1);
                 atomicAdd(cnt + mb, 1u);
                 atomicAdd(cnt + a.nmb, 1u);
@@ -713,7 +737,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
     if (warp == 1) tmem_dealloc(tmem_acc, kTmemCols);
 }
 
-// one GEMM of the update, as the host describes it to either launcher
+// one GEMM of the update, as the host describes it to either launcher.  kEpiWgrad: a_* / w_* are the row-major
+// [k_cols, m_rows] / [k_cols, n_rows] arrays (pitch lda / ldb) and are consumed MN-major.
 struct OpSpec {
     const void *a_hi, *a_lo;
     int m_rows, lda;
@@ -745,11 +770,18 @@ static int32_t launch_fused_ops(cudaStream_t s, const OpSpec* ops, int n_ops, in
     for (int i = 0; i < n_ops; ++i) {
         const OpSpec& o = ops[i];
         FusedOp& f = fa.op[i];
-        bool ok = make_map(&f.a_hi, o.a_hi, (uint64_t)o.m_rows, (uint64_t)o.k_cols, (uint64_t)o.lda, kBM) &&
-                  make_map(&f.w_hi, o.w_hi, (uint64_t)o.n_rows, (uint64_t)o.k_cols, (uint64_t)o.ldb, kFBN) &&
-                  make_map(&f.w_lo, o.w_lo, (uint64_t)o.n_rows, (uint64_t)o.k_cols, (uint64_t)o.ldb, kFBN);
+        const bool mn = o.epi == kEpiWgrad;  // operands given as [k_cols, m_rows] / [k_cols, n_rows] row-major
+        auto map_a = [&](CUtensorMap* m, const void* ptr) {
+            return mn ? make_map(m, ptr, (uint64_t)o.k_cols, (uint64_t)o.m_rows, (uint64_t)o.lda, 64)
+                      : make_map(m, ptr, (uint64_t)o.m_rows, (uint64_t)o.k_cols, (uint64_t)o.lda, kBM);
+        };
+        auto map_w = [&](CUtensorMap* m, const void* ptr) {
+            return mn ? make_map(m, ptr, (uint64_t)o.k_cols, (uint64_t)o.n_rows, (uint64_t)o.ldb, 64)
+                      : make_map(m, ptr, (uint64_t)o.n_rows, (uint64_t)o.k_cols, (uint64_t)o.ldb, kFBN);
+        };
+        bool ok = map_a(&f.a_hi, o.a_hi) && map_w(&f.w_hi, o.w_hi) && map_w(&f.w_lo, o.w_lo);
         f.a_lo = f.a_hi;
-        if (ok && o.a_lo) ok = make_map(&f.a_lo, o.a_lo, (uint64_t)o.m_rows, (uint64_t)o.k_cols, (uint64_t)o.lda, kBM);
+        if (ok && o.a_lo) ok = map_a(&f.a_lo, o.a_lo);
         if (!ok) return fail(BRL_E_LAUNCH, "brl_ppo_grad: cuTensorMapEncodeTiled failed");
         f.g = o.g;
         f.g.M = o.m_rows;
@@ -836,42 +868,39 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
     float* grads = static_cast<float*>(b[10]);
     const bool narrow = (p->reserved & 1) != 0;
     auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(sc + off); };
-    const int ldt = S.ldt;
     int32_t rc = BRL_OK;
 
     // 1. minibatch gather of the observation (src/update.py:194-199, cast of src/update.py:95)
     {
-        const dim3 grid((unsigned)((B + 31) / 32), kObsDimM / kGatherCols);
+        const unsigned grid = (unsigned)(((int64_t)B * (kObsDimM / 8) + 255) / 256);
         const int32_t* index = static_cast<const int32_t*>(b[3]);
-        uint16_t* o_r = reinterpret_cast<uint16_t*>(sc + S.obs_r);
-        uint16_t* o_t = reinterpret_cast<uint16_t*>(sc + S.obs_t);
-        if (p->flags & BRL_PPO_OBS_BF16) k_gather_obs<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(b[0]), index, B, ldt, o_r, o_t);
-        else if (p->flags & BRL_PPO_OBS_U8) k_gather_obs<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(b[0]), index, B, ldt, o_r, o_t);
-        else k_gather_obs<float><<<grid, 256, 0, s>>>(static_cast<const float*>(b[0]), index, B, ldt, o_r, o_t);
+        uint16_t* o = reinterpret_cast<uint16_t*>(sc + S.obs);
+        if (p->flags & BRL_PPO_OBS_BF16) k_gather_obs<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(b[0]), index, B, o);
+        else if (p->flags & BRL_PPO_OBS_U8) k_gather_obs<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(b[0]), index, B, o);
+        else k_gather_obs<float><<<grid, 256, 0, s>>>(static_cast<const float*>(b[0]), index, B, o);
     }
     // 2. the GEMMs.  Forward: layers 1..4 (activations kept row-major for the next layer / the ReLU mask and batch-major
     //    for the wgrad) + the head.  Backward: dgrad into layer l's pre-activation, dz_l = (dz_{l+1} . W_{l+1}^T) * [h_l > 0]
-    //    (dz_r[l-1] / dz_t[l-1], l = 1..4), and the wgrads dW_l = h_{l-1}^T . dz_l.
+    //    (S.dz_*[l-1], l = 1..4), and the wgrads dW_l = h_{l-1}^T . dz_l straight from the row-major h and dz.
     OpSpec fwd[5], bwd[kMaxOps];
     for (int l = 0; l < 4; ++l) {
         OpSpec& o = fwd[l];
         o = OpSpec{};
-        o.a_hi = l == 0 ? sc + S.obs_r : sc + S.h_r_hi[l - 1];
-        o.a_lo = l == 0 ? nullptr : sc + S.h_r_lo[l - 1];
+        o.a_hi = l == 0 ? sc + S.obs : sc + S.h_hi[l - 1];
+        o.a_lo = l == 0 ? nullptr : sc + S.h_lo[l - 1];
         o.m_rows = B; o.lda = L.k_in[l];
         o.w_hi = blob + L.w_hi[l]; o.w_lo = blob + L.w_lo[l];
         o.n_rows = kHidden; o.ldb = L.k_in[l]; o.k_cols = L.k_in[l];
         o.epi = kEpiFwd;
         o.g.bias = reinterpret_cast<const float*>(blob + L.bias[l]);
-        o.g.out_hi = bf(S.h_r_hi[l]); o.g.out_lo = bf(S.h_r_lo[l]);
-        o.g.out_t_hi = bf(S.h_t_hi[l]); o.g.out_t_lo = bf(S.h_t_lo[l]);
-        o.g.ld_out = kHidden; o.g.ld_t = ldt;
+        o.g.out_hi = bf(S.h_hi[l]); o.g.out_lo = bf(S.h_lo[l]);
+        o.g.ld_out = kHidden;
         o.dep = l - 1; o.dep_all = 0;
     }
     {
         OpSpec& o = fwd[4];
         o = OpSpec{};
-        o.a_hi = sc + S.h_r_hi[3]; o.a_lo = sc + S.h_r_lo[3]; o.m_rows = B; o.lda = kHidden;
+        o.a_hi = sc + S.h_hi[3]; o.a_lo = sc + S.h_lo[3]; o.m_rows = B; o.lda = kHidden;
         o.w_hi = blob + L.w_hi[4]; o.w_lo = blob + L.w_lo[4]; o.n_rows = kHeadPad; o.ldb = kHidden; o.k_cols = kHidden;
         o.epi = kEpiHead;
         o.g.bias = reinterpret_cast<const float*>(blob + L.bias[4]);
@@ -884,8 +913,8 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
     {   // head wgrad: [1024, 39] = h4^T . dz5 -> w4 grads (38 columns) + w5 grads (the value column)
         OpSpec& o = bwd[nb++];
         o = OpSpec{};
-        o.a_hi = sc + S.h_t_hi[3]; o.a_lo = sc + S.h_t_lo[3]; o.m_rows = kHidden; o.lda = ldt;
-        o.w_hi = sc + S.dz5_t_hi; o.w_lo = sc + S.dz5_t_lo; o.n_rows = kHeadPad; o.ldb = ldt; o.k_cols = B;
+        o.a_hi = sc + S.h_hi[3]; o.a_lo = sc + S.h_lo[3]; o.m_rows = kHidden; o.lda = kHidden;
+        o.w_hi = sc + S.dz5_hi; o.w_lo = sc + S.dz5_lo; o.n_rows = kHeadPad; o.ldb = kHeadPad; o.k_cols = B;
         o.epi = kEpiWgrad;
         o.g.c = grads + F.w[4]; o.g.ld_c = 38; o.g.n_c = 38; o.g.c2 = grads + F.w[5];
         o.dep = -1;
@@ -895,38 +924,40 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
             OpSpec& o = bwd[nb];
             o = OpSpec{};
             const int k_out = l == 4 ? kHeadPad : kHidden;  // width of dz_{l+1}
-            o.a_hi = l == 4 ? sc + S.dz5_r_hi : sc + S.dz_r_hi[l];
-            o.a_lo = l == 4 ? sc + S.dz5_r_lo : sc + S.dz_r_lo[l];
+            o.a_hi = l == 4 ? sc + S.dz5_hi : sc + S.dz_hi[l];
+            o.a_lo = l == 4 ? sc + S.dz5_lo : sc + S.dz_lo[l];
             o.m_rows = B; o.lda = k_out;
             o.w_hi = blob + T.wn_hi[l]; o.w_lo = blob + T.wn_lo[l]; o.n_rows = kHidden; o.ldb = k_out; o.k_cols = k_out;
             o.epi = kEpiDgrad;
-            o.g.out_hi = bf(S.dz_r_hi[l - 1]); o.g.out_lo = bf(S.dz_r_lo[l - 1]);
-            o.g.out_t_hi = bf(S.dz_t_hi[l - 1]); o.g.out_t_lo = bf(S.dz_t_lo[l - 1]);
-            o.g.ld_out = kHidden; o.g.ld_t = ldt;
-            o.g.relu_src = bf(S.h_r_hi[l - 1]);
+            o.g.out_hi = bf(S.dz_hi[l - 1]); o.g.out_lo = bf(S.dz_lo[l - 1]);
+            o.g.ld_out = kHidden;
+            o.g.relu_src = bf(S.h_hi[l - 1]);
             o.dep = l == 4 ? -1 : dgrad_op[l + 1]; o.dep_all = 0;
             dgrad_op[l] = nb++;
         }
         {   // wgrad of layer l (0-based parameter index l - 1): dW = h_{l-1}^T . dz_l
             OpSpec& o = bwd[nb++];
             o = OpSpec{};
-            o.a_hi = l == 1 ? sc + S.obs_t : sc + S.h_t_hi[l - 2];
-            o.a_lo = l == 1 ? nullptr : sc + S.h_t_lo[l - 2];
-            o.m_rows = l == 1 ? kObsDimM : kHidden; o.lda = ldt;
-            o.w_hi = sc + S.dz_t_hi[l - 1]; o.w_lo = sc + S.dz_t_lo[l - 1]; o.n_rows = kHidden; o.ldb = ldt; o.k_cols = B;
+            o.a_hi = l == 1 ? sc + S.obs : sc + S.h_hi[l - 2];
+            o.a_lo = l == 1 ? nullptr : sc + S.h_lo[l - 2];
+            o.m_rows = l == 1 ? kObsDimM : kHidden; o.lda = o.m_rows;
+            o.w_hi = sc + S.dz_hi[l - 1]; o.w_lo = sc + S.dz_lo[l - 1]; o.n_rows = kHidden; o.ldb = kHidden; o.k_cols = B;
             o.epi = kEpiWgrad;
             o.g.c = grads + F.w[l - 1]; o.g.ld_c = kHidden; o.g.n_c = kHidden;
             o.dep = dgrad_op[l]; o.dep_all = 1;
         }
     }
     const bool fused = (p->reserved & 2) == 0;  // tune bit 1: one launch per GEMM (bit 0 then picks 128 x 64 over 128 x 128 tiles)
-    const bool wide_fused = (p->reserved & 4) != 0;  // tune bit 2: 128 x 128 tiles in the fused launches
+    // Fused launches, measured on B200 at B = 1024 (scripts/exp_train_trace.py): the forward is a chain of layers with one tile
+    // per SM per layer, where 128 x 64 tiles win (68 vs 73 us); the backward has two independent GEMMs per layer (dgrad, wgrad)
+    // to fill the SMs, where 128 x 128 tiles move a third fewer operand bytes (76 vs 100 us).  Tune bit 2 / bit 4 flip them.
+    const bool wide_fwd = (p->reserved & 4) != 0, wide_bwd = (p->reserved & 16) == 0;
     unsigned long long* trace = (p->reserved & 8) ? reinterpret_cast<unsigned long long*>(sc + S.trace) : nullptr;  // tune bit 3
     const int nmb = ready_blocks(B);
     uint32_t* ready = reinterpret_cast<uint32_t*>(sc + S.ready);
     if (fused) {
         if (cudaMemsetAsync(ready, 0, ready_words(B) * sizeof(uint32_t), s) != cudaSuccess) return check_launch("brl_ppo_grad (memset)");
-        rc = wide_fused ? launch_fused_ops<128>(s, fwd, 5, nmb, ready, trace) : launch_fused_ops<64>(s, fwd, 5, nmb, ready, trace);
+        rc = wide_fwd ? launch_fused_ops<128>(s, fwd, 5, nmb, ready, trace) : launch_fused_ops<64>(s, fwd, 5, nmb, ready, trace);
     } else {
         for (int i = 0; i < 5 && rc == BRL_OK; ++i) rc = launch_op(narrow, s, fwd[i]);
     }
@@ -940,11 +971,10 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         lp.reserved = 0;
         if ((rc = brl_ppo_loss(stream, lb, &lp, sizeof lp)) != BRL_OK) return rc;
         k_head_grad_pack<<<(unsigned)(((int64_t)B * kHeadPad + 255) / 256), 256, 0, s>>>(
-            reinterpret_cast<const float*>(sc + S.dlogits), reinterpret_cast<const float*>(sc + S.dvalue), B, ldt, bf(S.dz5_r_hi), bf(S.dz5_r_lo),
-            bf(S.dz5_t_hi), bf(S.dz5_t_lo));
+            reinterpret_cast<const float*>(sc + S.dlogits), reinterpret_cast<const float*>(sc + S.dvalue), B, bf(S.dz5_hi), bf(S.dz5_lo));
     }
     // 4. backward GEMMs
-    if (fused) rc = wide_fused ? launch_fused_ops<128>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr)
+    if (fused) rc = wide_bwd ? launch_fused_ops<128>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr)
                                : launch_fused_ops<64>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr);
     else
         for (int i = 0; i < nb && rc == BRL_OK; ++i) rc = launch_op(narrow, s, bwd[i]);
@@ -952,12 +982,11 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
     // 5. bias gradients
     {
         BiasArgs a{};
-        for (int l = 0; l < 4; ++l) { a.t_hi[l] = bf(S.dz_t_hi[l]); a.t_lo[l] = bf(S.dz_t_lo[l]); }
+        for (int l = 0; l < 4; ++l) { a.hi[l] = bf(S.dz_hi[l]); a.lo[l] = bf(S.dz_lo[l]); }
         a.dlogits = reinterpret_cast<const float*>(sc + S.dlogits);
         a.dvalue = reinterpret_cast<const float*>(sc + S.dvalue);
-        a.grads = grads; a.B = B; a.ldt = ldt; a.F = F;
-        const int n_warps = 4 * kHidden + kHeadValid;
-        k_bias_grad<<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, s>>>(a);
+        a.grads = grads; a.B = B; a.F = F;
+        k_bias_grad<<<4 * (kHidden / 64) + 1, 256, 0, s>>>(a);
     }
     return check_launch("brl_ppo_grad");
 }

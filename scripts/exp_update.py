@@ -63,7 +63,7 @@ def main():
     flat_g = torch.empty_like(flat_p)
     stats = torch.zeros(8, dtype=torch.float32, device=dev)
     acc = torch.zeros(16, dtype=torch.float64, device=dev)
-    for tune, name in ((0, "tc_fused64"), (4, "tc_fused128"), (3, "tc_narrow")):
+    for tune, name in ((0, "tc_fused"), (16, "tc_fused_narrow_bwd"), (4, "tc_fused_wide_fwd"), (3, "tc_per_gemm_narrow")):
         st = [state]
 
         def step(i, tune=tune):

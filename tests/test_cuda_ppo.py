@@ -105,10 +105,10 @@ def _flat_order():
     (64, 200, torch.float32, 0),
     (333, 1000, torch.uint8, 0),       # ragged batch: row / K tails of every GEMM
     (333, 1000, torch.bfloat16, 3),    # tune 2 / 3: one launch per GEMM, 128 x 128 / 128 x 64 tiles
-    (1024, 3000, torch.bfloat16, 0),   # ppo.py's minibatch size; tune 0: the two fused persistent launches
+    (1024, 3000, torch.bfloat16, 0),   # ppo.py's minibatch size; tune 0: the two fused persistent launches (default)
     (1024, 2500, torch.float32, 2),
     (2048, 5000, torch.bfloat16, 0),   # 16 row blocks: more tiles than SMs in every op
-    (777, 2500, torch.uint8, 4),       # tune 4: fused launches with 128 x 128 tiles
+    (777, 2500, torch.uint8, 4 | 16),  # tune 4 / 16: the other tile width in the fused forward / backward launch
 ])
 def test_ppo_grad_matches_float64_autograd(B, total, obs_dtype, tune):
     """brl_ppo_grad (take + forward + loss + backward on tcgen05) vs float64 autograd of the restated
