@@ -64,54 +64,75 @@ struct PackArgs {  // layouts travel as kernel parameters (constant bank): index
     MlpLayout L;
     TrainBlob T;
     FlatLayout F;
+    int tile0[kNumLayers + 1];  // first block of each layer's 64 x 64 tiles
 };
 
-// 32 x 32 tile of layer blockIdx.z: fp32 W[in, out] -> Wn hi/lo [in, out_pad] (same orientation) and, through a
-// shared-memory transpose, Wt hi/lo [out_pad, in]; the head layer concatenates the policy (38) and value (1) columns.
+// 64 x 64 tile of one layer: fp32 W[in, out] -> Wn hi/lo [in, out_pad] (same orientation) and, through a shared-memory
+// transpose, Wt hi/lo [out_pad, in]; bf16 pairs are stored as 32-bit words.  The head layer concatenates the policy (38)
+// and value (1) columns.  Blocks are numbered over the layers' tiles (PackArgs.tile0), so none is launched idle.
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = pack_bf16x2(v0 - __low2float(h), v1 - __high2float(h));
+}
+
 __global__ void __launch_bounds__(256) k_pack_train(const __grid_constant__ PackArgs a) {
-    const int l = blockIdx.z;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < kNumLayers; ++k)
+        if ((int)blockIdx.x >= a.tile0[k]) l = k;
     const MlpLayout& L = a.L;
     const TrainBlob& T = a.T;
     const FlatLayout& F = a.F;
     const int k_in = L.k_in[l], n_pad = L.n_out[l];
-    const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
-    if (k0 >= k_in || n0 >= n_pad) return;
+    const int tiles_n = n_pad / 64, r = blockIdx.x - a.tile0[l];
+    const int k0 = (r / tiles_n) * 64, n0 = (r % tiles_n) * 64;
     const bool head = l == 4;
     const int n_src = head ? 38 : kHidden;
     const float* w = a.flat + F.w[l];
-    const float* w2 = head ? a.flat + F.w[5] : nullptr;
-    __shared__ float t[32][33];
+    __shared__ float t[64][65];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    __nv_bfloat16* wn_hi = l > 0 ? reinterpret_cast<__nv_bfloat16*>(a.blob + T.wn_hi[l]) : nullptr;
-    __nv_bfloat16* wn_lo = l > 0 ? reinterpret_cast<__nv_bfloat16*>(a.blob + T.wn_lo[l]) : nullptr;
-    for (int j = ty; j < 32; j += 8) {
-        const int k = k0 + j, n = n0 + tx;
-        float v = 0.0f;
-        if (n < n_src) v = w[(size_t)k * n_src + n];
-        else if (head && n == 38) v = w2[k];
-        t[j][tx] = v;
-        if (wn_hi) {
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            wn_hi[(size_t)k * n_pad + n] = h;
-            wn_lo[(size_t)k * n_pad + n] = __float2bfloat16_rn(v - __bfloat162float(h));
+    uint32_t* wn_hi = l > 0 ? reinterpret_cast<uint32_t*>(a.blob + T.wn_hi[l]) : nullptr;
+    uint32_t* wn_lo = l > 0 ? reinterpret_cast<uint32_t*>(a.blob + T.wn_lo[l]) : nullptr;
+    const int n = n0 + 2 * tx;
+    for (int j = ty; j < 64; j += 8) {
+        const int k = k0 + j;
+        float v0 = 0.0f, v1 = 0.0f;
+        if (k < k_in) {
+            if (!head) {
+                const float2 v = *reinterpret_cast<const float2*>(w + (size_t)k * n_src + n);
+                v0 = v.x; v1 = v.y;
+            } else {
+                v0 = n < 38 ? w[(size_t)k * 38 + n] : (n == 38 ? a.flat[F.w[5] + k] : 0.0f);
+                v1 = n + 1 < 38 ? w[(size_t)k * 38 + n + 1] : 0.0f;
+            }
+            if (wn_hi) {
+                uint32_t h, lo;
+                split_pair(v0, v1, h, lo);
+                wn_hi[((size_t)k * n_pad + n) >> 1] = h;
+                wn_lo[((size_t)k * n_pad + n) >> 1] = lo;
+            }
         }
+        t[j][2 * tx] = v0;
+        t[j][2 * tx + 1] = v1;
     }
     __syncthreads();
-    __nv_bfloat16* wt_hi = reinterpret_cast<__nv_bfloat16*>(a.blob + L.w_hi[l]);
-    __nv_bfloat16* wt_lo = reinterpret_cast<__nv_bfloat16*>(a.blob + L.w_lo[l]);
-    for (int j = ty; j < 32; j += 8) {
-        const int n = n0 + j, k = k0 + tx;
-        const float v = t[tx][j];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        wt_hi[(size_t)n * k_in + k] = h;
-        wt_lo[(size_t)n * k_in + k] = __float2bfloat16_rn(v - __bfloat162float(h));
-    }
-    if (blockIdx.y == 0 && ty == 0) {
-        const int n = n0 + tx;
+    uint32_t* wt_hi = reinterpret_cast<uint32_t*>(a.blob + L.w_hi[l]);
+    uint32_t* wt_lo = reinterpret_cast<uint32_t*>(a.blob + L.w_lo[l]);
+    const int k = k0 + 2 * tx;
+    if (k < k_in)  // k_in is even
+        for (int j = ty; j < 64; j += 8) {
+            uint32_t h, lo;
+            split_pair(t[2 * tx][j], t[2 * tx + 1][j], h, lo);
+            wt_hi[((size_t)(n0 + j) * k_in + k) >> 1] = h;
+            wt_lo[((size_t)(n0 + j) * k_in + k) >> 1] = lo;
+        }
+    if (k0 == 0 && threadIdx.x < 64) {
+        const int nb = n0 + threadIdx.x;
         float bv = 0.0f;
-        if (n < n_src) bv = a.flat[F.b[l] + n];
-        else if (head && n == 38) bv = a.flat[F.b[5]];
-        reinterpret_cast<float*>(a.blob + L.bias[l])[n] = bv;
+        if (nb < n_src) bv = a.flat[F.b[l] + nb];
+        else if (head && nb == 38) bv = a.flat[F.b[5]];
+        reinterpret_cast<float*>(a.blob + L.bias[l])[nb] = bv;
     }
 }
 
@@ -193,7 +214,7 @@ __global__ void __launch_bounds__(256) k_head_grad_pack(const float* __restrict_
 }
 
 // bias gradients: db[c] = sum_b dz[b, c].  Hidden layers: column sums of dz (hi + lo); a block owns 64 columns of one
-// layer, thread = (row group of 8, column pair), then a shared-memory reduction over the row groups.  Last block: the
+// layer, thread = (row group of 32, column pair), then a shared-memory reduction over the row groups.  Last block: the
 // head, column sums of the fp32 d loss / d (logits, value) themselves.
 struct BiasArgs {
     const __nv_bfloat16* hi[4];
@@ -204,17 +225,17 @@ struct BiasArgs {
     int64_t B;
     FlatLayout F;
 };
-__global__ void __launch_bounds__(256) k_bias_grad(const __grid_constant__ BiasArgs a) {
-    __shared__ float red[8][64];
-    const int tid = threadIdx.x, rg = tid >> 5, cp = tid & 31;
+__global__ void __launch_bounds__(1024) k_bias_grad(const __grid_constant__ BiasArgs a) {
+    __shared__ float red[32][65];
+    const int tid = threadIdx.x, rg = tid >> 5, cp = tid & 31;  // 32 row groups x 32 column pairs
     const int blocks_per_layer = kHidden / 64;
-    float s0 = 0.0f, s1 = 0.0f;
     if ((int)blockIdx.x < 4 * blocks_per_layer) {
         const int l = blockIdx.x / blocks_per_layer, c0 = (blockIdx.x % blocks_per_layer) * 64;
         const __nv_bfloat162* hi = reinterpret_cast<const __nv_bfloat162*>(a.hi[l] + c0) + cp;
         const __nv_bfloat162* lo = reinterpret_cast<const __nv_bfloat162*>(a.lo[l] + c0) + cp;
+        float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll 4
-        for (int64_t b = rg; b < a.B; b += 8) {
+        for (int64_t b = rg; b < a.B; b += 32) {
             const float2 h = __bfloat1622float2(hi[b * (kHidden / 2)]), r = __bfloat1622float2(lo[b * (kHidden / 2)]);
             s0 += h.x + r.x;
             s1 += h.y + r.y;
@@ -225,18 +246,20 @@ __global__ void __launch_bounds__(256) k_bias_grad(const __grid_constant__ BiasA
         if (tid < 64) {
             float s = 0.0f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s += red[k][tid];
+            for (int k = 0; k < 32; ++k) s += red[k][tid];
             a.grads[a.F.b[l] + c0 + tid] = s;
         }
-    } else {  // head: thread = (row group, column), 39 columns
-        const int c = tid & 63, g4 = tid >> 6;
+    } else {  // head: thread = (row group of 16, column), 39 columns
+        const int c = tid & 63, g16 = tid >> 6;
         float s = 0.0f;
         if (c < kHeadValid)
-            for (int64_t b = g4; b < a.B; b += 4) s += c < 38 ? a.dlogits[b * 38 + c] : a.dvalue[b];
-        red[g4][c] = s;
+            for (int64_t b = g16; b < a.B; b += 16) s += c < 38 ? a.dlogits[b * 38 + c] : a.dvalue[b];
+        red[g16][c] = s;
         __syncthreads();
         if (tid < kHeadValid) {
-            const float tot = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+            float tot = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) tot += red[k][tid];
             if (tid < 38) a.grads[a.F.b[4] + tid] = tot;
             else a.grads[a.F.b[5]] = tot;
         }
@@ -840,8 +863,14 @@ int32_t brl_mlp_pack_train(brl_stream_t stream, void** b, const void* opaque, si
     if (!p) return rc;
     BRL_REQUIRE(b[0], "params");
     BRL_REQUIRE(b[1], "blob");
-    PackArgs a{static_cast<const float*>(b[0]), static_cast<unsigned char*>(b[1]), mlp_layout(), train_blob(), flat_layout()};
-    k_pack_train<<<dim3(kHidden / 32, kHidden / 32, kNumLayers), 256, 0, (cudaStream_t)stream>>>(a);
+    PackArgs a{static_cast<const float*>(b[0]), static_cast<unsigned char*>(b[1]), mlp_layout(), train_blob(), flat_layout(), {}};
+    int tiles = 0;
+    for (int l = 0; l < kNumLayers; ++l) {
+        a.tile0[l] = tiles;
+        tiles += ((a.L.k_in[l] + 63) / 64) * (a.L.n_out[l] / 64);
+    }
+    a.tile0[kNumLayers] = tiles;
+    k_pack_train<<<(unsigned)tiles, 256, 0, (cudaStream_t)stream>>>(a);
     return check_launch("brl_mlp_pack_train");
 }
 
@@ -986,7 +1015,7 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         a.dlogits = reinterpret_cast<const float*>(sc + S.dlogits);
         a.dvalue = reinterpret_cast<const float*>(sc + S.dvalue);
         a.grads = grads; a.B = B; a.F = F;
-        k_bias_grad<<<4 * (kHidden / 64) + 1, 256, 0, s>>>(a);
+        k_bias_grad<<<4 * (kHidden / 64) + 1, 1024, 0, s>>>(a);
     }
     return check_launch("brl_ppo_grad");
 }
