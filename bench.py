@@ -551,8 +551,9 @@ def run_ppo_update(torch, dev):
                 "bound": "tensor", "achieved": mma_flop / (ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                 "frac": mma_flop / (ms * 1e-3) / 1e12 / tpeak,
                 "note": "achieved = bf16 MMA FLOPs issued by the 14 split GEMMs of one step / CUDA-event time of the WHOLE optimizer step "
-                        "(incl. take, loss, bias sums, Adam, re-pack); at 1024 samples the GEMMs are bound by the L2 -> SM operand "
-                        "fill (~60 B/clk/SM measured, scripts/exp_train_trace.py), not by the tensor pipe"}
+                        "(incl. take, loss, bias sums, Adam, re-pack); a 1024-row minibatch gives each GEMM 64 full-rate 128x128 tiles "
+                        "for 148 SMs and every layer is a dependency step, so the launch-level tensor-pipe activity is 19-30 % "
+                        "(profiles/r01_m_ppo_update_*, DESIGN.md section 3)"}
     out["speedup_tc_over_library_fp32"] = out["fp32"]["ms_per_optimizer_step"] / out["tc"]["ms_per_optimizer_step"]
     return out
 

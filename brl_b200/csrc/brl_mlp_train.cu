@@ -566,7 +566,11 @@ static int32_t launch_gemm(cudaStream_t s, const void* a_hi, const void* a_lo, i
 // earlier in the list, every CTA takes its tiles in list order and the grid never exceeds the SM count (1 CTA / SM),
 // so the waits cannot deadlock; spins are bounded (a protocol bug traps instead of hanging the GPU).
 struct FusedOp {
-    CUtensorMap a_hi, a_lo, w_hi, w_lo;
+    // One bulk-tensor request per operand per stage: a (hi, lo) pair is ONE map with a trailing dimension of 2 whose stride
+    // is the distance between the two arrays -- K-major {64 k, rows, 2}, MN-major {64 features, 64 samples, 64-feature
+    // chunks, 2} -- so the box lands as [hi tile][lo tile], the layout the MMA descriptors expect.  (Measured: a stage costs
+    // ~0.14 us per REQUEST whatever its size, scripts/exp_train_trace.py.)  The unsplit 0/1 observation keeps 2-D maps.
+    CUtensorMap a, w;
     GemmArgs g;
     int epi, split_a;
     int tile0;               // index of this op's first tile in the list
@@ -668,21 +672,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
                     const uint32_t sa = base + s * Cfg::kStageBytes;
                     const uint32_t sw = sa + 2 * Cfg::kABytes;
                     if (!mn) {
-                        tma_load_2d(sa, &op.a_hi, full_bar(s), kb * kBK, m0);
-                        if (split_a) tma_load_2d(sa + Cfg::kABytes, &op.a_lo, full_bar(s), kb * kBK, m0);
-                        tma_load_2d(sw, &op.w_hi, full_bar(s), kb * kBK, n0);
-                        tma_load_2d(sw + Cfg::kWBytes, &op.w_lo, full_bar(s), kb * kBK, n0);
+                        if (split_a) tma_load_3d(sa, &op.a, full_bar(s), kb * kBK, m0, 0);
+                        else tma_load_2d(sa, &op.a, full_bar(s), kb * kBK, m0);
+                        tma_load_3d(sw, &op.w, full_bar(s), kb * kBK, n0, 0);
                     } else {  // [batch, feature] row-major operands: boxes of {64 features, 64 samples}
+                        if (split_a) tma_load_4d(sa, &op.a, full_bar(s), 0, kb * kBK, m0 / 64, 0);
+                        else {
 #pragma unroll
-                        for (int j = 0; j < kBM / 64; ++j) {
-                            tma_load_2d(sa + j * kMnBox, &op.a_hi, full_bar(s), m0 + 64 * j, kb * kBK);
-                            if (split_a) tma_load_2d(sa + Cfg::kABytes + j * kMnBox, &op.a_lo, full_bar(s), m0 + 64 * j, kb * kBK);
+                            for (int j = 0; j < kBM / 64; ++j) tma_load_2d(sa + j * kMnBox, &op.a, full_bar(s), m0 + 64 * j, kb * kBK);
                         }
-#pragma unroll
-                        for (int j = 0; j < kFBN / 64; ++j) {
-                            tma_load_2d(sw + j * kMnBox, &op.w_hi, full_bar(s), n0 + 64 * j, kb * kBK);
-                            tma_load_2d(sw + Cfg::kWBytes + j * kMnBox, &op.w_lo, full_bar(s), n0 + 64 * j, kb * kBK);
-                        }
+                        tma_load_4d(sw, &op.w, full_bar(s), 0, kb * kBK, n0 / 64, 0);
                     }
                 }
                 trace_stamp(a, tile, 2);
@@ -794,17 +793,25 @@ static int32_t launch_fused_ops(cudaStream_t s, const OpSpec* ops, int n_ops, in
         const OpSpec& o = ops[i];
         FusedOp& f = fa.op[i];
         const bool mn = o.epi == kEpiWgrad;  // operands given as [k_cols, m_rows] / [k_cols, n_rows] row-major
-        auto map_a = [&](CUtensorMap* m, const void* ptr) {
-            return mn ? make_map(m, ptr, (uint64_t)o.k_cols, (uint64_t)o.m_rows, (uint64_t)o.lda, 64)
-                      : make_map(m, ptr, (uint64_t)o.m_rows, (uint64_t)o.k_cols, (uint64_t)o.lda, kBM);
+        // (hi, lo) pair of one operand as a single map; rows x cols = the 2-D extent of each array, pitch in elements
+        auto pair_map = [&](CUtensorMap* m, const void* hi, const void* lo, int feat_rows, int pitch, uint32_t box_feat) {
+            const uint64_t gap = (uint64_t)(static_cast<const char*>(lo) - static_cast<const char*>(hi));
+            if (!mn) {  // K-major: [feat_rows, k_cols]
+                const uint64_t dims[3] = {(uint64_t)o.k_cols, (uint64_t)feat_rows, 2}, str[2] = {(uint64_t)pitch * 2, gap};
+                const uint32_t box[3] = {(uint32_t)kBK, box_feat, 2};
+                return make_map_nd(m, hi, 3, dims, str, box);
+            }
+            // MN-major: [k_cols samples, feat_rows features], features in chunks of 64
+            const uint64_t dims[4] = {64, (uint64_t)o.k_cols, (uint64_t)((feat_rows + 63) / 64), 2}, str[3] = {(uint64_t)pitch * 2, 128, gap};
+            const uint32_t box[4] = {64, (uint32_t)kBK, box_feat / 64, 2};
+            return make_map_nd(m, hi, 4, dims, str, box);
         };
-        auto map_w = [&](CUtensorMap* m, const void* ptr) {
-            return mn ? make_map(m, ptr, (uint64_t)o.k_cols, (uint64_t)o.n_rows, (uint64_t)o.ldb, 64)
-                      : make_map(m, ptr, (uint64_t)o.n_rows, (uint64_t)o.k_cols, (uint64_t)o.ldb, kFBN);
-        };
-        bool ok = map_a(&f.a_hi, o.a_hi) && map_w(&f.w_hi, o.w_hi) && map_w(&f.w_lo, o.w_lo);
-        f.a_lo = f.a_hi;
-        if (ok && o.a_lo) ok = map_a(&f.a_lo, o.a_lo);
+        bool ok = pair_map(&f.w, o.w_hi, o.w_lo, o.n_rows, o.ldb, kFBN);
+        if (ok && o.a_lo) ok = pair_map(&f.a, o.a_hi, o.a_lo, o.m_rows, o.lda, kBM);
+        else if (ok) ok = mn ? make_map(&f.a, o.a_hi, (uint64_t)o.k_cols, (uint64_t)o.m_rows, (uint64_t)o.lda, 64)
+                             : make_map(&f.a, o.a_hi, (uint64_t)o.m_rows, (uint64_t)o.k_cols, (uint64_t)o.lda, kBM);
+        if (ok && o.a_lo && (static_cast<const char*>(o.a_lo) <= static_cast<const char*>(o.a_hi) || static_cast<const char*>(o.w_lo) <= static_cast<const char*>(o.w_hi)))
+            ok = false;  // the pair maps need lo above hi
         if (!ok) return fail(BRL_E_LAUNCH, "brl_ppo_grad: cuTensorMapEncodeTiled failed");
         f.g = o.g;
         f.g.M = o.m_rows;
