@@ -46,6 +46,22 @@ UNIT = "env-steps/s"
 SEED = 20241017
 
 
+class _StdoutToStderr:
+    """NCCL prints its version banner on fd 1 when the communicator is created; the contract is ONE JSON line on
+    stdout, so fd 1 points at stderr while torch.distributed / NCCL initialise."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -193,7 +209,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()  # creates the communicator (and prints NCCL's banner) now
     _lib.load()  # fail loudly if the CUDA library is missing
 
     table_np = synthetic_deal_table(N_DEALS, seed=0)

@@ -206,6 +206,45 @@ def test_ppo_grad_matches_float64_autograd(B, total, obs_dtype, tune):
     np.testing.assert_allclose(value.cpu().numpy(), vl.detach().numpy(), rtol=0, atol=5e-5 * max(1.0, float(vl.detach().abs().max())))
 
 
+def test_pack_train_blob_is_the_forward_blob_plus_input_gradient_weights():
+    """brl_mlp_pack_train's blob starts with exactly the bytes brl_mlp_pack produces (so the rollout kernels can read
+    it), followed by W[in, out_pad] as bf16 hi / lo whose sum reproduces W to 2^-17."""
+    from brl_b200 import _lib, ops
+    from brl_b200.models import LAYERS, init_params
+    from brl_b200.optim import flatten_params
+    params = init_params(21, DEV)
+    g = torch.Generator().manual_seed(1)
+    for name in params:
+        params[name]["b"] = torch.randn(params[name]["b"].shape, generator=g).to(DEV)
+    flat_p, _ = flatten_params(params)
+    assert flat_p.numel() == ops.mlp_num_params() == 3681319
+    blob = ops.mlp_pack_train(flat_p)
+    fwd = ops.mlp_pack([params[n]["w"] for n in LAYERS], [params[n]["b"] for n in LAYERS])
+    nf = _lib.load().brl_mlp_packed_bytes()
+    # padding bytes between the layers' sections are never written by either packer: compare the written ranges
+    off = 0
+    for li, (k_in, n_out) in enumerate(((480, 1024), (1024, 1024), (1024, 1024), (1024, 1024), (1024, 64))):
+        used = 2 * n_out * k_in * 2 + n_out * 4
+        assert torch.equal(blob[off:off + used], fwd[off:off + used]), li
+        off = (off + used + 255) & ~255
+    assert off == nf
+    # Wn sections: layers 1..3 [1024, 1024], head [1024, 64] (38 policy columns, the value column, zeros)
+    for li, n_pad in ((1, 1024), (2, 1024), (3, 1024), (4, 64)):
+        nbytes = 1024 * n_pad * 2
+        hi = blob[off:off + nbytes].view(torch.bfloat16).view(1024, n_pad).float()
+        lo = blob[off + nbytes:off + 2 * nbytes].view(torch.bfloat16).view(1024, n_pad).float()
+        off = (off + 2 * nbytes + 255) & ~255
+        if li < 4:
+            w = params[LAYERS[li]]["w"]
+        else:
+            w = torch.zeros((1024, 64), device=DEV)
+            w[:, :38] = params[LAYERS[4]]["w"]
+            w[:, 38] = params[LAYERS[5]]["w"][:, 0]
+        assert float((hi + lo - w).abs().max()) <= 2.0 ** -16 * float(w.abs().max())
+        assert torch.equal(hi, w.to(torch.bfloat16).float())
+    assert off == blob.numel()
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
 def test_update_step_matches_float64_reference(precision):
     """src/update.py:74-242 end to end on a small rollout with an injected permutation, through the library-GEMM
