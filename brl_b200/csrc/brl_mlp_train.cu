@@ -200,19 +200,6 @@ __global__ void __launch_bounds__(256) k_gather_obs(const T* __restrict__ obs, c
     *reinterpret_cast<uint4*>(out + b * kObsDimM + c) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// d loss / d (logits, value) f32 -> dz5 hi / lo [B, 64]; columns 39..63 are zero
-__global__ void __launch_bounds__(256) k_head_grad_pack(const float* __restrict__ dlogits, const float* __restrict__ dvalue, int64_t B,
-                                                        __nv_bfloat16* __restrict__ r_hi, __nv_bfloat16* __restrict__ r_lo) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B * kHeadPad) return;
-    const int64_t row = idx / kHeadPad;
-    const int c = (int)(idx % kHeadPad);
-    const float v = c < 38 ? dlogits[row * 38 + c] : (c == 38 ? dvalue[row] : 0.0f);
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    r_hi[idx] = h;
-    r_lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
-}
-
 // bias gradients: db[c] = sum_b dz[b, c].  Hidden layers: column sums of dz (hi + lo); a block owns 64 columns of one
 // layer, thread = (row group of 32, column pair), then a shared-memory reduction over the row groups.  Last block: the
 // head, column sums of the fp32 d loss / d (logits, value) themselves.
@@ -1005,9 +992,7 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         BrlPpoParams lp = *p;
         lp.flags &= (BRL_PPO_VALUE_CLIPPING | BRL_PPO_REWARD_SCALING | BRL_PPO_UNMASKED_POLICY);
         lp.reserved = 0;
-        if ((rc = brl_ppo_loss(stream, lb, &lp, sizeof lp)) != BRL_OK) return rc;
-        k_head_grad_pack<<<(unsigned)(((int64_t)B * kHeadPad + 255) / 256), 256, 0, s>>>(
-            reinterpret_cast<const float*>(sc + S.dlogits), reinterpret_cast<const float*>(sc + S.dvalue), B, bf(S.dz5_hi), bf(S.dz5_lo));
+        if ((rc = launch_ppo_loss(s, lb, &lp, sc + S.dz5_hi, sc + S.dz5_lo)) != BRL_OK) return rc;
     }
     // 4. backward GEMMs
     if (fused) rc = wide_bwd ? launch_fused_ops<128>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr)

@@ -3,6 +3,7 @@
 // own backward (d loss / d logits, d loss / d value in one pass over the minibatch), and the
 // optimizer step (optax.clip_by_global_norm + optax.adam) over a flat parameter buffer.
 // The MLP forward/backward GEMMs between them are plain library GEMMs (cuBLAS via torch).
+#include <cuda_bf16.h>
 #include <math.h>
 
 #include "common.h"
@@ -25,13 +26,17 @@ struct PpoArgs {
     float* dvalue;             // [B]
     float* stats;              // [8]
     double* acc;               // [16] scratch accumulators
+    // optional (brl_ppo_grad): d loss / d (logits, value) also as bf16 hi / lo rows [B, 64] (38 logits, value, zeros),
+    // the A operand of the head's input-gradient GEMM and the B operand of its weight-gradient GEMM
+    unsigned short* dz_hi;
+    unsigned short* dz_lo;
     int64_t B;
     float clip_eps, ent_coef, vf_coef, ill_coef;
     int value_clipping, reward_scaling, masked_policy;
 };
 
 // acc slots
-enum { kAccAdv = 0, kAccAdv2, kAccIll, kAccActor, kAccValue, kAccEnt, kAccKl, kAccClip };
+enum { kAccAdv = 0, kAccAdv2, kAccIll, kAccActor, kAccValue, kAccEnt, kAccKl, kAccClip, kAccTicket = 15 };
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -98,6 +103,29 @@ __global__ void __launch_bounds__(128) k_ppo_prepass(const PpoArgs a) {
     }
 }
 
+__device__ __forceinline__ void split_store(const PpoArgs& a, int64_t idx, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v), l = __float2bfloat16_rn(v - __bfloat162float(h));
+    a.dz_hi[idx] = *reinterpret_cast<const unsigned short*>(&h);
+    a.dz_lo[idx] = *reinterpret_cast<const unsigned short*>(&l);
+}
+
+// stats = {total_loss, value_loss, loss_actor, entropy, approx_kl, clipfracs, illegal_action_loss, 0}
+// (the aux tuple of _loss_fn, src/update.py:144-162); run by the last block of k_ppo_loss
+__device__ __forceinline__ void ppo_finalize(const PpoArgs& a) {
+    const volatile double* acc = a.acc;
+    const double B = (double)a.B;
+    const float value_loss = (float)(acc[kAccValue] / B), loss_actor = (float)(acc[kAccActor] / B);
+    const float entropy = (float)(acc[kAccEnt] / B), ill = 0.5f * (float)sqrt(acc[kAccIll]);
+    a.stats[0] = loss_actor + a.vf_coef * value_loss - a.ent_coef * entropy + a.ill_coef * ill;
+    a.stats[1] = value_loss;
+    a.stats[2] = loss_actor;
+    a.stats[3] = entropy;
+    a.stats[4] = (float)(acc[kAccKl] / B);
+    a.stats[5] = (float)(acc[kAccClip] / B);
+    a.stats[6] = ill;
+    a.stats[7] = 0.0f;
+}
+
 __global__ void __launch_bounds__(128) k_ppo_loss(const PpoArgs a, int have_prepass) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -150,7 +178,9 @@ __global__ void __launch_bounds__(128) k_ppo_loss(const PpoArgs a, int have_prep
             if (r.legal[k] && p[k] > 0.0f) d += a.ent_coef * invB * p[k] * (logp[k] + ent);  // -ent_coef * dH/dl
             if (a.ill_coef != 0.0f && ill_norm > 0.0f) d += a.ill_coef * (qi[k] * qi[k] - q[k] * s_i) / (2.0f * ill_norm);
             a.dlogits[b * kA + j] = d;
+            if (a.dz_hi) split_store(a, b * 64 + j, d);
         }
+        if (a.dz_hi && lane >= 7) split_store(a, b * 64 + 32 + lane, 0.0f);  // columns 39..63 (38 is the value, below)
         if (lane == 0) {
             // value loss (src/update.py:47-72)
             const float v = a.value[b], t = a.targets[src];
@@ -168,6 +198,7 @@ __global__ void __launch_bounds__(128) k_ppo_loss(const PpoArgs a, int have_prep
                 dv = v - t;
             }
             a.dvalue[b] = a.vf_coef * dv * invB;
+            if (a.dz_hi) split_store(a, b * 64 + 38, a.vf_coef * dv * invB);
             s_actor += (double)loss_actor;
             s_value += (double)vl;
             s_ent += (double)ent;
@@ -176,31 +207,34 @@ __global__ void __launch_bounds__(128) k_ppo_loss(const PpoArgs a, int have_prep
             s_ill += (double)s_i;
         }
     }
+    // block-level sums first (one set of same-address f64 atomics per block, not per warp), then the last block to
+    // arrive (ticket in acc[kAccTicket]) forms the statistics: no separate finalize launch
+    __shared__ double part[4][6];
+    __shared__ bool last_block;
+    const int w = threadIdx.x >> 5;
     if (lane == 0) {
-        atomicAdd(&a.acc[kAccActor], s_actor);
-        atomicAdd(&a.acc[kAccValue], s_value);
-        atomicAdd(&a.acc[kAccEnt], s_ent);
-        atomicAdd(&a.acc[kAccKl], s_kl);
-        atomicAdd(&a.acc[kAccClip], s_clip);
-        if (!have_prepass) atomicAdd(&a.acc[kAccIll], s_ill);
+        part[w][0] = s_actor; part[w][1] = s_value; part[w][2] = s_ent; part[w][3] = s_kl; part[w][4] = s_clip; part[w][5] = s_ill;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int k = threadIdx.x;
+        const double s = part[0][k] + part[1][k] + part[2][k] + part[3][k];
+        const int slot = k == 0 ? kAccActor : k == 1 ? kAccValue : k == 2 ? kAccEnt : k == 3 ? kAccKl : k == 4 ? kAccClip : kAccIll;
+        if (k < 5 || !have_prepass) atomicAdd(&a.acc[slot], s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(&a.acc[kAccTicket]), 1ull);
+        last_block = t == (unsigned long long)gridDim.x - 1ull;
+    }
+    __syncthreads();
+    if (last_block && threadIdx.x == 0) {
+        __threadfence();
+        ppo_finalize(a);
     }
 }
 
-// stats = {total_loss, value_loss, loss_actor, entropy, approx_kl, clipfracs, illegal_action_loss, 0}
-// (the aux tuple of _loss_fn, src/update.py:144-162)
-__global__ void k_ppo_finalize(const PpoArgs a) {
-    const double B = (double)a.B;
-    const float value_loss = (float)(a.acc[kAccValue] / B), loss_actor = (float)(a.acc[kAccActor] / B);
-    const float entropy = (float)(a.acc[kAccEnt] / B), ill = 0.5f * (float)sqrt(a.acc[kAccIll]);
-    a.stats[0] = loss_actor + a.vf_coef * value_loss - a.ent_coef * entropy + a.ill_coef * ill;
-    a.stats[1] = value_loss;
-    a.stats[2] = loss_actor;
-    a.stats[3] = entropy;
-    a.stats[4] = (float)(a.acc[kAccKl] / B);
-    a.stats[5] = (float)(a.acc[kAccClip] / B);
-    a.stats[6] = ill;
-    a.stats[7] = 0.0f;
-}
 
 // ---- optimizer: optax.chain(clip_by_global_norm(c), adam(lr, eps=1e-5)) (ppo.py:195-211) -------
 // VEC = 4: 128-bit accesses over the first n / 4 * 4 elements (16-byte-aligned buffers), the <= 3 tail elements by block 0
@@ -295,7 +329,12 @@ extern "C" {
 int32_t brl_ppo_loss(brl_stream_t stream, void** b, const void* opaque, size_t len) {
     if (opaque == nullptr || len != sizeof(BrlPpoParams))
         return fail(BRL_E_OPAQUE, "brl_ppo_loss: opaque must be one BrlPpoParams (%zu bytes), got %zu", sizeof(BrlPpoParams), len);
-    const BrlPpoParams* p = static_cast<const BrlPpoParams*>(opaque);
+    return brl::launch_ppo_loss((cudaStream_t)stream, b, static_cast<const BrlPpoParams*>(opaque), nullptr, nullptr);
+}
+
+}  // extern "C"
+
+int32_t brl::launch_ppo_loss(cudaStream_t stream, void** b, const BrlPpoParams* p, void* dz_hi, void* dz_lo) {
     if (p->batch <= 0) return fail(BRL_E_OPAQUE, "brl_ppo_loss: batch must be > 0");
     static const char* names[] = {"logits", "value", "index", "mask", "action", "old_log_prob", "old_value", "advantages",
                                   "targets", "dlogits", "dvalue", "stats", "scratch"};
@@ -315,6 +354,8 @@ int32_t brl_ppo_loss(brl_stream_t stream, void** b, const void* opaque, size_t l
     a.dvalue = static_cast<float*>(b[10]);
     a.stats = static_cast<float*>(b[11]);
     a.acc = static_cast<double*>(b[12]);
+    a.dz_hi = static_cast<unsigned short*>(dz_hi);
+    a.dz_lo = static_cast<unsigned short*>(dz_lo);
     a.B = p->batch;
     a.clip_eps = p->clip_eps;
     a.ent_coef = p->ent_coef;
@@ -330,9 +371,10 @@ int32_t brl_ppo_loss(brl_stream_t stream, void** b, const void* opaque, size_t l
     const int prepass = a.reward_scaling || a.ill_coef != 0.0f;
     if (prepass) k_ppo_prepass<<<grid, 128, 0, s>>>(a);
     k_ppo_loss<<<grid, 128, 0, s>>>(a, prepass);
-    k_ppo_finalize<<<1, 1, 0, s>>>(a);
     return check_launch("brl_ppo_loss");
 }
+
+extern "C" {
 
 int32_t brl_adam_clip(brl_stream_t stream, void** b, const void* opaque, size_t len) {
     if (opaque == nullptr || len != sizeof(BrlAdamParams))

@@ -42,6 +42,9 @@ inline const BrlParams* get_params(const void* opaque, size_t opaque_len, int32_
 int32_t launch_categorical(cudaStream_t stream, const float* logits, const unsigned char* mask, int32_t* action, float* log_prob,
                            int64_t n, int sample, uint64_t seed, int64_t env_offset, uint32_t step);
 
+// brl_ppo_loss's body (brl_ppo.cu), optionally also writing d loss / d (logits, value) as bf16 hi / lo rows [B, 64] for brl_ppo_grad
+int32_t launch_ppo_loss(cudaStream_t stream, void** buffers, const BrlPpoParams* p, void* dz_hi, void* dz_lo);
+
 #define BRL_REQUIRE(ptr, name)                                                            \
     do {                                                                                  \
         if ((ptr) == nullptr) return brl::fail(BRL_E_BUFFER, "%s: buffer '%s' is NULL", __func__, name); \

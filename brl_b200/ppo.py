@@ -89,7 +89,9 @@ def train(config: dict, rng: int, tables: Optional[Sequence] = None, eval_table=
     eval_table = as_table(eval_table) if eval_table is not None else _deals.synthetic_deal_table(config["hash_size"], seed=10_000)
 
     optimizer = make_optimizer(config)                                                            # ppo.py:195-211
-    actor_forward_pass = make_forward_pass(config["actor_activation"], config["actor_model_type"])
+    # "policy_precision" is this mirror's only extra key: None = the tensor-core kernels (rollout forward AND update),
+    # "fp32" = the library-GEMM cross-check path
+    actor_forward_pass = make_forward_pass(config["actor_activation"], config["actor_model_type"], config.get("policy_precision"))
     rng, _rng = brandom.split(rng)
     params = init_params(_rng & 0x7FFFFFFF, dev)                                                  # ppo.py:240-243
     opt_state = optimizer.init(params)
@@ -112,7 +114,7 @@ def train(config: dict, rng: int, tables: Optional[Sequence] = None, eval_table=
                                        config["num_eval_envs"], config["game_mode"], duplicate=True,
                                        team2_params=eval_opp_params)
 
-    opp_forward_pass = make_forward_pass(config["opp_activation"], config["opp_model_type"])
+    opp_forward_pass = make_forward_pass(config["opp_activation"], config["opp_model_type"], config.get("policy_precision"))
     envs = [BridgeBidding(table=t, device=dev) for t in tables]                                   # ppo.py:296-303
     roll_outs = [make_roll_out(config, env, actor_forward_pass, opp_forward_pass) for env in envs]
     calc_gae = make_calc_gae(config, actor_forward_pass)
