@@ -286,13 +286,25 @@ struct GemmCfg {
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// 32 accumulator columns of this thread's row; t_off2 != 0 (k_train_fused): the tile's products live in two column
+// blocks t_off2 apart (x.w_hi terms | x_hi.w_lo term) and their sum is the result
+__device__ __forceinline__ void tmem_ld32_sum(uint32_t taddr, uint32_t t_off2, uint32_t (&r)[32]) {
+    tmem_ld32(taddr, r);
+    if (t_off2 != 0u) {
+        uint32_t r2[32];
+        tmem_ld32(taddr + t_off2, r2);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
+    }
+}
+
 // forward / dgrad rows: x -> bf16 hi / lo, 128-bit stores
 template <int EPI>
-__device__ __forceinline__ void epilogue_act_row(uint32_t t_row, int n_cols, int n0, int row, bool row_ok, const GemmArgs& a) {
+__device__ __forceinline__ void epilogue_act_row(uint32_t t_row, int n_cols, int n0, int row, bool row_ok, const GemmArgs& a, uint32_t t_off2 = 0u) {
 #pragma unroll 1
     for (int c0 = 0; c0 < n_cols; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(t_row + (uint32_t)c0, r);
+        tmem_ld32_sum(t_row + (uint32_t)c0, t_off2, r);
         if (!row_ok) continue;
         const size_t ro = (size_t)row * a.ld_out + n0 + c0;
         uint32_t keep[16];
@@ -330,13 +342,32 @@ __device__ __forceinline__ void epilogue_act_row(uint32_t t_row, int n_cols, int
     }
 }
 
+// head rows (epilogue_head_row of the rollout forward, over the two column blocks): columns 0..37 logits, 38 value
+__device__ __forceinline__ void epilogue_head_row2(uint32_t t_row, uint32_t t_off2, const float* __restrict__ bias, bool row_ok,
+                                                   float* __restrict__ logits_row, float* __restrict__ value_row) {
+    uint32_t r0[32], r1[32];
+    tmem_ld32_sum(t_row, t_off2, r0);
+    tmem_ld32_sum(t_row + 32u, t_off2, r1);
+    if (row_ok) {
+        float2* pl = reinterpret_cast<float2*>(logits_row);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj)
+            pl[jj] = make_float2(__uint_as_float(r0[2 * jj]) + __ldg(bias + 2 * jj), __uint_as_float(r0[2 * jj + 1]) + __ldg(bias + 2 * jj + 1));
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj)
+            pl[16 + jj] = make_float2(__uint_as_float(r1[2 * jj]) + __ldg(bias + 32 + 2 * jj),
+                                      __uint_as_float(r1[2 * jj + 1]) + __ldg(bias + 32 + 2 * jj + 1));
+        *value_row = __uint_as_float(r1[6]) + __ldg(bias + 38);
+    }
+}
+
 // wgrad rows: the accumulator IS the gradient block; thread = one input feature (row of W)
 template <int BN>
-__device__ __forceinline__ void epilogue_wgrad_row(uint32_t t_row, int n0, int row, bool row_ok, const GemmArgs& a) {
+__device__ __forceinline__ void epilogue_wgrad_row(uint32_t t_row, int n0, int row, bool row_ok, const GemmArgs& a, uint32_t t_off2 = 0u) {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(t_row + (uint32_t)c0, r);
+        tmem_ld32_sum(t_row + (uint32_t)c0, t_off2, r);
         if (!row_ok) continue;
         if (a.c2 != nullptr) {  // fused head tile: 38 policy columns (row pitch 38 floats: 8-byte aligned) + the value column
 #pragma unroll
@@ -602,7 +633,11 @@ template <int kFBN>
 __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_constant__ FusedTrainArgs a) {
     using Cfg = FusedTrainCfg<kFBN>;
     constexpr int S = Cfg::kStages;
-    constexpr uint32_t kTmemCols = 2 * kFBN;
+    // The main loop is bound by the shared-memory port (TMA writes + the operand reads of the SS-mode MMAs), so
+    // the W_hi and W_lo tiles -- adjacent in a stage -- are consumed as ONE operand of N = 2 x kFBN: x_hi is read once for
+    // both of its products, which land in two column blocks of the accumulator (x.w_hi terms | x_hi.w_lo) that the
+    // epilogue adds.
+    constexpr uint32_t kBufCols = 2 * kFBN, kTmemCols = 2 * kBufCols;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_addr(smem_dyn) + 1023u) & ~1023u;
     const uint32_t bar_base = base + S * Cfg::kStageBytes;
@@ -681,11 +716,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
                 const FusedOp& op = a.op[fused_find_op(a, tile)];
                 const bool split_a = op.split_a != 0, mn = op.epi == kEpiWgrad;
                 const uint32_t idesc = mn ? umma_idesc_bf16_mn(kBM, kFBN) : umma_idesc_bf16(kBM, kFBN);
+                const uint32_t idesc2 = mn ? umma_idesc_bf16_mn(kBM, 2 * kFBN) : umma_idesc_bf16(kBM, 2 * kFBN);
                 const int k_blocks = op.g.k_blocks;
                 const uint32_t buf = j & 1u;
                 mbar_wait(tmem_empty_bar(buf), ((j >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t acc = tmem_acc + buf * kFBN;
+                const uint32_t acc = tmem_acc + buf * kBufCols;
                 for (int kb = 0; kb < k_blocks; ++kb, ++it) {
                     const int s = (int)(it % S);
                     mbar_wait(full_bar(s), (it / S) & 1u);
@@ -694,15 +730,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
                     const uint32_t sa_hi = base + s * Cfg::kStageBytes;
                     const uint32_t sa_lo = sa_hi + Cfg::kABytes;
                     const uint32_t sw_hi = sa_hi + 2 * Cfg::kABytes;
-                    const uint32_t sw_lo = sw_hi + Cfg::kWBytes;
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         const uint32_t koff = (uint32_t)k * kUmmaK * (mn ? 128u : 2u);
                         const uint64_t da_hi = mn ? operand_desc<true>(sa_hi + koff) : operand_desc<false>(sa_hi + koff);
                         const uint64_t dw_hi = mn ? operand_desc<true>(sw_hi + koff) : operand_desc<false>(sw_hi + koff);
-                        umma_bf16(acc, da_hi, dw_hi, idesc, (kb | k) != 0);
+                        umma_bf16(acc, da_hi, dw_hi, idesc2, (kb | k) != 0);  // x_hi . [w_hi ; w_lo]: the W_lo tile follows W_hi
                         if (split_a) umma_bf16(acc, mn ? operand_desc<true>(sa_lo + koff) : operand_desc<false>(sa_lo + koff), dw_hi, idesc, 1u);
-                        umma_bf16(acc, da_hi, mn ? operand_desc<true>(sw_lo + koff) : operand_desc<false>(sw_lo + koff), idesc, 1u);
                     }
                     umma_commit(empty_bar(s));
                 }
@@ -723,12 +757,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
             tc_fence_after();
             if (q == 0 && lane == 0) trace_stamp(a, tile, 5);
             const int row = m0 + q * 32 + lane;
-            const uint32_t t_row = tmem_acc + buf * kFBN + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_row = tmem_acc + buf * kBufCols + ((uint32_t)(q * 32) << 16);
             const bool row_ok = row < op.g.M;
-            if (op.epi == kEpiFwd) epilogue_act_row<kEpiFwd>(t_row, kFBN, n0, row, row_ok, op.g);
-            else if (op.epi == kEpiDgrad) epilogue_act_row<kEpiDgrad>(t_row, kFBN, n0, row, row_ok, op.g);
-            else if (op.epi == kEpiWgrad) epilogue_wgrad_row<kFBN>(t_row, n0, row, row_ok, op.g);
-            else epilogue_head_row(t_row, op.g.bias + n0, row_ok, op.g.logits + (size_t)row * 38, op.g.value + row);
+            if (op.epi == kEpiFwd) epilogue_act_row<kEpiFwd>(t_row, kFBN, n0, row, row_ok, op.g, (uint32_t)kFBN);
+            else if (op.epi == kEpiDgrad) epilogue_act_row<kEpiDgrad>(t_row, kFBN, n0, row, row_ok, op.g, (uint32_t)kFBN);
+            else if (op.epi == kEpiWgrad) epilogue_wgrad_row<kFBN>(t_row, n0, row, row_ok, op.g, (uint32_t)kFBN);
+            else epilogue_head_row2(t_row, (uint32_t)kFBN, op.g.bias + n0, row_ok, op.g.logits + (size_t)row * 38, op.g.value + row);
             tc_fence_before();
             __syncwarp();  // orders the other lanes' stores before lane 0's fence (the grid-barrier idiom: sync, one fence, one atomic)
             if (lane == 0) {

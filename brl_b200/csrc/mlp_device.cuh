@@ -189,7 +189,7 @@ static bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 }
 
 // general bf16 tensor map (rank <= 4), 128B swizzle, zero fill: dims / box innermost first, strides in bytes for dims 1..
-static bool make_map_nd(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+static inline bool make_map_nd(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
     cuuint64_t d[4], s[3];
     cuuint32_t b[4], e[4] = {1, 1, 1, 1};
     for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
