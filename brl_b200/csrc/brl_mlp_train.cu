@@ -209,9 +209,16 @@ struct BiasArgs {
     const float* dlogits;  // [B, 38]
     const float* dvalue;   // [B]
     float* grads;
+    double* sumsq;         // += sum of squares of the bias gradients, or NULL
     int64_t B;
     FlatLayout F;
 };
+__device__ __forceinline__ void bias_sumsq(const BiasArgs& a, float v) {  // called by whole warps
+    if (a.sumsq == nullptr) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(a.sumsq, (double)v);
+}
 __global__ void __launch_bounds__(1024) k_bias_grad(const __grid_constant__ BiasArgs a) {
     __shared__ float red[32][65];
     const int tid = threadIdx.x, rg = tid >> 5, cp = tid & 31;  // 32 row groups x 32 column pairs
@@ -235,6 +242,7 @@ __global__ void __launch_bounds__(1024) k_bias_grad(const __grid_constant__ Bias
 #pragma unroll
             for (int k = 0; k < 32; ++k) s += red[k][tid];
             a.grads[a.F.b[l] + c0 + tid] = s;
+            bias_sumsq(a, s * s);
         }
     } else {  // head: thread = (row group of 16, column), 39 columns
         const int c = tid & 63, g16 = tid >> 6;
@@ -243,12 +251,15 @@ __global__ void __launch_bounds__(1024) k_bias_grad(const __grid_constant__ Bias
             for (int64_t b = g16; b < a.B; b += 16) s += c < 38 ? a.dlogits[b * 38 + c] : a.dvalue[b];
         red[g16][c] = s;
         __syncthreads();
-        if (tid < kHeadValid) {
+        if (tid < 64) {  // both warps whole: bias_sumsq shuffles
             float tot = 0.0f;
+            if (tid < kHeadValid) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) tot += red[k][tid];
-            if (tid < 38) a.grads[a.F.b[4] + tid] = tot;
-            else a.grads[a.F.b[5]] = tot;
+                for (int k = 0; k < 16; ++k) tot += red[k][tid];
+                if (tid < 38) a.grads[a.F.b[4] + tid] = tot;
+                else a.grads[a.F.b[5]] = tot;
+            }
+            bias_sumsq(a, tot * tot);
         }
     }
 }
@@ -267,6 +278,7 @@ struct GemmArgs {
     float* c;
     float* c2;
     int ld_c, n_c;
+    double* sumsq;                     // kEpiWgrad: += sum of squares of the gradient block (for clip_by_global_norm), or NULL
     // kEpiHead
     float *logits, *value;
 };
@@ -364,11 +376,14 @@ __device__ __forceinline__ void epilogue_head_row2(uint32_t t_row, uint32_t t_of
 // wgrad rows: the accumulator IS the gradient block; thread = one input feature (row of W)
 template <int BN>
 __device__ __forceinline__ void epilogue_wgrad_row(uint32_t t_row, int n0, int row, bool row_ok, const GemmArgs& a, uint32_t t_off2 = 0u) {
+    float ss = 0.0f;  // this row's share of |g|^2 (padding columns of the head tile are exact zeros)
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32_sum(t_row + (uint32_t)c0, t_off2, r);
         if (!row_ok) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ss = fmaf(__uint_as_float(r[j]), __uint_as_float(r[j]), ss);
         if (a.c2 != nullptr) {  // fused head tile: 38 policy columns (row pitch 38 floats: 8-byte aligned) + the value column
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
@@ -385,6 +400,11 @@ __device__ __forceinline__ void epilogue_wgrad_row(uint32_t t_row, int n0, int r
                 pc[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
                                     __uint_as_float(r[4 * v + 3]));
         }
+    }
+    if (a.sumsq != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(a.sumsq, (double)ss);
     }
 }
 
@@ -939,6 +959,8 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
     // 2. the GEMMs.  Forward: layers 1..4 (activations kept row-major for the next layer / the ReLU mask and batch-major
     //    for the wgrad) + the head.  Backward: dgrad into layer l's pre-activation, dz_l = (dz_{l+1} . W_{l+1}^T) * [h_l > 0]
     //    (S.dz_*[l-1], l = 1..4), and the wgrads dW_l = h_{l-1}^T . dz_l straight from the row-major h and dz.
+    // |grads|^2 accumulates in acc[14] (zeroed with the rest of acc by the loss head, which runs before every wgrad)
+    double* grad_sumsq = static_cast<double*>(b[12]) + 14;
     OpSpec fwd[5], bwd[kMaxOps];
     for (int l = 0; l < 4; ++l) {
         OpSpec& o = fwd[l];
@@ -973,7 +995,7 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         o.a_hi = sc + S.h_hi[3]; o.a_lo = sc + S.h_lo[3]; o.m_rows = kHidden; o.lda = kHidden;
         o.w_hi = sc + S.dz5_hi; o.w_lo = sc + S.dz5_lo; o.n_rows = kHeadPad; o.ldb = kHeadPad; o.k_cols = B;
         o.epi = kEpiWgrad;
-        o.g.c = grads + F.w[4]; o.g.ld_c = 38; o.g.n_c = 38; o.g.c2 = grads + F.w[5];
+        o.g.c = grads + F.w[4]; o.g.ld_c = 38; o.g.n_c = 38; o.g.c2 = grads + F.w[5]; o.g.sumsq = grad_sumsq;
         o.dep = -1;
     }
     for (int l = 4; l >= 1; --l) {
@@ -1000,7 +1022,7 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
             o.m_rows = l == 1 ? kObsDimM : kHidden; o.lda = o.m_rows;
             o.w_hi = sc + S.dz_hi[l - 1]; o.w_lo = sc + S.dz_lo[l - 1]; o.n_rows = kHidden; o.ldb = kHidden; o.k_cols = B;
             o.epi = kEpiWgrad;
-            o.g.c = grads + F.w[l - 1]; o.g.ld_c = kHidden; o.g.n_c = kHidden;
+            o.g.c = grads + F.w[l - 1]; o.g.ld_c = kHidden; o.g.n_c = kHidden; o.g.sumsq = grad_sumsq;
             o.dep = dgrad_op[l]; o.dep_all = 1;
         }
     }
@@ -1040,7 +1062,7 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         for (int l = 0; l < 4; ++l) { a.hi[l] = bf(S.dz_hi[l]); a.lo[l] = bf(S.dz_lo[l]); }
         a.dlogits = reinterpret_cast<const float*>(sc + S.dlogits);
         a.dvalue = reinterpret_cast<const float*>(sc + S.dvalue);
-        a.grads = grads; a.B = B; a.F = F;
+        a.grads = grads; a.sumsq = grad_sumsq; a.B = B; a.F = F;
         k_bias_grad<<<4 * (kHidden / 64) + 1, 1024, 0, s>>>(a);
     }
     return check_launch("brl_ppo_grad");

@@ -376,7 +376,11 @@ int32_t brl::launch_ppo_loss(cudaStream_t stream, void** b, const BrlPpoParams* 
 
 extern "C" {
 
-int32_t brl_adam_clip(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+static int32_t adam_impl(brl_stream_t stream, void** b, const void* opaque, size_t len, bool presummed);
+int32_t brl_adam_clip(brl_stream_t stream, void** b, const void* opaque, size_t len) { return adam_impl(stream, b, opaque, len, false); }
+int32_t brl_adam_apply(brl_stream_t stream, void** b, const void* opaque, size_t len) { return adam_impl(stream, b, opaque, len, true); }
+
+static int32_t adam_impl(brl_stream_t stream, void** b, const void* opaque, size_t len, bool presummed) {
     if (opaque == nullptr || len != sizeof(BrlAdamParams))
         return fail(BRL_E_OPAQUE, "brl_adam_clip: opaque must be one BrlAdamParams (%zu bytes), got %zu", sizeof(BrlAdamParams), len);
     const BrlAdamParams* p = static_cast<const BrlAdamParams*>(opaque);
@@ -395,13 +399,13 @@ int32_t brl_adam_clip(brl_stream_t stream, void** b, const void* opaque, size_t 
     const int64_t items = aligned ? (p->n + 3) / 4 : p->n;
     unsigned grid = (unsigned)((items + 255) / 256);
     if (grid > 148u * 8u) grid = 148u * 8u;
-    if (cudaMemsetAsync(sumsq, 0, sizeof(double), s) != cudaSuccess) return check_launch("brl_adam_clip");
+    if (!presummed && cudaMemsetAsync(sumsq, 0, sizeof(double), s) != cudaSuccess) return check_launch("brl_adam_clip");
     const float bc1 = 1.0f - powf(p->beta1, (float)p->step), bc2 = 1.0f - powf(p->beta2, (float)p->step);
     if (aligned) {
-        k_sumsq<4><<<grid, 256, 0, s>>>(gg, p->n, sumsq);
+        if (!presummed) k_sumsq<4><<<grid, 256, 0, s>>>(gg, p->n, sumsq);
         k_adam<4><<<grid, 256, 0, s>>>(pp, gg, mm, vv, p->n, sumsq, p->max_grad_norm, p->lr, p->beta1, p->beta2, p->eps, bc1, bc2);
     } else {
-        k_sumsq<1><<<grid, 256, 0, s>>>(gg, p->n, sumsq);
+        if (!presummed) k_sumsq<1><<<grid, 256, 0, s>>>(gg, p->n, sumsq);
         k_adam<1><<<grid, 256, 0, s>>>(pp, gg, mm, vv, p->n, sumsq, p->max_grad_norm, p->lr, p->beta1, p->beta2, p->eps, bc1, bc2);
     }
     return check_launch("brl_adam_clip");

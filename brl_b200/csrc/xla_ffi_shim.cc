@@ -65,6 +65,7 @@ BRL_LEGACY_CUSTOM_CALL(brl_mlp_forward)
 BRL_LEGACY_CUSTOM_CALL(brl_policy_act)
 BRL_LEGACY_CUSTOM_CALL(brl_ppo_loss)
 BRL_LEGACY_CUSTOM_CALL(brl_adam_clip)
+BRL_LEGACY_CUSTOM_CALL(brl_adam_apply)
 BRL_LEGACY_CUSTOM_CALL(brl_gather_rows)
 BRL_LEGACY_CUSTOM_CALL(brl_mlp_pack_train)
 BRL_LEGACY_CUSTOM_CALL(brl_ppo_grad)

@@ -267,11 +267,17 @@ def ppo_loss(logits, value, index, mask, action, old_log_prob, old_value, adv, t
 
 
 def adam_clip(params, grads, m, v, scratch, *, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-5,
-              max_grad_norm=0.0) -> None:
-    """optax.chain(clip_by_global_norm, adam) on flat fp32 buffers, in place (ppo.py:195-211)."""
+              max_grad_norm=0.0, sumsq: Optional[torch.Tensor] = None) -> None:
+    """optax.chain(clip_by_global_norm, adam) on flat fp32 buffers, in place (ppo.py:195-211).  `sumsq` (f64[1], e.g.
+    `acc[14:15]` after `ppo_grad`): the gradient's sum of squares is already known, skip the pass that forms it."""
     p = _lib.BrlAdamParams(int(params.numel()), int(step), float(lr), float(beta1), float(beta2), float(eps),
                            float(max_grad_norm))
-    _call("brl_adam_clip", [_ptr(params), _ptr(grads), _ptr(m), _ptr(v), _ptr(scratch)], p)
+    if sumsq is not None:
+        if sumsq.dtype != torch.float64:
+            raise _lib.BrlError("adam_clip: sumsq must be float64")
+        _call("brl_adam_apply", [_ptr(params), _ptr(grads), _ptr(m), _ptr(v), _ptr(sumsq)], p)
+    else:
+        _call("brl_adam_clip", [_ptr(params), _ptr(grads), _ptr(m), _ptr(v), _ptr(scratch)], p)
 
 
 def mlp_num_params() -> int:

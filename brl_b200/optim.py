@@ -51,13 +51,14 @@ class AdamWithClip:
         """optax evaluates a schedule at the count BEFORE the increment."""
         return float(self.learning_rate(count)) if callable(self.learning_rate) else float(self.learning_rate)
 
-    def update_(self, flat_params: torch.Tensor, flat_grads: torch.Tensor, state: OptState) -> OptState:
-        """In place on `flat_params`, `state.mu`, `state.nu`; returns the advanced state."""
+    def update_(self, flat_params: torch.Tensor, flat_grads: torch.Tensor, state: OptState, sumsq=None) -> OptState:
+        """In place on `flat_params`, `state.mu`, `state.nu`; returns the advanced state.  `sumsq`: f64[1] sum of squares of
+        `flat_grads` when the producer of the gradient already formed it (ops.ppo_grad)."""
         scratch = self._scratch.get(flat_params.device)
         if scratch is None:
             scratch = self._scratch[flat_params.device] = torch.zeros(1, dtype=torch.float64, device=flat_params.device)
         ops.adam_clip(flat_params, flat_grads, state.mu, state.nu, scratch, step=state.count + 1, lr=self.lr_at(state.count),
-                      beta1=self.b1, beta2=self.b2, eps=self.eps, max_grad_norm=self.max_grad_norm)
+                      beta1=self.b1, beta2=self.b2, eps=self.eps, max_grad_norm=self.max_grad_norm, sumsq=sumsq)
         return OptState(state.count + 1, state.mu, state.nu)
 
 

@@ -112,7 +112,7 @@ def make_update_step(config, actor_forward_pass, optimizer, permutation_fn=None)
                 for mb in range(nmb):                                                  # src/update.py:207-209
                     ops.ppo_grad(obs, blob, scratch, perm[mb * mbs:(mb + 1) * mbs], mask, action, old_lp, old_v, adv, tgt,
                                  flat_g, stats_all[epoch, mb], acc, tune=tune, **cfg)  # src/update.py:164-167
-                    state = optimizer.update_(flat_p, flat_g, state)                  # src/update.py:168-169
+                    state = optimizer.update_(flat_p, flat_g, state, sumsq=acc[14:15])  # src/update.py:168-169
                     ops.mlp_pack_train(flat_p, out=blob)
             return finish()
 

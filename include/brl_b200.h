@@ -47,6 +47,7 @@
  *   brl_policy_act        forward.apply + masked Categorical sample / mode + log_prob, fused   src/roll_out.py:73-81
  *   brl_ppo_loss          _loss_fn + jax.value_and_grad w.r.t. the net outputs   src/update.py:91-167
  *   brl_adam_clip         optimizer.update + optax.apply_updates                  src/update.py:168-169, ppo.py:195-211
+ *   brl_adam_apply        the same with |grads|^2 taken from brl_ppo_grad (no pass over the gradient)
  *   brl_gather_rows       minibatch take(permutation)                             src/update.py:194-199
  *   brl_ppo_grad          jax.value_and_grad(_loss_fn)(params, traj, gae, targets) -> (loss_info, grads): minibatch
  *                         take + forward + loss + backward through the MLP on tcgen05   src/update.py:91-167,194-199
@@ -261,6 +262,9 @@ int32_t brl_ppo_loss(brl_stream_t, void **buffers, const void *opaque, size_t op
 /* optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, eps)) over one flat fp32 buffer.  opaque = BrlAdamParams.
  * buffers: [0] inout f32 params[n]  [1] in f32 grads[n]  [2] inout f32 m[n]  [3] inout f32 v[n]  [4] scratch f64[1] */
 int32_t brl_adam_clip(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+/* brl_adam_clip with the gradient's sum of squares supplied by the caller: [4] in f64[1] sum g^2 (brl_ppo_grad leaves it in
+ * element 14 of its f64[16] scratch, accumulated by the weight- and bias-gradient epilogues), no extra pass over the gradient. */
+int32_t brl_adam_apply(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 /* minibatch gather (jnp.take(x, permutation, axis=0), src/update.py:194-199): n_envs = B rows, k_steps = bytes per row.
  * buffers: [0] in src[total, row]  [1] in i32 index[B]  [2] out dst[B, row] */
 int32_t brl_gather_rows(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
@@ -288,7 +292,8 @@ int32_t brl_mlp_pack_train(brl_stream_t, void **buffers, const void *opaque, siz
  *          [2] scratch[brl_mlp_train_scratch_bytes(B)]  [3] in i32 index[B] (NULL = identity)  [4] in u8 mask[total,38]
  *          [5] in i32 action[total]  [6] in f32 old_log_prob[total]  [7] in f32 old_value[total]
  *          [8] in f32 advantages[total]  [9] in f32 targets[total]  [10] out f32 grads[brl_mlp_num_params()]
- *          [11] out f32 stats[8] (as brl_ppo_loss)  [12] scratch f64[16] */
+ *          [11] out f32 stats[8] (as brl_ppo_loss)  [12] scratch f64[16]; on return element 14 = sum of squares of grads
+ *               (the input of brl_adam_apply) */
 int32_t brl_ppo_grad(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
 /* ---- full evaluation statistics (src/evaluation.py:207-1032) ---------------------------------- */
@@ -342,6 +347,7 @@ void brl_mlp_forward_xla(brl_stream_t, void **buffers, const char *opaque, size_
 void brl_policy_act_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_ppo_loss_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_adam_clip_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_adam_apply_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_gather_rows_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_mlp_pack_train_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_ppo_grad_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);

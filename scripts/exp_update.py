@@ -70,7 +70,7 @@ def main():
             mb = i % nmb
             ops.ppo_grad(obs, blob, scratch, perm[mb * B:(mb + 1) * B], mask, action, old_lp, old_v, adv, tgt, flat_g, stats, acc,
                          tune=tune, **cfg)
-            st[0] = opt.update_(flat_p, flat_g, st[0])
+            st[0] = opt.update_(flat_p, flat_g, st[0], sumsq=acc[14:15])
             ops.mlp_pack_train(flat_p, out=blob)
 
         def grad_only(i, tune=tune):

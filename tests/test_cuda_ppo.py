@@ -185,6 +185,8 @@ def test_ppo_grad_matches_float64_autograd(B, total, obs_dtype, tune):
     np.testing.assert_allclose(got[:7], want, rtol=5e-5, atol=5e-6)   # three-term bf16 split forward vs float64
     gg = grads.cpu().numpy()
     assert np.isfinite(gg).all()                                         # every gradient element was written
+    # |grads|^2 for clip_by_global_norm comes out of the gradient epilogues (scratch element 14, input of brl_adam_apply)
+    np.testing.assert_allclose(float(acc[14]), float((gg.astype(np.float64) ** 2).sum()), rtol=1e-5)
     off = 0
     for k in _flat_order():
         want_g = ref[k].grad.numpy().reshape(-1)
