@@ -238,7 +238,9 @@ typedef struct BrlPpoParams {
     float vf_coef;         /* config["vf_coef"]                                          */
     float illegal_l2_coef; /* config["illegal_action_l2norm_coef"]                       */
     int32_t flags;         /* BRL_PPO_*                                                  */
-    int32_t reserved;
+    int32_t reserved;      /* 0.  brl_ppo_grad reads experiment bits here (0 = measured defaults): 2 = one launch per GEMM
+                              (then 1 = 128x64 instead of 128x128 tiles), 4 / 16 = the other tile width in the fused
+                              forward / backward launch, 8 = per-tile time stamps into the scratch (brl_mlp_train_trace_offset) */
 } BrlPpoParams;
 
 typedef struct BrlAdamParams {
