@@ -14,7 +14,7 @@ OPS = (
     "brl_make_keys", "brl_init", "brl_reset_fields", "brl_step", "brl_duplicate_step", "brl_duplicate_init",
     "brl_observe", "brl_legal_mask", "brl_rollout_random", "brl_imp_reward", "brl_gae", "brl_categorical",
     "brl_match_stats", "brl_state_fields", "brl_gather_reward", "brl_mlp_pack", "brl_obs_to_bf16", "brl_mlp_forward", "brl_policy_act",
-    "brl_ppo_loss", "brl_adam_clip", "brl_adam_apply", "brl_gather_rows", "brl_eval_act_log", "brl_eval_summary", "brl_mlp_pack_train", "brl_ppo_grad",
+    "brl_ppo_loss", "brl_adam_clip", "brl_adam_apply", "brl_gather_rows", "brl_eval_act_log", "brl_eval_summary", "brl_mlp_pack_train", "brl_mlp_adam_step", "brl_ppo_grad",
 )
 HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host", "brl_env_rollout_host",
             "brl_env_rollout_host_async", "brl_env_wait", "brl_env_trajectory")

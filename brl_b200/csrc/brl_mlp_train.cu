@@ -6,12 +6,14 @@
 // tcgen05 with the same three-term bf16 split as the rollout forward (brl_mlp.cu), so gradients are
 // fp32-class (the reference differentiates in fp32).
 //
-// All three GEMM shapes are  C[M, N] = A[M, K] . Bt[N, K]^T  with both operands K-major, so one kernel
-// (k_gemm_tc: TMA producer warp, single-lane tcgen05.mma issuer, four epilogue warps, persistent tiles,
-// double-buffered TMEM accumulator) serves all of them; they differ in the epilogue:
-//   forward  h_l  = relu(h_{l-1} . W_l + b_l)      A = h_{l-1} [B, in]      Bt = W_l^T [out, in]   (packed "Wt")
-//   dgrad    dz_{l-1} = (dz_l . W_l^T) * (h_{l-1} > 0)   A = dz_l [B, out]  Bt = W_l [in, out]     (packed "Wn")
-//   wgrad    dW_l = h_{l-1}^T . dz_l               A = h_{l-1}^T [in, B]    Bt = dz_l^T [out, B]
+// All three GEMM shapes are  C[M, N] = A[M, K] . Bt[N, K]^T, so one pipeline (k_train_fused: TMA producer lane,
+// single-lane tcgen05.mma issuer, four epilogue warps, persistent tiles, double-buffered TMEM accumulator) serves all
+// of them; they differ in the epilogue and in how the operands lie in memory:
+//   forward  h_l  = relu(h_{l-1} . W_l + b_l)      A = h_{l-1} [B, in] K-major     Bt^T = W_l [in, out]  MN-major
+//   dgrad    dz_{l-1} = (dz_l . W_l^T) * (h_{l-1} > 0)   A = dz_l [B, out] K-major  Bt = W_l [in, out]    K-major
+//   wgrad    dW_l = h_{l-1}^T . dz_l               A^T = h_{l-1} [B, in] MN-major  Bt^T = dz_l [B, out]  MN-major
+// i.e. ONE copy of the weights, in haiku's own [in, out] orientation (bf16 hi / lo, "Wn"), feeds the forward (as an
+// MN-major operand) and the dgrad (as a K-major one): training never transposes anything.
 // The wgrad contracts over the batch, i.e. over the ROW index of the row-major activations and dz's the other
 // two GEMMs read and write.  No transposed copies are made: the wgrad stages {64 features x 64 samples} TMA
 // boxes of those same arrays and hands them to tcgen05.mma as MN-major operands (feature index contiguous,
@@ -39,100 +41,117 @@ __host__ __device__ inline FlatLayout flat_layout() {
     return F;
 }
 
-// ---- training blob: the forward blob (MlpLayout, usable by brl_mlp_forward as is) + W in its own
-// orientation [in, out_pad] as bf16 hi / lo for the dgrad GEMMs of layers 1..4 ------------------------
+// ---- training blob: per layer (4 hidden + the fused 64-wide head) the bias in fp32 and W[in, out_pad] as bf16 hi / lo ----
 struct TrainBlob {
-    size_t wn_hi[kNumLayers], wn_lo[kNumLayers], total;
+    size_t bias[kNumLayers], wn_hi[kNumLayers], wn_lo[kNumLayers], total;
+    int k_in[kNumLayers], n_pad[kNumLayers];
 };
 __host__ __device__ inline TrainBlob train_blob() {
-    const MlpLayout L = mlp_layout();
     TrainBlob T{};
-    size_t off = L.total;
-    for (int l = 1; l < kNumLayers; ++l) {
-        const size_t bytes = (size_t)L.k_in[l] * L.n_out[l] * 2;
-        T.wn_hi[l] = off; off += bytes;
+    size_t off = 0;
+    for (int l = 0; l < kNumLayers; ++l) {
+        T.k_in[l] = l == 0 ? kObsDimM : kHidden;
+        T.n_pad[l] = l == 4 ? kHeadPad : kHidden;
+        const size_t bytes = (size_t)T.k_in[l] * T.n_pad[l] * 2;
+        T.wn_hi[l] = off; off += bytes;     // lo directly above hi: the pair is one 4-D / 3-D tensor map
         T.wn_lo[l] = off; off += bytes;
+        T.bias[l] = off; off += (size_t)T.n_pad[l] * 4;
         off = (off + 255) & ~(size_t)255;
     }
     T.total = off;
     return T;
 }
 
-struct PackArgs {  // layouts travel as kernel parameters (constant bank): indexing them by layer costs no local memory
-    const float* flat;
+// ---- optimizer step + re-pack in one pass (or the pack alone) -----------------------------------------------------
+// optax.chain(clip_by_global_norm, adam(eps)) over the flat buffer exactly as brl_adam_apply (csrc/brl_ppo.cu), and in the
+// same pass the refreshed parameter goes out as bf16 hi / lo (weights, same [in, out] orientation) or fp32 (biases) into the
+// training blob.  The four hidden layers (w and b ranges all multiples of 4 floats) take the 128-bit path; the head's
+// (1024 x 38, 38, 1024 x 1, 1) ranges are remapped element-wise into its 64-wide padded tile.
+struct AdamPackArgs {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    const double* sumsq;
     unsigned char* blob;
-    MlpLayout L;
-    TrainBlob T;
+    float max_norm, lr, b1, b2, eps, bc1, bc2;
     FlatLayout F;
-    int tile0[kNumLayers + 1];  // first block of each layer's 64 x 64 tiles
+    TrainBlob T;
 };
 
-// 64 x 64 tile of one layer: fp32 W[in, out] -> Wn hi/lo [in, out_pad] (same orientation) and, through a shared-memory
-// transpose, Wt hi/lo [out_pad, in]; bf16 pairs are stored as 32-bit words.  The head layer concatenates the policy (38)
-// and value (1) columns.  Blocks are numbered over the layers' tiles (PackArgs.tile0), so none is launched idle.
+__device__ __forceinline__ float adam_elem(const AdamPackArgs& a, float p, float g, float& m, float& v, float scale) {
+    const float gi = g * scale;
+    m = a.b1 * m + (1.0f - a.b1) * gi;
+    v = a.b2 * v + (1.0f - a.b2) * gi * gi;
+    return p - a.lr * (m / a.bc1) / (sqrtf(v / a.bc2) + a.eps);
+}
 __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = pack_bf16x2(v0 - __low2float(h), v1 - __high2float(h));
 }
 
-__global__ void __launch_bounds__(256) k_pack_train(const __grid_constant__ PackArgs a) {
-    int l = 0;
-#pragma unroll
-    for (int k = 1; k < kNumLayers; ++k)
-        if ((int)blockIdx.x >= a.tile0[k]) l = k;
-    const MlpLayout& L = a.L;
-    const TrainBlob& T = a.T;
-    const FlatLayout& F = a.F;
-    const int k_in = L.k_in[l], n_pad = L.n_out[l];
-    const int tiles_n = n_pad / 64, r = blockIdx.x - a.tile0[l];
-    const int k0 = (r / tiles_n) * 64, n0 = (r % tiles_n) * 64;
-    const bool head = l == 4;
-    const int n_src = head ? 38 : kHidden;
-    const float* w = a.flat + F.w[l];
-    __shared__ float t[64][65];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    uint32_t* wn_hi = l > 0 ? reinterpret_cast<uint32_t*>(a.blob + T.wn_hi[l]) : nullptr;
-    uint32_t* wn_lo = l > 0 ? reinterpret_cast<uint32_t*>(a.blob + T.wn_lo[l]) : nullptr;
-    const int n = n0 + 2 * tx;
-    for (int j = ty; j < 64; j += 8) {
-        const int k = k0 + j;
-        float v0 = 0.0f, v1 = 0.0f;
-        if (k < k_in) {
-            if (!head) {
-                const float2 v = *reinterpret_cast<const float2*>(w + (size_t)k * n_src + n);
-                v0 = v.x; v1 = v.y;
-            } else {
-                v0 = n < 38 ? w[(size_t)k * 38 + n] : (n == 38 ? a.flat[F.w[5] + k] : 0.0f);
-                v1 = n + 1 < 38 ? w[(size_t)k * 38 + n + 1] : 0.0f;
-            }
-            if (wn_hi) {
-                uint32_t h, lo;
-                split_pair(v0, v1, h, lo);
-                wn_hi[((size_t)k * n_pad + n) >> 1] = h;
-                wn_lo[((size_t)k * n_pad + n) >> 1] = lo;
-            }
-        }
-        t[j][2 * tx] = v0;
-        t[j][2 * tx + 1] = v1;
+template <bool ADAM>
+__global__ void __launch_bounds__(256) k_adam_pack(const __grid_constant__ AdamPackArgs a) {
+    float scale = 1.0f;
+    if (ADAM && a.max_norm > 0.0f) {  // optax.clip_by_global_norm: g * (max_norm / norm) only when norm >= max_norm
+        const float norm = (float)sqrt(*a.sumsq);
+        if (!(norm < a.max_norm)) scale = a.max_norm / norm;
     }
-    __syncthreads();
-    uint32_t* wt_hi = reinterpret_cast<uint32_t*>(a.blob + L.w_hi[l]);
-    uint32_t* wt_lo = reinterpret_cast<uint32_t*>(a.blob + L.w_lo[l]);
-    const int k = k0 + 2 * tx;
-    if (k < k_in)  // k_in is even
-        for (int j = ty; j < 64; j += 8) {
-            uint32_t h, lo;
-            split_pair(t[2 * tx][j], t[2 * tx + 1][j], h, lo);
-            wt_hi[((size_t)(n0 + j) * k_in + k) >> 1] = h;
-            wt_lo[((size_t)(n0 + j) * k_in + k) >> 1] = lo;
+    const size_t n_hidden = a.F.w[4];  // flat ranges [0, w[4]) = w0, b0 .. w3, b3, every boundary a multiple of 4
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < n_hidden / 4; i4 += stride) {
+        const size_t i = 4 * i4;
+        float4 p4 = reinterpret_cast<const float4*>(a.p)[i4];
+        if (ADAM) {
+            const float4 g4 = reinterpret_cast<const float4*>(a.g)[i4];
+            float4 m4 = reinterpret_cast<float4*>(a.m)[i4], v4 = reinterpret_cast<float4*>(a.v)[i4];
+            p4.x = adam_elem(a, p4.x, g4.x, m4.x, v4.x, scale);
+            p4.y = adam_elem(a, p4.y, g4.y, m4.y, v4.y, scale);
+            p4.z = adam_elem(a, p4.z, g4.z, m4.z, v4.z, scale);
+            p4.w = adam_elem(a, p4.w, g4.w, m4.w, v4.w, scale);
+            reinterpret_cast<float4*>(a.p)[i4] = p4;
+            reinterpret_cast<float4*>(a.m)[i4] = m4;
+            reinterpret_cast<float4*>(a.v)[i4] = v4;
         }
-    if (k0 == 0 && threadIdx.x < 64) {
-        const int nb = n0 + threadIdx.x;
-        float bv = 0.0f;
-        if (nb < n_src) bv = a.flat[F.b[l] + nb];
-        else if (head && nb == 38) bv = a.flat[F.b[5]];
-        reinterpret_cast<float*>(a.blob + L.bias[l])[nb] = bv;
+        int l = 0;
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+            if (i >= a.F.w[k]) l = k;
+        if (i < a.F.b[l]) {  // weight: same offset inside Wn[l] (n_pad == n_out for the hidden layers)
+            const size_t e = i - a.F.w[l];
+            uint2 hi, lo;
+            split_pair(p4.x, p4.y, hi.x, lo.x);
+            split_pair(p4.z, p4.w, hi.y, lo.y);
+            *reinterpret_cast<uint2*>(a.blob + a.T.wn_hi[l] + 2 * e) = hi;
+            *reinterpret_cast<uint2*>(a.blob + a.T.wn_lo[l] + 2 * e) = lo;
+        } else {
+            *reinterpret_cast<float4*>(a.blob + a.T.bias[l] + 4 * (i - a.F.b[l])) = p4;
+        }
+    }
+    // head: w4 [1024, 38], b4 [38], w5 [1024, 1], b5 [1] -> Wn[4] [1024, 64] (columns 39..63 stay zero), bias[4] [64]
+    for (size_t i = n_hidden + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.F.total; i += stride) {
+        float p = a.p[i];
+        if (ADAM) {
+            float m = a.m[i], v = a.v[i];
+            p = adam_elem(a, p, a.g[i], m, v, scale);
+            a.p[i] = p;
+            a.m[i] = m;
+            a.v[i] = v;
+        }
+        size_t e;        // element of Wn[4], or
+        int bias_col = -1;
+        if (i < a.F.b[4]) { const size_t r = i - a.F.w[4]; e = (r / 38) * kHeadPad + r % 38; }
+        else if (i < a.F.w[5]) { bias_col = (int)(i - a.F.b[4]); e = 0; }
+        else if (i < a.F.b[5]) { e = (i - a.F.w[5]) * kHeadPad + 38; }
+        else { bias_col = 38; e = 0; }
+        if (bias_col >= 0) {
+            reinterpret_cast<float*>(a.blob + a.T.bias[4])[bias_col] = p;
+        } else {
+            const __nv_bfloat16 h = __float2bfloat16_rn(p);
+            reinterpret_cast<__nv_bfloat16*>(a.blob + a.T.wn_hi[4])[e] = h;
+            reinterpret_cast<__nv_bfloat16*>(a.blob + a.T.wn_lo[4])[e] = __float2bfloat16_rn(p - __bfloat162float(h));
+        }
     }
 }
 
@@ -290,14 +309,6 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t saddr) {
     return MN ? umma_desc_mn_sw128(saddr, kMnBox) : umma_desc_sw128(saddr);
 }
 
-template <int BN, bool SPLIT_A, bool SPLIT_W>
-struct GemmCfg {
-    static constexpr uint32_t kABytes = kBM * kBK * 2, kWBytes = BN * kBK * 2;
-    static constexpr uint32_t kStageBytes = kABytes * (SPLIT_A ? 2 : 1) + kWBytes * (SPLIT_W ? 2 : 1);
-    static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (int)(kSmemBudget / kStageBytes);
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-};
-
 // 32 accumulator columns of this thread's row; t_off2 != 0 (k_train_fused): the tile's products live in two column
 // blocks t_off2 apart (x.w_hi terms | x_hi.w_lo term) and their sum is the result
 __device__ __forceinline__ void tmem_ld32_sum(uint32_t taddr, uint32_t t_off2, uint32_t (&r)[32]) {
@@ -312,7 +323,7 @@ __device__ __forceinline__ void tmem_ld32_sum(uint32_t taddr, uint32_t t_off2, u
 
 // forward / dgrad rows: x -> bf16 hi / lo, 128-bit stores
 template <int EPI>
-__device__ __forceinline__ void epilogue_act_row(uint32_t t_row, int n_cols, int n0, int row, bool row_ok, const GemmArgs& a, uint32_t t_off2 = 0u) {
+__device__ __forceinline__ void epilogue_act_row(uint32_t t_row, int n_cols, int n0, int row, bool row_ok, const GemmArgs& a, uint32_t t_off2) {
 #pragma unroll 1
     for (int c0 = 0; c0 < n_cols; c0 += 32) {
         uint32_t r[32];
@@ -375,7 +386,7 @@ __device__ __forceinline__ void epilogue_head_row2(uint32_t t_row, uint32_t t_of
 
 // wgrad rows: the accumulator IS the gradient block; thread = one input feature (row of W)
 template <int BN>
-__device__ __forceinline__ void epilogue_wgrad_row(uint32_t t_row, int n0, int row, bool row_ok, const GemmArgs& a, uint32_t t_off2 = 0u) {
+__device__ __forceinline__ void epilogue_wgrad_row(uint32_t t_row, int n0, int row, bool row_ok, const GemmArgs& a, uint32_t t_off2) {
     float ss = 0.0f;  // this row's share of |g|^2 (padding columns of the head tile are exact zeros)
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -408,190 +419,6 @@ __device__ __forceinline__ void epilogue_wgrad_row(uint32_t t_row, int n0, int r
     }
 }
 
-template <int BN, bool SPLIT_A, bool SPLIT_W, int EPI>
-__global__ void __launch_bounds__(kMlpThreads, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const GemmArgs a) {
-    // Same pipeline as k_mlp_layer (brl_mlp.cu): persistent CTAs walk tiles blockIdx.x, + gridDim.x, ... (n-tile fastest);
-    // the shared-memory stage ring runs across tile boundaries; two TMEM accumulators overlap epilogue and main loop.
-    using Cfg = GemmCfg<BN, SPLIT_A, SPLIT_W>;
-    constexpr bool MN = EPI == kEpiWgrad;  // the wgrad contracts over the batch: MN-major operands
-    constexpr int S = Cfg::kStages;
-    constexpr uint32_t kTmemCols = 2 * BN;
-    extern __shared__ unsigned char smem_dyn[];
-    const uint32_t base = (smem_addr(smem_dyn) + 1023u) & ~1023u;
-    const uint32_t bar_base = base + S * Cfg::kStageBytes;  // full[S], empty[S], tmem_full[2], tmem_empty[2]
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-    auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
-    auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
-    __shared__ uint32_t tmem_base_s;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles_n = a.n_tiles_n, n_tiles = a.n_tiles;
-
-    // Programmatic dependent launch: the GEMMs of one update form a chain of short kernels, so the next one may be
-    // scheduled now and run its prologue (barrier init, tensor-memory allocation, descriptor prefetch) on free SMs /
-    // behind this one's tail; it touches no global data before griddepcontrol.wait below.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w_hi) : "memory");
-        if (SPLIT_A) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_lo) : "memory");
-        if (SPLIT_W) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w_lo) : "memory");
-        for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 1) tmem_alloc(smem_addr(&tmem_base_s), kTmemCols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(&tmem_base_s);
-    asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the preceding kernels wrote is visible from here on
-
-    if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer =====
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles_n) * kBM, n0 = (tile % n_tiles_n) * BN;
-                for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
-                    const int s = (int)(it % S);
-                    mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
-                    mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
-                    uint32_t dst = base + s * Cfg::kStageBytes;
-                    if (!MN) {
-                        tma_load_2d(dst, &tm_a_hi, full_bar(s), kb * kBK, m0);
-                        dst += Cfg::kABytes;
-                        if (SPLIT_A) { tma_load_2d(dst, &tm_a_lo, full_bar(s), kb * kBK, m0); dst += Cfg::kABytes; }
-                        tma_load_2d(dst, &tm_w_hi, full_bar(s), kb * kBK, n0);
-                        dst += Cfg::kWBytes;
-                        if (SPLIT_W) tma_load_2d(dst, &tm_w_lo, full_bar(s), kb * kBK, n0);
-                    } else {  // operands are [batch, feature] row-major: boxes of {64 features, 64 samples}, kMnBox bytes each
-#pragma unroll
-                        for (int j = 0; j < kBM / 64; ++j) tma_load_2d(dst + j * kMnBox, &tm_a_hi, full_bar(s), m0 + 64 * j, kb * kBK);
-                        dst += Cfg::kABytes;
-                        if (SPLIT_A) {
-#pragma unroll
-                            for (int j = 0; j < kBM / 64; ++j) tma_load_2d(dst + j * kMnBox, &tm_a_lo, full_bar(s), m0 + 64 * j, kb * kBK);
-                            dst += Cfg::kABytes;
-                        }
-#pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(dst + j * kMnBox, &tm_w_hi, full_bar(s), n0 + 64 * j, kb * kBK);
-                        dst += Cfg::kWBytes;
-                        if (SPLIT_W) {
-#pragma unroll
-                            for (int j = 0; j < BN / 64; ++j) tma_load_2d(dst + j * kMnBox, &tm_w_lo, full_bar(s), n0 + 64 * j, kb * kBK);
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer =====
-            constexpr uint32_t idesc = MN ? umma_idesc_bf16_mn(kBM, BN) : umma_idesc_bf16(kBM, BN);
-            uint32_t it = 0, j = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
-                const uint32_t buf = j & 1u;
-                mbar_wait(tmem_empty_bar(buf), ((j >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t acc = tmem_acc + buf * BN;
-                for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
-                    const int s = (int)(it % S);
-                    mbar_wait(full_bar(s), (it / S) & 1u);
-                    tc_fence_after();
-                    const uint32_t sa_hi = base + s * Cfg::kStageBytes;
-                    const uint32_t sa_lo = sa_hi + Cfg::kABytes;
-                    const uint32_t sw_hi = sa_hi + Cfg::kABytes * (SPLIT_A ? 2 : 1);
-                    const uint32_t sw_lo = sw_hi + Cfg::kWBytes;
-#pragma unroll
-                    for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        // K-major: 16 K elements = 32 bytes along the 128-byte row; MN-major: 16 K rows of 128 bytes
-                        const uint32_t koff = (uint32_t)k * kUmmaK * (MN ? 128u : 2u);
-                        const uint64_t da_hi = operand_desc<MN>(sa_hi + koff), dw_hi = operand_desc<MN>(sw_hi + koff);
-                        umma_bf16(acc, da_hi, dw_hi, idesc, (kb | k) != 0);
-                        if (SPLIT_A) umma_bf16(acc, operand_desc<MN>(sa_lo + koff), dw_hi, idesc, 1u);
-                        if (SPLIT_W) umma_bf16(acc, da_hi, operand_desc<MN>(sw_lo + koff), idesc, 1u);
-                    }
-                    umma_commit(empty_bar(s));
-                }
-                umma_commit(tmem_full_bar(buf));
-            }
-        }
-    } else {  // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        const int q = warp & 3;
-        uint32_t j = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
-            const int m0 = (tile / n_tiles_n) * kBM, n0 = (tile % n_tiles_n) * BN;
-            const uint32_t buf = j & 1u;
-            mbar_wait(tmem_full_bar(buf), (j >> 1) & 1u);
-            tc_fence_after();
-            const int row = m0 + q * 32 + lane;
-            const uint32_t t_row = tmem_acc + buf * BN + ((uint32_t)(q * 32) << 16);
-            if (EPI == kEpiFwd || EPI == kEpiDgrad) epilogue_act_row<EPI>(t_row, BN, n0, row, row < a.M, a);
-            else if (EPI == kEpiWgrad) epilogue_wgrad_row<BN>(t_row, n0, row, row < a.M, a);
-            else epilogue_head_row(t_row, a.bias + n0, row < a.M, a.logits + (size_t)row * 38, a.value + row);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(buf)) : "memory");
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_acc, kTmemCols);
-}
-
-// A [m_rows, k_cols] (pitch lda), Bt [n_rows, k_cols] (pitch ldb), both bf16 K-major; hi / lo pairs.
-// kEpiWgrad: the same logical operands stored transposed, [k_cols, m_rows] / [k_cols, n_rows] (MN-major).
-template <int BN, bool SPLIT_A, bool SPLIT_W, int EPI>
-static int32_t launch_gemm(cudaStream_t s, const void* a_hi, const void* a_lo, int m_rows, int lda, const void* w_hi, const void* w_lo,
-                           int n_rows, int ldb, int k_cols, GemmArgs args) {
-    using Cfg = GemmCfg<BN, SPLIT_A, SPLIT_W>;
-    CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
-    constexpr bool MN = EPI == kEpiWgrad;  // operands given as [k_cols, m_rows] / [k_cols, n_rows] row-major
-    bool ok = MN ? make_map(&ta_hi, a_hi, (uint64_t)k_cols, (uint64_t)m_rows, (uint64_t)lda, 64) &&
-                       make_map(&tw_hi, w_hi, (uint64_t)k_cols, (uint64_t)n_rows, (uint64_t)ldb, 64)
-                 : make_map(&ta_hi, a_hi, (uint64_t)m_rows, (uint64_t)k_cols, (uint64_t)lda, kBM) &&
-                       make_map(&tw_hi, w_hi, (uint64_t)n_rows, (uint64_t)k_cols, (uint64_t)ldb, BN);
-    ta_lo = ta_hi;
-    tw_lo = tw_hi;
-    if (ok && SPLIT_A) ok = MN ? make_map(&ta_lo, a_lo, (uint64_t)k_cols, (uint64_t)m_rows, (uint64_t)lda, 64)
-                               : make_map(&ta_lo, a_lo, (uint64_t)m_rows, (uint64_t)k_cols, (uint64_t)lda, kBM);
-    if (ok && SPLIT_W) ok = MN ? make_map(&tw_lo, w_lo, (uint64_t)k_cols, (uint64_t)n_rows, (uint64_t)ldb, 64)
-                               : make_map(&tw_lo, w_lo, (uint64_t)n_rows, (uint64_t)k_cols, (uint64_t)ldb, BN);
-    if (!ok) return fail(BRL_E_LAUNCH, "brl_ppo_grad: cuTensorMapEncodeTiled failed");
-    auto kern = k_gemm_tc<BN, SPLIT_A, SPLIT_W, EPI>;
-    static bool attr_set = false;  // idempotent; a race only repeats the call
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
-            return fail(BRL_E_LAUNCH, "brl_ppo_grad: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);
-        attr_set = true;
-    }
-    args.M = m_rows;
-    args.k_blocks = (k_cols + kBK - 1) / kBK;
-    args.n_tiles_n = (n_rows + BN - 1) / BN;
-    args.n_tiles = args.n_tiles_n * ((m_rows + kBM - 1) / kBM);
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(args.n_tiles < n_sm ? args.n_tiles : n_sm));
-    cfg.blockDim = dim3(kMlpThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = s;
-    cudaLaunchAttribute at{};
-    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at.val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = &at;
-    cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tw_hi, tw_lo, args) != cudaSuccess) return check_launch("brl_ppo_grad (GEMM launch)");
-    return BRL_OK;
-}
-
 // ---- all GEMMs of the forward (or of the backward) as ONE persistent launch ----------------------------------------
 // At a 1024-sample minibatch each GEMM is ~128 tiles of ~6 us on 148 SMs: run one launch per GEMM and the fixed costs
 // (launch gap, barrier / tensor-memory set-up, pipeline fill, the un-overlapped epilogue of each CTA's single tile)
@@ -611,6 +438,7 @@ struct FusedOp {
     CUtensorMap a, w;
     GemmArgs g;
     int epi, split_a;
+    int a_mn, w_mn;          // operand stored with its M / N index contiguous (MN-major) instead of K
     int tile0;               // index of this op's first tile in the list
     int dep;                 // producing op of this launch, -1 = none (inputs complete before the launch)
     int dep_all;             // 1: wait for all of the producer's tiles, 0: for its row block m0 / 128
@@ -692,7 +520,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
                 const FusedOp& op = a.op[o];
                 const int r = tile - op.tile0;
                 const int mb = r / op.g.n_tiles_n, m0 = mb * kBM, n0 = (r % op.g.n_tiles_n) * kFBN;
-                const bool split_a = op.split_a != 0, mn = op.epi == kEpiWgrad;
+                const bool split_a = op.split_a != 0, a_mn = op.a_mn != 0, w_mn = op.w_mn != 0;
                 const uint32_t tx = Cfg::kABytes * (split_a ? 2u : 1u) + 2u * Cfg::kWBytes;
                 trace_stamp(a, tile, 0);
                 if (op.dep >= 0) {
@@ -713,18 +541,18 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
                     mbar_expect_tx(full_bar(s), tx);
                     const uint32_t sa = base + s * Cfg::kStageBytes;
                     const uint32_t sw = sa + 2 * Cfg::kABytes;
-                    if (!mn) {
+                    // K-major operand: {64 k, rows (, hi / lo)}; MN-major: {64 features, 64 k rows, 64-feature chunks, hi / lo}
+                    if (!a_mn) {
                         if (split_a) tma_load_3d(sa, &op.a, full_bar(s), kb * kBK, m0, 0);
                         else tma_load_2d(sa, &op.a, full_bar(s), kb * kBK, m0);
-                        tma_load_3d(sw, &op.w, full_bar(s), kb * kBK, n0, 0);
-                    } else {  // [batch, feature] row-major operands: boxes of {64 features, 64 samples}
-                        if (split_a) tma_load_4d(sa, &op.a, full_bar(s), 0, kb * kBK, m0 / 64, 0);
-                        else {
+                    } else if (split_a) {
+                        tma_load_4d(sa, &op.a, full_bar(s), 0, kb * kBK, m0 / 64, 0);
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < kBM / 64; ++j) tma_load_2d(sa + j * kMnBox, &op.a, full_bar(s), m0 + 64 * j, kb * kBK);
-                        }
-                        tma_load_4d(sw, &op.w, full_bar(s), 0, kb * kBK, n0 / 64, 0);
+                        for (int j = 0; j < kBM / 64; ++j) tma_load_2d(sa + j * kMnBox, &op.a, full_bar(s), m0 + 64 * j, kb * kBK);
                     }
+                    if (!w_mn) tma_load_3d(sw, &op.w, full_bar(s), kb * kBK, n0, 0);
+                    else tma_load_4d(sw, &op.w, full_bar(s), 0, kb * kBK, n0 / 64, 0);
                 }
                 trace_stamp(a, tile, 2);
             }
@@ -734,9 +562,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
             uint32_t it = 0, j = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
                 const FusedOp& op = a.op[fused_find_op(a, tile)];
-                const bool split_a = op.split_a != 0, mn = op.epi == kEpiWgrad;
-                const uint32_t idesc = mn ? umma_idesc_bf16_mn(kBM, kFBN) : umma_idesc_bf16(kBM, kFBN);
-                const uint32_t idesc2 = mn ? umma_idesc_bf16_mn(kBM, 2 * kFBN) : umma_idesc_bf16(kBM, 2 * kFBN);
+                const bool split_a = op.split_a != 0, a_mn = op.a_mn != 0, w_mn = op.w_mn != 0;
+                const uint32_t majors = (a_mn ? 1u << 15 : 0u) | (w_mn ? 1u << 16 : 0u);
+                const uint32_t idesc = umma_idesc_bf16(kBM, kFBN) | majors, idesc2 = umma_idesc_bf16(kBM, 2 * kFBN) | majors;
                 const int k_blocks = op.g.k_blocks;
                 const uint32_t buf = j & 1u;
                 mbar_wait(tmem_empty_bar(buf), ((j >> 1) & 1u) ^ 1u);
@@ -752,11 +580,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
                     const uint32_t sw_hi = sa_hi + 2 * Cfg::kABytes;
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint32_t koff = (uint32_t)k * kUmmaK * (mn ? 128u : 2u);
-                        const uint64_t da_hi = mn ? operand_desc<true>(sa_hi + koff) : operand_desc<false>(sa_hi + koff);
-                        const uint64_t dw_hi = mn ? operand_desc<true>(sw_hi + koff) : operand_desc<false>(sw_hi + koff);
+                        // 16 K elements further: 32 bytes along a K-major row, 16 rows of 128 bytes in an MN-major tile
+                        const uint32_t koff_a = (uint32_t)k * kUmmaK * (a_mn ? 128u : 2u), koff_w = (uint32_t)k * kUmmaK * (w_mn ? 128u : 2u);
+                        const uint64_t da_hi = a_mn ? operand_desc<true>(sa_hi + koff_a) : operand_desc<false>(sa_hi + koff_a);
+                        const uint64_t dw_hi = w_mn ? operand_desc<true>(sw_hi + koff_w) : operand_desc<false>(sw_hi + koff_w);
                         umma_bf16(acc, da_hi, dw_hi, idesc2, (kb | k) != 0);  // x_hi . [w_hi ; w_lo]: the W_lo tile follows W_hi
-                        if (split_a) umma_bf16(acc, mn ? operand_desc<true>(sa_lo + koff) : operand_desc<false>(sa_lo + koff), dw_hi, idesc, 1u);
+                        if (split_a) umma_bf16(acc, a_mn ? operand_desc<true>(sa_lo + koff_a) : operand_desc<false>(sa_lo + koff_a), dw_hi, idesc, 1u);
                     }
                     umma_commit(empty_bar(s));
                 }
@@ -800,30 +629,18 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_train_fused(const __grid_con
     if (warp == 1) tmem_dealloc(tmem_acc, kTmemCols);
 }
 
-// one GEMM of the update, as the host describes it to either launcher.  kEpiWgrad: a_* / w_* are the row-major
-// [k_cols, m_rows] / [k_cols, n_rows] arrays (pitch lda / ldb) and are consumed MN-major.
+// one GEMM of the update, C[m_rows, n_rows] = A . Bt^T over k_cols, as the host describes it.  A K-major operand is the
+// row-major [m_rows (n_rows), k_cols] array, an MN-major one (a_mn / w_mn) the row-major [k_cols, m_rows (n_rows)] array;
+// lda / ldb = row pitch in elements, *_lo = NULL for an operand that is exact in bf16 (the 0/1 observation).
 struct OpSpec {
     const void *a_hi, *a_lo;
-    int m_rows, lda;
+    int m_rows, lda, a_mn;
     const void *w_hi, *w_lo;
-    int n_rows, ldb, k_cols;
+    int n_rows, ldb, w_mn, k_cols;
     int epi;
     GemmArgs g;
     int dep, dep_all;
 };
-
-static int32_t launch_op(bool narrow, cudaStream_t s, const OpSpec& o) {
-    const bool sa = o.a_lo != nullptr;
-#define BRL_GEMM(BN, SA, EPI) launch_gemm<BN, SA, true, EPI>(s, o.a_hi, o.a_lo, o.m_rows, o.lda, o.w_hi, o.w_lo, o.n_rows, o.ldb, o.k_cols, o.g)
-    if (o.epi == kEpiHead) return BRL_GEMM(kHeadPad, true, kEpiHead);
-    if (o.epi == kEpiWgrad && o.n_rows == kHeadPad) return BRL_GEMM(kHeadPad, true, kEpiWgrad);
-    if (o.epi == kEpiFwd) return narrow ? (sa ? BRL_GEMM(64, true, kEpiFwd) : BRL_GEMM(64, false, kEpiFwd))
-                                        : (sa ? BRL_GEMM(128, true, kEpiFwd) : BRL_GEMM(128, false, kEpiFwd));
-    if (o.epi == kEpiDgrad) return narrow ? BRL_GEMM(64, true, kEpiDgrad) : BRL_GEMM(128, true, kEpiDgrad);
-    return narrow ? (sa ? BRL_GEMM(64, true, kEpiWgrad) : BRL_GEMM(64, false, kEpiWgrad))
-                  : (sa ? BRL_GEMM(128, true, kEpiWgrad) : BRL_GEMM(128, false, kEpiWgrad));
-#undef BRL_GEMM
-}
 
 template <int kFBN>
 static int32_t launch_fused_ops(cudaStream_t s, const OpSpec* ops, int n_ops, int nmb, uint32_t* ready, unsigned long long* trace) {
@@ -833,26 +650,24 @@ static int32_t launch_fused_ops(cudaStream_t s, const OpSpec* ops, int n_ops, in
     for (int i = 0; i < n_ops; ++i) {
         const OpSpec& o = ops[i];
         FusedOp& f = fa.op[i];
-        const bool mn = o.epi == kEpiWgrad;  // operands given as [k_cols, m_rows] / [k_cols, n_rows] row-major
-        // (hi, lo) pair of one operand as a single map; rows x cols = the 2-D extent of each array, pitch in elements
-        auto pair_map = [&](CUtensorMap* m, const void* hi, const void* lo, int feat_rows, int pitch, uint32_t box_feat) {
+        // (hi, lo) pair of one operand as a single map; feat = the operand's M / N extent, pitch in elements
+        auto pair_map = [&](CUtensorMap* m, const void* hi, const void* lo, bool mn, int feat, int pitch, uint32_t box_feat) {
+            if (static_cast<const char*>(lo) <= static_cast<const char*>(hi)) return false;  // the trailing dimension steps hi -> lo
             const uint64_t gap = (uint64_t)(static_cast<const char*>(lo) - static_cast<const char*>(hi));
-            if (!mn) {  // K-major: [feat_rows, k_cols]
-                const uint64_t dims[3] = {(uint64_t)o.k_cols, (uint64_t)feat_rows, 2}, str[2] = {(uint64_t)pitch * 2, gap};
+            if (!mn) {  // K-major: [feat, k_cols]
+                const uint64_t dims[3] = {(uint64_t)o.k_cols, (uint64_t)feat, 2}, str[2] = {(uint64_t)pitch * 2, gap};
                 const uint32_t box[3] = {(uint32_t)kBK, box_feat, 2};
                 return make_map_nd(m, hi, 3, dims, str, box);
             }
-            // MN-major: [k_cols samples, feat_rows features], features in chunks of 64
-            const uint64_t dims[4] = {64, (uint64_t)o.k_cols, (uint64_t)((feat_rows + 63) / 64), 2}, str[3] = {(uint64_t)pitch * 2, 128, gap};
+            // MN-major: [k_cols, feat], features in chunks of 64
+            const uint64_t dims[4] = {64, (uint64_t)o.k_cols, (uint64_t)((feat + 63) / 64), 2}, str[3] = {(uint64_t)pitch * 2, 128, gap};
             const uint32_t box[4] = {64, (uint32_t)kBK, box_feat / 64, 2};
             return make_map_nd(m, hi, 4, dims, str, box);
         };
-        bool ok = pair_map(&f.w, o.w_hi, o.w_lo, o.n_rows, o.ldb, kFBN);
-        if (ok && o.a_lo) ok = pair_map(&f.a, o.a_hi, o.a_lo, o.m_rows, o.lda, kBM);
-        else if (ok) ok = mn ? make_map(&f.a, o.a_hi, (uint64_t)o.k_cols, (uint64_t)o.m_rows, (uint64_t)o.lda, 64)
-                             : make_map(&f.a, o.a_hi, (uint64_t)o.m_rows, (uint64_t)o.k_cols, (uint64_t)o.lda, kBM);
-        if (ok && o.a_lo && (static_cast<const char*>(o.a_lo) <= static_cast<const char*>(o.a_hi) || static_cast<const char*>(o.w_lo) <= static_cast<const char*>(o.w_hi)))
-            ok = false;  // the pair maps need lo above hi
+        bool ok = pair_map(&f.w, o.w_hi, o.w_lo, o.w_mn != 0, o.n_rows, o.ldb, kFBN);
+        if (ok && o.a_lo) ok = pair_map(&f.a, o.a_hi, o.a_lo, o.a_mn != 0, o.m_rows, o.lda, kBM);
+        else if (ok) ok = o.a_mn ? make_map(&f.a, o.a_hi, (uint64_t)o.k_cols, (uint64_t)o.m_rows, (uint64_t)o.lda, 64)
+                                 : make_map(&f.a, o.a_hi, (uint64_t)o.m_rows, (uint64_t)o.k_cols, (uint64_t)o.lda, kBM);
         if (!ok) return fail(BRL_E_LAUNCH, "brl_ppo_grad: cuTensorMapEncodeTiled failed");
         f.g = o.g;
         f.g.M = o.m_rows;
@@ -861,6 +676,8 @@ static int32_t launch_fused_ops(cudaStream_t s, const OpSpec* ops, int n_ops, in
         f.g.n_tiles = f.g.n_tiles_n * ((o.m_rows + kBM - 1) / kBM);
         f.epi = o.epi;
         f.split_a = o.a_lo != nullptr;
+        f.a_mn = o.a_mn;
+        f.w_mn = o.w_mn;
         f.tile0 = tiles;
         tiles += f.g.n_tiles;
         f.dep = o.dep;
@@ -905,21 +722,55 @@ int64_t brl_mlp_train_blob_bytes(void) { return (int64_t)train_blob().total; }
 int64_t brl_mlp_train_scratch_bytes(int64_t batch) { return batch > 0 ? (int64_t)train_scratch(batch).total : 0; }
 int64_t brl_mlp_train_trace_offset(int64_t batch) { return batch > 0 ? (int64_t)train_scratch(batch).trace : 0; }
 
+static unsigned adam_pack_grid() {
+    const size_t items = flat_layout().w[4] / 4;  // the 128-bit body; the head's 40 K elements ride along
+    size_t g = (items + 255) / 256;
+    return (unsigned)(g > 148 * 8 ? 148 * 8 : g);
+}
+
 int32_t brl_mlp_pack_train(brl_stream_t stream, void** b, const void* opaque, size_t len) {
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
     BRL_REQUIRE(b[0], "params");
     BRL_REQUIRE(b[1], "blob");
-    PackArgs a{static_cast<const float*>(b[0]), static_cast<unsigned char*>(b[1]), mlp_layout(), train_blob(), flat_layout(), {}};
-    int tiles = 0;
-    for (int l = 0; l < kNumLayers; ++l) {
-        a.tile0[l] = tiles;
-        tiles += ((a.L.k_in[l] + 63) / 64) * (a.L.n_out[l] / 64);
-    }
-    a.tile0[kNumLayers] = tiles;
-    k_pack_train<<<(unsigned)tiles, 256, 0, (cudaStream_t)stream>>>(a);
+    cudaStream_t s = (cudaStream_t)stream;
+    AdamPackArgs a{};
+    a.p = static_cast<float*>(b[0]);
+    a.blob = static_cast<unsigned char*>(b[1]);
+    a.F = flat_layout();
+    a.T = train_blob();
+    // the head tile's padding columns (39..63) and bias entries are never written by the packer: zero them once here
+    if (cudaMemsetAsync(a.blob + a.T.wn_hi[4], 0, a.T.total - a.T.wn_hi[4], s) != cudaSuccess) return check_launch("brl_mlp_pack_train");
+    k_adam_pack<false><<<adam_pack_grid(), 256, 0, s>>>(a);
     return check_launch("brl_mlp_pack_train");
+}
+
+int32_t brl_mlp_adam_step(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    if (opaque == nullptr || len != sizeof(BrlAdamParams))
+        return fail(BRL_E_OPAQUE, "brl_mlp_adam_step: opaque must be one BrlAdamParams (%zu bytes), got %zu", sizeof(BrlAdamParams), len);
+    const BrlAdamParams* p = static_cast<const BrlAdamParams*>(opaque);
+    static const char* names[] = {"params", "grads", "m", "v", "sumsq", "blob"};
+    for (int k = 0; k < 6; ++k) {
+        if (b[k] == nullptr) return fail(BRL_E_BUFFER, "brl_mlp_adam_step: buffer '%s' is NULL", names[k]);
+        if (k != 4 && (reinterpret_cast<uintptr_t>(b[k]) & 15u) != 0) return fail(BRL_E_BUFFER, "brl_mlp_adam_step: buffer '%s' is not 16-byte aligned", names[k]);
+    }
+    if (p->n != (int64_t)flat_layout().total || p->step <= 0)
+        return fail(BRL_E_OPAQUE, "brl_mlp_adam_step: n must be brl_mlp_num_params() and step (1-based) > 0");
+    AdamPackArgs a{};
+    a.p = static_cast<float*>(b[0]);
+    a.g = static_cast<const float*>(b[1]);
+    a.m = static_cast<float*>(b[2]);
+    a.v = static_cast<float*>(b[3]);
+    a.sumsq = static_cast<const double*>(b[4]);
+    a.blob = static_cast<unsigned char*>(b[5]);
+    a.max_norm = p->max_grad_norm; a.lr = p->lr; a.b1 = p->beta1; a.b2 = p->beta2; a.eps = p->eps;
+    a.bc1 = 1.0f - powf(p->beta1, (float)p->step);
+    a.bc2 = 1.0f - powf(p->beta2, (float)p->step);
+    a.F = flat_layout();
+    a.T = train_blob();
+    k_adam_pack<true><<<adam_pack_grid(), 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("brl_mlp_adam_step");
 }
 
 int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t len) {
@@ -936,14 +787,12 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
     if (encode_fn() == nullptr) return fail(BRL_E_LAUNCH, "brl_ppo_grad: cuTensorMapEncodeTiled not available from the driver");
     cudaStream_t s = (cudaStream_t)stream;
     const int B = (int)p->batch;
-    const MlpLayout L = mlp_layout();
     const TrainBlob T = train_blob();
     const FlatLayout F = flat_layout();
     const TrainScratch S = train_scratch(B);
     const unsigned char* blob = static_cast<const unsigned char*>(b[1]);
     unsigned char* sc = static_cast<unsigned char*>(b[2]);
     float* grads = static_cast<float*>(b[10]);
-    const bool narrow = (p->reserved & 1) != 0;
     auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(sc + off); };
     int32_t rc = BRL_OK;
 
@@ -962,38 +811,33 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
     // |grads|^2 accumulates in acc[14] (zeroed with the rest of acc by the loss head, which runs before every wgrad)
     double* grad_sumsq = static_cast<double*>(b[12]) + 14;
     OpSpec fwd[5], bwd[kMaxOps];
-    for (int l = 0; l < 4; ++l) {
+    for (int l = 0; l < 5; ++l) {  // forward: A = previous activation (K-major), W = Wn[l] [in, out_pad] (MN-major)
         OpSpec& o = fwd[l];
         o = OpSpec{};
         o.a_hi = l == 0 ? sc + S.obs : sc + S.h_hi[l - 1];
         o.a_lo = l == 0 ? nullptr : sc + S.h_lo[l - 1];
-        o.m_rows = B; o.lda = L.k_in[l];
-        o.w_hi = blob + L.w_hi[l]; o.w_lo = blob + L.w_lo[l];
-        o.n_rows = kHidden; o.ldb = L.k_in[l]; o.k_cols = L.k_in[l];
-        o.epi = kEpiFwd;
-        o.g.bias = reinterpret_cast<const float*>(blob + L.bias[l]);
-        o.g.out_hi = bf(S.h_hi[l]); o.g.out_lo = bf(S.h_lo[l]);
-        o.g.ld_out = kHidden;
+        o.m_rows = B; o.lda = T.k_in[l];
+        o.w_hi = blob + T.wn_hi[l]; o.w_lo = blob + T.wn_lo[l]; o.w_mn = 1;
+        o.n_rows = T.n_pad[l]; o.ldb = T.n_pad[l]; o.k_cols = T.k_in[l];
+        o.g.bias = reinterpret_cast<const float*>(blob + T.bias[l]);
+        if (l < 4) {
+            o.epi = kEpiFwd;
+            o.g.out_hi = bf(S.h_hi[l]); o.g.out_lo = bf(S.h_lo[l]);
+            o.g.ld_out = kHidden;
+        } else {
+            o.epi = kEpiHead;
+            o.g.logits = reinterpret_cast<float*>(sc + S.logits);
+            o.g.value = reinterpret_cast<float*>(sc + S.value);
+        }
         o.dep = l - 1; o.dep_all = 0;
-    }
-    {
-        OpSpec& o = fwd[4];
-        o = OpSpec{};
-        o.a_hi = sc + S.h_hi[3]; o.a_lo = sc + S.h_lo[3]; o.m_rows = B; o.lda = kHidden;
-        o.w_hi = blob + L.w_hi[4]; o.w_lo = blob + L.w_lo[4]; o.n_rows = kHeadPad; o.ldb = kHidden; o.k_cols = kHidden;
-        o.epi = kEpiHead;
-        o.g.bias = reinterpret_cast<const float*>(blob + L.bias[4]);
-        o.g.logits = reinterpret_cast<float*>(sc + S.logits);
-        o.g.value = reinterpret_cast<float*>(sc + S.value);
-        o.dep = 3; o.dep_all = 0;
     }
     int nb = 0;
     int dgrad_op[5] = {-1, -1, -1, -1, -1};  // op index (in bwd) that produced dz of layer l (1..4)
     {   // head wgrad: [1024, 39] = h4^T . dz5 -> w4 grads (38 columns) + w5 grads (the value column)
         OpSpec& o = bwd[nb++];
         o = OpSpec{};
-        o.a_hi = sc + S.h_hi[3]; o.a_lo = sc + S.h_lo[3]; o.m_rows = kHidden; o.lda = kHidden;
-        o.w_hi = sc + S.dz5_hi; o.w_lo = sc + S.dz5_lo; o.n_rows = kHeadPad; o.ldb = kHeadPad; o.k_cols = B;
+        o.a_hi = sc + S.h_hi[3]; o.a_lo = sc + S.h_lo[3]; o.m_rows = kHidden; o.lda = kHidden; o.a_mn = 1;
+        o.w_hi = sc + S.dz5_hi; o.w_lo = sc + S.dz5_lo; o.n_rows = kHeadPad; o.ldb = kHeadPad; o.w_mn = 1; o.k_cols = B;
         o.epi = kEpiWgrad;
         o.g.c = grads + F.w[4]; o.g.ld_c = 38; o.g.n_c = 38; o.g.c2 = grads + F.w[5]; o.g.sumsq = grad_sumsq;
         o.dep = -1;
@@ -1019,27 +863,22 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
             o = OpSpec{};
             o.a_hi = l == 1 ? sc + S.obs : sc + S.h_hi[l - 2];
             o.a_lo = l == 1 ? nullptr : sc + S.h_lo[l - 2];
-            o.m_rows = l == 1 ? kObsDimM : kHidden; o.lda = o.m_rows;
-            o.w_hi = sc + S.dz_hi[l - 1]; o.w_lo = sc + S.dz_lo[l - 1]; o.n_rows = kHidden; o.ldb = kHidden; o.k_cols = B;
+            o.m_rows = l == 1 ? kObsDimM : kHidden; o.lda = o.m_rows; o.a_mn = 1;
+            o.w_hi = sc + S.dz_hi[l - 1]; o.w_lo = sc + S.dz_lo[l - 1]; o.n_rows = kHidden; o.ldb = kHidden; o.w_mn = 1; o.k_cols = B;
             o.epi = kEpiWgrad;
             o.g.c = grads + F.w[l - 1]; o.g.ld_c = kHidden; o.g.n_c = kHidden; o.g.sumsq = grad_sumsq;
             o.dep = dgrad_op[l]; o.dep_all = 1;
         }
     }
-    const bool fused = (p->reserved & 2) == 0;  // tune bit 1: one launch per GEMM (bit 0 then picks 128 x 64 over 128 x 128 tiles)
-    // Fused launches, measured on B200 at B = 1024 (scripts/exp_train_trace.py): the forward is a chain of layers with one tile
-    // per SM per layer, where 128 x 64 tiles win (68 vs 73 us); the backward has two independent GEMMs per layer (dgrad, wgrad)
-    // to fill the SMs, where 128 x 128 tiles move a third fewer operand bytes (76 vs 100 us).  Tune bit 2 / bit 4 flip them.
-    const bool wide_fwd = (p->reserved & 4) != 0, wide_bwd = (p->reserved & 16) == 0;
-    unsigned long long* trace = (p->reserved & 8) ? reinterpret_cast<unsigned long long*>(sc + S.trace) : nullptr;  // tune bit 3
     const int nmb = ready_blocks(B);
     uint32_t* ready = reinterpret_cast<uint32_t*>(sc + S.ready);
-    if (fused) {
-        if (cudaMemsetAsync(ready, 0, ready_words(B) * sizeof(uint32_t), s) != cudaSuccess) return check_launch("brl_ppo_grad (memset)");
-        rc = wide_fwd ? launch_fused_ops<128>(s, fwd, 5, nmb, ready, trace) : launch_fused_ops<64>(s, fwd, 5, nmb, ready, trace);
-    } else {
-        for (int i = 0; i < 5 && rc == BRL_OK; ++i) rc = launch_op(narrow, s, fwd[i]);
-    }
+    unsigned long long* trace = (p->reserved & 8) ? reinterpret_cast<unsigned long long*>(sc + S.trace) : nullptr;  // tune bit 3
+    // Tile widths, measured on B200 at B = 1024 (scripts/exp_train_trace.py): the forward is a chain of layers with one tile
+    // per SM per layer, where 128 x 64 tiles win; the backward has two independent GEMMs per layer (dgrad, wgrad) to fill the
+    // SMs, where 128 x 128 tiles move a third fewer operand bytes.  Tune bit 2 / bit 4 flip them.
+    const bool wide_fwd = (p->reserved & 4) != 0, wide_bwd = (p->reserved & 16) == 0;
+    if (cudaMemsetAsync(ready, 0, ready_words(B) * sizeof(uint32_t), s) != cudaSuccess) return check_launch("brl_ppo_grad (memset)");
+    rc = wide_fwd ? launch_fused_ops<128>(s, fwd, 5, nmb, ready, trace) : launch_fused_ops<64>(s, fwd, 5, nmb, ready, trace);
     if (rc != BRL_OK) return rc;
     if ((rc = check_launch("brl_ppo_grad (forward)")) != BRL_OK) return rc;
     // 3. loss head + its backward (src/update.py:97-162)
@@ -1051,10 +890,8 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         if ((rc = launch_ppo_loss(s, lb, &lp, sc + S.dz5_hi, sc + S.dz5_lo)) != BRL_OK) return rc;
     }
     // 4. backward GEMMs
-    if (fused) rc = wide_bwd ? launch_fused_ops<128>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr)
-                               : launch_fused_ops<64>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr);
-    else
-        for (int i = 0; i < nb && rc == BRL_OK; ++i) rc = launch_op(narrow, s, bwd[i]);
+    rc = wide_bwd ? launch_fused_ops<128>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr)
+                  : launch_fused_ops<64>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr);
     if (rc != BRL_OK) return rc;
     // 5. bias gradients
     {

@@ -68,6 +68,7 @@ BRL_LEGACY_CUSTOM_CALL(brl_adam_clip)
 BRL_LEGACY_CUSTOM_CALL(brl_adam_apply)
 BRL_LEGACY_CUSTOM_CALL(brl_gather_rows)
 BRL_LEGACY_CUSTOM_CALL(brl_mlp_pack_train)
+BRL_LEGACY_CUSTOM_CALL(brl_mlp_adam_step)
 BRL_LEGACY_CUSTOM_CALL(brl_ppo_grad)
 BRL_LEGACY_CUSTOM_CALL(brl_eval_act_log)
 BRL_LEGACY_CUSTOM_CALL(brl_eval_summary)

@@ -285,8 +285,8 @@ def mlp_num_params() -> int:
 
 
 def mlp_pack_train(flat_params: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Flat fp32 parameters (optim.flatten_params order) -> the training blob of `ppo_grad`; its head is a valid
-    `packed` argument of `mlp_forward` / `policy_act`.  Re-run after every optimizer step."""
+    """Flat fp32 parameters (optim.flatten_params order) -> the training blob of `ppo_grad`: W[in, out] as bf16 hi / lo in
+    haiku's orientation + fp32 biases.  Once per parameter set; `mlp_adam_step` keeps it current inside the update loop."""
     L = _lib.load()
     if flat_params.dtype != torch.float32 or flat_params.numel() != L.brl_mlp_num_params():
         raise _lib.BrlError("mlp_pack_train needs the flat fp32 parameter buffer of the DeepMind MLP")
@@ -294,6 +294,17 @@ def mlp_pack_train(flat_params: torch.Tensor, out: Optional[torch.Tensor] = None
         out = torch.empty(L.brl_mlp_train_blob_bytes(), dtype=torch.uint8, device=flat_params.device)
     _call("brl_mlp_pack_train", [_ptr(flat_params), _ptr(out)], _params(0))
     return out
+
+
+def mlp_adam_step(params, grads, m, v, sumsq, blob, *, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-5,
+                  max_grad_norm=0.0) -> None:
+    """optax.chain(clip_by_global_norm, adam) on the flat MLP parameters, in place, and the training blob refreshed in
+    the same pass (ppo.py:195-211, src/update.py:168-169).  `sumsq`: f64[1] = `acc[14:15]` after `ppo_grad`."""
+    if sumsq.dtype != torch.float64:
+        raise _lib.BrlError("mlp_adam_step: sumsq must be float64")
+    p = _lib.BrlAdamParams(int(params.numel()), int(step), float(lr), float(beta1), float(beta2), float(eps),
+                           float(max_grad_norm))
+    _call("brl_mlp_adam_step", [_ptr(params), _ptr(grads), _ptr(m), _ptr(v), _ptr(sumsq), _ptr(blob)], p)
 
 
 def mlp_train_scratch(batch: int, device) -> torch.Tensor:

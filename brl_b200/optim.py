@@ -62,6 +62,14 @@ class AdamWithClip:
         return OptState(state.count + 1, state.mu, state.nu)
 
 
+    def update_mlp_(self, flat_params, flat_grads, state: OptState, sumsq, blob) -> OptState:
+        """`update_` for the flat DeepMind-MLP parameters with `ops.ppo_grad`'s sum of squares, refreshing the training
+        blob in the same kernel pass (brl_mlp_adam_step)."""
+        ops.mlp_adam_step(flat_params, flat_grads, state.mu, state.nu, sumsq, blob, step=state.count + 1, lr=self.lr_at(state.count),
+                          beta1=self.b1, beta2=self.b2, eps=self.eps, max_grad_norm=self.max_grad_norm)
+        return OptState(state.count + 1, state.mu, state.nu)
+
+
 def make_optimizer(config) -> AdamWithClip:
     """ppo.py:186-211 from the same config keys."""
     lr = config["lr"]

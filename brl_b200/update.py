@@ -6,7 +6,8 @@ Two back ends, selected by the forward pass's precision:
   "tc" / "tc-bf16" (default for ReLU nets)  `brl_ppo_grad`: minibatch take, forward with kept
       activations, loss head + its backward, and the backward GEMMs all in hand-written kernels
       on tcgen05 (csrc/brl_mlp_train.cu, three-term bf16 split = fp32-class gradients), then
-      `brl_adam_clip` and `brl_mlp_pack_train` -- no library GEMM, no autograd tape;
+      `brl_mlp_adam_step` (clip + Adam + refresh of the kernels' weight layout in one pass) -- no
+      library GEMM, no autograd tape;
   "fp32" (and tanh nets)  the minibatch gather, loss head and clip + Adam step are the same
       kernels (csrc/brl_ppo.cu) around plain library GEMMs (cuBLAS fp32 through torch
       autograd) -- kept as the independent cross-check of the tensor-core path.
@@ -112,8 +113,7 @@ def make_update_step(config, actor_forward_pass, optimizer, permutation_fn=None)
                 for mb in range(nmb):                                                  # src/update.py:207-209
                     ops.ppo_grad(obs, blob, scratch, perm[mb * mbs:(mb + 1) * mbs], mask, action, old_lp, old_v, adv, tgt,
                                  flat_g, stats_all[epoch, mb], acc, tune=tune, **cfg)  # src/update.py:164-167
-                    state = optimizer.update_(flat_p, flat_g, state, sumsq=acc[14:15])  # src/update.py:168-169
-                    ops.mlp_pack_train(flat_p, out=blob)
+                    state = optimizer.update_mlp_(flat_p, flat_g, state, acc[14:15], blob)  # src/update.py:168-169
             return finish()
 
         leaves = {name: {k: new_params[name][k].detach().requires_grad_() for k in ("w", "b")} for name in LAYERS}

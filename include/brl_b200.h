@@ -51,7 +51,8 @@
  *   brl_gather_rows       minibatch take(permutation)                             src/update.py:194-199
  *   brl_ppo_grad          jax.value_and_grad(_loss_fn)(params, traj, gae, targets) -> (loss_info, grads): minibatch
  *                         take + forward + loss + backward through the MLP on tcgen05   src/update.py:91-167,194-199
- *   brl_mlp_pack_train    flat fp32 params -> device layout for brl_ppo_grad (both weight orientations)
+ *   brl_mlp_pack_train    flat fp32 params -> device layout for brl_ppo_grad
+ *   brl_mlp_adam_step     optimizer.update + apply_updates + refresh of that layout, one pass   src/update.py:168-169
  *   brl_eval_act_log      make_action + make_step_log of evaluate / duplicate_evaluate   src/evaluation.py:236-385, 650-745
  *   brl_eval_summary      make_terminated_log + the log_info means                        src/evaluation.py:448-596, 839-1027
  *   brl_mlp_pack          the params pytree (bridge_models/<name>.pkl, ppo.py:351-362) -> device layout
@@ -238,9 +239,9 @@ typedef struct BrlPpoParams {
     float vf_coef;         /* config["vf_coef"]                                          */
     float illegal_l2_coef; /* config["illegal_action_l2norm_coef"]                       */
     int32_t flags;         /* BRL_PPO_*                                                  */
-    int32_t reserved;      /* 0.  brl_ppo_grad reads experiment bits here (0 = measured defaults): 2 = one launch per GEMM
-                              (then 1 = 128x64 instead of 128x128 tiles), 4 / 16 = the other tile width in the fused
-                              forward / backward launch, 8 = per-tile time stamps into the scratch (brl_mlp_train_trace_offset) */
+    int32_t reserved;      /* 0.  brl_ppo_grad reads experiment bits here (0 = measured defaults): 4 / 16 = the other tile
+                              width (128x128 / 128x64) in the fused forward / backward launch, 8 = per-tile time stamps
+                              into the scratch (brl_mlp_train_trace_offset) */
 } BrlPpoParams;
 
 typedef struct BrlAdamParams {
@@ -281,11 +282,18 @@ int64_t brl_mlp_train_blob_bytes(void);
 int64_t brl_mlp_train_scratch_bytes(int64_t batch);
 int64_t brl_mlp_train_trace_offset(int64_t batch); /* debug: offset in the scratch of the u64[2][4096][8] tile time stamps written when
                                                         BrlPpoParams.reserved bit 3 is set (scripts/exp_train_trace.py) */
-/* flat params -> training blob: the forward layout of brl_mlp_pack (the blob is also a valid `packed` argument of
- * brl_mlp_forward / brl_policy_act) followed by W[in,out_pad] bf16 hi / lo for the input-gradient GEMMs.
- * Run after every optimizer step.  opaque = BrlParams (fields unused).
+/* flat params -> training blob: per layer (4 hidden + the 64-wide policy/value head tile) W[in, out_pad] as bf16 hi / lo in
+ * haiku's own orientation -- the forward reads it as an MN-major tensor-core operand, the input-gradient GEMM as a K-major
+ * one, so training keeps ONE copy of the weights and never transposes -- and the bias in fp32.  Needed once per parameter
+ * set; inside the update loop brl_mlp_adam_step keeps the blob current.  opaque = BrlParams (fields unused).
  * buffers: [0] in f32 params[brl_mlp_num_params()]  [1] out blob[brl_mlp_train_blob_bytes()] */
 int32_t brl_mlp_pack_train(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+/* optimizer.update + optax.apply_updates (src/update.py:168-169, ppo.py:195-211) for the flat MLP parameters, with the
+ * refreshed parameters written into the training blob in the same pass: brl_adam_apply + brl_mlp_pack_train as one kernel.
+ * opaque = BrlAdamParams (n = brl_mlp_num_params()).
+ * buffers: [0] inout f32 params[n]  [1] in f32 grads[n]  [2] inout f32 m[n]  [3] inout f32 v[n]
+ *          [4] in f64[1] sum of squares of grads (element 14 of brl_ppo_grad's scratch)  [5] inout blob */
+int32_t brl_mlp_adam_step(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 /* One minibatch of `jax.value_and_grad(_loss_fn, has_aux=True)(params, traj_batch, gae, targets)` (src/update.py:164-167):
  * take(index) of the observations, forward with the activations kept, brl_ppo_loss, backward GEMMs (input gradients with
  * the ReLU mask fused, weight gradients contracted over the batch, bias gradients), all products as three-term bf16
@@ -352,6 +360,7 @@ void brl_adam_clip_xla(brl_stream_t, void **buffers, const char *opaque, size_t 
 void brl_adam_apply_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_gather_rows_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_mlp_pack_train_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_mlp_adam_step_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_ppo_grad_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_eval_act_log_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_eval_summary_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);

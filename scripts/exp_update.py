@@ -63,15 +63,14 @@ def main():
     flat_g = torch.empty_like(flat_p)
     stats = torch.zeros(8, dtype=torch.float32, device=dev)
     acc = torch.zeros(16, dtype=torch.float64, device=dev)
-    for tune, name in ((0, "tc_fused"), (16, "tc_fused_narrow_bwd"), (4, "tc_fused_wide_fwd"), (3, "tc_per_gemm_narrow")):
+    for tune, name in ((0, "tc_fused"), (16, "tc_fused_narrow_bwd"), (4, "tc_fused_wide_fwd")):
         st = [state]
 
         def step(i, tune=tune):
             mb = i % nmb
             ops.ppo_grad(obs, blob, scratch, perm[mb * B:(mb + 1) * B], mask, action, old_lp, old_v, adv, tgt, flat_g, stats, acc,
                          tune=tune, **cfg)
-            st[0] = opt.update_(flat_p, flat_g, st[0], sumsq=acc[14:15])
-            ops.mlp_pack_train(flat_p, out=blob)
+            st[0] = opt.update_mlp_(flat_p, flat_g, st[0], acc[14:15], blob)
 
         def grad_only(i, tune=tune):
             mb = i % nmb

@@ -104,9 +104,9 @@ def _flat_order():
 @pytest.mark.parametrize("B,total,obs_dtype,tune", [
     (64, 200, torch.float32, 0),
     (333, 1000, torch.uint8, 0),       # ragged batch: row / K tails of every GEMM
-    (333, 1000, torch.bfloat16, 3),    # tune 2 / 3: one launch per GEMM, 128 x 128 / 128 x 64 tiles
+    (333, 1000, torch.bfloat16, 4),    # tune 4 / 16: the other tile width in the fused forward / backward launch
     (1024, 3000, torch.bfloat16, 0),   # ppo.py's minibatch size; tune 0: the two fused persistent launches (default)
-    (1024, 2500, torch.float32, 2),
+    (1024, 2500, torch.float32, 16),
     (2048, 5000, torch.bfloat16, 0),   # 16 row blocks: more tiles than SMs in every op
     (777, 2500, torch.uint8, 4 | 16),  # tune 4 / 16: the other tile width in the fused forward / backward launch
 ])
@@ -199,52 +199,58 @@ def test_ppo_grad_matches_float64_autograd(B, total, obs_dtype, tune):
         bad = np.abs(got_g - want_g) > tol
         assert not bad.any(), (k, int(bad.sum()), float(np.abs(got_g - want_g).max()), scale)
     assert off == gg.size
-    # the training blob is a valid forward blob: logits / value of the rollout kernels agree with the float64 net
-    logits = torch.empty((B, 38), dtype=torch.float32, device=DEV)
-    value = torch.empty(B, dtype=torch.float32, device=DEV)
-    xb = ops.obs_to_bf16(obs[idx].to(torch.float32).to(DEV).contiguous())
-    ops.mlp_forward(xb, blob, ops.mlp_scratch(B, DEV), logits, value)
-    np.testing.assert_allclose(logits.cpu().numpy(), lg.detach().numpy(), rtol=0, atol=5e-5 * float(lg.detach().abs().max()))
-    np.testing.assert_allclose(value.cpu().numpy(), vl.detach().numpy(), rtol=0, atol=5e-5 * max(1.0, float(vl.detach().abs().max())))
 
 
-def test_pack_train_blob_is_the_forward_blob_plus_input_gradient_weights():
-    """brl_mlp_pack_train's blob starts with exactly the bytes brl_mlp_pack produces (so the rollout kernels can read
-    it), followed by W[in, out_pad] as bf16 hi / lo whose sum reproduces W to 2^-17."""
-    from brl_b200 import _lib, ops
-    from brl_b200.models import LAYERS, init_params
+def _check_train_blob(blob, params):
+    """W[in, out_pad] as bf16 hi / lo (hi = bf16(w), hi + lo = w to 2^-16) and the fp32 bias, per layer."""
+    from brl_b200.models import LAYERS
+    off = 0
+    for li, (k_in, n_pad) in enumerate(((480, 1024), (1024, 1024), (1024, 1024), (1024, 1024), (1024, 64))):
+        nbytes = k_in * n_pad * 2
+        hi = blob[off:off + nbytes].view(torch.bfloat16).view(k_in, n_pad).float()
+        lo = blob[off + nbytes:off + 2 * nbytes].view(torch.bfloat16).view(k_in, n_pad).float()
+        bias = blob[off + 2 * nbytes:off + 2 * nbytes + 4 * n_pad].view(torch.float32)
+        off = (off + 2 * nbytes + 4 * n_pad + 255) & ~255
+        if li < 4:
+            w, b = params[LAYERS[li]]["w"], params[LAYERS[li]]["b"]
+        else:  # 38 policy columns, the value column, zeros
+            w = torch.zeros((1024, 64), device=DEV)
+            w[:, :38] = params[LAYERS[4]]["w"]
+            w[:, 38] = params[LAYERS[5]]["w"][:, 0]
+            b = torch.zeros(64, device=DEV)
+            b[:38] = params[LAYERS[4]]["b"]
+            b[38] = params[LAYERS[5]]["b"][0]
+        assert torch.equal(hi, w.to(torch.bfloat16).float()), li
+        assert float((hi + lo - w).abs().max()) <= 2.0 ** -16 * float(w.abs().max()), li
+        assert torch.equal(bias, b), li
+    assert off == blob.numel()
+
+
+def test_pack_train_and_adam_step_keep_the_blob_current():
+    """brl_mlp_pack_train lays the parameters out for brl_ppo_grad; brl_mlp_adam_step = brl_adam_clip on the flat buffer
+    (bit-identical parameters and moments) with the blob refreshed in the same pass."""
+    from brl_b200 import ops
+    from brl_b200.models import init_params
     from brl_b200.optim import flatten_params
     params = init_params(21, DEV)
     g = torch.Generator().manual_seed(1)
     for name in params:
         params[name]["b"] = torch.randn(params[name]["b"].shape, generator=g).to(DEV)
-    flat_p, _ = flatten_params(params)
+    flat_p, views = flatten_params(params)
     assert flat_p.numel() == ops.mlp_num_params() == 3681319
     blob = ops.mlp_pack_train(flat_p)
-    fwd = ops.mlp_pack([params[n]["w"] for n in LAYERS], [params[n]["b"] for n in LAYERS])
-    nf = _lib.load().brl_mlp_packed_bytes()
-    # padding bytes between the layers' sections are never written by either packer: compare the written ranges
-    off = 0
-    for li, (k_in, n_out) in enumerate(((480, 1024), (1024, 1024), (1024, 1024), (1024, 1024), (1024, 64))):
-        used = 2 * n_out * k_in * 2 + n_out * 4
-        assert torch.equal(blob[off:off + used], fwd[off:off + used]), li
-        off = (off + used + 255) & ~255
-    assert off == nf
-    # Wn sections: layers 1..3 [1024, 1024], head [1024, 64] (38 policy columns, the value column, zeros)
-    for li, n_pad in ((1, 1024), (2, 1024), (3, 1024), (4, 64)):
-        nbytes = 1024 * n_pad * 2
-        hi = blob[off:off + nbytes].view(torch.bfloat16).view(1024, n_pad).float()
-        lo = blob[off + nbytes:off + 2 * nbytes].view(torch.bfloat16).view(1024, n_pad).float()
-        off = (off + 2 * nbytes + 255) & ~255
-        if li < 4:
-            w = params[LAYERS[li]]["w"]
-        else:
-            w = torch.zeros((1024, 64), device=DEV)
-            w[:, :38] = params[LAYERS[4]]["w"]
-            w[:, 38] = params[LAYERS[5]]["w"][:, 0]
-        assert float((hi + lo - w).abs().max()) <= 2.0 ** -16 * float(w.abs().max())
-        assert torch.equal(hi, w.to(torch.bfloat16).float())
-    assert off == blob.numel()
+    _check_train_blob(blob, views)
+    p2, m2, v2 = flat_p.clone(), torch.zeros_like(flat_p), torch.zeros_like(flat_p)
+    m1, v1 = torch.zeros_like(flat_p), torch.zeros_like(flat_p)
+    scratch = torch.zeros(1, dtype=torch.float64, device=DEV)
+    for step, gscale in enumerate([1.0, 1e-4, 0.3]):  # global norm above and below max_grad_norm
+        grads = torch.randn(flat_p.shape, generator=g).to(DEV) * gscale
+        sumsq = (grads.double() ** 2).sum().reshape(1)
+        ops.mlp_adam_step(flat_p, grads, m1, v1, sumsq, blob, step=step + 1, lr=1e-3, max_grad_norm=0.5)
+        ops.adam_clip(p2, grads, m2, v2, scratch, step=step + 1, lr=1e-3, max_grad_norm=0.5)
+        # the clip scale comes from a differently-ordered f64 sum: identical to the last bit or one ulp of the norm apart
+        assert float((flat_p - p2).abs().max()) <= 1e-9 and float((m1 - m2).abs().max()) <= 1e-9 * gscale
+        _check_train_blob(blob, views)   # `views` are views into flat_p: the refreshed parameters
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
