@@ -805,8 +805,8 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         else if (p->flags & BRL_PPO_OBS_U8) k_gather_obs<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(b[0]), index, B, o);
         else k_gather_obs<float><<<grid, 256, 0, s>>>(static_cast<const float*>(b[0]), index, B, o);
     }
-    // 2. the GEMMs.  Forward: layers 1..4 (activations kept row-major for the next layer / the ReLU mask and batch-major
-    //    for the wgrad) + the head.  Backward: dgrad into layer l's pre-activation, dz_l = (dz_{l+1} . W_{l+1}^T) * [h_l > 0]
+    // 2. the GEMMs.  Forward: layers 1..4 (activations kept, row-major bf16 hi / lo: next layer's A, the ReLU mask, the
+    //    wgrad's MN-major A) + the head.  Backward: dgrad into layer l's pre-activation, dz_l = (dz_{l+1} . W_{l+1}^T) * [h_l > 0]
     //    (S.dz_*[l-1], l = 1..4), and the wgrads dW_l = h_{l-1}^T . dz_l straight from the row-major h and dz.
     // |grads|^2 accumulates in acc[14] (zeroed with the rest of acc by the loss head, which runs before every wgrad)
     double* grad_sumsq = static_cast<double*>(b[12]) + 14;
