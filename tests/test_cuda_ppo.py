@@ -102,12 +102,14 @@ def _flat_order():
 
 
 @pytest.mark.parametrize("B,total,obs_dtype,tune", [
+    (5, 60, torch.float32, 0),         # a handful of samples: one ragged row block everywhere
     (64, 200, torch.float32, 0),
     (333, 1000, torch.uint8, 0),       # ragged batch: row / K tails of every GEMM
     (333, 1000, torch.bfloat16, 4),    # tune 4 / 16: the other tile width in the fused forward / backward launch
     (1024, 3000, torch.bfloat16, 0),   # ppo.py's minibatch size; tune 0: the two fused persistent launches (default)
     (1024, 2500, torch.float32, 16),
     (2048, 5000, torch.bfloat16, 0),   # 16 row blocks: more tiles than SMs in every op
+    (4096, 9000, torch.uint8, 0),      # 32 row blocks: several tiles per SM in every op, > 4096 tiles in the launch
     (777, 2500, torch.uint8, 4 | 16),  # tune 4 / 16: the other tile width in the fused forward / backward launch
 ])
 def test_ppo_grad_matches_float64_autograd(B, total, obs_dtype, tune):
