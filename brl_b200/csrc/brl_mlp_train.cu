@@ -93,6 +93,8 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
 
 template <bool ADAM>
 __global__ void __launch_bounds__(256) k_adam_pack(const __grid_constant__ AdamPackArgs a) {
+    pdl_trigger();
+    pdl_wait();
     float scale = 1.0f;
     if (ADAM && a.max_norm > 0.0f) {  // optax.clip_by_global_norm: g * (max_norm / norm) only when norm >= max_norm
         const float norm = (float)sqrt(*a.sumsq);
@@ -208,6 +210,8 @@ template <class T>
 __global__ void __launch_bounds__(256) k_gather_obs(const T* __restrict__ obs, const int32_t* __restrict__ index, int64_t B,
                                                     uint16_t* __restrict__ out) {
     // 8 consecutive observation bits per thread: one 128-bit store
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * (kObsDimM / 8)) return;
     const int64_t b = i / (kObsDimM / 8);
@@ -240,6 +244,8 @@ __device__ __forceinline__ void bias_sumsq(const BiasArgs& a, float v) {  // cal
 }
 __global__ void __launch_bounds__(1024) k_bias_grad(const __grid_constant__ BiasArgs a) {
     __shared__ float red[32][65];
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x, rg = tid >> 5, cp = tid & 31;  // 32 row groups x 32 column pairs
     const int blocks_per_layer = kHidden / 64;
     if ((int)blockIdx.x < 4 * blocks_per_layer) {
@@ -742,7 +748,7 @@ int32_t brl_mlp_pack_train(brl_stream_t stream, void** b, const void* opaque, si
     a.T = train_blob();
     // the head tile's padding columns (39..63) and bias entries are never written by the packer: zero them once here
     if (cudaMemsetAsync(a.blob + a.T.wn_hi[4], 0, a.T.total - a.T.wn_hi[4], s) != cudaSuccess) return check_launch("brl_mlp_pack_train");
-    k_adam_pack<false><<<adam_pack_grid(), 256, 0, s>>>(a);
+    launch_pdl(k_adam_pack<false>, dim3(adam_pack_grid()), dim3(256), 0, s, a);
     return check_launch("brl_mlp_pack_train");
 }
 
@@ -769,7 +775,7 @@ int32_t brl_mlp_adam_step(brl_stream_t stream, void** b, const void* opaque, siz
     a.bc2 = 1.0f - powf(p->beta2, (float)p->step);
     a.F = flat_layout();
     a.T = train_blob();
-    k_adam_pack<true><<<adam_pack_grid(), 256, 0, (cudaStream_t)stream>>>(a);
+    launch_pdl(k_adam_pack<true>, dim3(adam_pack_grid()), dim3(256), 0, (cudaStream_t)stream, a);
     return check_launch("brl_mlp_adam_step");
 }
 
@@ -796,14 +802,18 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
     auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(sc + off); };
     int32_t rc = BRL_OK;
 
+    // 0. counters and accumulators first, so that nothing but kernels (launched with programmatic dependent launch) follows
+    if (cudaMemsetAsync(sc + S.ready, 0, ready_words(B) * sizeof(uint32_t), s) != cudaSuccess ||
+        cudaMemsetAsync(b[12], 0, 16 * sizeof(double), s) != cudaSuccess)
+        return check_launch("brl_ppo_grad (memset)");
     // 1. minibatch gather of the observation (src/update.py:194-199, cast of src/update.py:95)
     {
         const unsigned grid = (unsigned)(((int64_t)B * (kObsDimM / 8) + 255) / 256);
         const int32_t* index = static_cast<const int32_t*>(b[3]);
         uint16_t* o = reinterpret_cast<uint16_t*>(sc + S.obs);
-        if (p->flags & BRL_PPO_OBS_BF16) k_gather_obs<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(b[0]), index, B, o);
-        else if (p->flags & BRL_PPO_OBS_U8) k_gather_obs<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(b[0]), index, B, o);
-        else k_gather_obs<float><<<grid, 256, 0, s>>>(static_cast<const float*>(b[0]), index, B, o);
+        if (p->flags & BRL_PPO_OBS_BF16) launch_pdl(k_gather_obs<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(b[0]), index, (int64_t)B, o);
+        else if (p->flags & BRL_PPO_OBS_U8) launch_pdl(k_gather_obs<uint8_t>, dim3(grid), dim3(256), 0, s, static_cast<const uint8_t*>(b[0]), index, (int64_t)B, o);
+        else launch_pdl(k_gather_obs<float>, dim3(grid), dim3(256), 0, s, static_cast<const float*>(b[0]), index, (int64_t)B, o);
     }
     // 2. the GEMMs.  Forward: layers 1..4 (activations kept, row-major bf16 hi / lo: next layer's A, the ReLU mask, the
     //    wgrad's MN-major A) + the head.  Backward: dgrad into layer l's pre-activation, dz_l = (dz_{l+1} . W_{l+1}^T) * [h_l > 0]
@@ -877,7 +887,6 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
     // per SM per layer, where 128 x 64 tiles win; the backward has two independent GEMMs per layer (dgrad, wgrad) to fill the
     // SMs, where 128 x 128 tiles move a third fewer operand bytes.  Tune bit 2 / bit 4 flip them.
     const bool wide_fwd = (p->reserved & 4) != 0, wide_bwd = (p->reserved & 16) == 0;
-    if (cudaMemsetAsync(ready, 0, ready_words(B) * sizeof(uint32_t), s) != cudaSuccess) return check_launch("brl_ppo_grad (memset)");
     rc = wide_fwd ? launch_fused_ops<128>(s, fwd, 5, nmb, ready, trace) : launch_fused_ops<64>(s, fwd, 5, nmb, ready, trace);
     if (rc != BRL_OK) return rc;
     if ((rc = check_launch("brl_ppo_grad (forward)")) != BRL_OK) return rc;
@@ -887,7 +896,7 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         BrlPpoParams lp = *p;
         lp.flags &= (BRL_PPO_VALUE_CLIPPING | BRL_PPO_REWARD_SCALING | BRL_PPO_UNMASKED_POLICY);
         lp.reserved = 0;
-        if ((rc = launch_ppo_loss(s, lb, &lp, sc + S.dz5_hi, sc + S.dz5_lo)) != BRL_OK) return rc;
+        if ((rc = launch_ppo_loss(s, lb, &lp, sc + S.dz5_hi, sc + S.dz5_lo, /*acc_zeroed=*/true)) != BRL_OK) return rc;
     }
     // 4. backward GEMMs
     rc = wide_bwd ? launch_fused_ops<128>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr)
@@ -900,7 +909,7 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         a.dlogits = reinterpret_cast<const float*>(sc + S.dlogits);
         a.dvalue = reinterpret_cast<const float*>(sc + S.dvalue);
         a.grads = grads; a.sumsq = grad_sumsq; a.B = B; a.F = F;
-        k_bias_grad<<<4 * (kHidden / 64) + 1, 1024, 0, s>>>(a);
+        launch_pdl(k_bias_grad, dim3(4 * (kHidden / 64) + 1), dim3(1024), 0, s, a);
     }
     return check_launch("brl_ppo_grad");
 }

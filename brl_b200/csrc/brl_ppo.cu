@@ -127,6 +127,8 @@ __device__ __forceinline__ void ppo_finalize(const PpoArgs& a) {
 }
 
 __global__ void __launch_bounds__(128) k_ppo_loss(const PpoArgs a, int have_prepass) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float invB = 1.0f / (float)a.B;
@@ -329,12 +331,12 @@ extern "C" {
 int32_t brl_ppo_loss(brl_stream_t stream, void** b, const void* opaque, size_t len) {
     if (opaque == nullptr || len != sizeof(BrlPpoParams))
         return fail(BRL_E_OPAQUE, "brl_ppo_loss: opaque must be one BrlPpoParams (%zu bytes), got %zu", sizeof(BrlPpoParams), len);
-    return brl::launch_ppo_loss((cudaStream_t)stream, b, static_cast<const BrlPpoParams*>(opaque), nullptr, nullptr);
+    return brl::launch_ppo_loss((cudaStream_t)stream, b, static_cast<const BrlPpoParams*>(opaque), nullptr, nullptr, false);
 }
 
 }  // extern "C"
 
-int32_t brl::launch_ppo_loss(cudaStream_t stream, void** b, const BrlPpoParams* p, void* dz_hi, void* dz_lo) {
+int32_t brl::launch_ppo_loss(cudaStream_t stream, void** b, const BrlPpoParams* p, void* dz_hi, void* dz_lo, bool acc_zeroed) {
     if (p->batch <= 0) return fail(BRL_E_OPAQUE, "brl_ppo_loss: batch must be > 0");
     static const char* names[] = {"logits", "value", "index", "mask", "action", "old_log_prob", "old_value", "advantages",
                                   "targets", "dlogits", "dvalue", "stats", "scratch"};
@@ -365,12 +367,12 @@ int32_t brl::launch_ppo_loss(cudaStream_t stream, void** b, const BrlPpoParams* 
     a.reward_scaling = (p->flags & BRL_PPO_REWARD_SCALING) != 0;
     a.masked_policy = (p->flags & BRL_PPO_UNMASKED_POLICY) == 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (cudaMemsetAsync(a.acc, 0, 16 * sizeof(double), s) != cudaSuccess) return check_launch("brl_ppo_loss");
+    if (!acc_zeroed && cudaMemsetAsync(a.acc, 0, 16 * sizeof(double), s) != cudaSuccess) return check_launch("brl_ppo_loss");
     unsigned grid = (unsigned)((a.B + 3) / 4);
     if (grid > 148u * 8u) grid = 148u * 8u;
     const int prepass = a.reward_scaling || a.ill_coef != 0.0f;
     if (prepass) k_ppo_prepass<<<grid, 128, 0, s>>>(a);
-    k_ppo_loss<<<grid, 128, 0, s>>>(a, prepass);
+    launch_pdl(k_ppo_loss, dim3(grid), dim3(128), 0, s, a, prepass);
     return check_launch("brl_ppo_loss");
 }
 

@@ -43,7 +43,31 @@ int32_t launch_categorical(cudaStream_t stream, const float* logits, const unsig
                            int64_t n, int sample, uint64_t seed, int64_t env_offset, uint32_t step);
 
 // brl_ppo_loss's body (brl_ppo.cu), optionally also writing d loss / d (logits, value) as bf16 hi / lo rows [B, 64] for brl_ppo_grad
-int32_t launch_ppo_loss(cudaStream_t stream, void** buffers, const BrlPpoParams* p, void* dz_hi, void* dz_lo);
+// acc_zeroed: the caller already cleared the f64[16] scratch on this stream (keeps a memset out of a PDL kernel chain)
+int32_t launch_ppo_loss(cudaStream_t stream, void** buffers, const BrlPpoParams* p, void* dz_hi, void* dz_lo, bool acc_zeroed);
+
+// Programmatic dependent launch for the short kernels of a dependent chain (the PPO optimizer step): the kernel may be
+// scheduled while its predecessor in the stream drains; it must execute pdl_wait() before touching global memory and
+// should call pdl_trigger() first so that ITS successor can be scheduled early too.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 #define BRL_REQUIRE(ptr, name)                                                            \
     do {                                                                                  \
