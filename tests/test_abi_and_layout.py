@@ -52,6 +52,34 @@ def test_usage_errors_are_reported_without_a_gpu():
         _lib.call("brl_gae", 0, [None] * 6, p)
 
 
+def test_ppo_update_ops_validate_their_arguments_without_a_gpu():
+    """brl_ppo_grad / brl_mlp_adam_step / brl_mlp_pack_train reject bad calls before any CUDA work; the size queries are
+    pure host arithmetic."""
+    from brl_b200 import _lib
+    L = _lib.load()
+    n = L.brl_mlp_num_params()
+    assert n == 480 * 1024 + 1024 + 3 * (1024 * 1024 + 1024) + 1024 * 38 + 38 + 1024 + 1 == 3681319
+    # per layer W[in, out_pad] as bf16 hi + lo, fp32 bias, 256-byte aligned sections
+    assert L.brl_mlp_train_blob_bytes() == sum(((2 * k * m * 2 + 4 * m + 255) // 256) * 256
+                                               for k, m in ((480, 1024), (1024, 1024), (1024, 1024), (1024, 1024), (1024, 64)))
+    assert L.brl_mlp_train_scratch_bytes(0) == 0
+    assert 0 < L.brl_mlp_train_scratch_bytes(64) < L.brl_mlp_train_scratch_bytes(1024) < L.brl_mlp_train_scratch_bytes(4096)
+    assert 0 < L.brl_mlp_train_trace_offset(1024) < L.brl_mlp_train_scratch_bytes(1024)
+    bufs = (ctypes.c_void_p * 13)()
+    pp = _lib.BrlPpoParams(1024, 4096, 0.2, 0.01, 0.5, 0.0, _lib.PPO_VALUE_CLIPPING, 0)
+    assert L.brl_ppo_grad(None, bufs, ctypes.byref(pp), ctypes.sizeof(pp)) == -2 and b"'obs' is NULL" in L.brl_last_error()
+    assert L.brl_ppo_grad(None, bufs, ctypes.byref(pp), 8) == -1 and b"BrlPpoParams" in L.brl_last_error()
+    pp.batch = 0
+    assert L.brl_ppo_grad(None, bufs, ctypes.byref(pp), ctypes.sizeof(pp)) == -1 and b"batch" in L.brl_last_error()
+    ap = _lib.BrlAdamParams(n, 1, 1e-3, 0.9, 0.999, 1e-5, 0.5)
+    assert L.brl_mlp_adam_step(None, bufs, ctypes.byref(ap), ctypes.sizeof(ap)) == -2 and b"'params' is NULL" in L.brl_last_error()
+    fake = (ctypes.c_void_p * 6)(*[ctypes.c_void_p(4096)] * 6)   # never dereferenced: the size check fails first
+    ap.n = 12345
+    assert L.brl_mlp_adam_step(None, fake, ctypes.byref(ap), ctypes.sizeof(ap)) == -1 and b"brl_mlp_num_params" in L.brl_last_error()
+    bp = _lib.BrlParams(0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0)
+    assert L.brl_mlp_pack_train(None, bufs, ctypes.byref(bp), ctypes.sizeof(bp)) == -2 and b"params" in L.brl_last_error()
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "brl_b200")
     for dirpath, _, files in os.walk(pkg):
