@@ -475,18 +475,21 @@ def run_policy_rollout(torch, table_np, dev):
         state = env.init(env.make_keys(SEED, n))
         runner = (params, None, state, state.observation, torch.zeros((), dtype=torch.int64, device=dev), brandom.PRNGKey(3))
         roll_out, calc_gae = make_roll_out(config, env, fp, fp), make_calc_gae(config, fp)
-        reps = 3 if prec != "fp32" else 1
-        runner, traj = roll_out(runner, opp)  # warm-up
-        calc_gae(runner, traj)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
+        reps = 5 if prec != "fp32" else 1
+        for _ in range(2 if prec != "fp32" else 1):  # warm-up (lazy allocations, parameter packing, clocks)
             runner, traj = roll_out(runner, opp)
             calc_gae(runner, traj)
-        e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        times = []
+        for _ in range(reps):  # one rollout + GAE per timed interval; the median is reported
+            e0.record()
+            runner, traj = roll_out(runner, opp)
+            calc_gae(runner, traj)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = statistics.median(times)
         x = traj.obs[0]
         for _ in range(3):
             fp.apply(params, x)
@@ -498,7 +501,7 @@ def run_policy_rollout(torch, table_np, dev):
         torch.cuda.synchronize()
         fms = e0.elapsed_time(e1) / 20
         mma_factor = {"tc": (2 * 480 + 3 * (3 * 1024 + 39)) / (480 + 3 * 1024 + 39.0), "tc-bf16": 1.0}.get(prec)
-        out[prec] = {"ms_per_rollout_plus_gae": ms, "env_steps_per_sec": n * T * 4 / (ms * 1e-3),
+        out[prec] = {"ms_per_rollout_plus_gae": ms, "ms_min_max": [min(times), max(times)], "env_steps_per_sec": n * T * 4 / (ms * 1e-3),
                      "agent_steps_per_sec": n * T / (ms * 1e-3), "forward_ms_8192": fms,
                      "forward_model_TFLOPs": flops / (fms * 1e-3) / 1e12}
         if mma_factor:

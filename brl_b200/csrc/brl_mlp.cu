@@ -646,12 +646,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_ml
                 epilogue_head_act_row(t_row, a.bias[4], row < a.M, row, a.logits, a.value, a.act);
             }
             tc_fence_before();
-            __threadfence();  // this lane's activation stores are visible GPU-wide before the count below
-            __syncwarp();
+            __syncwarp();  // orders the other lanes' activation stores before lane 0's fence (sync, one fence, one atomic)
             if (lane == 0) {
                 asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(lead_tmem_empty0 + 8u * buf) : "memory");
                 if (f.layer < 4) {
-                    __threadfence();
+                    __threadfence();  // cumulative: the warp's rows are visible GPU-wide before the count below
                     atomicAdd(a.ready + (size_t)f.layer * 2 * a.nmb + 2 * f.mb + rank, 1u);
                 }
             }
