@@ -27,13 +27,14 @@ def main():
         if iters <= 0:
             continue
         with tempfile.TemporaryDirectory() as tmp:
-            cfg = dict(total_timesteps=8192 * 32 * (iters + 1), num_eval_envs=1000, num_eval_step=1000, num_prioritized_envs=100,
+            cfg = dict(total_timesteps=8192 * 32 * (iters + 2), num_eval_envs=1000, num_eval_step=1000, num_prioritized_envs=100,
                        save_model=False, log_path=tmp, policy_precision=None if prec == "tc" else prec)
             _, logs = ppo.train(cfg, brandom.PRNGKey(0), tables=tables, eval_table=eval_table, device="cuda:0")
-        logs = logs[1:]  # the first iteration pays lazy initialisation
+        logs = logs[2:]  # the first two iterations pay lazy initialisation (library load, the second deal table's buffers)
         mean = lambda k: sum(log[k] for log in logs) / len(logs)  # noqa: E731
         out[prec] = {"iterations_timed": len(logs), "rollout_s": mean("time/rollout"), "calc_gae_s": mean("time/calc_gae"),
-                     "update_s": mean("time/update"), "rollout+gae+update_s": mean("time/rollout") + mean("time/calc_gae") + mean("time/update"),
+                     "update_s": mean("time/update"), "rollout_s_each": [round(log["time/rollout"], 4) for log in logs],
+                     "table_rotated_before": ["table" in log for log in logs], "rollout+gae+update_s": mean("time/rollout") + mean("time/calc_gae") + mean("time/update"),
                      "agent_steps_per_s": 8192 * 32 / (mean("time/rollout") + mean("time/calc_gae") + mean("time/update")),
                      "last_total_loss": logs[-1]["train/total_loss"], "last_entropy": logs[-1]["train/policy_entropy"]}
     if "tc" in out and "fp32" in out:
