@@ -235,16 +235,16 @@ def main():
         torch.cuda.synchronize()
 
     def reduce_stats():
-        # the single collective of the path: episode statistics summed over ranks
-        sums = torch.zeros(8, dtype=torch.float64, device=dev)
-        sums[:4] = stats.to(torch.float64)
+        # the single collective of the path: episode statistics summed over ranks.  The rollout kernel
+        # accumulates them as integers (exact), so the NCCL all-reduce runs on the kernel's own i64[4] buffer in place:
+        # no torch kernel between the last launch and the collective.
         if world > 1:
-            dist.all_reduce(sums)
-        return sums
+            dist.all_reduce(stats)
+        return stats
 
     for i in range(args.warmup):
         one_step(i)
-    reduce_stats()  # warm the (lazy-loaded) torch / NCCL kernels outside the timed region
+    reduce_stats()  # warm the NCCL kernel outside the timed region
     barrier()
     stats.zero_()
     sampler = ClockSampler(local)
@@ -254,6 +254,11 @@ def main():
     # every launch, as earlier revisions had, costs 2.6 us per step on this stream (scripts/exp_bench_overheads.py).
     begin, last, end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     barrier()
+    if world > 1:
+        # line the ranks' STREAMS up as well: the host barrier above leaves tens of microseconds of skew between the ranks'
+        # first launches, which the closing all-reduce would turn into waiting time on the early ranks.  After this
+        # (untimed) collective every rank's timed region starts within NCCL's own completion skew.
+        dist.all_reduce(torch.zeros(1, device=dev))
     begin.record()
     for i in range(args.steps):
         one_step(args.warmup + i)
@@ -308,7 +313,7 @@ def main():
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * k, "avg_launch_ms": avg_kernel_ms},
             "cpu_baseline": cpu, "clocks": clocks,
             "episode_stats": {"finished_auctions": float(sums[0]), "sum_reward_player0": float(sums[1]),
-                              "env_steps": float(sums[2]), "collective": "1 NCCL all-reduce of f64[8]" if world > 1 else "none (1 rank)"},
+                              "env_steps": float(sums[2]), "collective": "1 NCCL all-reduce of i64[4], in place on the kernel's statistics buffer" if world > 1 else "none (1 rank)"},
         }
         line.update(extra)
         print(json.dumps(line))
@@ -319,37 +324,27 @@ def main():
 def run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps, warmup):
     """Public host-buffer C-ABI, copies inside the timed region.
 
-    `e2e` (headline): one `brl_env_rollout_host` call per bench step = the same 32 x 8192
-    env-steps as `value`.  HOST in: the randomness of the action choice, u32[32, 8192] from
-    pinned memory (4 B per env-step -- the `action` input of the algorithmic byte count; the
-    host owns the PRNG stream the way the reference's host owns the jax key).  HOST out: the
-    step's result, rewards f32[32, 8192, 4] + terminated u8[32, 8192] + the statistics vector.
-    The observation / mask trajectories stay in HBM for the device-resident consumer, exactly as
-    `traj_batch` does in the reference (src/roll_out.py:105-108).
-    `full_io`: the other extreme -- one env.step per call with EVERY Env-surface output copied to
-    the host (PCIe-bound by construction: 536 B per env-step in pgx's bool observation dtype)."""
+    `e2e` (headline): one `brl_env_rollout_host_compact_async` call per bench step = the same 32 x 8192 env-steps as
+    `value`, three calls in flight.  HOST in: the randomness of the action choice from pinned memory (the `action` input
+    of the algorithmic byte count; the host owns the PRNG stream the way the reference's host owns the jax key) as
+    u16[32, 8192] (2 B per env-step; the k-th legal action is (u16 * #legal) >> 16).  HOST out: the step's result as
+    i16[32, 8192] = 2 * rewards[player 0] + terminated -- lossless for rewards f32[.., 4] + terminated u8, which is what
+    roll_out's consumer reads (src/roll_out.py:86-94) -- + the statistics vector.  The observation / mask / f32 reward
+    trajectories stay in HBM for the device-resident consumer, exactly as `traj_batch` does in the reference
+    (src/roll_out.py:105-108).  Sub-entries: `u32_uniforms` (compact result, 4 B/env-step in), `f32_payload` (round 1's
+    payload: u32 in, rewards f32[4] + terminated u8 out = 17 B/env-step), `sync_per_call` (f32 payload, blocking).
+    `full_io`: the other extreme -- one env.step per call with EVERY Env-surface output copied to the host (PCIe-bound
+    by construction: 536 B per env-step in pgx's bool observation dtype)."""
     import ctypes as C
     L = _lib.load()
     tbl = np.ascontiguousarray(table_np)
     k = T_STEPS
-    # ---- headline: rollout per call --------------------------------------------------------
-    h = L.brl_env_create(n, offset, tbl.ctypes.data, tbl.shape[0], SEED, _lib.F_AUTORESET)
-    if not h:
-        raise RuntimeError("brl_env_create failed: " + L.brl_last_error().decode())
     rng = np.random.default_rng(SEED + offset)
     n_pool = min(steps + warmup, 16)  # pre-generated host randomness ("the dataset"), cycled
-    pool = torch.from_numpy(rng.integers(0, 2 ** 32, size=(n_pool, k, n), dtype=np.uint32).view(np.int32)).pin_memory()
-    rew = torch.zeros((k, n, 4), dtype=torch.float32).pin_memory()
-    term = torch.zeros((k, n), dtype=torch.uint8).pin_memory()
-    stats = torch.zeros(4, dtype=torch.int64).pin_memory()
+    pool32 = torch.from_numpy(rng.integers(0, 2 ** 32, size=(n_pool, k, n), dtype=np.uint32).view(np.int32)).pin_memory()
+    pool16 = torch.from_numpy((pool32.numpy().view(np.uint32) >> 16).astype(np.uint16).view(np.int16)).pin_memory()
     vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-    rc = L.brl_env_init_host(h, None, None, None, None, None)
-    assert rc == 0, L.brl_last_error()
-
-    def one(i):
-        rc = L.brl_env_rollout_host(h, k, vp(pool[i % n_pool]), vp(rew), vp(term), vp(stats))
-        if rc != 0:
-            raise RuntimeError(L.brl_last_error().decode())
+    depth = max(1, min(4, int(os.environ.get("BRL_E2E_DEPTH", "3"))))  # BRL_ENV_PIPELINE_DEPTH = 4 staging slots
 
     def timed(fn_loop):
         if world > 1:
@@ -363,50 +358,80 @@ def run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps, warmu
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    # (a) one synchronous call per bench step
-    for i in range(warmup):
-        one(i)
-    dt_sync = timed(lambda: [one(warmup + i) for i in range(steps)])
-    # (b) the same calls pipelined three deep (brl_env_rollout_host_async + brl_env_wait): step i-2's result is read on
-    #     the host while steps i-1 and i are in flight; every step still copies its own inputs in and its own results out
-    depth = max(1, min(4, int(os.environ.get("BRL_E2E_DEPTH", "3"))))  # BRL_ENV_PIPELINE_DEPTH = 4 staging slots
-    rew2 = [rew] + [torch.zeros_like(rew).pin_memory() for _ in range(depth - 1)]
-    term2 = [term] + [torch.zeros_like(term).pin_memory() for _ in range(depth - 1)]
-    stats2 = [stats] + [torch.zeros_like(stats).pin_memory() for _ in range(depth - 1)]
-    seen = [0]
+    def leg(kind):
+        """kind: 'compact16' | 'compact32' | 'f32'.  Returns (seconds for `steps` pipelined calls, finished auctions the
+        host read, seconds for `steps` blocking calls or None)."""
+        flags = _lib.F_AUTORESET | (_lib.F_UNIFORM_U16 if kind == "compact16" else 0)
+        h = L.brl_env_create(n, offset, tbl.ctypes.data, tbl.shape[0], SEED, flags)
+        if not h:
+            raise RuntimeError("brl_env_create failed: " + L.brl_last_error().decode())
+        rc = L.brl_env_init_host(h, None, None, None, None, None)
+        assert rc == 0, L.brl_last_error()
+        pool = pool16 if kind == "compact16" else pool32
+        stats = [torch.zeros(4, dtype=torch.int64).pin_memory() for _ in range(depth)]
+        if kind == "f32":
+            rew = [torch.zeros((k, n, 4), dtype=torch.float32).pin_memory() for _ in range(depth)]
+            term = [torch.zeros((k, n), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+            submit = lambda i, j: L.brl_env_rollout_host_async(h, k, vp(pool[i % n_pool]), vp(rew[j]), vp(term[j]), vp(stats[j]))  # noqa: E731
+        else:
+            res = [torch.zeros((k, n), dtype=torch.int16).pin_memory() for _ in range(depth)]
+            submit = lambda i, j: L.brl_env_rollout_host_compact_async(h, k, vp(pool[i % n_pool]), vp(res[j]), vp(stats[j]))  # noqa: E731
+        seen = [0]
 
-    def pipelined(count, base):
-        inflight = []
-        for i in range(count):
-            j = i % depth
-            if len(inflight) == depth:  # slot j's host buffers are about to be reused: consume their result first
-                t0_, j0 = inflight.pop(0)
+        def pipelined(count, base):
+            inflight = []
+            for i in range(count):
+                j = i % depth
+                if len(inflight) == depth:  # slot j's host buffers are about to be reused: consume their result first
+                    t0_, j0 = inflight.pop(0)
+                    if L.brl_env_wait(h, t0_) != 0:
+                        raise RuntimeError(L.brl_last_error().decode())
+                    seen[0] += int(stats[j0][0])   # the host consumes an older step's result while newer ones run
+                t = submit(base + i, j)
+                if t <= 0:
+                    raise RuntimeError(L.brl_last_error().decode())
+                inflight.append((t, j))
+            for t0_, j0 in inflight:
                 if L.brl_env_wait(h, t0_) != 0:
                     raise RuntimeError(L.brl_last_error().decode())
-                seen[0] += int(stats2[j0][0])      # the host consumes an older step's result while newer ones run
-            t = L.brl_env_rollout_host_async(h, k, vp(pool[(base + i) % n_pool]), vp(rew2[j]), vp(term2[j]), vp(stats2[j]))
-            if t <= 0:
-                raise RuntimeError(L.brl_last_error().decode())
-            inflight.append((t, j))
-        for t0_, j0 in inflight:
-            if L.brl_env_wait(h, t0_) != 0:
-                raise RuntimeError(L.brl_last_error().decode())
-            seen[0] += int(stats2[j0][0])
+                seen[0] += int(stats[j0][0])
 
-    pipelined(warmup, 0)
-    seen[0] = 0
-    dt = timed(lambda: pipelined(steps, warmup))
-    finished = seen[0]
-    L.brl_env_destroy(h)
-    res = {"value": n * k * steps * world / dt, "unit": UNIT, "h2d_bytes_per_step": n * k * 4,
-           "d2h_bytes_per_step": n * k * 17 + 32, "steps": steps, "ms_per_step": 1e3 * dt / steps,
-           "api": "brl_env_rollout_host_async + brl_env_wait (C ABI, host buffers), three calls in flight: per bench step H2D "
-                  "u32[32,8192] action randomness from pinned memory, one fused rollout launch, D2H rewards f32[32,8192,4] + "
-                  "terminated u8[32,8192] + stats into pinned memory, read by the host while the next steps compute; obs/mask "
-                  "trajectories stay in HBM for the device-resident learner (as traj_batch does in the reference)",
+        pipelined(warmup, 0)
+        seen[0] = 0
+        dt = timed(lambda: pipelined(steps, warmup))
+        finished = seen[0]
+        dt_sync = None
+        if kind == "f32":  # one blocking call per bench step (results written in place into the pinned buffers)
+            def one(i):
+                if L.brl_env_rollout_host(h, k, vp(pool[i % n_pool]), vp(rew[0]), vp(term[0]), vp(stats[0])) != 0:
+                    raise RuntimeError(L.brl_last_error().decode())
+            for i in range(warmup):
+                one(i)
+            dt_sync = timed(lambda: [one(warmup + i) for i in range(steps)])
+        L.brl_env_destroy(h)
+        return dt, finished, dt_sync
+
+    dt16, finished, _ = leg("compact16")
+    dt32, _, _ = leg("compact32")
+    dtf, _, dt_sync = leg("f32")
+    tot = n * k * steps * world
+    res = {"value": tot / dt16, "unit": UNIT, "h2d_bytes_per_step": n * k * 2, "d2h_bytes_per_step": n * k * 2 + 32,
+           "steps": steps, "ms_per_step": 1e3 * dt16 / steps,
+           "api": "brl_env_rollout_host_compact_async + brl_env_wait (C ABI, host buffers), three calls in flight: per bench "
+                  "step H2D u16[32,8192] action randomness from pinned memory, one fused rollout launch writing the full "
+                  "trajectory (incl. f32 rewards / u8 terminated) to HBM, D2H result i16[32,8192] = 2*rewards[player 0] + "
+                  "terminated (lossless: rewards are s*[+,+,-,-]) + stats into pinned memory, read by the host while the next "
+                  "steps compute; obs/mask trajectories stay in HBM for the device-resident learner (as traj_batch does "
+                  "in the reference)",
            "timed_with": "host wall clock around the whole loop, max over ranks", "finished_auctions_read_on_host": finished,
-           "sync_per_call": {"value": n * k * steps * world / dt_sync, "ms_per_step": 1e3 * dt_sync / steps,
-                             "api": "brl_env_rollout_host: same copies, one blocking call per step (results written in place "
+           "u32_uniforms": {"value": tot / dt32, "ms_per_step": 1e3 * dt32 / steps, "h2d_bytes_per_step": n * k * 4,
+                            "d2h_bytes_per_step": n * k * 2 + 32},
+           "f32_payload": {"value": tot / dtf, "ms_per_step": 1e3 * dtf / steps, "h2d_bytes_per_step": n * k * 4,
+                           "d2h_bytes_per_step": n * k * 17 + 32,
+                           "api": "brl_env_rollout_host_async: u32 uniforms in, rewards f32[32,8192,4] + terminated u8 out "
+                                  "(round 1's e2e payload)"},
+           "sync_per_call": {"value": tot / dt_sync, "ms_per_step": 1e3 * dt_sync / steps,
+                             "api": "brl_env_rollout_host: f32 payload, one blocking call per step (results written in place "
                                     "into the pinned buffers by the kernel, no overlap between steps)"}}
 
     # ---- full I/O: every Env-surface output to the host, one env.step per call -------------------

@@ -17,7 +17,8 @@ OPS = (
     "brl_ppo_loss", "brl_adam_clip", "brl_adam_apply", "brl_gather_rows", "brl_eval_act_log", "brl_eval_summary", "brl_mlp_pack_train", "brl_mlp_adam_step", "brl_ppo_grad",
 )
 HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host", "brl_env_rollout_host",
-            "brl_env_rollout_host_async", "brl_env_wait", "brl_env_trajectory")
+            "brl_env_rollout_host_async", "brl_env_wait", "brl_env_trajectory", "brl_env_rollout_host_compact_async",
+            "brl_env_rollout_host_compact", "brl_result16_decode")
 MISC = ("brl_last_error", "brl_abi_version", "brl_mlp_packed_bytes", "brl_mlp_scratch_bytes", "brl_eval_num_sums",
         "brl_mlp_num_params", "brl_mlp_train_blob_bytes", "brl_mlp_train_scratch_bytes", "brl_mlp_train_trace_offset")
 XLA_LEGACY = tuple(op + "_xla" for op in OPS)  # legacy XLA GPU custom-call targets (csrc/xla_ffi_shim.cc)
@@ -34,6 +35,9 @@ F_QUAD_LAST = 0x0100
 F_MLP_BF16 = 0x0200
 F_EVAL_INDICATOR_BIDS = 0x0400
 F_HOST_STAGED = 0x0800
+F_RESULT_I16 = 0x1000
+F_UNIFORM_U16 = 0x2000
+ABI_VERSION = 2  # include/brl_b200.h BRL_ABI_VERSION; load() refuses a library built from other headers
 EVAL_ACC_COLS = 76
 
 
@@ -88,10 +92,13 @@ def load():
     path = _build.LIB
     if not os.path.exists(path) or _build._stale():
         try:
-            path = _build.build()
+            path = _build.build()  # serialised across processes by a file lock, installed with os.replace
         except Exception as exc:  # no nvcc on this box and no prebuilt library
             if not os.path.exists(_build.LIB):
                 raise BrlError(f"libbrl_b200.so is missing and cannot be built ({exc}); there is no CPU fallback") from exc
+            import warnings
+            warnings.warn(f"brl_b200: sources are newer than {_build.LIB} and the rebuild failed ({exc}); loading the "
+                          "existing library (its ABI version is checked below)", RuntimeWarning)
             path = _build.LIB
     try:
         L = C.CDLL(path)
@@ -103,6 +110,9 @@ def load():
         fn.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t]
     L.brl_last_error.restype = C.c_char_p
     L.brl_abi_version.restype = C.c_int32
+    if L.brl_abi_version() != ABI_VERSION:
+        raise BrlError(f"{path} reports ABI version {L.brl_abi_version()}, this package expects {ABI_VERSION}: "
+                       "rebuild with `python -m brl_b200.build --force`")
     L.brl_mlp_packed_bytes.restype = C.c_int64
     L.brl_mlp_scratch_bytes.restype = C.c_int64
     L.brl_mlp_scratch_bytes.argtypes = [C.c_int64]
@@ -126,6 +136,12 @@ def load():
     L.brl_env_rollout_host_async.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.brl_env_wait.restype = C.c_int32
     L.brl_env_wait.argtypes = [C.c_void_p, C.c_int64]
+    L.brl_env_rollout_host_compact_async.restype = C.c_int64
+    L.brl_env_rollout_host_compact_async.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.brl_env_rollout_host_compact.restype = C.c_int32
+    L.brl_env_rollout_host_compact.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.brl_result16_decode.restype = None
+    L.brl_result16_decode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.brl_env_trajectory.restype = C.c_int32
     L.brl_env_trajectory.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     _LIB = L

@@ -52,14 +52,39 @@ def _xla_ffi_include():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile and link in-tree.  Concurrent callers (torchrun ranks that all see a stale library) are serialised by
+    an exclusive file lock: the first one builds, the others wake up to a fresh library and return.  Objects go to a
+    per-process directory and the library is moved into place with os.replace, so nobody ever dlopens a half-written file."""
     if not force and not _stale():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     procs = []
+    obj_dir = os.path.join(LIB_DIR, f"obj.{os.getpid()}")
+    os.makedirs(obj_dir, exist_ok=True)
+    tmp_lib = os.path.join(obj_dir, "libbrl_b200.so")
+    try:
+        return _compile_and_link(nvcc, obj_dir, tmp_lib, objs, procs, verbose)
+    finally:
+        shutil.rmtree(obj_dir, ignore_errors=True)
+
+
+def _compile_and_link(nvcc, obj_dir, tmp_lib, objs, procs, verbose):
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, os.path.splitext(src)[0] + ".o")
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc, *NVCC_FLAGS, *_xla_ffi_include(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -71,10 +96,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose:
             print(out)
-    link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp_lib, *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp_lib, LIB)
     return LIB
 
 

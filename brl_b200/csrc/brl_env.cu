@@ -54,6 +54,8 @@ struct EnvArgs {
     int32_t* action_out;
     unsigned long long* stats;
     const uint32_t* uniforms;  // rollout: caller-supplied u32[K, n] action uniforms (NULL -> Philox)
+    int16_t* result16;         // rollout: compact result i16[K, n] = 2 * rewards[player 0] + terminated (BRL_F_RESULT_I16)
+    int uniform16;             // rollout: `uniforms` is u16[K, n] (BRL_F_UNIFORM_U16); u32 uniform = u16 << 16
     // produce-kernel inputs
     const uint64_t* keys;
     const int32_t* in_deal;
@@ -258,6 +260,38 @@ __global__ void __launch_bounds__(256) k_step(const EnvArgs a) {
     emit_block<EPW, OBS>(t, (int)threadIdx.x, (int)blockDim.x, env_base, n_valid, a.obs, a.mask, a.mask_vec);
 }
 
+// caller-supplied action uniform of trajectory row `idx`: u32, or u16 widened to the top half of a u32 (the k-th
+// legal action is mulhi(u, #legal), so a 16-bit uniform picks (u16 * #legal) >> 16)
+__device__ __forceinline__ uint32_t load_uniform(const EnvArgs& a, int64_t idx) {
+    return a.uniform16 ? (uint32_t)reinterpret_cast<const uint16_t*>(a.uniforms)[idx] << 16 : a.uniforms[idx];
+}
+
+// warp-specialised rollout: the writer warps fetch the caller's uniforms of steps [s0, s0 + kUChunk) for the block's envs
+// (row r of the chunk by warp r % n_writers; every load of a warp is issued before the first one is consumed)
+constexpr int kUChunk = 32;
+__device__ __forceinline__ void load_uniform_chunk(const EnvArgs& a, uint32_t (*buf)[32], int s0, int64_t i, bool active, int warp,
+                                                   int n_writers, int lane) {
+    for (int base = warp; base < kUChunk; base += 8 * n_writers) {
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = base + j * n_writers;
+            v[j] = (active && r < kUChunk && s0 + r < a.k_steps) ? load_uniform(a, (int64_t)(s0 + r) * a.n + i) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = base + j * n_writers;
+            if (r < kUChunk) buf[r][lane] = v[j];
+        }
+    }
+}
+
+// compact step result: rewards are s * [+1, +1, -1, -1] by player id with s an integer score in [-7600, 7600]
+// (env_device.cuh env_step; no illegal actions on the random-legal path), so 2 * s + terminated is lossless in 16 bits
+__device__ __forceinline__ int16_t pack_result16(float rew0, uint32_t term) {
+    return (int16_t)(2 * (int)rew0 + (int)(term & 1u));
+}
+
 // ---- K auto-reset steps with in-kernel random-legal actions ----------------------------
 template <int EPW, int OBS>
 __global__ void __launch_bounds__(128) k_rollout(const EnvArgs a) {
@@ -275,13 +309,14 @@ __global__ void __launch_bounds__(128) k_rollout(const EnvArgs a) {
         const int64_t row0 = (int64_t)s * a.n;
         if (lane < EPW) {
             if (active) {
-                const uint32_t u = a.uniforms ? a.uniforms[row0 + i]
+                const uint32_t u = a.uniforms ? load_uniform(a, row0 + i)
                                               : action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)s);
                 int32_t act = kth_legal_action(env_legal_mask(e), u);
                 float4 rew = env_step_autoreset_cached(e, cache, act, a.table, a.n_deals, a.illegal_penalty, a.illegal_bonus);
                 n_term += f_terminated(e);
                 rew0 += (long long)rew.x;
                 write_scalars(a, row0 + i, e, rew, false);
+                if (a.result16) a.result16[row0 + i] = pack_result16(rew.x, f_terminated(e));
                 if (a.action_out) a.action_out[row0 + i] = act;
                 stage_env<EPW>(t, lane, e, cache.cur, f_cur_seat(e), a.obs != nullptr);
             } else {
@@ -389,7 +424,7 @@ __device__ unsigned long long g_role_cycles[8];
 template <int EPB, int OBS>
 __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
     __shared__ WsTile<EPB> tiles[2];
-    __shared__ uint32_t uniforms[2][32];
+    __shared__ uint32_t uniforms[2][kUChunk][32];  // action uniforms, double-buffered chunks of kUChunk steps
     __shared__ uint4 row_slots[2 * EPB * 3];
     __shared__ unsigned long long row_bars[2 * EPB];
     const RowSlots rs{row_slots, row_bars, EPB};
@@ -417,9 +452,14 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
             cache.prime(e, rs, lane, a.table, a.n_deals);
             mask = env_legal_mask(e);
         }
+    } else if (a.uniforms) {
+        // Caller-supplied uniforms are read in bursts of kUChunk steps (here: chunk 0), all warps' loads in flight at once
+        // and before the store stream starts: a 128-byte read per block per step, trickling into DRAM between the
+        // trajectory's writes, cost 6-13 % of the whole kernel (read/write turnarounds; the pool is evicted from L2
+        // by the 519 MB the launch writes), scripts/exp_e2e_gap.py.
+        load_uniform_chunk(a, uniforms[0], 0, i, active, warp, n_writers, lane);
     } else if (warp == 0) {
-        uniforms[0][lane] = a.uniforms ? (active ? a.uniforms[i] : 0u)
-                                       : action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step);
+        uniforms[0][0][lane] = action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step);
     }
     __syncthreads();
     BRL_T0();
@@ -428,7 +468,7 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
             if (s < a.k_steps) {
                 WsTile<EPB>& t = tiles[s & 1];
                 if (active) {
-                    int32_t act = kth_legal_action(mask, uniforms[s & 1][lane]);
+                    int32_t act = kth_legal_action(mask, uniforms[(s / kUChunk) & 1][s % kUChunk][lane]);
                     float4 rew = env_step_autoreset_prefetch(e, cache, rs, lane, act, a.table, a.n_deals, a.illegal_penalty,
                                                              a.illegal_bonus);
                     n_term += f_terminated(e);
@@ -471,14 +511,20 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                     const int64_t row = row0 + i;
                     if (a.rewards) a.rewards[row] = t.rew[lane];
                     if (a.terminated) a.terminated[row] = t.term[lane];
+                    if (a.result16) a.result16[row] = pack_result16(t.rew[lane].x, t.term[lane]);
                     if (a.current_player) a.current_player[row] = (int8_t)t.cur[lane];
                     if (a.action_out) a.action_out[row] = (int32_t)t.act[lane];
                 }
             }
-            if (warp == 0 && s + 1 < a.k_steps)
-                uniforms[(s + 1) & 1][lane] =
-                    a.uniforms ? (active ? a.uniforms[(int64_t)(s + 1) * a.n + i] : 0u)
-                               : action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)(s + 1));
+            if (s + 1 < a.k_steps) {
+                if (a.uniforms) {  // next chunk: the env warp is still reading the other buffer
+                    if ((s + 1) % kUChunk == 0)
+                        load_uniform_chunk(a, uniforms[((s + 1) / kUChunk) & 1], s + 1, i, active, warp, n_writers, lane);
+                } else if (warp == 0) {
+                    uniforms[((s + 1) / kUChunk) & 1][(s + 1) % kUChunk][lane] =
+                        action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)(s + 1));
+                }
+            }
         }
         BRL_ACC(is_env_warp ? 0 : (warp == 0 ? 2 : 4));
         __syncthreads();
@@ -994,6 +1040,14 @@ int32_t brl_rollout_random(brl_stream_t stream, void** b, const void* opaque, si
     a.action_out = static_cast<int32_t*>(b[7]);
     a.stats = static_cast<unsigned long long*>(b[8]);
     a.uniforms = static_cast<const uint32_t*>(b[9]);
+    a.uniform16 = (p->flags & BRL_F_UNIFORM_U16) ? 1 : 0;
+    if (a.uniforms && (reinterpret_cast<uintptr_t>(a.uniforms) & (a.uniform16 ? 1u : 3u)))
+        return fail(BRL_E_BUFFER, "brl_rollout_random: uniforms is misaligned for its element type");
+    if (p->flags & BRL_F_RESULT_I16) {
+        a.result16 = static_cast<int16_t*>(b[10]);
+        if (a.result16 == nullptr || (reinterpret_cast<uintptr_t>(a.result16) & 1u))
+            return fail(BRL_E_BUFFER, "brl_rollout_random: BRL_F_RESULT_I16 needs an i16-aligned buffer [10]");
+    }
     if ((rc = check_outputs(a, "brl_rollout_random")) != BRL_OK) return rc;
     if (p->flags & (1 << 20)) launch_rollout(a, (cudaStream_t)stream);
     else launch_rollout_ws(a, (cudaStream_t)stream);

@@ -41,6 +41,7 @@ struct BrlEnv {
     float* a_rewards[BRL_ENV_PIPELINE_DEPTH];
     uint8_t* a_term[BRL_ENV_PIPELINE_DEPTH];
     uint32_t* a_uniforms[BRL_ENV_PIPELINE_DEPTH];
+    int16_t* a_result[BRL_ENV_PIPELINE_DEPTH];
     unsigned long long* a_stats[BRL_ENV_PIPELINE_DEPTH];
     cudaEvent_t a_in[BRL_ENV_PIPELINE_DEPTH], a_kernel[BRL_ENV_PIPELINE_DEPTH], a_done[BRL_ENV_PIPELINE_DEPTH];
 };
@@ -137,6 +138,7 @@ void brl_env_destroy(BrlEnv* env) {
     }
     for (int c = 0; c < BRL_ENV_PIPELINE_DEPTH; ++c) {
         cudaFree(env->a_rewards[c]); cudaFree(env->a_term[c]); cudaFree(env->a_uniforms[c]); cudaFree(env->a_stats[c]);
+        cudaFree(env->a_result[c]);
         if (env->a_in[c]) cudaEventDestroy(env->a_in[c]);
         if (env->a_kernel[c]) cudaEventDestroy(env->a_kernel[c]);
         if (env->a_done[c]) cudaEventDestroy(env->a_done[c]);
@@ -282,25 +284,24 @@ int32_t brl_env_rollout_host(BrlEnv* env, int32_t k_steps, const uint32_t* unifo
     return BRL_OK;
 }
 
-// Pipelined form of brl_env_rollout_host: returns as soon as the work is enqueued; call c's H2D runs under
-// call c-1's kernel and its D2H under call c+1's kernel (BRL_ENV_PIPELINE_DEPTH staging slots, three streams).
-// The host buffers of call c are valid after brl_env_wait(env, ticket_c); at most BRL_ENV_PIPELINE_DEPTH calls
-// may be in flight (a deeper submit waits on the device for the slot it reuses).  Three in flight keep the
-// GPU fed: with two, the host learns that D2H(c-1) is done only as kernel c ends, too late to enqueue c+1.
-int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t* uniforms, float* rewards,
-                                   uint8_t* terminated, uint64_t* stats) {
-    if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "brl_env_rollout_host_async: bad handle");
-    if (k_steps <= 0) return brl::fail(BRL_E_OPAQUE, "brl_env_rollout_host_async: k_steps must be > 0");
+// Shared body of the pipelined calls.  `result16` != NULL selects the compact payload: the kernel writes the f32
+// rewards / u8 terminated trajectories into the device-resident trajectory (brl_env_trajectory) and the 2-byte step
+// result into the slot's staging buffer, which is all that crosses PCIe; uniforms are u16 or u32 per the env's flags.
+static int64_t rollout_async(BrlEnv* env, const char* fn, int32_t k_steps, const void* uniforms, float* rewards,
+                             uint8_t* terminated, int16_t* result16, uint64_t* stats) {
+    if (!env || env->magic != kMagic) return brl::fail(BRL_E_HANDLE, "%s: bad handle", fn);
+    if (k_steps <= 0) return brl::fail(BRL_E_OPAQUE, "%s: k_steps must be > 0", fn);
     if (!ensure_trajectory(env, k_steps)) return BRL_E_LAUNCH;
     const size_t rows = (size_t)k_steps * (size_t)env->n;
     if (env->a_k < k_steps) {
         if (!ok(cudaDeviceSynchronize(), "sync before staging resize")) return BRL_E_LAUNCH;
         for (int c = 0; c < BRL_ENV_PIPELINE_DEPTH; ++c) {
-            cudaFree(env->a_rewards[c]); cudaFree(env->a_term[c]); cudaFree(env->a_uniforms[c]);
-            env->a_rewards[c] = nullptr; env->a_term[c] = nullptr; env->a_uniforms[c] = nullptr;
+            cudaFree(env->a_rewards[c]); cudaFree(env->a_term[c]); cudaFree(env->a_uniforms[c]); cudaFree(env->a_result[c]);
+            env->a_rewards[c] = nullptr; env->a_term[c] = nullptr; env->a_uniforms[c] = nullptr; env->a_result[c] = nullptr;
             bool good = ok(cudaMalloc(&env->a_rewards[c], rows * 16), "malloc staging rewards") &&
                         ok(cudaMalloc(&env->a_term[c], rows), "malloc staging terminated") &&
                         ok(cudaMalloc(&env->a_uniforms[c], rows * 4), "malloc staging uniforms") &&
+                        ok(cudaMalloc(&env->a_result[c], rows * 2), "malloc staging result") &&
                         (env->a_stats[c] != nullptr || (ok(cudaMalloc(&env->a_stats[c], 32), "malloc staging stats") &&
                                                         ok(cudaMemset(env->a_stats[c], 0, 32), "memset stats"))) &&
                         (env->a_in[c] != nullptr || ok(cudaEventCreateWithFlags(&env->a_in[c], cudaEventDisableTiming), "event")) &&
@@ -313,10 +314,12 @@ int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t*
     }
     const int slot = (int)(env->a_calls % BRL_ENV_PIPELINE_DEPTH);
     const bool reuse = env->a_calls >= BRL_ENV_PIPELINE_DEPTH;
+    const bool compact = result16 != nullptr;
+    const size_t ubytes = (compact && (env->flags & BRL_F_UNIFORM_U16)) ? 2 : 4;
     cudaStream_t s = env->stream;
     if (uniforms) {
         if (reuse && !ok(cudaStreamWaitEvent(env->s_in, env->a_kernel[slot], 0), "wait event")) return BRL_E_LAUNCH;
-        if (!ok(cudaMemcpyAsync(env->a_uniforms[slot], uniforms, rows * 4, cudaMemcpyHostToDevice, env->s_in), "H2D uniforms") ||
+        if (!ok(cudaMemcpyAsync(env->a_uniforms[slot], uniforms, rows * ubytes, cudaMemcpyHostToDevice, env->s_in), "H2D uniforms") ||
             !ok(cudaEventRecord(env->a_in[slot], env->s_in), "event record") || !ok(cudaStreamWaitEvent(s, env->a_in[slot], 0), "wait event"))
             return BRL_E_LAUNCH;
     }
@@ -324,13 +327,20 @@ int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t*
     if (reuse && !ok(cudaStreamWaitEvent(s, env->a_done[slot], 0), "wait event")) return BRL_E_LAUNCH;
     BrlParams p = params_of(env, 0);
     p.k_steps = k_steps;
-    void* b[10] = {env->d_state, env->d_table, env->t_obs, env->t_mask, env->a_rewards[slot], env->a_term[slot],
-                   env->t_cur, env->t_action, env->a_stats[slot], uniforms ? (void*)env->a_uniforms[slot] : nullptr};
+    p.flags &= ~(BRL_F_UNIFORM_U16 | BRL_F_RESULT_I16);
+    if (compact) p.flags |= BRL_F_RESULT_I16 | (ubytes == 2 ? BRL_F_UNIFORM_U16 : 0);
+    void* b[11] = {env->d_state, env->d_table, env->t_obs, env->t_mask,
+                   compact ? (void*)env->t_rewards : (void*)env->a_rewards[slot],
+                   compact ? (void*)env->t_term : (void*)env->a_term[slot],
+                   env->t_cur, env->t_action, env->a_stats[slot], uniforms ? (void*)env->a_uniforms[slot] : nullptr,
+                   compact ? (void*)env->a_result[slot] : nullptr};
     int32_t rc = brl_rollout_random((brl_stream_t)s, b, &p, sizeof(p));
     if (rc != BRL_OK) return rc;
     env->step += (uint32_t)k_steps;
     if (!ok(cudaEventRecord(env->a_kernel[slot], s), "event record") ||
         !ok(cudaStreamWaitEvent(env->s_out, env->a_kernel[slot], 0), "wait event"))
+        return BRL_E_LAUNCH;
+    if (compact && !ok(cudaMemcpyAsync(result16, env->a_result[slot], rows * 2, cudaMemcpyDeviceToHost, env->s_out), "D2H result"))
         return BRL_E_LAUNCH;
     if (rewards && !ok(cudaMemcpyAsync(rewards, env->a_rewards[slot], rows * 16, cudaMemcpyDeviceToHost, env->s_out), "D2H rewards"))
         return BRL_E_LAUNCH;
@@ -341,6 +351,38 @@ int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t*
     if (!ok(cudaMemsetAsync(env->a_stats[slot], 0, 32, env->s_out), "memset stats")) return BRL_E_LAUNCH;
     if (!ok(cudaEventRecord(env->a_done[slot], env->s_out), "event record")) return BRL_E_LAUNCH;
     return ++env->a_calls;
+}
+
+// Pipelined form of brl_env_rollout_host: returns as soon as the work is enqueued; call c's H2D runs under
+// call c-1's kernel and its D2H under call c+1's kernel (BRL_ENV_PIPELINE_DEPTH staging slots, three streams).
+// The host buffers of call c are valid after brl_env_wait(env, ticket_c); at most BRL_ENV_PIPELINE_DEPTH calls
+// may be in flight (a deeper submit waits on the device for the slot it reuses).  Three in flight keep the
+// GPU fed: with two, the host learns that D2H(c-1) is done only as kernel c ends, too late to enqueue c+1.
+int64_t brl_env_rollout_host_async(BrlEnv* env, int32_t k_steps, const uint32_t* uniforms, float* rewards,
+                                   uint8_t* terminated, uint64_t* stats) {
+    return rollout_async(env, "brl_env_rollout_host_async", k_steps, uniforms, rewards, terminated, nullptr, stats);
+}
+
+int64_t brl_env_rollout_host_compact_async(BrlEnv* env, int32_t k_steps, const void* uniforms, int16_t* result,
+                                           uint64_t* stats) {
+    if (result == nullptr) return brl::fail(BRL_E_BUFFER, "brl_env_rollout_host_compact_async: result is NULL");
+    return rollout_async(env, "brl_env_rollout_host_compact_async", k_steps, uniforms, nullptr, nullptr, result, stats);
+}
+
+int32_t brl_env_rollout_host_compact(BrlEnv* env, int32_t k_steps, const void* uniforms, int16_t* result, uint64_t* stats) {
+    const int64_t t = brl_env_rollout_host_compact_async(env, k_steps, uniforms, result, stats);
+    if (t <= 0) return (int32_t)t;
+    return brl_env_wait(env, t);
+}
+
+// host-side decode of the compact payload into the Env-surface arrays (plain CPU loop over host memory)
+void brl_result16_decode(const int16_t* result, int64_t rows, float* rewards, uint8_t* terminated) {
+    for (int64_t r = 0; r < rows; ++r) {
+        const int32_t w = result[r];
+        const float sc = (float)(w >> 1);
+        if (rewards) { rewards[4 * r] = sc; rewards[4 * r + 1] = sc; rewards[4 * r + 2] = -sc; rewards[4 * r + 3] = -sc; }
+        if (terminated) terminated[r] = (uint8_t)(w & 1);
+    }
 }
 
 int32_t brl_env_wait(BrlEnv* env, int64_t ticket) {

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import (BrlParams, F_ACCUMULATE, F_AUTORESET, F_MLP_BF16, F_OBS_BF16, F_OBS_U8, F_QUAD_LAST,
-                   F_RANDOM_ACTION, F_SAMPLE)
+                   F_RANDOM_ACTION, F_RESULT_I16, F_SAMPLE, F_UNIFORM_U16)
 
 NUM_ACTIONS = 38
 OBS_DIM = 480
@@ -158,17 +158,34 @@ def legal_mask(state, mask: torch.Tensor, tune: int = 0) -> None:
 
 def rollout_random(state, table, k_steps: int, out: Optional[EnvOutputs], *, seed=0, step0=0, env_offset=0,
                    action_out=None, stats=None, obs_only: Optional[torch.Tensor] = None, tune: int = 0,
-                   uniforms: Optional[torch.Tensor] = None) -> None:
-    """K auto-reset random-legal steps in ONE launch; `out` holds [K, n, ...] trajectories."""
+                   uniforms: Optional[torch.Tensor] = None, result16: Optional[torch.Tensor] = None) -> None:
+    """K auto-reset random-legal steps in ONE launch; `out` holds [K, n, ...] trajectories.
+    `uniforms`: caller-owned randomness, int32/uint32 [K, n], or int16/uint16 [K, n] (stands for u16 << 16);
+    `result16`: int16 [K, n] compact result = 2 * rewards[player 0] + terminated (decode_result16)."""
     n = state.shape[1]
+    extra = 0
+    if uniforms is not None and uniforms.element_size() == 2:
+        extra |= F_UNIFORM_U16
+    if result16 is not None:
+        if result16.dtype != torch.int16:
+            raise TypeError("result16 must be an int16 tensor")
+        extra |= F_RESULT_I16
     if out is not None:
         ptrs, flag = out.ptrs(), out.flag()
     else:
         ptrs = [_ptr(obs_only), None, None, None, None]
         flag = obs_flag(obs_only.dtype) if obs_only is not None else 0
-    _call("brl_rollout_random", [_ptr(state), _ptr(table), *ptrs, _ptr(action_out), _ptr(stats), _ptr(uniforms)],
-              _params(n, flags=flag | tune, n_deals=table.shape[0], stride=state.shape[1], seed=seed, step=step0,
+    _call("brl_rollout_random", [_ptr(state), _ptr(table), *ptrs, _ptr(action_out), _ptr(stats), _ptr(uniforms),
+                                 _ptr(result16)],
+              _params(n, flags=flag | tune | extra, n_deals=table.shape[0], stride=state.shape[1], seed=seed, step=step0,
                       env_offset=env_offset, k_steps=k_steps))
+
+
+def decode_result16(result16: torch.Tensor):
+    """compact rollout result -> (rewards f32[..., 4], terminated u8[...]) exactly as the Env surface gives them"""
+    w = result16.to(torch.int32)
+    s = (w >> 1).to(torch.float32)
+    return torch.stack((s, s, -s, -s), dim=-1), (w & 1).to(torch.uint8)
 
 
 def imp_reward(a_rewards, b_rewards, out) -> None:

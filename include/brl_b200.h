@@ -72,7 +72,7 @@ extern "C" {
 typedef struct CUstream_st *brl_stream_t; /* == cudaStream_t */
 #endif
 
-#define BRL_ABI_VERSION 1
+#define BRL_ABI_VERSION 2
 #define BRL_NUM_ACTIONS 38      /* 0 Pass, 1 X, 2 XX, 3..37 = 1C..7NT (src/duplicate.py:9-12) */
 #define BRL_OBS_DIM 480         /* ppo.py:241, wb5/utils.py:48-52 */
 #define BRL_NUM_PLAYERS 4
@@ -89,6 +89,8 @@ typedef struct CUstream_st *brl_stream_t; /* == cudaStream_t */
 #define BRL_F_SAMPLE        0x0040 /* brl_categorical: Gumbel-argmax sample instead of mode */
 #define BRL_F_QUAD_LAST     0x0100 /* with ACCUMULATE: write the OR-ed terminated flag back into the state (src/utils.py:128) */
 #define BRL_F_MLP_BF16      0x0200 /* brl_mlp_forward: one bf16 product per term instead of the 3-term split */
+#define BRL_F_RESULT_I16    0x1000 /* brl_rollout_random: also write the compact result i16[K,n] into buffers[10] */
+#define BRL_F_UNIFORM_U16   0x2000 /* brl_rollout_random / brl_env_rollout_host_compact*: caller-supplied uniforms are u16[K,n] */
 #define BRL_F_HOST_STAGED   0x0800 /* brl_env_create: never write results straight into pinned host buffers (always stage + copy) */
 
 /* tuning (0 = automatic): bits 16-17 envs per block of the one-launch kernels (1->8, 2->16, 3->32), bits 18-19 warps
@@ -172,7 +174,13 @@ int32_t brl_legal_mask(brl_stream_t, void **buffers, const void *opaque, size_t 
  *          [6] out current_player[K,n]  [7] out i32 action[K,n]
  *          [8] inout u64 stats[4] = {terminal steps, sum reward[player 0] (two's complement), calls, 0}
  *          [9] in u32 uniforms[K,n] (optional): caller-owned randomness; action = the
- *              mulhi(u, #legal)-th legal action.  NULL -> Philox(seed, env_offset+i, step+s). */
+ *              mulhi(u, #legal)-th legal action.  NULL -> Philox(seed, env_offset+i, step+s).
+ *              With BRL_F_UNIFORM_U16 the buffer is u16[K,n] and stands for the u32 uniform u16 << 16.
+ *          [10] out i16 result[K,n] -- read ONLY with BRL_F_RESULT_I16: the step result in 2 bytes,
+ *              result = 2 * rewards[player 0] + terminated.  Lossless on this path: pgx rewards are
+ *              s * [+1,+1,-1,-1] by player id (players 0/1 partners) with s an integer duplicate score,
+ *              |s| <= 7600, and random-legal play never takes the illegal-action branch.  Decode:
+ *              terminated = result & 1, s = result >> 1 (arithmetic) -- brl_result16_decode. */
 int32_t brl_rollout_random(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
 /* buffers: [0] in f32 a_rewards[n,4]  [1] in f32 b_rewards[n,4]  [2] out f32 imp[n,4] */
@@ -401,6 +409,17 @@ int32_t brl_env_rollout_host(BrlEnv *env, int32_t k_steps, const uint32_t *unifo
 int64_t brl_env_rollout_host_async(BrlEnv *env, int32_t k_steps, const uint32_t *uniforms, float *rewards,
                                    uint8_t *terminated, uint64_t *stats);
 int32_t brl_env_wait(BrlEnv *env, int64_t ticket);
+/* Compact-payload forms (same rollout, same device-resident trajectory incl. f32 rewards / u8 terminated, see
+ * brl_env_trajectory): what crosses PCIe is 2 bytes per env-step each way instead of 4 in + 17 out.
+ * HOST in: uniforms u32[k_steps,n], or u16[k_steps,n] when the env was created with BRL_F_UNIFORM_U16 (NULL -> in-kernel
+ * Philox).  HOST out: result i16[k_steps,n] = 2 * rewards[player 0] + terminated (lossless, see brl_rollout_random
+ * buffers[10]; this is what roll_out's consumer reads: rewards[actor] and done, src/roll_out.py:86-94), stats u64[4].
+ * Tickets share brl_env_wait and the BRL_ENV_PIPELINE_DEPTH staging slots with brl_env_rollout_host_async. */
+int64_t brl_env_rollout_host_compact_async(BrlEnv *env, int32_t k_steps, const void *uniforms, int16_t *result,
+                                           uint64_t *stats);
+int32_t brl_env_rollout_host_compact(BrlEnv *env, int32_t k_steps, const void *uniforms, int16_t *result, uint64_t *stats);
+/* host-side decode of `rows` compact results into rewards f32[rows,4] / terminated u8[rows] (either may be NULL) */
+void brl_result16_decode(const int16_t *result, int64_t rows, float *rewards, uint8_t *terminated);
 /* device pointers of the last rollout's trajectory: obs, mask, rewards, terminated, current_player, action */
 int32_t brl_env_trajectory(BrlEnv *env, void **out_ptrs6);
 
