@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-policy", action="store_true", help="skip the configs[2] policy-rollout leg")
     ap.add_argument("--no-update", action="store_true", help="skip the PPO-update leg (SURVEY 8f-1)")
+    ap.add_argument("--no-matches", action="store_true", help="skip the configs[0] / [3] / [4] duplicate-match legs")
+    ap.add_argument("--league", action="store_true", help="run the configs[4] 1M-env league leg below 8 GPUs too")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -285,6 +287,13 @@ def main():
                   warmup=args.warmup)
 
     extra = {}
+    # ---- the north-star multi-GPU configs (all ranks take part; one all-reduce each) ----------------------------------
+    if not args.no_matches:
+        extra["dup_selfplay_65536"] = run_dup_selfplay(torch, dist, dev, rank, world, table_np)
+        if world >= 8 or args.league:
+            extra["league_1M"] = run_league(torch, dist, dev, rank, world, table_np)
+        if rank == 0:
+            extra["c1_eval_match"] = run_c1(torch, dev)
     if args.sweep and rank == 0:
         extra["sweep"] = run_sweep(torch, ops, table, dev, peak)
 
@@ -474,6 +483,109 @@ def run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps, warmu
     return res
 
 
+def _weights(name):
+    """bundled model pickle shipped as a data fixture (tests/golden/_weights, copied by __graft_entry__.build())"""
+    path = os.path.join(ROOT, "tests", "golden", "_weights", name)
+    return path if os.path.exists(path) else None
+
+
+def _timed_match(torch, dist, dev, world, fn, reps):
+    """CUDA-event time of `fn()` (which ends in its own all-reduce), max over ranks; best of `reps` after one warm-up"""
+    fn()
+    best, res = None, None
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = float(t) if best is None else min(best, float(t))
+    return best, res
+
+
+def run_dup_selfplay(torch, dist, dev, rank, world, table_np, n_total=65536):
+    """BASELINE.json configs[3]: duplicate self-play match (src/evaluation.py:69-204), 65,536 envs in total sharded by
+    GLOBAL env index over the ranks (strong scaling: the total is fixed), one all-reduce of the f64[8] IMP statistics.
+    Keys use global indices, so the statistics are identical for every rank count."""
+    from brl_b200 import BridgeBidding, dist as bdist, random as brandom
+    from brl_b200.evaluation import make_simple_duplicate_evaluate
+    from brl_b200.models import init_params, load_params
+    lo, hi = bdist.shard_range(n_total, rank, world)
+    env = BridgeBidding(table=table_np, device=dev)
+    w1, w2 = _weights("model-pretrained-rl.pkl"), _weights("model-pretrained-rl-with-fsp.pkl")
+    if w1 and w2:
+        p1, p2, who = load_params(w1, dev), load_params(w2, dev), "model-pretrained-rl.pkl vs model-pretrained-rl-with-fsp.pkl (bundled weights)"
+    else:
+        p1, p2, who = init_params(1, dev), init_params(2, dev), "random-init nets (weight fixtures missing)"
+    evaluate = make_simple_duplicate_evaluate(env, "relu", "DeepMind", "relu", "DeepMind", hi - lo, env_offset=lo)
+    ms, res = _timed_match(torch, dist, dev, world, lambda: evaluate(p1, p2, brandom.PRNGKey(1)), reps=2)
+    (mean, se, win), _, _, _ = res
+    fwd = torch.tensor([float(evaluate.rows_forwarded)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(fwd)
+    return {"workload": "configs[3]: duplicate self-play, 65,536 envs total, DeepMind MLP per team, argmax play; " + who,
+            "n_envs_total": n_total, "n_gpus": world, "scaling": "strong", "ms_per_match": ms,
+            "boards_per_sec": 2 * n_total / (ms * 1e-3), "env_steps_per_sec": float(fwd) / (ms * 1e-3),
+            "net_rows_forwarded": float(fwd), "imp_mean": mean, "imp_se": se, "win_rate": win,
+            "collective": "1 NCCL all-reduce of f64[8] per match" if world > 1 else "none (1 rank)",
+            "note": "env_steps = live (env, call) pairs = rows sent through a net: each net runs only on the live envs its "
+                    "team decides (brl_team_rows + brl_policy_act_rows)"}
+
+
+def run_league(torch, dist, dev, rank, world, table_np, n_total=1 << 20):
+    """BASELINE.json configs[4]: FSP/PFSP league probe (ppo.py:399-440): the learner against the pool of the 5 bundled
+    models, 1,048,576 envs in total, block m of the global env range plays pool model m, every block sharded over the
+    ranks; one all-reduce of f64[5, 8]."""
+    from brl_b200 import BridgeBidding, random as brandom
+    from brl_b200.evaluation import make_league_evaluate
+    from brl_b200.models import init_params, load_params
+    names = ("model-sl.pkl", "model-from-scratch-rl.pkl", "model-pretrained-rl.pkl", "model-pretrained-rl-with-fsp.pkl",
+             "model-pretrained-rl-with-pfsp.pkl")
+    paths = [_weights(n) for n in names]
+    env = BridgeBidding(table=table_np, device=dev)
+    if all(paths):
+        pool, actor, who = [load_params(p, dev) for p in paths], load_params(paths[2], dev), "bundled weights: learner = model-pretrained-rl"
+    else:
+        pool, actor, who = [init_params(100 + m, dev) for m in range(5)], init_params(1, dev), "random-init nets (weight fixtures missing)"
+    league = make_league_evaluate(env, "relu", "DeepMind", n_total, len(pool))
+    ms, res = _timed_match(torch, dist, dev, world, lambda: league(actor, pool, brandom.PRNGKey(1)), reps=1)
+    return {"workload": "configs[4]: league probe, learner vs the pool of 5 models, 1,048,576 envs total; " + who,
+            "n_envs_total": n_total, "n_gpus": world, "scaling": "strong", "ms_per_league": ms,
+            "boards_per_sec": 2 * n_total / (ms * 1e-3), "pool": list(names),
+            "imp_mean": [r[0] for r in res], "imp_se": [r[1] for r in res], "win_rate": [r[2] for r in res],
+            "collective": "1 NCCL all-reduce of f64[5,8]" if world > 1 else "none (1 rank)"}
+
+
+def run_c1(torch, dev):
+    """BASELINE.json configs[0]: eval.py duplicate match model-pretrained-rl.pkl vs model-sl.pkl, num_eval_envs=100, on the
+    1000 real boards (eval.py:43-65).  IMP mean +- SE must equal the golden values the oracle + the reference's own scorer
+    produced (tests/golden/make_c1_golden.py); the oracle is not touched here."""
+    import numpy as np
+    from brl_b200 import BridgeBidding, random as brandom
+    from brl_b200.evaluation import make_simple_duplicate_evaluate
+    from brl_b200.models import load_params
+    w1, w2 = _weights("model-pretrained-rl.pkl"), _weights("model-sl.pkl")
+    if not (w1 and w2):
+        return {"unavailable": "weight fixtures missing (tests/golden/_weights)"}
+    boards = np.load(os.path.join(ROOT, "tests", "golden", "boards_wb5_1000.npz"))["table"]
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "c1_eval_match.npz"))
+    env = BridgeBidding(table=boards, device=dev)
+    p1, p2 = load_params(w1, dev), load_params(w2, dev)
+    evaluate = make_simple_duplicate_evaluate(env, "relu", "DeepMind", "relu", "DeepMind", 100)
+    ms, res = _timed_match(torch, None, dev, 1, lambda: evaluate(p1, p2, brandom.PRNGKey(0)), reps=3)
+    (mean, se, win), _, _, cum = res
+    return {"workload": "configs[0]: eval.py model-pretrained-rl.pkl vs model-sl.pkl, num_eval_envs=100, 1000 real boards",
+            "ms_per_match": ms, "imp_mean": mean, "imp_se": se, "win_rate": win,
+            "golden_imp_mean": float(gold["stats"][0]), "golden_imp_se": float(gold["stats"][1]),
+            "equals_golden": bool((cum.cpu().numpy() == gold["imps"]).all())}
+
+
 def run_policy_rollout(torch, table_np, dev):
     """BASELINE.json configs[2]: ppo.py rollout, num_envs=8192, num_steps=32, DeepMind 4x1024 ReLU policy
     (random init) for actor and opponent, competitive quad step, + GAE.  Secondary to the headline metric:
@@ -495,8 +607,9 @@ def run_policy_rollout(torch, table_np, dev):
             tpeak = float(json.load(fh)["bf16_tflops"])
     except Exception:
         tpeak = 1590.0
+    from scripts.torch_baseline import TorchForwardPass  # cuBLAS comparison leg only; not a product back end
     for prec in ("tc", "tc-bf16", "fp32"):
-        fp = make_forward_pass("relu", "DeepMind", precision=prec)
+        fp = TorchForwardPass("relu", "fp32") if prec == "fp32" else make_forward_pass("relu", "DeepMind", precision=prec)
         params, opp = init_params(1, dev), init_params(2, dev)
         state = env.init(env.make_keys(SEED, n))
         runner = (params, None, state, state.observation, torch.zeros((), dtype=torch.int64, device=dev), brandom.PRNGKey(3))
@@ -575,11 +688,12 @@ def run_ppo_update(torch, dev):
     mma_flop = 2.0 * mbs * ((480 * H * 2 + 3 * H * H * 3 + H * hp * 3) + (hp * H * 3 + 3 * H * H * 3) + (H * hp * 3 + 3 * H * H * 3 + 480 * H * 2))
     out = {"workload": f"ppo.py update on the configs[2] rollout: {T} x {n} samples, minibatch {mbs}, 1 epoch = {nmb} optimizer steps "
                        "(take + forward + loss + backward + clip_by_global_norm + Adam each); synthetic trajectory, random-init net"}
+    from scripts.torch_baseline import TorchForwardPass, make_update_step_autograd  # comparison leg only
     for prec, reps in (("tc", 3), ("fp32", 1)):
-        fp = make_forward_pass("relu", "DeepMind", precision=prec)
         params = init_params(1, dev)
         opt = AdamWithClip(1e-4, eps=1e-5, max_grad_norm=0.5)
-        update_step = make_update_step(config, fp, opt)
+        update_step = (make_update_step(config, make_forward_pass("relu", "DeepMind"), opt) if prec == "tc"
+                       else make_update_step_autograd(config, TorchForwardPass("relu", "fp32"), opt))
         runner = (params, opt.init(params), None, None, 0, brandom.PRNGKey(5))
         runner, info0 = update_step(runner, traj, adv, tgt)  # warm-up epoch
         torch.cuda.synchronize()

@@ -13,13 +13,15 @@ from . import build as _build
 OPS = (
     "brl_make_keys", "brl_init", "brl_reset_fields", "brl_step", "brl_duplicate_step", "brl_duplicate_init",
     "brl_observe", "brl_legal_mask", "brl_rollout_random", "brl_imp_reward", "brl_gae", "brl_categorical",
-    "brl_match_stats", "brl_state_fields", "brl_gather_reward", "brl_mlp_pack", "brl_obs_to_bf16", "brl_mlp_forward", "brl_policy_act",
+    "brl_match_stats", "brl_state_fields", "brl_gather_reward", "brl_team_rows", "brl_mlp_pack", "brl_obs_to_bf16", "brl_mlp_forward", "brl_policy_act",
+    "brl_policy_act_rows",
     "brl_ppo_loss", "brl_adam_clip", "brl_adam_apply", "brl_gather_rows", "brl_eval_act_log", "brl_eval_summary", "brl_mlp_pack_train", "brl_mlp_adam_step", "brl_ppo_grad",
 )
 HOST_API = ("brl_env_create", "brl_env_destroy", "brl_env_init_host", "brl_env_step_host", "brl_env_rollout_host",
             "brl_env_rollout_host_async", "brl_env_wait", "brl_env_trajectory", "brl_env_rollout_host_compact_async",
             "brl_env_rollout_host_compact", "brl_result16_decode")
-MISC = ("brl_last_error", "brl_abi_version", "brl_mlp_packed_bytes", "brl_mlp_scratch_bytes", "brl_eval_num_sums",
+MISC = ("brl_last_error", "brl_abi_version", "brl_mlp_packed_bytes", "brl_mlp_scratch_bytes", "brl_mlp_rows_scratch_bytes",
+        "brl_xla_layout", "brl_xla_unreported_failures", "brl_eval_num_sums",
         "brl_mlp_num_params", "brl_mlp_train_blob_bytes", "brl_mlp_train_scratch_bytes", "brl_mlp_train_trace_offset")
 XLA_LEGACY = tuple(op + "_xla" for op in OPS)  # legacy XLA GPU custom-call targets (csrc/xla_ffi_shim.cc)
 ALL_SYMBOLS = OPS + HOST_API + MISC + XLA_LEGACY
@@ -69,8 +71,9 @@ class BrlAdamParams(C.Structure):
                 ("eps", C.c_float), ("max_grad_norm", C.c_float)]
 
 
-PPO_VALUE_CLIPPING, PPO_REWARD_SCALING, PPO_UNMASKED_POLICY = 1, 2, 4
+PPO_VALUE_CLIPPING, PPO_REWARD_SCALING, PPO_UNMASKED_POLICY, PPO_ILLEGAL_STAT = 1, 2, 4, 8
 PPO_OBS_U8, PPO_OBS_BF16 = 0x10, 0x20
+PPO_SCRATCH_BYTES = 188416  # include/brl_b200.h BRL_PPO_SCRATCH_BYTES
 
 
 class BrlError(RuntimeError):
@@ -90,7 +93,10 @@ def load():
     if _LIB is not None:
         return _LIB
     path = _build.LIB
-    if not os.path.exists(path) or _build._stale():
+    override = os.environ.get("BRL_B200_LIB")  # debug builds (e.g. -DBRL_GRAM_TIMING, -DBRL_ROLE_TIMING) of the same sources
+    if override:
+        path = override
+    elif not os.path.exists(path) or _build._stale():
         try:
             path = _build.build()  # serialised across processes by a file lock, installed with os.replace
         except Exception as exc:  # no nvcc on this box and no prebuilt library
@@ -116,6 +122,15 @@ def load():
     L.brl_mlp_packed_bytes.restype = C.c_int64
     L.brl_mlp_scratch_bytes.restype = C.c_int64
     L.brl_mlp_scratch_bytes.argtypes = [C.c_int64]
+    L.brl_mlp_rows_scratch_bytes.restype = C.c_int64
+    L.brl_mlp_rows_scratch_bytes.argtypes = [C.c_int64]
+    L.brl_xla_layout.restype = C.c_char_p
+    L.brl_xla_layout.argtypes = [C.c_char_p]
+    L.brl_xla_unreported_failures.restype = C.c_longlong
+    for name in XLA_LEGACY:
+        fn = getattr(L, name)
+        fn.restype = None
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t, C.c_void_p]
     L.brl_mlp_num_params.restype = C.c_int64
     L.brl_mlp_train_blob_bytes.restype = C.c_int64
     L.brl_mlp_train_scratch_bytes.restype = C.c_int64

@@ -61,12 +61,15 @@ __global__ void __launch_bounds__(128) k_gae(const uint8_t* __restrict__ done, c
 __global__ void __launch_bounds__(128) k_categorical(const float* __restrict__ logits, const uint8_t* __restrict__ mask,
                                                      int32_t* __restrict__ action, float* __restrict__ log_prob,
                                                      int64_t n, int sample, uint64_t seed, int64_t env_offset,
-                                                     uint32_t step) {
+                                                     uint32_t step, const int32_t* __restrict__ row_index,
+                                                     float* __restrict__ logits_by_env) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t row = warp; row < n; row += n_warps) {
-        const float* l = logits + row * kNumActions;
+    for (int64_t r = warp; r < n; r += n_warps) {
+        // row_index: logits are compact ([n, 38] for the listed rows); mask / action / log_prob / RNG counter are by env
+        const int64_t row = row_index ? (int64_t)row_index[r] : r;
+        const float* l = logits + r * kNumActions;
         const uint8_t* m = mask ? mask + row * kNumActions : nullptr;
         float best = -INFINITY, mx = -INFINITY;
         int best_a = kNumActions;
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(128) k_categorical(const float* __restrict__ l
         for (int k = 0; k < 2; ++k) {
             int a = lane + 32 * k;
             ok[k] = a < kNumActions && (m == nullptr || m[a] != 0);
+            if (logits_by_env && a < kNumActions) logits_by_env[row * kNumActions + a] = l[a];
             lv[k] = ok[k] ? l[a] : -INFINITY;
             if (ok[k]) {
                 float v = lv[k];
@@ -111,6 +115,42 @@ __global__ void __launch_bounds__(128) k_categorical(const float* __restrict__ l
             if (log_prob) log_prob[row] = la - mx - logf(se);
         }
     }
+}
+
+// ---- live-env compaction by acting team -- src/evaluation.py:124-151 ---------------------------
+// The reference's vmapped loop runs BOTH teams' nets on every env every iteration and selects by
+// `current_player < 2`, and keeps stepping finished envs until the slowest auction ends.  Here the envs still playing
+// are listed per acting team (players 0/1 = team 1) so each net runs on exactly the rows it decides.  One block =
+// 1024 consecutive envs: ballot + popc give every env its slot inside the block, one atomicAdd per block and team
+// reserves the block's range (rows ascend within a block; block order is the order of arrival -- the consumers are
+// row-order independent).
+__global__ void __launch_bounds__(1024) k_team_rows(const int8_t* __restrict__ player, const uint8_t* __restrict__ done,
+                                                    int32_t* __restrict__ rows1, int32_t* __restrict__ rows2,
+                                                    int32_t* __restrict__ counts, int64_t n) {
+    __shared__ int warp_cnt[2][32];
+    __shared__ int base[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const bool live = i < n && (done == nullptr || done[i] == 0);
+    const bool t1 = live && player[i] < 2, t2 = live && !t1;
+    const unsigned b1 = __ballot_sync(0xffffffffu, t1), b2 = __ballot_sync(0xffffffffu, t2);
+    if (lane == 0) { warp_cnt[0][warp] = __popc(b1); warp_cnt[1][warp] = __popc(b2); }
+    __syncthreads();
+    if (warp < 2) {  // exclusive scan of the 32 warp counts of team `warp`
+        const int c = warp_cnt[warp][lane];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        warp_cnt[warp][lane] = incl - c;
+        if (lane == 31) base[warp] = incl > 0 ? atomicAdd(&counts[warp], incl) : 0;
+    }
+    __syncthreads();
+    const unsigned below = (1u << lane) - 1u;
+    if (t1) rows1[base[0] + warp_cnt[0][warp] + __popc(b1 & below)] = (int32_t)i;
+    if (t2) rows2[base[1] + warp_cnt[1][warp] + __popc(b2 & below)] = (int32_t)i;
 }
 
 // ---- _imp_reward -- src/duplicate.py:15-70 ----------------------------------------------------
@@ -162,10 +202,10 @@ __global__ void __launch_bounds__(256) k_gather_reward(const float* __restrict__
 
 
 int32_t launch_categorical(cudaStream_t stream, const float* logits, const unsigned char* mask, int32_t* action, float* log_prob,
-                           int64_t n, int sample, uint64_t seed, int64_t env_offset, uint32_t step) {
+                           int64_t n, int sample, uint64_t seed, int64_t env_offset, uint32_t step, const int32_t* row_index, float* logits_by_env) {
     unsigned grid = (unsigned)((n + 3) / 4);  // one warp per env row
     if (grid > 148u * 16u) grid = 148u * 16u;
-    k_categorical<<<grid, 128, 0, stream>>>(logits, mask, action, log_prob, n, sample, seed, env_offset, step);
+    k_categorical<<<grid, 128, 0, stream>>>(logits, mask, action, log_prob, n, sample, seed, env_offset, step, row_index, logits_by_env);
     return check_launch("brl_categorical");
 }
 
@@ -202,7 +242,24 @@ int32_t brl_categorical(brl_stream_t stream, void** b, const void* opaque, size_
     if (p->n_envs == 0) return BRL_OK;
     return launch_categorical((cudaStream_t)stream, static_cast<const float*>(b[0]), static_cast<const uint8_t*>(b[1]),
                               static_cast<int32_t*>(b[2]), static_cast<float*>(b[3]), p->n_envs,
-                              (p->flags & BRL_F_SAMPLE) ? 1 : 0, p->seed, p->env_offset, p->step);
+                              (p->flags & BRL_F_SAMPLE) ? 1 : 0, p->seed, p->env_offset, p->step, nullptr);
+}
+
+int32_t brl_team_rows(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "current_player");
+    BRL_REQUIRE(b[2], "rows_team1");
+    BRL_REQUIRE(b[3], "rows_team2");
+    BRL_REQUIRE(b[4], "counts");
+    if (cudaMemsetAsync(b[4], 0, 2 * sizeof(int32_t), (cudaStream_t)stream) != cudaSuccess) return check_launch("brl_team_rows");
+    if (p->n_envs == 0) return BRL_OK;
+    unsigned grid = (unsigned)((p->n_envs + 1023) / 1024);
+    k_team_rows<<<grid, 1024, 0, (cudaStream_t)stream>>>(static_cast<const int8_t*>(b[0]), static_cast<const uint8_t*>(b[1]),
+                                                         static_cast<int32_t*>(b[2]), static_cast<int32_t*>(b[3]),
+                                                         static_cast<int32_t*>(b[4]), p->n_envs);
+    return check_launch("brl_team_rows");
 }
 
 int32_t brl_imp_reward(brl_stream_t stream, void** b, const void* opaque, size_t len) {

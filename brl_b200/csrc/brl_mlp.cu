@@ -104,6 +104,7 @@ struct ActArgs {
     int64_t env_offset;
     uint32_t step;
     int sample;
+    const int32_t* row_index;  // [n] or NULL: row r of the batch is env row_index[r] (mask / action / log_prob / value / RNG by env)
 };
 
 __device__ __forceinline__ void epilogue_head_act_row(uint32_t t_row, const float* __restrict__ bias, bool row_ok, int64_t row,
@@ -118,6 +119,7 @@ __device__ __forceinline__ void epilogue_head_act_row(uint32_t t_row, const floa
 #pragma unroll
     for (int k = 0; k < 7; ++k) l[32 + k] = __uint_as_float(r1[k]) + __ldg(bias + 32 + k);
     l[39] = 0.0f;
+    if (act.row_index) row = act.row_index[row];  // a listed batch: every per-env array below is addressed by env
     if (logits) {
         float2* pl = reinterpret_cast<float2*>(logits + row * 38);
 #pragma unroll
@@ -794,6 +796,15 @@ static int32_t launch_fused(cudaStream_t s, const void* obs, const unsigned char
     return BRL_OK;
 }
 
+__global__ void __launch_bounds__(256) k_gather_obs_rows(const uint4* __restrict__ src, const int32_t* __restrict__ index,
+                                                         uint4* __restrict__ dst, int64_t n, int w) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * w) return;
+    const int64_t r = i / w;
+    const int c = (int)(i - r * w);
+    dst[i] = src[(int64_t)index[r] * w + c];
+}
+
 }  // namespace brl
 
 using namespace brl;
@@ -865,7 +876,7 @@ static int32_t mlp_forward_impl(const char* who, cudaStream_t s, const BrlParams
         return check_launch(who);
     }
     // per-layer launches.  The head reads buffer 1, so buffer 0 is free to hold logits / value the caller did not ask for.
-    float* lg = logits ? logits : reinterpret_cast<float*>(buf_hi[0]);
+    float* lg = (logits && !act.row_index) ? logits : reinterpret_cast<float*>(buf_hi[0]);  // listed batch: compact here, scattered below
     float* vl = value ? value : reinterpret_cast<float*>(buf_lo[0]);
     const void* in_hi = obs;
     const void* in_lo = nullptr;
@@ -911,7 +922,9 @@ static int32_t mlp_forward_impl(const char* who, cudaStream_t s, const BrlParams
     }
     rc = check_launch(who);
     if (rc != BRL_OK || act.action == nullptr) return rc;
-    return launch_categorical(s, lg, act.mask, act.action, act.log_prob, M, act.sample, act.seed, act.env_offset, act.step);
+    if (act.row_index && value != nullptr) return fail(BRL_E_OPAQUE, "%s: a row-indexed batch below the fused-launch size has no value output", who);
+    return launch_categorical(s, lg, act.mask, act.action, act.log_prob, M, act.sample, act.seed, act.env_offset, act.step, act.row_index,
+                              act.row_index ? logits : nullptr);
 }
 
 int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_t len) {
@@ -926,6 +939,47 @@ int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_
     if (p->n_envs == 0) return BRL_OK;
     return mlp_forward_impl("brl_mlp_forward", (cudaStream_t)stream, p, b[0], static_cast<const unsigned char*>(b[1]),
                             static_cast<__nv_bfloat16*>(b[2]), static_cast<float*>(b[3]), static_cast<float*>(b[4]), ActArgs{});
+}
+
+int64_t brl_mlp_rows_scratch_bytes(int64_t n_rows) {  // brl_mlp_scratch_bytes + the gathered bf16 observation rows
+    return brl_mlp_scratch_bytes(n_rows) + n_rows * (int64_t)kObsDimM * 2;
+}
+
+// `team1_forward_pass.apply` + masked Categorical on the LISTED envs only (src/evaluation.py:124-151 without running
+// either net on envs it does not decide): gather the rows' observations (one 960-byte bf16 row per thread group), run
+// the forward on the compact batch, and let the head epilogue read mask[env] and write action[env] / log_prob[env].
+int32_t brl_policy_act_rows(brl_stream_t stream, void** b, const void* opaque, size_t len) {
+    int32_t rc;
+    const BrlParams* p = get_params(opaque, len, &rc);
+    if (!p) return rc;
+    BRL_REQUIRE(b[0], "obs_bf16");
+    BRL_REQUIRE(b[1], "packed");
+    BRL_REQUIRE(b[2], "scratch");
+    BRL_REQUIRE(b[4], "action");
+    BRL_REQUIRE(b[5], "row_index");
+    if ((reinterpret_cast<uintptr_t>(b[0]) | reinterpret_cast<uintptr_t>(b[2])) & 15u)
+        return fail(BRL_E_BUFFER, "brl_policy_act_rows: obs / scratch must be 16-byte aligned");
+    if (b[3] != nullptr && (reinterpret_cast<uintptr_t>(b[3]) & 1u)) return fail(BRL_E_BUFFER, "brl_policy_act_rows: mask is misaligned");
+    if (b[7] != nullptr && (reinterpret_cast<uintptr_t>(b[7]) & 7u)) return fail(BRL_E_BUFFER, "brl_policy_act_rows: logits is misaligned");
+    if (p->n_envs == 0) return BRL_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = p->n_envs;
+    unsigned char* scratch = static_cast<unsigned char*>(b[2]);
+    uint4* gathered = reinterpret_cast<uint4*>(scratch + brl_mlp_scratch_bytes(n));
+    const int w = kObsDimM * 2 / 16;  // uint4 per bf16 observation row
+    k_gather_obs_rows<<<(unsigned)((n * w + 255) / 256), 256, 0, s>>>(static_cast<const uint4*>(b[0]), static_cast<const int32_t*>(b[5]),
+                                                                     gathered, n, w);
+    ActArgs act{};
+    act.mask = static_cast<const uint8_t*>(b[3]);
+    act.action = static_cast<int32_t*>(b[4]);
+    act.log_prob = static_cast<float*>(b[6]);
+    act.seed = p->seed;
+    act.env_offset = p->env_offset;
+    act.step = p->step;
+    act.sample = (p->flags & BRL_F_SAMPLE) ? 1 : 0;
+    act.row_index = static_cast<const int32_t*>(b[5]);
+    return mlp_forward_impl("brl_policy_act_rows", s, p, gathered, static_cast<const unsigned char*>(b[1]),
+                            reinterpret_cast<__nv_bfloat16*>(scratch), static_cast<float*>(b[7]), nullptr, act);
 }
 
 int32_t brl_policy_act(brl_stream_t stream, void** b, const void* opaque, size_t len) {

@@ -20,6 +20,7 @@
 // umma_desc_mn_sw128), so the same kernel serves it too.  Bias gradients are column sums of the dz's.
 #include "common.h"
 #include "mlp_device.cuh"
+#include "ppo_gram.cuh"
 
 namespace brl {
 
@@ -235,6 +236,8 @@ struct BiasArgs {
     double* sumsq;         // += sum of squares of the bias gradients, or NULL
     int64_t B;
     FlatLayout F;
+    GramArgs gram;         // deferred spectral-norm statistic: its serial tail runs in one spare block (n_gram partials; 0 = none)
+    int n_gram;
 };
 __device__ __forceinline__ void bias_sumsq(const BiasArgs& a, float v) {  // called by whole warps
     if (a.sumsq == nullptr) return;
@@ -243,11 +246,21 @@ __device__ __forceinline__ void bias_sumsq(const BiasArgs& a, float v) {  // cal
     if ((threadIdx.x & 31) == 0) atomicAdd(a.sumsq, (double)v);
 }
 __global__ void __launch_bounds__(1024) k_bias_grad(const __grid_constant__ BiasArgs a) {
-    __shared__ float red[32][65];
+    // a block either sums bias columns (red) or runs the Gram tail (GramSmem): one shared buffer for both
+    constexpr size_t kSmemBytes = sizeof(GramSmem) > sizeof(float) * 32 * 65 ? sizeof(GramSmem) : sizeof(float) * 32 * 65;
+    __shared__ __align__(16) unsigned char smem_raw[kSmemBytes];
+    float (*red)[65] = reinterpret_cast<float (*)[65]>(smem_raw);
     pdl_trigger();
     pdl_wait();
     const int tid = threadIdx.x, rg = tid >> 5, cp = tid & 31;  // 32 row groups x 32 column pairs
     const int blocks_per_layer = kHidden / 64;
+    if ((int)blockIdx.x > 4 * blocks_per_layer) {
+        // one spare block (the bias sums occupy 65 of the 148 SMs): sum + eigen-solve of the illegal-probability Gram matrix
+        // for the logged illegal_action_loss (ppo_gram.cuh), deferred to here when its coefficient is 0 so that the serial
+        // tail runs beside the bias sums instead of between the loss head and the backward GEMMs
+        gram_tail(a.gram, a.n_gram, *reinterpret_cast<GramSmem*>(smem_raw));
+        return;
+    }
     if ((int)blockIdx.x < 4 * blocks_per_layer) {
         const int l = blockIdx.x / blocks_per_layer, c0 = (blockIdx.x % blocks_per_layer) * 64;
         const __nv_bfloat162* hi = reinterpret_cast<const __nv_bfloat162*>(a.hi[l] + c0) + cp;
@@ -891,13 +904,14 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
     if (rc != BRL_OK) return rc;
     if ((rc = check_launch("brl_ppo_grad (forward)")) != BRL_OK) return rc;
     // 3. loss head + its backward (src/update.py:97-162)
-    {
-        void* lb[13] = {sc + S.logits, sc + S.value, b[3], b[4], b[5], b[6], b[7], b[8], b[9], sc + S.dlogits, sc + S.dvalue, b[11], b[12]};
-        BrlPpoParams lp = *p;
-        lp.flags &= (BRL_PPO_VALUE_CLIPPING | BRL_PPO_REWARD_SCALING | BRL_PPO_UNMASKED_POLICY);
-        lp.reserved = 0;
-        if ((rc = launch_ppo_loss(s, lb, &lp, sc + S.dz5_hi, sc + S.dz5_lo, /*acc_zeroed=*/true)) != BRL_OK) return rc;
-    }
+    void* loss_buffers[13] = {sc + S.logits, sc + S.value, b[3], b[4], b[5], b[6], b[7], b[8], b[9], sc + S.dlogits, sc + S.dvalue, b[11], b[12]};
+    BrlPpoParams loss_params = *p;
+    loss_params.flags &= (BRL_PPO_VALUE_CLIPPING | BRL_PPO_REWARD_SCALING | BRL_PPO_UNMASKED_POLICY | BRL_PPO_ILLEGAL_STAT);
+    loss_params.reserved = 0;
+    const bool defer_illegal = p->illegal_l2_coef == 0.0f;  // only the logged statistic needs the spectral norm: off the critical path
+    const bool skip_illegal = defer_illegal && !(p->flags & BRL_PPO_ILLEGAL_STAT);  // statistic not asked for: stats[6] = NaN
+    if ((rc = launch_ppo_loss(s, loss_buffers, &loss_params, sc + S.dz5_hi, sc + S.dz5_lo, /*acc_zeroed=*/true, defer_illegal)) != BRL_OK)
+        return rc;
     // 4. backward GEMMs
     rc = wide_bwd ? launch_fused_ops<128>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr)
                   : launch_fused_ops<64>(s, bwd, nb, nmb, ready + (size_t)kMaxOps * (nmb + 1), trace ? trace + (size_t)kTraceTiles * 8 : nullptr);
@@ -909,7 +923,9 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         a.dlogits = reinterpret_cast<const float*>(sc + S.dlogits);
         a.dvalue = reinterpret_cast<const float*>(sc + S.dvalue);
         a.grads = grads; a.sumsq = grad_sumsq; a.B = B; a.F = F;
-        launch_pdl(k_bias_grad, dim3(4 * (kHidden / 64) + 1), dim3(1024), 0, s, a);
+        a.n_gram = (defer_illegal && !skip_illegal) ? gram_blocks(B, 1024) : 0;
+        if (a.n_gram) a.gram = gram_args(loss_buffers, &loss_params, static_cast<float*>(b[11]) + 6);
+        launch_pdl(k_bias_grad, dim3(4 * (kHidden / 64) + 1 + (a.n_gram ? 1 : 0)), dim3(1024), 0, s, a);
     }
     return check_launch("brl_ppo_grad");
 }

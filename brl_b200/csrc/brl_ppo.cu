@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "common.h"
+#include "ppo_gram.cuh"
 
 namespace brl {
 
@@ -25,7 +26,11 @@ struct PpoArgs {
     float* dlogits;            // [B, 38]
     float* dvalue;             // [B]
     float* stats;              // [8]
-    double* acc;               // [16] scratch accumulators
+    double* acc;               // [16] scratch accumulators; the rest of the BRL_PPO_SCRATCH_BYTES scratch follows:
+    double* spec;              // [40] {sigma_max, v[38], 0} of the illegal-probability matrix (k_ppo_illegal_gram)
+    float* gram_part;          // [kGramBlocks][38 * 38] per-block partial Gram matrices
+    int defer_illegal;         // the statistic is formed later (a spare block of k_bias_grad); only valid with ill_coef == 0
+    int skip_illegal;          // ... or not at all (BRL_PPO_ILLEGAL_STAT clear): stats[6] = NaN
     // optional (brl_ppo_grad): d loss / d (logits, value) also as bf16 hi / lo rows [B, 64] (38 logits, value, zeros),
     // the A operand of the head's input-gradient GEMM and the B operand of its weight-gradient GEMM
     unsigned short* dz_hi;
@@ -36,7 +41,8 @@ struct PpoArgs {
 };
 
 // acc slots
-enum { kAccAdv = 0, kAccAdv2, kAccIll, kAccActor, kAccValue, kAccEnt, kAccKl, kAccClip, kAccTicket = 15 };
+enum { kAccAdv = 0, kAccAdv2, kAccIll, kAccActor, kAccValue, kAccEnt, kAccKl, kAccClip, kAccGramTicket = 13, kAccTicket = 15 };
+static_assert(128 + 40 * 8 <= 512 && 512 + kGramBlocks * kGramN * 4 <= BRL_PPO_SCRATCH_BYTES, "scratch layout");
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -75,32 +81,41 @@ struct Row {
     }
 };
 
-// sum over the minibatch of: advantages, advantages^2 (src/update.py:35-36) and the squared
-// unmasked probability mass on illegal actions (src/update.py:138-142)
+// sum over the minibatch of advantages and advantages^2 (reward scaling, src/update.py:35-36)
 __global__ void __launch_bounds__(128) k_ppo_prepass(const PpoArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    double s_adv = 0.0, s_adv2 = 0.0, s_ill = 0.0;
-    for (int64_t b = warp; b < a.B; b += nw) {
-        const int64_t src = a.index ? a.index[b] : b;
-        Row r;
-        r.load(a, b, src, lane);
-        float q[2], lq[2];
-        r.softmax(r.in, q, lq);
-        float ill = (r.in[0] && !r.legal[0] ? q[0] * q[0] : 0.0f) + (r.in[1] && !r.legal[1] ? q[1] * q[1] : 0.0f);
-        ill = warp_sum(ill);
-        if (lane == 0) {
-            double g = (double)a.adv[src];
-            s_adv += g;
-            s_adv2 += g * g;
-            s_ill += (double)ill;
-        }
+    double s_adv = 0.0, s_adv2 = 0.0;
+    for (int64_t b = warp * 32 + lane; b < a.B; b += nw * 32) {
+        const double g = (double)a.adv[a.index ? a.index[b] : b];
+        s_adv += g;
+        s_adv2 += g * g;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_adv += __shfl_xor_sync(0xffffffffu, s_adv, o);
+        s_adv2 += __shfl_xor_sync(0xffffffffu, s_adv2, o);
     }
     if (lane == 0) {
         atomicAdd(&a.acc[kAccAdv], s_adv);
         atomicAdd(&a.acc[kAccAdv2], s_adv2);
-        atomicAdd(&a.acc[kAccIll], s_ill);
     }
+}
+
+// illegal_action_loss as the spectral norm (ppo_gram.cuh): partials + tail before the loss kernel, which then has sigma_1 / v_1
+// for the statistic and the gradient
+__global__ void __launch_bounds__(1024) k_ppo_illegal_gram(const GramArgs g) {
+    __shared__ GramSmem sm;
+    pdl_trigger();
+    pdl_wait();
+    gram_block<1024>(g, (int)blockIdx.x, (int)gridDim.x, sm);
+}
+// the partial Gram matrices only (deferred statistic: the tail runs in a spare block of k_bias_grad)
+__global__ void __launch_bounds__(1024) k_ppo_gram_partial(const GramArgs g) {
+    __shared__ float X[64 * kGramPad];
+    pdl_trigger();
+    pdl_wait();
+    gram_partial<1024>(g, (int)blockIdx.x, (int)gridDim.x, X);
 }
 
 __device__ __forceinline__ void split_store(const PpoArgs& a, int64_t idx, float v) {
@@ -115,14 +130,15 @@ __device__ __forceinline__ void ppo_finalize(const PpoArgs& a) {
     const volatile double* acc = a.acc;
     const double B = (double)a.B;
     const float value_loss = (float)(acc[kAccValue] / B), loss_actor = (float)(acc[kAccActor] / B);
-    const float entropy = (float)(acc[kAccEnt] / B), ill = 0.5f * (float)sqrt(acc[kAccIll]);
+    const float entropy = (float)(acc[kAccEnt] / B), ill = a.defer_illegal ? 0.0f : 0.5f * (float)((const volatile double*)a.spec)[0];
     a.stats[0] = loss_actor + a.vf_coef * value_loss - a.ent_coef * entropy + a.ill_coef * ill;
     a.stats[1] = value_loss;
     a.stats[2] = loss_actor;
     a.stats[3] = entropy;
     a.stats[4] = (float)(acc[kAccKl] / B);
     a.stats[5] = (float)(acc[kAccClip] / B);
-    a.stats[6] = ill;
+    if (a.skip_illegal) a.stats[6] = __int_as_float(0x7fc00000);  // NaN: not computed, never a stale or wrong number
+    else if (!a.defer_illegal) a.stats[6] = ill;
     a.stats[7] = 0.0f;
 }
 
@@ -132,15 +148,22 @@ __global__ void __launch_bounds__(128) k_ppo_loss(const PpoArgs a, int have_prep
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float invB = 1.0f / (float)a.B;
-    float g_mean = 0.0f, g_istd = 1.0f, ill_norm = 0.0f;
+    float g_mean = 0.0f, g_istd = 1.0f;
     if (have_prepass) {
         double m = a.acc[kAccAdv] / (double)a.B;
         double var = a.acc[kAccAdv2] / (double)a.B - m * m;
         g_mean = (float)m;
         g_istd = 1.0f / ((float)sqrt(var > 0.0 ? var : 0.0) + 1e-8f);
-        ill_norm = (float)sqrt(a.acc[kAccIll]);
     }
-    double s_actor = 0.0, s_value = 0.0, s_ent = 0.0, s_kl = 0.0, s_clip = 0.0, s_ill = 0.0;
+    // spectral norm of the illegal-probability matrix and its top right singular vector (k_ppo_illegal_gram)
+    const float sigma = a.defer_illegal ? 0.0f : (float)a.spec[0];
+    const bool ill_grad = a.ill_coef != 0.0f && sigma > 0.0f;
+    float v1[2] = {0.0f, 0.0f};
+    if (ill_grad) {
+        v1[0] = (float)a.spec[1 + lane];
+        v1[1] = lane < kA - 32 ? (float)a.spec[33 + lane] : 0.0f;
+    }
+    double s_actor = 0.0, s_value = 0.0, s_ent = 0.0, s_kl = 0.0, s_clip = 0.0;
     for (int64_t b = warp; b < a.B; b += nw) {
         const int64_t src = a.index ? a.index[b] : b;
         Row r;
@@ -168,9 +191,10 @@ __global__ void __launch_bounds__(128) k_ppo_loss(const PpoArgs a, int have_prep
         // entropy of the masked distribution (src/update.py:136-137)
         float ent = -((r.legal[0] && p[0] > 0.0f ? p[0] * logp[0] : 0.0f) + (r.legal[1] && p[1] > 0.0f ? p[1] * logp[1] : 0.0f));
         ent = warp_sum(ent);
-        // illegal-action loss (src/update.py:138-142): squared unmasked mass on illegal actions
+        // illegal-action loss (src/update.py:138-142): x = unmasked probabilities of the illegal actions, t = x . v_1;
+        // d (coef * sigma_1 / 2) / d logits_j = coef / 2 * (t / sigma_1) * (x_j v_j - q_j t)
         float qi[2] = {r.in[0] && !r.legal[0] ? q[0] : 0.0f, r.in[1] && !r.legal[1] ? q[1] : 0.0f};
-        const float s_i = warp_sum(qi[0] * qi[0] + qi[1] * qi[1]);
+        const float t_i = ill_grad ? warp_sum(qi[0] * v1[0] + qi[1] * v1[1]) : 0.0f;
         // d total / d logits
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -178,7 +202,7 @@ __global__ void __launch_bounds__(128) k_ppo_loss(const PpoArgs a, int have_prep
             if (!r.in[k]) continue;
             float d = c_ratio * ((j == act ? 1.0f : 0.0f) - pol_p[k]);
             if (r.legal[k] && p[k] > 0.0f) d += a.ent_coef * invB * p[k] * (logp[k] + ent);  // -ent_coef * dH/dl
-            if (a.ill_coef != 0.0f && ill_norm > 0.0f) d += a.ill_coef * (qi[k] * qi[k] - q[k] * s_i) / (2.0f * ill_norm);
+            if (ill_grad) d += a.ill_coef * 0.5f * (t_i / sigma) * (qi[k] * v1[k] - q[k] * t_i);
             a.dlogits[b * kA + j] = d;
             if (a.dz_hi) split_store(a, b * 64 + j, d);
         }
@@ -206,23 +230,22 @@ __global__ void __launch_bounds__(128) k_ppo_loss(const PpoArgs a, int have_prep
             s_ent += (double)ent;
             s_kl += (double)((ratio - 1.0f) - logratio);
             s_clip += fabsf(ratio - 1.0f) > a.clip_eps ? 1.0 : 0.0;
-            s_ill += (double)s_i;
         }
     }
     // block-level sums first (one set of same-address f64 atomics per block, not per warp), then the last block to
     // arrive (ticket in acc[kAccTicket]) forms the statistics: no separate finalize launch
-    __shared__ double part[4][6];
+    __shared__ double part[4][5];
     __shared__ bool last_block;
     const int w = threadIdx.x >> 5;
     if (lane == 0) {
-        part[w][0] = s_actor; part[w][1] = s_value; part[w][2] = s_ent; part[w][3] = s_kl; part[w][4] = s_clip; part[w][5] = s_ill;
+        part[w][0] = s_actor; part[w][1] = s_value; part[w][2] = s_ent; part[w][3] = s_kl; part[w][4] = s_clip;
     }
     __syncthreads();
-    if (threadIdx.x < 6) {
+    if (threadIdx.x < 5) {
         const int k = threadIdx.x;
         const double s = part[0][k] + part[1][k] + part[2][k] + part[3][k];
-        const int slot = k == 0 ? kAccActor : k == 1 ? kAccValue : k == 2 ? kAccEnt : k == 3 ? kAccKl : k == 4 ? kAccClip : kAccIll;
-        if (k < 5 || !have_prepass) atomicAdd(&a.acc[slot], s);
+        const int slot = k == 0 ? kAccActor : k == 1 ? kAccValue : k == 2 ? kAccEnt : k == 3 ? kAccKl : kAccClip;
+        atomicAdd(&a.acc[slot], s);
     }
     __threadfence();
     __syncthreads();
@@ -331,12 +354,33 @@ extern "C" {
 int32_t brl_ppo_loss(brl_stream_t stream, void** b, const void* opaque, size_t len) {
     if (opaque == nullptr || len != sizeof(BrlPpoParams))
         return fail(BRL_E_OPAQUE, "brl_ppo_loss: opaque must be one BrlPpoParams (%zu bytes), got %zu", sizeof(BrlPpoParams), len);
-    return brl::launch_ppo_loss((cudaStream_t)stream, b, static_cast<const BrlPpoParams*>(opaque), nullptr, nullptr, false);
+    return brl::launch_ppo_loss((cudaStream_t)stream, b, static_cast<const BrlPpoParams*>(opaque), nullptr, nullptr, false, false);
 }
 
 }  // extern "C"
 
-int32_t brl::launch_ppo_loss(cudaStream_t stream, void** b, const BrlPpoParams* p, void* dz_hi, void* dz_lo, bool acc_zeroed) {
+// blocks of `threads` threads that form the partial Gram matrices (2 samples per warp and chunk)
+int brl::gram_blocks(int64_t B, int threads) {
+    const int64_t chunk = 2 * (threads / 32), want = (B + chunk - 1) / chunk;
+    return (int)(want < kGramBlocks ? want : kGramBlocks);
+}
+
+brl::GramArgs brl::gram_args(void** b, const BrlPpoParams* p, float* stat) {
+    GramArgs g{};
+    g.logits = static_cast<const float*>(b[0]);
+    g.index = static_cast<const int32_t*>(b[2]);
+    g.mask = static_cast<const uint8_t*>(b[3]);
+    g.B = p->batch;
+    g.ticket = reinterpret_cast<unsigned long long*>(static_cast<double*>(b[12]) + kAccGramTicket);
+    g.spec = reinterpret_cast<double*>(static_cast<unsigned char*>(b[12]) + 128);
+    g.part = reinterpret_cast<float*>(static_cast<unsigned char*>(b[12]) + 512);
+    g.stat = stat;
+    g.tol = stat ? 3e-4f : 1e-6f;  // statistic only (deferred) vs v_1 feeding the loss gradient
+    return g;
+}
+
+int32_t brl::launch_ppo_loss(cudaStream_t stream, void** b, const BrlPpoParams* p, void* dz_hi, void* dz_lo, bool acc_zeroed,
+                             bool defer_illegal) {
     if (p->batch <= 0) return fail(BRL_E_OPAQUE, "brl_ppo_loss: batch must be > 0");
     static const char* names[] = {"logits", "value", "index", "mask", "action", "old_log_prob", "old_value", "advantages",
                                   "targets", "dlogits", "dvalue", "stats", "scratch"};
@@ -356,6 +400,9 @@ int32_t brl::launch_ppo_loss(cudaStream_t stream, void** b, const BrlPpoParams* 
     a.dvalue = static_cast<float*>(b[10]);
     a.stats = static_cast<float*>(b[11]);
     a.acc = static_cast<double*>(b[12]);
+    if (reinterpret_cast<uintptr_t>(b[12]) & 15u) return fail(BRL_E_BUFFER, "brl_ppo_loss: scratch is not 16-byte aligned");
+    a.spec = reinterpret_cast<double*>(static_cast<unsigned char*>(b[12]) + 128);
+    a.gram_part = reinterpret_cast<float*>(static_cast<unsigned char*>(b[12]) + 512);
     a.dz_hi = static_cast<unsigned short*>(dz_hi);
     a.dz_lo = static_cast<unsigned short*>(dz_lo);
     a.B = p->batch;
@@ -370,8 +417,17 @@ int32_t brl::launch_ppo_loss(cudaStream_t stream, void** b, const BrlPpoParams* 
     if (!acc_zeroed && cudaMemsetAsync(a.acc, 0, 16 * sizeof(double), s) != cudaSuccess) return check_launch("brl_ppo_loss");
     unsigned grid = (unsigned)((a.B + 3) / 4);
     if (grid > 148u * 8u) grid = 148u * 8u;
-    const int prepass = a.reward_scaling || a.ill_coef != 0.0f;
-    if (prepass) k_ppo_prepass<<<grid, 128, 0, s>>>(a);
+    const int prepass = a.reward_scaling;
+    if (prepass) k_ppo_prepass<<<grid > 32u ? 32u : grid, 128, 0, s>>>(a);
+    a.defer_illegal = defer_illegal && a.ill_coef == 0.0f;
+    a.skip_illegal = a.defer_illegal && !(p->flags & BRL_PPO_ILLEGAL_STAT);
+    if (!a.skip_illegal) {
+        const GramArgs g = brl::gram_args(b, p, nullptr);
+        const unsigned gram_blocks = (unsigned)brl::gram_blocks(a.B, 1024);
+        auto kern = a.defer_illegal ? k_ppo_gram_partial : k_ppo_illegal_gram;
+        if (prepass) kern<<<gram_blocks, 1024, 0, s>>>(g);  // a plain launch may not be followed by a PDL one that skips it
+        else launch_pdl(kern, dim3(gram_blocks), dim3(1024), 0, s, g);
+    }
     launch_pdl(k_ppo_loss, dim3(grid), dim3(128), 0, s, a, prepass);
     return check_launch("brl_ppo_loss");
 }

@@ -40,11 +40,19 @@ inline const BrlParams* get_params(const void* opaque, size_t opaque_len, int32_
 
 // masked categorical over f32 logits[n,38] (brl_algo.cu); shared by brl_categorical and the unfused brl_policy_act path
 int32_t launch_categorical(cudaStream_t stream, const float* logits, const unsigned char* mask, int32_t* action, float* log_prob,
-                           int64_t n, int sample, uint64_t seed, int64_t env_offset, uint32_t step);
+                           int64_t n, int sample, uint64_t seed, int64_t env_offset, uint32_t step, const int32_t* row_index = nullptr,
+                           float* logits_by_env = nullptr);
 
 // brl_ppo_loss's body (brl_ppo.cu), optionally also writing d loss / d (logits, value) as bf16 hi / lo rows [B, 64] for brl_ppo_grad
 // acc_zeroed: the caller already cleared the f64[16] scratch on this stream (keeps a memset out of a PDL kernel chain)
-int32_t launch_ppo_loss(cudaStream_t stream, void** buffers, const BrlPpoParams* p, void* dz_hi, void* dz_lo, bool acc_zeroed);
+// defer_illegal (honoured only when illegal_l2_coef == 0): only the partial Gram matrices are formed before the loss kernel;
+// the caller runs gram_tail() itself later (brl_ppo_grad: a spare block of k_bias_grad) with gram_args(buffers, p, &stats[6])
+// and gram_blocks(batch, 1024) partials
+int32_t launch_ppo_loss(cudaStream_t stream, void** buffers, const BrlPpoParams* p, void* dz_hi, void* dz_lo, bool acc_zeroed,
+                        bool defer_illegal);
+struct GramArgs;
+GramArgs gram_args(void** loss_buffers, const BrlPpoParams* p, float* stat);
+int gram_blocks(int64_t batch, int threads);
 
 // Programmatic dependent launch for the short kernels of a dependent chain (the PPO optimizer step): the kernel may be
 // scheduled while its predecessor in the stream drains; it must execute pdl_wait() before touching global memory and

@@ -1,77 +1,147 @@
 // xla_ffi_shim.cc -- adapters that expose the C-ABI ops (include/brl_b200.h) to a jitted
 // JAX program, so that brl's `ppo.py` / `eval.py` loops can call the CUDA env as a drop-in
-// for `pgx.bridge_bidding` (src/roll_out.py:51, src/duplicate.py:149, src/gae.py:32-38).
+// for `pgx.bridge_bidding` (src/roll_out.py:51, src/duplicate.py:134,149, src/gae.py:32-38).
 //
-// STATUS: this image has neither jax/jaxlib nor the XLA FFI headers, so this file is
-// compiled ONLY when `xla/ffi/api/ffi.h` is on the include path (build.py probes
-// `jaxlib.include` / `jax.ffi.include_dir()`); it is NOT built or exercised in this
-// environment -- INTEGRATION.md says so.  The product path here is driven through the
-// same symbols from Python/ctypes with torch-owned buffers.
-//
-// Two conventions, both thin because the core ABI already has the custom-call shape:
-//   (1) legacy GPU custom call, API_VERSION_STATUS_RETURNING (what jax 0.4.23 -- the
-//       version brl pins, requirements.txt:25-26 -- offers):
-//         void f(cudaStream_t, void** buffers, const char* opaque, size_t len, XlaCustomCallStatus*)
-//       `buffers` = operands then results, exactly the order each op documents;
-//   (2) typed FFI (jax >= 0.4.31): XLA_FFI_DEFINE_HANDLER_SYMBOL over ffi::Buffer args.
+// ONE table (BRL_XLA_OPS) drives both XLA conventions.  Per op it holds a layout string with one character per
+// buffer of the op, in the op's documented order:
+//     i  input            -> an XLA operand
+//     o  output           -> an XLA result
+//     s  scratch          -> an XLA result nobody reads
+//     x  updated in place -> an XLA operand AND the result aliased to it (input_output_aliases /
+//                            operand_output_aliases); the adapter checks the two pointers are equal
+// XLA hands a custom call its operands first, then its results, each in declaration order; the adapter re-orders them
+// into the op's buffer list.  An op's optional (NULL-able) buffers are all present in its XLA form.
+//   (1) legacy GPU custom call, API_VERSION_STATUS_RETURNING (what jax 0.4.23 -- the version brl pins,
+//       requirements.txt:25-26 -- offers):
+//         void <op>_xla(cudaStream_t, void** buffers, const char* opaque, size_t len, XlaCustomCallStatus*)
+//       opaque = the bytes of one BrlParams (BrlPpoParams / BrlAdamParams for the update ops).  Always built; exercised by
+//       tests/test_cuda_xla.py through ctypes with exactly this signature.
+//   (2) typed FFI (jax >= 0.4.31): <op>_ffi = one generic handler over RemainingArgs / RemainingRets + a byte-span
+//       attribute "opaque", instantiated per op by the same table.  Compiled only when `xla/ffi/api/ffi.h` is on the
+//       include path (build.py probes jaxlib); this image has no jaxlib, so (2) has never been compiled here --
+//       INTEGRATION.md says so.
+// A failing op reports through XlaCustomCallStatusSetFailure, which XLA's runtime exports: the symbol is looked up with
+// dlsym(RTLD_DEFAULT) at call time (this library is not linked against XLA).  If the process has no such symbol the
+// failure cannot reach XLA; it is then counted (brl_xla_unreported_failures) and stays readable in brl_last_error().
 #if defined(__has_include)
 #if __has_include("xla/ffi/api/ffi.h")
 #define BRL_HAVE_XLA_FFI 1
 #endif
 #endif
 
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cstdio>
 #include <cstring>
 
 #include "../../include/brl_b200.h"
 
-// ---- (1) legacy custom calls: always compilable, no XLA headers needed ----------------
-// XlaCustomCallStatus is opaque; failure is reported through the symbol XLA provides.
-extern "C" {
-struct XlaCustomCallStatus_;
-typedef struct XlaCustomCallStatus_ XlaCustomCallStatus;
-#if defined(BRL_HAVE_XLA_FFI) || defined(BRL_LINK_XLA_STATUS)
-void XlaCustomCallStatusSetFailure(XlaCustomCallStatus*, const char*, size_t);
-#else
-static void XlaCustomCallStatusSetFailure(XlaCustomCallStatus*, const char*, size_t) {}
-#endif
+#define BRL_XLA_OPS(X) \
+    X(brl_make_keys, "o") \
+    X(brl_init, "iioooooo") \
+    X(brl_reset_fields, "iiiiiiioooooo") \
+    X(brl_step, "iiiooooooo") \
+    X(brl_duplicate_step, "iiixxxxxxxxxxxxoooooo") \
+    X(brl_duplicate_init, "iioooooo") \
+    X(brl_observe, "iiio") \
+    X(brl_legal_mask, "io") \
+    X(brl_rollout_random, "xiooooooxio") \
+    X(brl_imp_reward, "iio") \
+    X(brl_gae, "iiiioo") \
+    X(brl_categorical, "iioo") \
+    X(brl_match_stats, "ix") \
+    X(brl_state_fields, "iooooooooooo") \
+    X(brl_gather_reward, "iio") \
+    X(brl_team_rows, "iiooo") \
+    X(brl_mlp_pack, "iiiiiiiiiiiio") \
+    X(brl_obs_to_bf16, "io") \
+    X(brl_mlp_forward, "iisoo") \
+    X(brl_policy_act, "iisioooo") \
+    X(brl_policy_act_rows, "iisixixx") \
+    X(brl_ppo_loss, "iiiiiiiiiooos") \
+    X(brl_adam_clip, "xixxs") \
+    X(brl_adam_apply, "xixxi") \
+    X(brl_gather_rows, "iio") \
+    X(brl_eval_act_log, "iiiiiox") \
+    X(brl_eval_summary, "iiiiiiiiiiiiiiix") \
+    X(brl_mlp_pack_train, "io") \
+    X(brl_mlp_adam_step, "xixxix") \
+    X(brl_ppo_grad, "iisiiiiiiioos") \
+    /* end */
 
-#define BRL_LEGACY_CUSTOM_CALL(op)                                                              \
-    void op##_xla(brl_stream_t stream, void** buffers, const char* opaque, size_t opaque_len,   \
-                  XlaCustomCallStatus* status) {                                                \
-        if (op(stream, buffers, opaque, opaque_len) != BRL_OK) {                                \
-            const char* msg = brl_last_error();                                                 \
-            XlaCustomCallStatusSetFailure(status, msg, std::strlen(msg));                       \
-        }                                                                                       \
+namespace {
+constexpr int kMaxBuffers = 32;
+
+typedef void (*status_fn_t)(XlaCustomCallStatus_*, const char*, size_t);
+std::atomic<status_fn_t> g_status_fn{nullptr};
+std::atomic<long long> g_unreported{0};
+
+void report_failure(XlaCustomCallStatus_* status, const char* msg) {
+    status_fn_t fn = g_status_fn.load(std::memory_order_acquire);
+    if (fn == nullptr) {
+        fn = reinterpret_cast<status_fn_t>(dlsym(RTLD_DEFAULT, "XlaCustomCallStatusSetFailure"));
+        if (fn != nullptr) g_status_fn.store(fn, std::memory_order_release);
     }
+    if (fn != nullptr && status != nullptr) fn(status, msg, std::strlen(msg));
+    else g_unreported.fetch_add(1, std::memory_order_relaxed);
+}
 
-BRL_LEGACY_CUSTOM_CALL(brl_make_keys)
-BRL_LEGACY_CUSTOM_CALL(brl_init)
-BRL_LEGACY_CUSTOM_CALL(brl_reset_fields)
-BRL_LEGACY_CUSTOM_CALL(brl_step)
-BRL_LEGACY_CUSTOM_CALL(brl_duplicate_step)
-BRL_LEGACY_CUSTOM_CALL(brl_duplicate_init)
-BRL_LEGACY_CUSTOM_CALL(brl_observe)
-BRL_LEGACY_CUSTOM_CALL(brl_legal_mask)
-BRL_LEGACY_CUSTOM_CALL(brl_rollout_random)
-BRL_LEGACY_CUSTOM_CALL(brl_imp_reward)
-BRL_LEGACY_CUSTOM_CALL(brl_gae)
-BRL_LEGACY_CUSTOM_CALL(brl_categorical)
-BRL_LEGACY_CUSTOM_CALL(brl_match_stats)
-BRL_LEGACY_CUSTOM_CALL(brl_state_fields)
-BRL_LEGACY_CUSTOM_CALL(brl_gather_reward)
-BRL_LEGACY_CUSTOM_CALL(brl_mlp_pack)
-BRL_LEGACY_CUSTOM_CALL(brl_obs_to_bf16)
-BRL_LEGACY_CUSTOM_CALL(brl_mlp_forward)
-BRL_LEGACY_CUSTOM_CALL(brl_policy_act)
-BRL_LEGACY_CUSTOM_CALL(brl_ppo_loss)
-BRL_LEGACY_CUSTOM_CALL(brl_adam_clip)
-BRL_LEGACY_CUSTOM_CALL(brl_adam_apply)
-BRL_LEGACY_CUSTOM_CALL(brl_gather_rows)
-BRL_LEGACY_CUSTOM_CALL(brl_mlp_pack_train)
-BRL_LEGACY_CUSTOM_CALL(brl_mlp_adam_step)
-BRL_LEGACY_CUSTOM_CALL(brl_ppo_grad)
-BRL_LEGACY_CUSTOM_CALL(brl_eval_act_log)
-BRL_LEGACY_CUSTOM_CALL(brl_eval_summary)
+// XLA order (operands, then results) -> the op's buffer order.  Returns NULL on success, else a message.
+const char* reorder(const char* layout, void* const* xla, void** out, char* msg, size_t msg_len) {
+    int n_in = 0;
+    for (const char* c = layout; *c; ++c) n_in += (*c == 'i' || *c == 'x');
+    int in = 0, res = n_in, k = 0;
+    for (const char* c = layout; *c; ++c, ++k) {
+        if (k >= kMaxBuffers) return "layout too long";
+        if (*c == 'i') out[k] = xla[in++];
+        else if (*c == 'o' || *c == 's') out[k] = xla[res++];
+        else {  // 'x'
+            out[k] = xla[in++];
+            if (xla[res++] != out[k]) {
+                std::snprintf(msg, msg_len, "buffer %d is updated in place: alias the result to the operand (input_output_aliases)", k);
+                return msg;
+            }
+        }
+    }
+    for (; k < kMaxBuffers; ++k) out[k] = nullptr;
+    return nullptr;
+}
+
+void legacy_call(brl_op_fn op, const char* name, const char* layout, brl_stream_t stream, void** buffers, const char* opaque,
+                 size_t opaque_len, XlaCustomCallStatus_* status) {
+    void* b[kMaxBuffers];
+    char msg[160];
+    if (const char* err = reorder(layout, buffers, b, msg, sizeof(msg))) {
+        char full[224];
+        std::snprintf(full, sizeof(full), "%s_xla: %s", name, err);
+        report_failure(status, full);
+        return;
+    }
+    if (op(stream, b, opaque, opaque_len) != BRL_OK) report_failure(status, brl_last_error());
+}
+}  // namespace
+
+extern "C" {
+
+#define BRL_LEGACY_CUSTOM_CALL(op, layout)                                                                        \
+    void op##_xla(brl_stream_t stream, void** buffers, const char* opaque, size_t opaque_len,                     \
+                  struct XlaCustomCallStatus_* status) {                                                          \
+        legacy_call(op, #op, layout, stream, buffers, opaque, opaque_len, status); \
+    }
+BRL_XLA_OPS(BRL_LEGACY_CUSTOM_CALL)
+
+// layout string of an op ("brl_step" -> "iiiooooooo"), NULL for an unknown name: the registration code on the JAX side
+// derives operand / result order and the aliases from it
+const char* brl_xla_layout(const char* op_name) {
+#define BRL_LAYOUT_CASE(op, layout) \
+    if (std::strcmp(op_name, #op) == 0) return layout;
+    BRL_XLA_OPS(BRL_LAYOUT_CASE)
+    return nullptr;
+}
+
+long long brl_xla_unreported_failures(void) { return g_unreported.load(std::memory_order_relaxed); }
+
 }  // extern "C"
 
 // ---- (2) typed FFI handlers --------------------------------------------------------------
@@ -80,52 +150,31 @@ BRL_LEGACY_CUSTOM_CALL(brl_eval_summary)
 namespace ffi = xla::ffi;
 
 namespace {
-ffi::Error to_error(int32_t rc) {
-    return rc == BRL_OK ? ffi::Error::Success() : ffi::Error(ffi::ErrorCode::kInvalidArgument, brl_last_error());
-}
-
-BrlParams params(int64_t n, int64_t stride, int32_t n_deals, int32_t flags, uint64_t seed, uint32_t step,
-                 int32_t k_steps, int64_t env_offset) {
-    BrlParams p{};
-    p.n_envs = n; p.state_stride = stride; p.n_deals = n_deals; p.flags = flags; p.seed = seed; p.step = step;
-    p.k_steps = k_steps; p.env_offset = env_offset; p.illegal_penalty = -1.0f; p.illegal_bonus = 1.0f;
-    return p;
-}
-
-// env.step(state, action): state/outputs are natively batched, so jax.vmap folds into N
-// (ffi_call(..., vmap_method="broadcast_all") with the batch axis leading).
-ffi::Error StepImpl(cudaStream_t stream, ffi::AnyBuffer state, ffi::Buffer<ffi::S32> action, ffi::AnyBuffer table,
-                    ffi::Result<ffi::AnyBuffer> state_out, ffi::Result<ffi::AnyBuffer> obs,
-                    ffi::Result<ffi::AnyBuffer> mask, ffi::Result<ffi::AnyBuffer> rewards,
-                    ffi::Result<ffi::AnyBuffer> terminated, ffi::Result<ffi::AnyBuffer> current_player, int32_t flags) {
-    const int64_t n = action.element_count();
-    void* b[10] = {state.untyped_data(), action.untyped_data(), table.untyped_data(), state_out->untyped_data(),
-                   obs->untyped_data(), mask->untyped_data(), rewards->untyped_data(), terminated->untyped_data(),
-                   current_player->untyped_data(), nullptr};
-    BrlParams p = params(n, n, (int32_t)(table.element_count() / BRL_DEAL_ROW_BYTES), flags, 0, 0, 0, 0);
-    return to_error(brl_step((brl_stream_t)stream, b, &p, sizeof(p)));
-}
-
-ffi::Error GaeImpl(cudaStream_t stream, ffi::AnyBuffer done, ffi::Buffer<ffi::F32> value, ffi::Buffer<ffi::F32> reward,
-                   ffi::Buffer<ffi::F32> last_val, ffi::Result<ffi::Buffer<ffi::F32>> adv,
-                   ffi::Result<ffi::Buffer<ffi::F32>> targets, float gamma, float gae_lambda) {
-    const int64_t n = last_val.element_count();
-    void* b[6] = {done.untyped_data(), value.untyped_data(), reward.untyped_data(), last_val.untyped_data(),
-                  adv->untyped_data(), targets->untyped_data()};
-    BrlParams p = params(n, n, 0, 0, 0, 0, (int32_t)(value.element_count() / n), 0);
-    p.gamma = gamma; p.gae_lambda = gae_lambda;
-    return to_error(brl_gae((brl_stream_t)stream, b, &p, sizeof(p)));
+ffi::Error typed_call(brl_op_fn op, const char* name, const char* layout, cudaStream_t stream, ffi::RemainingArgs args,
+                      ffi::RemainingRets rets, ffi::Span<const uint8_t> opaque) {
+    void* xla[kMaxBuffers];
+    size_t n = 0;
+    for (size_t i = 0; i < args.size() && n < kMaxBuffers; ++i) xla[n++] = args.get<ffi::AnyBuffer>(i).value().untyped_data();
+    for (size_t i = 0; i < rets.size() && n < kMaxBuffers; ++i) xla[n++] = rets.get<ffi::AnyBuffer>(i).value()->untyped_data();
+    if (n != std::strlen(layout) + (size_t)[&] { int x = 0; for (const char* c = layout; *c; ++c) x += *c == 'x'; return x; }())
+        return ffi::Error(ffi::ErrorCode::kInvalidArgument, std::string(name) + "_ffi: wrong number of operands + results");
+    void* b[kMaxBuffers];
+    char msg[160];
+    if (const char* err = reorder(layout, xla, b, msg, sizeof(msg)))
+        return ffi::Error(ffi::ErrorCode::kInvalidArgument, std::string(name) + "_ffi: " + err);
+    if (op((brl_stream_t)stream, b, opaque.begin(), opaque.size()) != BRL_OK)
+        return ffi::Error(ffi::ErrorCode::kInvalidArgument, brl_last_error());
+    return ffi::Error::Success();
 }
 }  // namespace
 
-XLA_FFI_DEFINE_HANDLER_SYMBOL(brl_step_ffi, StepImpl,
-                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
-                                  .Arg<ffi::AnyBuffer>().Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::AnyBuffer>()
-                                  .Ret<ffi::AnyBuffer>().Ret<ffi::AnyBuffer>().Ret<ffi::AnyBuffer>().Ret<ffi::AnyBuffer>()
-                                  .Ret<ffi::AnyBuffer>().Ret<ffi::AnyBuffer>().Attr<int32_t>("flags"));
-XLA_FFI_DEFINE_HANDLER_SYMBOL(brl_gae_ffi, GaeImpl,
-                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
-                                  .Arg<ffi::AnyBuffer>().Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>()
-                                  .Attr<float>("gamma").Attr<float>("gae_lambda"));
+#define BRL_TYPED_FFI(op, layout)                                                                                         \
+    static ffi::Error op##_ffi_impl(cudaStream_t stream, ffi::RemainingArgs args, ffi::RemainingRets rets,                \
+                                    ffi::Span<const uint8_t> opaque) {                                                    \
+        return typed_call(op, #op, layout, stream, args, rets, opaque);                                                   \
+    }                                                                                                                     \
+    XLA_FFI_DEFINE_HANDLER_SYMBOL(op##_ffi, op##_ffi_impl,                                                                \
+                                  ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().RemainingArgs().RemainingRets() \
+                                      .Attr<ffi::Span<const uint8_t>>("opaque"));
+BRL_XLA_OPS(BRL_TYPED_FFI)
 #endif  // BRL_HAVE_XLA_FFI

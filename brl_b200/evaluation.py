@@ -14,6 +14,38 @@ from .utils import single_play_step_two_policy_commpetitive_deterministic
 _CHECK_EVERY = 8  # stepping a finished env is a zero-reward no-op, so the all-done test needs no per-step sync
 
 
+class _TeamRows:
+    """Per-iteration lists of the envs still playing, split by the team of the player to act (brl_team_rows).  The
+    reference's vmapped loop (src/evaluation.py:124-151) runs BOTH nets on every env and keeps forwarding finished envs
+    until the slowest auction ends; here each net runs on exactly the envs it decides.  The two counts come back to the
+    host once per iteration (8 bytes): they size the two forward launches and are the loop's termination test."""
+
+    def __init__(self, n: int, device):
+        self.rows1 = torch.empty(n, dtype=torch.int32, device=device)
+        self.rows2 = torch.empty(n, dtype=torch.int32, device=device)
+        self.counts = torch.zeros(2, dtype=torch.int32, device=device)
+        self.host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self.forwarded = 0  # rows sent through a net so far (tests / bench: compare with iterations * 2 * n)
+
+    def split(self, current_player, done_u8):
+        ops.team_rows(current_player, done_u8, self.rows1, self.rows2, self.counts)
+        self.host.copy_(self.counts, non_blocking=True)
+        torch.cuda.current_stream(self.counts.device).synchronize()
+        c1, c2 = int(self.host[0]), int(self.host[1])
+        self.forwarded += c1 + c2
+        return self.rows1[:c1], self.rows2[:c2]
+
+
+def _bf16_state(env, keys):
+    """env.init with the observation written directly in bf16 (the tensor-core nets' input dtype; the observation of
+    these loops is read by the nets only)"""
+    n = keys.shape[0]
+    from .env import State
+    packed, out = ops.new_state(n, env.device), ops.EnvOutputs(n, env.device, torch.bfloat16)
+    ops.init(keys, env.table, packed, out)
+    return State(env, packed, out)
+
+
 def make_simple_evaluate(eval_env, team1_activation, team1_model_type, team2_activation, team2_model_type,
                          team2_model_path, num_eval_envs, team2_params=None):
     """src/evaluation.py:11-66: deterministic quad steps vs a fixed opponent; mean raw score."""
@@ -21,10 +53,13 @@ def make_simple_evaluate(eval_env, team1_activation, team1_model_type, team2_act
     opp_forward_pass = make_forward_pass(activation=team2_activation, model_type=team2_model_type)
     opp_params = team2_params if team2_params is not None else load_params(team2_model_path, eval_env.device)
 
-    def simple_evaluate(actor_params, rng):
+    def simple_evaluate(actor_params, rng, trace=None):
+        """`trace` (a list, tests only) receives the four sub-step action tensors of every quad step and finally
+        ("R", per-env return) -- the inputs of an oracle replay."""
         step_fn = single_play_step_two_policy_commpetitive_deterministic(
             step_fn=eval_env.step, actor_params=actor_params, actor_forward_pass=actor_forward_pass,
             opp_params=opp_params, opp_forward_pass=opp_forward_pass)
+        step_fn.trace = trace
         rng_key, sub_key = brandom.split(rng)
         state = eval_env.init(eval_env.make_keys(sub_key, num_eval_envs))
         R = torch.zeros(num_eval_envs, dtype=torch.float32, device=eval_env.device)
@@ -42,6 +77,8 @@ def make_simple_evaluate(eval_env, team1_activation, team1_model_type, team2_act
             it += 1
             if it % _CHECK_EVERY == 0 and bool(state._terminated_u8.all()):
                 break
+        if trace is not None:
+            trace.append(("R", R.clone()))
         return R.mean()
 
     return simple_evaluate
@@ -61,31 +98,28 @@ def make_simple_duplicate_evaluate(eval_env, team1_activation, team1_model_type,
         statistics there and skip the all-reduce (the league evaluator reduces all its matches at once)."""
         step_fn = duplicate_step(eval_env.step)
         rng_key, sub_key = brandom.split(rng_key)
-        state = eval_env.init(eval_env.make_keys(sub_key, num_eval_envs, env_offset))      # :93-95
+        state = _bf16_state(eval_env, eval_env.make_keys(sub_key, num_eval_envs, env_offset))  # :93-95
         table_a_info = Table_info.from_state(state)                                        # :97-112
         table_b_info = Table_info.from_state(state)
         dev = eval_env.device
         cum_return = torch.zeros(num_eval_envs, dtype=torch.float32, device=dev)
-        a1 = torch.empty(num_eval_envs, dtype=torch.int32, device=dev)
-        a2 = torch.empty_like(a1)
-        count = 0
+        action = torch.zeros(num_eval_envs, dtype=torch.int32, device=dev)  # finished envs keep a (no-op) Pass
+        teams = _TeamRows(num_eval_envs, dev)
         while True:
-            # :124-151 -- under vmap both nets run on every env; the team of current_player picks
-            l1, _ = team1_forward_pass.apply(team1_params, state.observation)
-            l2, _ = team2_forward_pass.apply(team2_params, state.observation)
-            ops.categorical(l1.contiguous(), state._mask_u8, a1, None, sample=False)
-            ops.categorical(l2.contiguous(), state._mask_u8, a2, None, sample=False)
-            action = torch.where(state.current_player < 2, a1, a2)
+            # :124-151 -- team 1's net decides for players 0/1, team 2's for players 2/3; finished envs are skipped
+            rows1, rows2 = teams.split(state.current_player, state._terminated_u8)
+            if rows1.shape[0] + rows2.shape[0] == 0:                                       # :120-122 ~terminated.all()
+                break
+            team1_forward_pass.act_rows(team1_params, state.observation, state._mask_u8, action, rows1)
+            team2_forward_pass.act_rows(team2_params, state.observation, state._mask_u8, action, rows2)
             if trace is not None:  # tests replay the same action sequence on the oracle
-                trace.append((action.clone(), l1.clone(), l2.clone()))
+                trace.append((action.clone(), None, None))
             if record is not None:
                 record.append((action.cpu(), table_a_info.terminated.view(torch.uint8).cpu(),
                                table_b_info.terminated.view(torch.uint8).cpu()))
             state, table_a_info, table_b_info = step_fn(state, action, table_a_info, table_b_info)  # :164
             cum_return += state.rewards[:, 0]                                              # :167-169
-            count += 1
-            if count % _CHECK_EVERY == 0 and bool(state._terminated_u8.all()):
-                break
+        duplicate_evaluate.rows_forwarded = teams.forwarded
         if local_sums is not None:
             ops.match_stats(cum_return, local_sums)
             return None, table_a_info, table_b_info, cum_return
@@ -173,25 +207,31 @@ def make_evaluate(eval_env, team1_activation, team1_model_type, team2_activation
         acc = torch.zeros((n, ops._lib.EVAL_ACC_COLS), dtype=torch.float32, device=dev)
         cum_return = torch.zeros(n, dtype=torch.float32, device=dev)
         rewards = torch.zeros((n, 4), dtype=torch.float32, device=dev)
-        action = torch.empty(n, dtype=torch.int32, device=dev)
-        count = 0
+        action = torch.zeros(n, dtype=torch.int32, device=dev)
+        # each live env's row holds the logits of the team that acts there (scattered by the listed forward)
+        logits = torch.zeros((n, ops.NUM_ACTIONS), dtype=torch.float32, device=dev)
+        teams = _TeamRows(n, dev)
         while True:
-            l1, _ = actor_forward_pass.apply(actor_params, state.observation)
-            l2 = opp_forward_pass.apply(opp_params, state.observation)[0] if opp_params is not None else None
-            ops.eval_act_log(l1.contiguous(), None if l2 is None else l2.contiguous(), state._mask_u8, state.current_player,
+            rows1, rows2 = teams.split(state.current_player, state._terminated_u8)
+            if rows1.shape[0] + rows2.shape[0] == 0:
+                return state, acc, cum_return, rewards
+            actor_forward_pass.act_rows(actor_params, state.observation, state._mask_u8, action, rows1, logits=logits)
+            if opp_params is not None:
+                opp_forward_pass.act_rows(opp_params, state.observation, state._mask_u8, action, rows2, logits=logits)
+            # the step's decision + update_log_info (unmasked-softmax illegal mass, bid histograms) from the acting
+            # team's logits; free-run: team 2 always passes
+            ops.eval_act_log(logits, logits if opp_params is not None else None, state._mask_u8, state.current_player,
                              state._terminated_u8, action, acc, indicator_bids=not duplicate)
             if trace is not None:
-                trace.append((action.clone(), l1.clone(), None if l2 is None else l2.clone()))
+                lg = logits.clone()  # row i = the logits of the team acting in env i
+                trace.append((action.clone(), lg, lg if opp_params is not None else None))
             state = step(state, action)
             rewards += state.rewards
             cum_return += state.rewards[:, 0]
-            count += 1
-            if count % _CHECK_EVERY == 0 and bool(state._terminated_u8.all()):
-                return state, acc, cum_return, rewards
 
     def evaluate(actor_params, rng_key, trace=None):
         rng_key, sub_key = brandom.split(rng_key)
-        state = eval_env.init(eval_env.make_keys(sub_key, n, env_offset))
+        state = _bf16_state(eval_env, eval_env.make_keys(sub_key, n, env_offset))
         state, acc, cum_return, rewards = _loop(actor_params, rng_key, lambda s, a: eval_env.step(s, a, inplace=True),
                                                 state, trace)
         f = ops.state_fields(state._packed)
@@ -205,7 +245,7 @@ def make_evaluate(eval_env, team1_activation, team1_model_type, team2_activation
     def duplicate_evaluate(actor_params, rng_key, trace=None):
         step_fn = duplicate_step(eval_env.step)
         rng_key, sub_key = brandom.split(rng_key)
-        state = eval_env.init(eval_env.make_keys(sub_key, n, env_offset))
+        state = _bf16_state(eval_env, eval_env.make_keys(sub_key, n, env_offset))
         infos = [Table_info.from_state(state), Table_info.from_state(state)]
 
         def step(s, a):

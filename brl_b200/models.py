@@ -2,12 +2,11 @@
 actor-critic (src/models.py:23-33); parameters keep haiku's layout
 (`actor_critic/linear{,_1..5}` -> {'w' [in,out], 'b'}).
 
-precision:
-  "tc"      hand-written TMA + tcgen05 forward (csrc/brl_mlp.cu), 3-term bf16 split with fp32
-            accumulation in tensor memory -- fp32-class results (the reference computes in fp32);
-  "tc-bf16" the same kernels with a single bf16 product per term;
-  "fp32" / "tf32" / "bf16"  library GEMM chain (cuBLAS through torch.addmm), kept as the
-            independent cross-check of the tensor-core path and for tanh nets.
+precision (both run the hand-written TMA + tcgen05 forward of csrc/brl_mlp.cu; there is no library back end in the
+product -- the cuBLAS cross-check lives in scripts/torch_baseline.py):
+  "tc"      3-term bf16 split with fp32 accumulation in tensor memory -- fp32-class results (the reference
+            computes in fp32);
+  "tc-bf16" a single bf16 product per term.
 """
 from __future__ import annotations
 
@@ -49,11 +48,17 @@ def load_params(path: str, device="cuda") -> Dict[str, Dict[str, torch.Tensor]]:
 
 
 def init_params(seed: int, device="cuda") -> Dict[str, Dict[str, torch.Tensor]]:
-    """Random-init weights of the architecture (haiku default: truncated-normal, stddev 1/sqrt(fan_in))."""
+    """Random-init weights of the architecture: haiku's default `hk.initializers.TruncatedNormal(stddev=1/sqrt(fan_in))`,
+    i.e. a standard normal truncated to [-2, 2] by RESAMPLING (not clipping), scaled by 1/sqrt(fan_in); biases zero."""
     rng = np.random.default_rng(seed)
     out = {}
     for name, (fi, fo) in zip(LAYERS, SIZES):
-        w = np.clip(rng.normal(0, 1, (fi, fo)), -2, 2).astype(np.float32) / np.sqrt(fi).astype(np.float32)
+        w = rng.normal(0, 1, (fi, fo))
+        bad = np.abs(w) > 2
+        while bad.any():  # rejection-resample the ~4.6 % of draws outside two sigma
+            w[bad] = rng.normal(0, 1, int(bad.sum()))
+            bad = np.abs(w) > 2
+        w = w.astype(np.float32) / np.sqrt(fi).astype(np.float32)
         out[name] = {"w": torch.as_tensor(w, device=device), "b": torch.zeros(fo, dtype=torch.float32, device=device)}
     return out
 
@@ -73,20 +78,22 @@ class ForwardPass:
     def __init__(self, activation: str = "relu", model_type: str = "DeepMind", precision: str = None):
         if model_type != "DeepMind":
             raise NotImplementedError("only the DeepMind 4x1024 net is on the hot path (SURVEY 8a a16)")
-        self._activation = torch.relu if activation == "relu" else torch.tanh
-        if precision is None:  # the tensor-core kernels fuse ReLU (all five bundled models are ReLU nets)
-            precision = "tc" if activation == "relu" else "fp32"
-        if precision not in ("tc", "tc-bf16", "fp32", "tf32", "bf16"):
-            raise ValueError(f"unknown precision {precision!r}")
+        if activation != "relu":  # all five bundled models and every ppo.py default are ReLU nets (src/models.py:28-31)
+            raise NotImplementedError("the tensor-core forward fuses ReLU into its epilogues; tanh nets are not on the hot "
+                                      "path (a cuBLAS forward for them: scripts/torch_baseline.TorchForwardPass)")
+        if precision is None:
+            precision = "tc"
+        if precision not in ("tc", "tc-bf16"):
+            raise ValueError(f"unknown precision {precision!r}: the product path has no library back end "
+                             "(scripts/torch_baseline.py holds the cuBLAS cross-check)")
+        self._activation = torch.relu
         self.precision = precision
-        if precision in ("tc", "tc-bf16") and activation != "relu":
-            raise NotImplementedError("the tensor-core forward fuses ReLU; use a library precision for tanh nets")
         self._scratch = None
 
     @property
     def input_dtype(self):
         """dtype the forward consumes without a cast (env kernels can write the 0/1 observation in it directly)"""
-        return torch.bfloat16 if self.precision in ("tc", "tc-bf16") else torch.float32
+        return torch.bfloat16
 
     def _packed(self, params):
         """bf16 hi/lo blob of `params`, re-packed when any tensor was replaced or updated in place."""
@@ -113,17 +120,23 @@ class ForwardPass:
         """`logits, value = apply(params, x)` followed by the masked categorical of src/roll_out.py:77-81 /
         src/utils.py:83-88, written into caller buffers.  The tensor-core precisions do it in one call
         (`brl_policy_act`: from 4096 envs on a single persistent launch with the sampler in the head epilogue)."""
-        if self.precision in ("tc", "tc-bf16"):
-            n = x.shape[0]
-            xb = ops.obs_to_bf16(x.contiguous())
-            self._ensure_scratch(n, x.device)
-            ops.policy_act(xb, self._packed(params), self._scratch, mask, action, log_prob, value, sample=sample, seed=seed,
-                           env_offset=env_offset, single_bf16=self.precision == "tc-bf16")
+        n = x.shape[0]
+        xb = ops.obs_to_bf16(x.contiguous())
+        self._ensure_scratch(n, x.device)
+        ops.policy_act(xb, self._packed(params), self._scratch, mask, action, log_prob, value, sample=sample, seed=seed,
+                       env_offset=env_offset, single_bf16=self.precision == "tc-bf16")
+
+    def act_rows(self, params, obs_bf16: torch.Tensor, mask, action: torch.Tensor, rows: torch.Tensor, log_prob=None,
+                 logits=None, *, sample: bool = False, seed: int = 0, env_offset: int = 0):
+        """`act` for the envs listed in `rows` only (int32 indices into the full per-env arrays)."""
+        n = rows.shape[0]
+        if n == 0:
             return
-        logits, v = self.apply(params, x)
-        ops.categorical(logits.contiguous(), mask, action, log_prob, sample=sample, seed=seed, env_offset=env_offset)
-        if value is not None:
-            value.copy_(v)
+        need = ops._lib.load().brl_mlp_rows_scratch_bytes(n)
+        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != obs_bf16.device:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=obs_bf16.device)
+        ops.policy_act_rows(obs_bf16, self._packed(params), self._scratch, mask, action, rows, log_prob, logits, sample=sample, seed=seed,
+                            env_offset=env_offset, single_bf16=self.precision == "tc-bf16")
 
     def _ensure_scratch(self, n, device):
         if self._scratch is None or self._scratch.numel() < ops._lib.load().brl_mlp_scratch_bytes(n) or \
@@ -131,20 +144,7 @@ class ForwardPass:
             self._scratch = ops.mlp_scratch(n, device)
 
     def apply(self, params, x: torch.Tensor):
-        if self.precision in ("tc", "tc-bf16"):
-            return self._apply_tc(params, x)
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = self.precision == "tf32"
-        try:
-            dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
-            h = x.to(dt)
-            for name in LAYERS[:4]:
-                h = self._activation(torch.addmm(params[name]["b"].to(dt), h, params[name]["w"].to(dt)))
-            logits = torch.addmm(params[LAYERS[4]]["b"].to(dt), h, params[LAYERS[4]]["w"].to(dt)).float()
-            value = torch.addmm(params[LAYERS[5]]["b"].to(dt), h, params[LAYERS[5]]["w"].to(dt)).float().squeeze(-1)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
-        return logits, value
+        return self._apply_tc(params, x)
 
 
 def make_forward_pass(activation: str = "relu", model_type: str = "DeepMind", precision: str = None) -> ForwardPass:

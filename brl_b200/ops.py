@@ -270,6 +270,41 @@ def policy_act(obs_bf16: torch.Tensor, packed: torch.Tensor, scratch: torch.Tens
                   env_offset=env_offset, step=step_index))
 
 
+def mlp_rows_scratch(n_rows: int, device) -> torch.Tensor:
+    return torch.empty(_lib.load().brl_mlp_rows_scratch_bytes(n_rows), dtype=torch.uint8, device=device)
+
+
+def policy_act_rows(obs_bf16: torch.Tensor, packed: torch.Tensor, scratch: torch.Tensor, mask: Optional[torch.Tensor],
+                    action: torch.Tensor, rows: torch.Tensor, log_prob: Optional[torch.Tensor] = None,
+                    logits: Optional[torch.Tensor] = None, *, sample: bool = False,
+                    seed: int = 0, env_offset: int = 0, step_index: int = 0, single_bf16: bool = False, tune: int = 0) -> None:
+    """`policy_act` restricted to the envs listed in `rows` (int32): only their observations are read and only their
+    action / log_prob entries written (src/evaluation.py:124-151 without forwarding envs a net does not decide)."""
+    n = rows.shape[0]
+    if n == 0:
+        return
+    if obs_bf16.dtype != torch.bfloat16 or rows.dtype != torch.int32:
+        raise _lib.BrlError("policy_act_rows needs a bf16 observation and int32 rows")
+    if scratch.numel() < _lib.load().brl_mlp_rows_scratch_bytes(n):
+        raise _lib.BrlError("policy_act_rows: scratch too small (ops.mlp_rows_scratch)")
+    _call("brl_policy_act_rows", [_ptr(obs_bf16), _ptr(packed), _ptr(scratch), _ptr(mask), _ptr(action), _ptr(rows), _ptr(log_prob),
+                                  _ptr(logits)],
+          _params(n, flags=(F_MLP_BF16 if single_bf16 else 0) | (F_SAMPLE if sample else 0) | tune, seed=seed,
+                  env_offset=env_offset, step=step_index))
+
+
+def team_rows(current_player: torch.Tensor, done: Optional[torch.Tensor], rows1: torch.Tensor, rows2: torch.Tensor,
+              counts: torch.Tensor) -> None:
+    """rows of the live envs (done == 0) split by acting team: players 0/1 -> rows1, players 2/3 -> rows2; counts i32[2]."""
+    _call("brl_team_rows", [_ptr(current_player), _ptr(done), _ptr(rows1), _ptr(rows2), _ptr(counts)],
+          _params(current_player.shape[0]))
+
+
+def ppo_scratch(device) -> torch.Tensor:
+    """scratch of ppo_loss / ppo_grad as a float64 tensor (element 14 = sum of squares of the gradient after ppo_grad)"""
+    return torch.zeros(_lib.PPO_SCRATCH_BYTES // 8, dtype=torch.float64, device=device)
+
+
 def ppo_loss(logits, value, index, mask, action, old_log_prob, old_value, adv, targets, dlogits, dvalue, stats, scratch,
              *, clip_eps, ent_coef, vf_coef, illegal_l2_coef=0.0, value_clipping=True, reward_scaling=False,
              masked_policy=True) -> None:
@@ -330,9 +365,10 @@ def mlp_train_scratch(batch: int, device) -> torch.Tensor:
 
 def ppo_grad(obs, blob, scratch, index, mask, action, old_log_prob, old_value, adv, targets, grads, stats, acc, *, clip_eps,
              ent_coef, vf_coef, illegal_l2_coef=0.0, value_clipping=True, reward_scaling=False, masked_policy=True,
-             tune: int = 0) -> None:
+             illegal_stat: bool = True, tune: int = 0) -> None:
     """One minibatch of jax.value_and_grad(_loss_fn) (src/update.py:91-167): take(index), forward, loss, backward
-    through the MLP on tcgen05 -> flat fp32 gradients (+ the loss statistics of `ppo_loss`)."""
+    through the MLP on tcgen05 -> flat fp32 gradients (+ the loss statistics of `ppo_loss`).  `illegal_stat=False` (only
+    honoured with illegal_l2_coef == 0): skip the logged illegal_action_loss (stats[6] = NaN), ~19 us per call."""
     L = _lib.load()
     B = int(index.shape[0]) if index is not None else int(obs.shape[0])
     if obs.dtype == torch.bool:
@@ -346,7 +382,7 @@ def ppo_grad(obs, blob, scratch, index, mask, action, old_log_prob, old_value, a
     if grads.dtype != torch.float32 or grads.numel() != L.brl_mlp_num_params():
         raise _lib.BrlError("ppo_grad: grads must be the flat fp32 gradient buffer")
     flags = (_lib.PPO_VALUE_CLIPPING if value_clipping else 0) | (_lib.PPO_REWARD_SCALING if reward_scaling else 0) | \
-            (0 if masked_policy else _lib.PPO_UNMASKED_POLICY) | oflag
+            (0 if masked_policy else _lib.PPO_UNMASKED_POLICY) | (_lib.PPO_ILLEGAL_STAT if illegal_stat else 0) | oflag
     p = _lib.BrlPpoParams(B, int(action.numel()), float(clip_eps), float(ent_coef), float(vf_coef), float(illegal_l2_coef),
                           flags, int(tune))
     _call("brl_ppo_grad", [_ptr(obs), _ptr(blob), _ptr(scratch), _ptr(index), _ptr(mask), _ptr(action), _ptr(old_log_prob),

@@ -65,7 +65,13 @@ def pfsp_probabilities(imp_list: np.ndarray, prior_t: float) -> np.ndarray:
 
 
 def train(config: dict, rng: int, tables: Optional[Sequence] = None, eval_table=None, device="cuda",
-          log_fn: Optional[Callable[[dict], None]] = None, eval_opp_params=None, np_rng: Optional[np.random.Generator] = None):
+          log_fn: Optional[Callable[[dict], None]] = None, eval_opp_params=None, np_rng: Optional[np.random.Generator] = None,
+          forward_pass_factory=None, update_step_factory=None):
+    """`forward_pass_factory(activation, model_type)` / `update_step_factory(config, forward_pass, optimizer)` replace
+    `make_forward_pass` / `make_update_step` -- the hook the cuBLAS cross-check (scripts/torch_baseline.py) plugs into;
+    the defaults are the tensor-core kernels and nothing else."""
+    make_fp = forward_pass_factory or make_forward_pass
+    make_us = update_step_factory or make_update_step
     cfg = dict(default_config())
     cfg.update(config)
     config = cfg
@@ -89,9 +95,7 @@ def train(config: dict, rng: int, tables: Optional[Sequence] = None, eval_table=
     eval_table = as_table(eval_table) if eval_table is not None else _deals.synthetic_deal_table(config["hash_size"], seed=10_000)
 
     optimizer = make_optimizer(config)                                                            # ppo.py:195-211
-    # "policy_precision" is this mirror's only extra key: None = the tensor-core kernels (rollout forward AND update),
-    # "fp32" = the library-GEMM cross-check path
-    actor_forward_pass = make_forward_pass(config["actor_activation"], config["actor_model_type"], config.get("policy_precision"))
+    actor_forward_pass = make_fp(config["actor_activation"], config["actor_model_type"])
     rng, _rng = brandom.split(rng)
     params = init_params(_rng & 0x7FFFFFFF, dev)                                                  # ppo.py:240-243
     opt_state = optimizer.init(params)
@@ -114,11 +118,11 @@ def train(config: dict, rng: int, tables: Optional[Sequence] = None, eval_table=
                                        config["num_eval_envs"], config["game_mode"], duplicate=True,
                                        team2_params=eval_opp_params)
 
-    opp_forward_pass = make_forward_pass(config["opp_activation"], config["opp_model_type"], config.get("policy_precision"))
+    opp_forward_pass = make_fp(config["opp_activation"], config["opp_model_type"])
     envs = [BridgeBidding(table=t, device=dev) for t in tables]                                   # ppo.py:296-303
     roll_outs = [make_roll_out(config, env, actor_forward_pass, opp_forward_pass) for env in envs]
     calc_gae = make_calc_gae(config, actor_forward_pass)
-    update_step = make_update_step(config, actor_forward_pass, optimizer)
+    update_step = make_us(config, actor_forward_pass, optimizer)
 
     rng, _rng = brandom.split(rng)
     env, roll_out = envs[0], roll_outs[0]
@@ -133,15 +137,22 @@ def train(config: dict, rng: int, tables: Optional[Sequence] = None, eval_table=
         opp_params = load_params(config["opp_model_path"], dev) if config["opp_model_path"] else eval_opp_params
     else:
         opp_params = params
-    zoo: List[dict] = []          # past models (ppo.py keeps them as params-XXXXXXXX.pkl under save_model_path)
+    # past models.  ppo.py keeps them on disk (params-XXXXXXXX.pkl under save_model_path) and loads one at a time; here
+    # they are host-memory NumPy dicts (14.7 MB each, never resident in HBM) and only exist when the league can use them
+    zoo: List[dict] = []
+    use_zoo = bool(config["self_play"]) and float(config["ratio_model_zoo"]) > 0.0
+
+    def zoo_model(k: int) -> dict:
+        return {name: {kk: torch.as_tensor(v, device=dev) for kk, v in zoo[k][name].items()} for name in LAYERS}
     save_dir = os.path.join(config["log_path"], config["exp_name"], config["save_model_path"])
     if config["save_model"]:
         os.makedirs(save_dir, exist_ok=True)
     logs = []
     for i in range(config["num_updates"]):
         if i != 0 and i % config["save_model_interval"] == 0:                                      # ppo.py:351-362
-            zoo.append(runner_state[0])
-            zoo[:] = zoo[-config["num_model_zoo"]:]
+            if use_zoo:
+                zoo.append(params_to_host(runner_state[0]))
+                zoo[:] = zoo[-config["num_model_zoo"]:]
             if config["save_model"]:
                 save_params(runner_state[0], os.path.join(save_dir, f"params-{i:08}.pkl"))
         t0 = time.time()
@@ -158,11 +169,11 @@ def train(config: dict, rng: int, tables: Optional[Sequence] = None, eval_table=
                 if len(zoo) != 0 and np_rng.binomial(1, config["ratio_model_zoo"]):
                     if config["prioritized_fictitious"]:
                         imp_list = np.zeros(len(zoo))
-                        for k, past in enumerate(zoo):
-                            (imp_list[k], _, _), _, _, _ = simple_duplicate_evaluate(runner_state[0], past, eval_rng)
-                        opp_params = zoo[np_rng.choice(len(zoo), p=pfsp_probabilities(imp_list, config["prior_t"]))]
+                        for k in range(len(zoo)):  # one past model on the device at a time
+                            (imp_list[k], _, _), _, _, _ = simple_duplicate_evaluate(runner_state[0], zoo_model(k), eval_rng)
+                        opp_params = zoo_model(int(np_rng.choice(len(zoo), p=pfsp_probabilities(imp_list, config["prior_t"]))))
                     else:
-                        opp_params = zoo[np_rng.integers(len(zoo))]
+                        opp_params = zoo_model(int(np_rng.integers(len(zoo))))
                 else:
                     opp_params = runner_state[0]
         (imp_opp_before, _, _), _, _, _ = simple_duplicate_evaluate(runner_state[0], opp_params, eval_rng)

@@ -2,15 +2,10 @@
 fresh permutation split into `num_minibatches` minibatches; per minibatch the net is re-run,
 the PPO loss and its gradient are formed, and the optimizer steps.
 
-Two back ends, selected by the forward pass's precision:
-  "tc" / "tc-bf16" (default for ReLU nets)  `brl_ppo_grad`: minibatch take, forward with kept
-      activations, loss head + its backward, and the backward GEMMs all in hand-written kernels
-      on tcgen05 (csrc/brl_mlp_train.cu, three-term bf16 split = fp32-class gradients), then
-      `brl_mlp_adam_step` (clip + Adam + refresh of the kernels' weight layout in one pass) -- no
-      library GEMM, no autograd tape;
-  "fp32" (and tanh nets)  the minibatch gather, loss head and clip + Adam step are the same
-      kernels (csrc/brl_ppo.cu) around plain library GEMMs (cuBLAS fp32 through torch
-      autograd) -- kept as the independent cross-check of the tensor-core path.
+One back end: `brl_ppo_grad` -- minibatch take, forward with kept activations, loss head + its backward, and the
+backward GEMMs all in hand-written kernels on tcgen05 (csrc/brl_mlp_train.cu, three-term bf16 split = fp32-class
+gradients) -- then `brl_mlp_adam_step` (clip + Adam + refresh of the kernels' weight layout in one pass).  No library
+GEMM, no autograd tape.  (The cuBLAS-fp32 + autograd cross-check of this path is scripts/torch_baseline.py.)
 Functional semantics are kept: the caller's `params` / `opt_state` are not modified (ppo.py
 keeps the pre-update params as `opp_params`), a new flat copy is updated and returned."""
 from __future__ import annotations
@@ -19,36 +14,9 @@ import torch
 
 from . import ops
 from . import random as brandom
-from .models import LAYERS
 from .optim import OptState, flatten_params
 
 _STAT_NAMES = ("total_loss", "value_loss", "loss_actor", "entropy", "approx_kl", "clipflacs", "illegal_action_loss")
-
-
-class _LossHead(torch.autograd.Function):
-    """total_loss(logits, value) with the gradient produced by the same kernel pass."""
-
-    @staticmethod
-    def forward(ctx, logits, value, call):
-        dlogits, dvalue, stats = torch.empty_like(logits), torch.empty_like(value), call["stats"]
-        ops.ppo_loss(logits, value, call["index"], call["mask"], call["action"], call["old_log_prob"], call["old_value"],
-                     call["adv"], call["targets"], dlogits, dvalue, stats, call["scratch"], **call["cfg"])
-        ctx.save_for_backward(dlogits, dvalue)
-        return stats[0].clone()
-
-    @staticmethod
-    def backward(ctx, gout):
-        dlogits, dvalue = ctx.saved_tensors
-        return gout * dlogits, gout * dvalue, None
-
-
-def _forward_autograd(p, x, act):
-    h = x
-    for name in LAYERS[:4]:
-        h = act(torch.addmm(p[name]["b"], h, p[name]["w"]))
-    logits = torch.addmm(p[LAYERS[4]]["b"], h, p[LAYERS[4]]["w"])
-    value = torch.addmm(p[LAYERS[5]]["b"], h, p[LAYERS[5]]["w"]).squeeze(-1)
-    return logits, value
 
 
 def make_update_step(config, actor_forward_pass, optimizer, permutation_fn=None):
@@ -59,8 +27,18 @@ def make_update_step(config, actor_forward_pass, optimizer, permutation_fn=None)
                illegal_l2_coef=config.get("illegal_action_l2norm_coef", 0.0),
                value_clipping=bool(config.get("value_clipping", True)),
                reward_scaling=bool(config.get("reward_scaling", False)), masked_policy=masked)
-    act = getattr(actor_forward_pass, "_activation", torch.relu)
-    tensor_core = getattr(actor_forward_pass, "precision", "fp32") in ("tc", "tc-bf16") and act is torch.relu
+    # illegal_action_loss = ||probs * ~mask||_2 / 2 is the SPECTRAL norm of the [minibatch, 38] matrix (src/update.py:141-142): a
+    # 38 x 38 eigen-problem per minibatch.  With the default illegal_action_l2norm_coef = 0 it is a logged statistic only,
+    # and ppo.py logs just the LAST minibatch of the last epoch (ppo.py:505, `illegal_action_loss[-1][-1]`).  "last" (default)
+    # computes it for the last minibatch of every epoch and leaves NaN elsewhere in loss_info -- never a wrong number;
+    # "all" fills every entry as the reference does, at ~19 us (11 %) per optimizer step (scripts/exp_gram_cost.py).
+    # A non-zero coefficient needs the norm for the gradient and always computes it.
+    stat_mode = config.get("illegal_action_loss_stat", "last")
+    if stat_mode not in ("last", "all"):
+        raise ValueError("illegal_action_loss_stat must be 'last' or 'all'")
+    if getattr(actor_forward_pass, "precision", None) not in ("tc", "tc-bf16"):
+        raise TypeError("make_update_step needs a brl_b200.models.ForwardPass (tensor-core ReLU net); there is no library "
+                        "back end on the product path")
     tune = int(config.get("brl_train_tune", 0))
 
     def default_permutation(rng, batch_size, device):
@@ -91,7 +69,7 @@ def make_update_step(config, actor_forward_pass, optimizer, permutation_fn=None)
         state = OptState(opt_state.count, opt_state.mu.clone(), opt_state.nu.clone())
         n_epochs = int(config["update_epochs"])
         stats_all = torch.zeros((n_epochs, nmb, 8), dtype=torch.float32, device=dev)
-        acc = torch.zeros(16, dtype=torch.float64, device=dev)
+        acc = ops.ppo_scratch(dev)
 
         def permutation(_rng):
             return (permutation_fn(_rng, batch_size) if permutation_fn is not None
@@ -103,47 +81,17 @@ def make_update_step(config, actor_forward_pass, optimizer, permutation_fn=None)
             cols = [stats_all[:, :, i] for i in range(7)]
             return (new_params, state, env_state, last_obs, terminated_count, rng), (cols[0], tuple(cols[1:]))
 
-        if tensor_core:
-            blob = ops.mlp_pack_train(flat_p)
-            scratch = ops.mlp_train_scratch(mbs, dev)
-            flat_g = torch.empty_like(flat_p)
-            for epoch in range(n_epochs):
-                rng, _rng = brandom.split(rng)                                        # src/update.py:187
-                perm = permutation(_rng)
-                for mb in range(nmb):                                                  # src/update.py:207-209
-                    ops.ppo_grad(obs, blob, scratch, perm[mb * mbs:(mb + 1) * mbs], mask, action, old_lp, old_v, adv, tgt,
-                                 flat_g, stats_all[epoch, mb], acc, tune=tune, **cfg)  # src/update.py:164-167
-                    state = optimizer.update_mlp_(flat_p, flat_g, state, acc[14:15], blob)  # src/update.py:168-169
-            return finish()
-
-        leaves = {name: {k: new_params[name][k].detach().requires_grad_() for k in ("w", "b")} for name in LAYERS}
-        flat_g = torch.zeros_like(flat_p)
-        off = 0
-        for name in LAYERS:  # gradients accumulate straight into the flat buffer the optimizer kernel reads
-            for k in ("w", "b"):
-                t = leaves[name][k]
-                t.grad = flat_g[off: off + t.numel()].view(t.shape)
-                off += t.numel()
-        call = dict(mask=mask, action=action, old_log_prob=old_lp, old_value=old_v, adv=adv, targets=tgt, cfg=cfg, scratch=acc)
-        x_mb = torch.empty((mbs, obs.shape[1]), dtype=obs.dtype, device=dev)
-        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = False  # the reference computes in fp32
-        try:
-            for epoch in range(n_epochs):
-                rng, _rng = brandom.split(rng)                                        # src/update.py:187
-                perm = permutation(_rng)
-                for mb in range(nmb):                                                  # src/update.py:207-209
-                    index = perm[mb * mbs:(mb + 1) * mbs]
-                    ops.gather_rows(obs, index, x_mb)
-                    x = x_mb.to(torch.float32)                                         # src/update.py:95
-                    logits, value = _forward_autograd(leaves, x, act)
-                    call["index"], call["stats"] = index, stats_all[epoch, mb]
-                    loss = _LossHead.apply(logits.contiguous(), value.contiguous(), call)
-                    flat_g.zero_()
-                    loss.backward()
-                    state = optimizer.update_(flat_p, flat_g, state)                  # src/update.py:168-169
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        blob = ops.mlp_pack_train(flat_p)
+        scratch = ops.mlp_train_scratch(mbs, dev)
+        flat_g = torch.empty_like(flat_p)
+        for epoch in range(n_epochs):
+            rng, _rng = brandom.split(rng)                                        # src/update.py:187
+            perm = permutation(_rng)
+            for mb in range(nmb):                                                  # src/update.py:207-209
+                ops.ppo_grad(obs, blob, scratch, perm[mb * mbs:(mb + 1) * mbs], mask, action, old_lp, old_v, adv, tgt,
+                             flat_g, stats_all[epoch, mb], acc, tune=tune, illegal_stat=stat_mode == "all" or mb == nmb - 1,
+                             **cfg)                                                # src/update.py:164-167
+                state = optimizer.update_mlp_(flat_p, flat_g, state, acc[14:15], blob)  # src/update.py:168-169
         return finish()
 
     return update_step

@@ -233,11 +233,27 @@ int32_t brl_mlp_forward(brl_stream_t, void **buffers, const void *opaque, size_t
  *          [7] out f32 logits[n,38] (NULL ok)
  * params: flags BRL_F_SAMPLE / BRL_F_MLP_BF16, seed, env_offset, step as for brl_categorical. */
 int32_t brl_policy_act(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+/* brl_policy_act on a LIST of envs: n_envs = number of listed rows.  obs / mask / action / log_prob are the full per-env
+ * arrays; only the listed envs are read and written.  This is how the evaluation loops (src/evaluation.py:124-151) avoid
+ * the reference's vmap waste of running both teams' nets on every env and of forwarding finished envs.
+ * buffers: [0] in bf16 obs[total,480]  [1] in packed parameters  [2] scratch (brl_mlp_rows_scratch_bytes(n_envs))
+ *          [3] in u8 mask[total,38] (NULL -> unmasked)  [4] out i32 action[total]  [5] in i32 row_index[n_envs]
+ *          [6] out f32 log_prob[total] (NULL ok)  [7] out f32 logits[total,38] (NULL ok; rows of the listed envs)
+ * The Gumbel noise of BRL_F_SAMPLE is keyed by env_offset + row_index[r], i.e. identical to the unlisted call. */
+int64_t brl_mlp_rows_scratch_bytes(int64_t n_rows);
+int32_t brl_policy_act_rows(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
+/* Rows of the envs still playing, split by the team of the player to act (players 0/1 = team 1, 2/3 = team 2).
+ * buffers: [0] in i8 current_player[n]  [1] in u8 done[n] (NULL -> all live)  [2] out i32 rows_team1[n]
+ *          [3] out i32 rows_team2[n]  [4] out i32 counts[2] */
+int32_t brl_team_rows(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
 /* ---- PPO update, non-GEMM part (src/update.py:74-242, ppo.py:195-211) ----------------------- */
 #define BRL_PPO_VALUE_CLIPPING  0x1 /* config["value_clipping"]  (src/update.py:47-62) */
 #define BRL_PPO_REWARD_SCALING  0x2 /* config["reward_scaling"]: (gae - mean) / (std + 1e-8) per minibatch (src/update.py:31-45) */
 #define BRL_PPO_UNMASKED_POLICY 0x4 /* actor_illegal_action_penalty mode: log-prob from the unmasked softmax (src/update.py:18-24) */
+#define BRL_PPO_ILLEGAL_STAT    0x8 /* brl_ppo_grad with illegal_l2_coef == 0: also form the logged illegal_action_loss (a 38 x 38
+                                       eigen-problem per minibatch, ~19 us); clear: stats[6] = NaN.  With a non-zero coefficient
+                                       and in brl_ppo_loss the norm is always formed (the gradient needs it). */
 
 typedef struct BrlPpoParams {
     int64_t batch;         /* samples in this minibatch                                  */
@@ -251,6 +267,8 @@ typedef struct BrlPpoParams {
                               width (128x128 / 128x64) in the fused forward / backward launch, 8 = per-tile time stamps
                               into the scratch (brl_mlp_train_trace_offset) */
 } BrlPpoParams;
+
+#define BRL_PPO_SCRATCH_BYTES 188416 /* scratch of brl_ppo_loss / brl_ppo_grad (buffers[12]) */
 
 typedef struct BrlAdamParams {
     int64_t n;             /* elements of the flat parameter buffer                      */
@@ -268,7 +286,9 @@ typedef struct BrlAdamParams {
  *          [5] in f32 old_log_prob[total]  [6] in f32 old_value[total]  [7] in f32 advantages[total]
  *          [8] in f32 targets[total]  [9] out f32 dlogits[B,38]  [10] out f32 dvalue[B]
  *          [11] out f32 stats[8] = {total_loss, value_loss, loss_actor, entropy, approx_kl, clipfracs,
- *               illegal_action_loss, 0}  [12] scratch f64[16] */
+ *               illegal_action_loss, 0}  [12] scratch, BRL_PPO_SCRATCH_BYTES, 16-byte aligned (f64[16] accumulators, then the
+ *               38 x 38 Gram partials of the illegal-probability matrix: illegal_action_loss is its SPECTRAL norm / 2,
+ *               jnp.linalg.norm(X, ord=2) of a 2-D array, src/update.py:141-142) */
 int32_t brl_ppo_loss(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 /* optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, eps)) over one flat fp32 buffer.  opaque = BrlAdamParams.
  * buffers: [0] inout f32 params[n]  [1] in f32 grads[n]  [2] inout f32 m[n]  [3] inout f32 v[n]  [4] scratch f64[1] */
@@ -310,8 +330,8 @@ int32_t brl_mlp_adam_step(brl_stream_t, void **buffers, const void *opaque, size
  *          [2] scratch[brl_mlp_train_scratch_bytes(B)]  [3] in i32 index[B] (NULL = identity)  [4] in u8 mask[total,38]
  *          [5] in i32 action[total]  [6] in f32 old_log_prob[total]  [7] in f32 old_value[total]
  *          [8] in f32 advantages[total]  [9] in f32 targets[total]  [10] out f32 grads[brl_mlp_num_params()]
- *          [11] out f32 stats[8] (as brl_ppo_loss)  [12] scratch f64[16]; on return element 14 = sum of squares of grads
- *               (the input of brl_adam_apply) */
+ *          [11] out f32 stats[8] (as brl_ppo_loss)  [12] scratch, BRL_PPO_SCRATCH_BYTES (as brl_ppo_loss); on return its f64
+ *               element 14 = sum of squares of grads (the input of brl_adam_apply) */
 int32_t brl_ppo_grad(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
 /* ---- full evaluation statistics (src/evaluation.py:207-1032) ---------------------------------- */
@@ -337,12 +357,20 @@ int32_t brl_eval_summary(brl_stream_t, void **buffers, const void *opaque, size_
 
 /* -------------------------------------------------------------------------
  * Legacy XLA GPU custom-call targets (API_VERSION_STATUS_RETURNING -- the convention
- * of jax/jaxlib 0.4.23, the version brl pins in requirements.txt:25-26): same buffers
- * and opaque as the op they wrap; a failing op sets the XLA status instead of returning
- * a code.  Register with xla_client.register_custom_call_target(name, capsule, "CUDA")
- * (INTEGRATION.md).  Typed-FFI handlers (brl_step_ffi, brl_gae_ffi) are built only when
- * the XLA FFI headers are present (csrc/xla_ffi_shim.cc).
+ * of jax/jaxlib 0.4.23, the version brl pins in requirements.txt:25-26).  `buffers` arrive in
+ * XLA's order -- the op's inputs (operands) first, then its outputs (results), each in the
+ * order the op documents; a buffer the op updates in place is an operand AND an aliased result
+ * (input_output_aliases) -- and are re-ordered into the op's list by csrc/xla_ffi_shim.cc from
+ * the per-op layout string `brl_xla_layout(name)` returns (one char per op buffer: i input,
+ * o output, s scratch output, x in place).  `opaque` = the bytes of the op's params struct.  A
+ * failing op sets the XLA status through XlaCustomCallStatusSetFailure, looked up in the process
+ * at call time; without that symbol the failure is counted in brl_xla_unreported_failures() and
+ * stays in brl_last_error().  Register with xla_client.register_custom_call_target(name,
+ * capsule, "CUDA").  Typed-FFI handlers `<op>_ffi` for the same table are built
+ * only when the XLA FFI headers are present.
  * ------------------------------------------------------------------------- */
+const char *brl_xla_layout(const char *op_name);
+long long brl_xla_unreported_failures(void);
 struct XlaCustomCallStatus_;
 void brl_make_keys_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_init_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
@@ -363,6 +391,8 @@ void brl_mlp_pack_xla(brl_stream_t, void **buffers, const char *opaque, size_t o
 void brl_obs_to_bf16_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_mlp_forward_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_policy_act_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_policy_act_rows_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
+void brl_team_rows_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_ppo_loss_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_adam_clip_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);
 void brl_adam_apply_xla(brl_stream_t, void **buffers, const char *opaque, size_t opaque_len, struct XlaCustomCallStatus_ *status);

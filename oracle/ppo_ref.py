@@ -35,7 +35,8 @@ def loss_fn(logits, value, mask, action, old_log_prob, old_value, gae, targets, 
     # 0 * log 0 := 0 (distrax); the select is applied BEFORE the product so autograd never sees 0 * inf
     entropy = -(p_masked * torch.where(mask, logp_masked, torch.zeros_like(logp_masked))).sum(1).mean()  # :133-137
     probs = torch.softmax(logits, dim=1)                               # :139-140
-    illegal_action_loss = torch.linalg.norm((probs * (~mask)).reshape(-1), ord=2) / 2                    # :141-142
+    # jnp.linalg.norm(x, ord=2) of a 2-D [minibatch, 38] array is the SPECTRAL norm (largest singular value), not Frobenius
+    illegal_action_loss = torch.linalg.matrix_norm(probs * (~mask), ord=2) / 2                          # :141-142
     total = loss_actor + vf_coef * value_loss - ent_coef * entropy + illegal_l2_coef * illegal_action_loss  # :144-149
     approx_kl = ((ratio - 1) - logratio).mean()                        # :153
     clipflacs = ((ratio - 1.0).abs() > clip_eps).to(logits.dtype).mean()   # :154-156

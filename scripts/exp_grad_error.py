@@ -41,7 +41,7 @@ flat_p, _ = flatten_params(params)
 blob = ops.mlp_pack_train(flat_p)
 grads = torch.empty_like(flat_p)
 stats = torch.zeros(8, device=DEV)
-acc = torch.zeros(16, dtype=torch.float64, device=DEV)
+acc = ops.ppo_scratch(DEV)
 ops.ppo_grad(f32(obs), blob, ops.mlp_train_scratch(B, DEV), None, mask.to(torch.uint8).to(DEV), action.to(DEV), f32(old_lp), f32(old_v),
              f32(adv), f32(tgt), grads, stats, acc, **cfg)
 got_tc = grads.cpu().numpy().astype(np.float64)

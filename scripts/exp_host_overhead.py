@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from brl_b200 import ops, BridgeBidding
 from brl_b200 import random as brandom
 from brl_b200.deals import synthetic_deal_table
+from scripts.torch_baseline import TorchForwardPass  # noqa: E402
 from brl_b200.models import LAYERS, init_params, make_forward_pass
 from brl_b200.roll_out import make_roll_out
 dev = "cuda:0"
@@ -26,7 +27,7 @@ def host_and_gpu(fn, reps=50):
 
 
 for prec in ("tc", "tc-bf16"):
-    fp = make_forward_pass(precision=prec)
+    fp = make_forward_pass(precision=prec) if prec.startswith("tc") else TorchForwardPass("relu", prec)
     a = torch.empty(n, dtype=torch.int32, device=dev)
     xb = ops.obs_to_bf16(state.observation)
     print(prec, "fp.act(bf16 obs)      host %.1f us  gpu %.1f us" % host_and_gpu(lambda: fp.act(params, xb, state._mask_u8, a, sample=True, seed=3)))
@@ -37,7 +38,7 @@ print("env.step autoreset        host %.1f us  gpu %.1f us" % host_and_gpu(lambd
 config = dict(actor_illegal_action_mask=True, actor_illegal_action_penalty=False, game_mode="competitive",
               num_steps=32, reward_scale=7600.0, gamma=1.0, gae_lambda=0.95)
 for prec in ("tc", "tc-bf16"):
-    fp = make_forward_pass(precision=prec)
+    fp = make_forward_pass(precision=prec) if prec.startswith("tc") else TorchForwardPass("relu", prec)
     opp = init_params(2, dev)
     roll = make_roll_out(config, env, fp, fp)
     runner = [(params, None, state, state.observation, torch.zeros((), dtype=torch.int64, device=dev), brandom.PRNGKey(3))]

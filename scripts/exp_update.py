@@ -62,7 +62,7 @@ def main():
     scratch = ops.mlp_train_scratch(B, dev)
     flat_g = torch.empty_like(flat_p)
     stats = torch.zeros(8, dtype=torch.float32, device=dev)
-    acc = torch.zeros(16, dtype=torch.float64, device=dev)
+    acc = ops.ppo_scratch(dev)
     for tune, name in ((0, "tc_fused"), (16, "tc_fused_narrow_bwd"), (4, "tc_fused_wide_fwd")):
         st = [state]
 

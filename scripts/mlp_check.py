@@ -11,6 +11,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from brl_b200 import ops  # noqa: E402
 from brl_b200.deals import synthetic_deal_table  # noqa: E402
+from scripts.torch_baseline import TorchForwardPass  # noqa: E402
 from brl_b200.models import LAYERS, init_params, make_forward_pass  # noqa: E402
 
 dev = "cuda:0"
@@ -61,7 +62,7 @@ def main():
         scale_l, scale_v = float(l64.abs().max()), float(v64.abs().max())
         row = {"n_envs": n}
         for prec in modes:
-            fp = make_forward_pass(precision=prec)
+            fp = make_forward_pass(precision=prec) if prec.startswith("tc") else TorchForwardPass("relu", prec)
             logits, value = fp.apply(params, x)
             torch.cuda.synchronize()
             el = float((logits.double() - l64).abs().max()) / scale_l

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--fp32-iters", type=int, default=1)
     args = ap.parse_args()
+    from scripts.torch_baseline import TorchForwardPass, make_update_step_autograd
     from brl_b200 import ppo, random as brandom
     from brl_b200.deals import synthetic_deal_table
     tables = [synthetic_deal_table(100_000, seed=k) for k in range(2)]
@@ -28,8 +29,10 @@ def main():
             continue
         with tempfile.TemporaryDirectory() as tmp:
             cfg = dict(total_timesteps=8192 * 32 * (iters + 2), num_eval_envs=1000, num_eval_step=1000, num_prioritized_envs=100,
-                       save_model=False, log_path=tmp, policy_precision=None if prec == "tc" else prec)
-            _, logs = ppo.train(cfg, brandom.PRNGKey(0), tables=tables, eval_table=eval_table, device="cuda:0")
+                       save_model=False, log_path=tmp)
+            hooks = {} if prec == "tc" else dict(forward_pass_factory=lambda act, mt: TorchForwardPass(act, "fp32"),
+                                                 update_step_factory=make_update_step_autograd)
+            _, logs = ppo.train(cfg, brandom.PRNGKey(0), tables=tables, eval_table=eval_table, device="cuda:0", **hooks)
         logs = logs[2:]  # the first two iterations pay lazy initialisation (library load, the second deal table's buffers)
         mean = lambda k: sum(log[k] for log in logs) / len(logs)  # noqa: E731
         out[prec] = {"iterations_timed": len(logs), "rollout_s": mean("time/rollout"), "calc_gae_s": mean("time/calc_gae"),

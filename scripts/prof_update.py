@@ -28,7 +28,7 @@ blob = ops.mlp_pack_train(flat_p)
 scratch = ops.mlp_train_scratch(B, dev)
 flat_g = torch.empty_like(flat_p)
 stats = torch.zeros(8, dtype=torch.float32, device=dev)
-acc = torch.zeros(16, dtype=torch.float64, device=dev)
+acc = ops.ppo_scratch(dev)
 cfg = dict(clip_eps=0.2, ent_coef=0.01, vf_coef=0.5, illegal_l2_coef=0.0, value_clipping=True, reward_scaling=False, masked_policy=True)
 for i in range(iters):
     ops.ppo_grad(obs, blob, scratch, perm[i * B:(i + 1) * B], mask, action, old_lp, old_v, adv, tgt, flat_g, stats, acc, tune=tune, **cfg)

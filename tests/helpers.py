@@ -17,6 +17,23 @@ def load_boards():
     return {k: z[k] for k in z.files}
 
 
+def load_c1():
+    """configs[0] golden match (tests/golden/make_c1_golden.py)"""
+    z = np.load(os.path.join(GOLDEN, "c1_eval_match.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def weight_path(name):
+    """bundled model pickle shipped as a fixture (git-ignored; __graft_entry__.build() copies it from the reference)"""
+    path = os.path.join(GOLDEN, "_weights", name)
+    if not os.path.exists(path):
+        ref = os.path.join("/root/reference/bridge_models", name)
+        if os.path.exists(ref):
+            return ref
+        raise FileNotFoundError(f"{path} is missing: run `python __graft_entry__.py` (build) where /root/reference is mounted")
+    return path
+
+
 def load_auctions():
     z = np.load(os.path.join(GOLDEN, "auctions.npz"))
     return {k: z[k] for k in z.files}

@@ -214,6 +214,8 @@ def test_simple_duplicate_evaluate_matches_oracle_replay():
     assert ref.export()["terminated"].all()
     assert (cum.cpu().numpy() == cum_ref).all()
     assert agree / total > 0.995, f"argmax agreement {agree}/{total} (near-ties flip between cuBLAS and NumPy summation order)"
+    # each net ran only on the live envs its team decides (src/evaluation.py:124-151 runs both nets on all n every iteration)
+    assert evaluate.rows_forwarded == total and total < len(trace) * n
     want_stats = orc.match_stats(cum_ref)
     np.testing.assert_allclose([mean, se, win], want_stats, rtol=1e-9, atol=1e-12)
     for buf, info in ((info_a, ref.info_a), (info_b, ref.info_b)):
@@ -223,14 +225,51 @@ def test_simple_duplicate_evaluate_matches_oracle_replay():
         assert (buf.last_bidder.cpu().numpy() == info["last_bidder"]).all()
 
 
-def test_simple_evaluate_runs_to_completion():
+def test_simple_evaluate_matches_oracle_replay():
+    """src/evaluation.py:11-66 (the per-iteration strength probe of ppo.py:366): deterministic quad steps against a
+    fixed opponent on the 1000 real boards; the traced sub-step actions are replayed on the oracle and the per-env
+    return R = sum of rewards[actor] must be bit-equal, R.mean() equal, and the GPU's argmax decisions must be the
+    float64 NumPy MLP's wherever they are not near-ties."""
+    from brl_b200 import BridgeBidding
     from brl_b200.evaluation import make_simple_evaluate
-    from brl_b200.models import init_params
+    from brl_b200.models import init_params, params_to_numpy
     from brl_b200 import random as brandom
-    env, _ = _mk_env()
-    ev = make_simple_evaluate(env, "relu", "DeepMind", "relu", "DeepMind", None, 128, team2_params=init_params(3, DEV))
-    r = ev(init_params(4, DEV), brandom.PRNGKey(5))
-    assert np.isfinite(float(r)) and abs(float(r)) <= 7600
+    from oracle import oracle as orc
+    boards = H.load_boards()
+    env = BridgeBidding(table=boards["table"], device=DEV)
+    n = 128
+    p_actor, p_opp = init_params(4, DEV), init_params(3, DEV)
+    ev = make_simple_evaluate(env, "relu", "DeepMind", "relu", "DeepMind", None, n, team2_params=p_opp)
+    trace = []
+    rng = brandom.PRNGKey(5)
+    mean = ev(p_actor, rng, trace=trace)
+    tag, R = trace.pop()
+    assert tag == "R" and len(trace) % 4 == 0
+    _, sub = brandom.split(rng)
+    ref = orc.OracleEnv(boards["table"], n)
+    ref.init(env.make_keys(sub, n).cpu().numpy().view(np.uint64))
+    np_actor, np_opp = params_to_numpy(p_actor), params_to_numpy(p_opp)
+    R_ref = np.zeros(n, np.float32)
+    agree = total = 0
+    for it in range(len(trace) // 4):
+        actor = ref.export()["current_player"].astype(np.int64)
+        rew = np.zeros((n, 4), np.float32)
+        for k in range(4):
+            e = ref.export()
+            live = e["terminated"] == 0
+            got = trace[4 * it + k].cpu().numpy()
+            lg, _ = orc.mlp_forward(np_opp if k in (1, 3) else np_actor, e["observation"])   # src/utils.py:150-196
+            want, _ = orc.categorical(lg, e["legal_action_mask"], sample=False)
+            agree += int((want[live] == got[live]).sum())
+            total += int(live.sum())
+            ref.step(got)                                # a finished env: zero-reward no-op (src/evaluation.py:31-33)
+            rew += ref.export()["rewards"]
+        R_ref += rew[np.arange(n), actor]                                                    # src/evaluation.py:58
+    assert ref.export()["terminated"].all()
+    assert (R.cpu().numpy() == R_ref).all()
+    assert abs(float(mean) - float(R_ref.astype(np.float64).mean())) <= 1e-6 * max(1.0, abs(float(R_ref.mean())))
+    assert np.abs(R_ref).max() <= 7600 and (R_ref != 0).any()
+    assert agree / total > 0.995, f"argmax agreement {agree}/{total}"
 
 
 def test_league_evaluate_equals_separate_matches():
@@ -253,3 +292,34 @@ def test_league_evaluate_equals_separate_matches():
         (mean, se, win), _, _, _ = single(actor, pool[m], rng)
         np.testing.assert_allclose(res[m], (mean, se, win), rtol=1e-12)
     assert len({round(r[0], 6) for r in res}) == n_models  # three different opponents, three different results
+
+
+def test_c1_eval_match_with_bundled_weights_reproduces_golden():
+    """BASELINE configs[0] / eval.py:43-65: model-pretrained-rl.pkl vs model-sl.pkl, num_eval_envs=100, on the GPU path
+    (tensor-core forward, duplicate_step kernel).  Every live decision must equal the frozen float64 decision (the
+    smallest top-2 gap of the match is 1.4e-3, far above the forward's 1e-5 error), and IMP mean +- SE, the per-board
+    IMPs and both tables' contracts must equal the golden values, which the reference's own scorer reproduced."""
+    from brl_b200 import BridgeBidding
+    from brl_b200.evaluation import make_simple_duplicate_evaluate
+    from brl_b200.models import load_params
+    from brl_b200 import random as brandom
+    g = H.load_c1()
+    boards = H.load_boards()
+    env = BridgeBidding(table=boards["table"], device=DEV)
+    n = int(g["n"])
+    p1, p2 = (load_params(H.weight_path(str(m)), DEV) for m in g["models"])
+    evaluate = make_simple_duplicate_evaluate(env, "relu", "DeepMind", "relu", "DeepMind", n)
+    trace = []
+    (mean, se, win), info_a, info_b, cum = evaluate(p1, p2, brandom.PRNGKey(int(g["seed"])), trace=trace)
+    steps = g["actions"].shape[0]
+    assert len(trace) >= steps
+    for t in range(steps):
+        live = g["live"][t] != 0
+        got = trace[t][0].cpu().numpy()
+        assert (got[live] == g["actions"][t][live]).all(), f"step {t}: decisions differ from the float64 golden ones"
+    assert (cum.cpu().numpy() == g["imps"]).all()
+    np.testing.assert_allclose([mean, se, win], g["stats"], rtol=1e-9, atol=1e-12)
+    for k, info in (("a", info_a), ("b", info_b)):
+        assert (info.last_bid.cpu().numpy() == g[k + "_last_bid"]).all()
+        assert (info.last_bidder.cpu().numpy() == g[k + "_last_bidder"]).all()
+        assert (info.rewards.cpu().numpy() == g[k + "_rewards"]).all()

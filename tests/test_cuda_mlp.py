@@ -61,10 +61,11 @@ def test_tc_forward_matches_float64_reference(n):
 def test_tc_forward_tracks_cublas_fp32():
     """independent cross-check against the library GEMM chain (cuBLAS fp32 through torch)"""
     from brl_b200.models import make_forward_pass
+    from scripts.torch_baseline import TorchForwardPass
     params = _params(3)
     x = _real_obs(4096)
     lt, vt = make_forward_pass(precision="tc").apply(params, x)
-    lf, vf = make_forward_pass(precision="fp32").apply(params, x)
+    lf, vf = TorchForwardPass("relu", "fp32").apply(params, x)
     assert float((lt - lf).abs().max()) <= 5e-5 * float(lf.abs().max())
     assert float((vt - vf).abs().max()) <= 5e-5 * max(float(vf.abs().max()), 1e-3)
 
@@ -131,3 +132,65 @@ def test_policy_act_equals_forward_then_categorical(n, sample):
         a3 = torch.full_like(a_ref, -7)
         ops.policy_act(x, blob, scratch, m, a3, sample=sample, seed=99, env_offset=1000)
         assert torch.equal(a3, a_ref)
+
+
+def test_product_forward_has_no_library_back_end():
+    """north_star: no multi-backend dispatch.  The product's forward pass is the tensor-core kernel or nothing."""
+    from brl_b200.models import make_forward_pass
+    for bad in ("fp32", "tf32", "bf16"):
+        with pytest.raises(ValueError):
+            make_forward_pass(precision=bad)
+    with pytest.raises(NotImplementedError):
+        make_forward_pass(activation="tanh")
+    with pytest.raises(NotImplementedError):
+        make_forward_pass(model_type="FAIR")
+
+
+def test_team_rows_lists_live_envs_by_acting_team():
+    from brl_b200 import ops
+    for n in (1, 37, 1024, 5000, 70_001):
+        g = torch.Generator(device=DEV).manual_seed(n)
+        player = torch.randint(0, 4, (n,), generator=g, device=DEV).to(torch.int8)
+        done = (torch.rand(n, generator=g, device=DEV) < 0.4).to(torch.uint8)
+        r1, r2 = torch.full((n,), -1, dtype=torch.int32, device=DEV), torch.full((n,), -1, dtype=torch.int32, device=DEV)
+        counts = torch.full((2,), 99, dtype=torch.int32, device=DEV)
+        ops.team_rows(player, done, r1, r2, counts)
+        c1, c2 = counts.tolist()
+        want1 = torch.nonzero((done == 0) & (player < 2))[:, 0].to(torch.int32)
+        want2 = torch.nonzero((done == 0) & (player >= 2))[:, 0].to(torch.int32)
+        assert c1 == want1.numel() and c2 == want2.numel()
+        assert torch.equal(torch.sort(r1[:c1]).values, want1) and torch.equal(torch.sort(r2[:c2]).values, want2)
+        # rows ascend inside each 1024-env block (ballot order)
+        if n <= 1024:
+            assert torch.equal(r1[:c1], want1) and torch.equal(r2[:c2], want2)
+        ops.team_rows(player, None, r1, r2, counts)   # done = NULL: every env is live
+        assert int(counts.sum()) == n
+
+
+@pytest.mark.parametrize("n,n_rows", [(300, 100), (9000, 4096 + 77), (20_000, 13_000)])
+@pytest.mark.parametrize("sample", [False, True])
+def test_policy_act_rows_equals_full_policy_act_on_the_listed_envs(n, n_rows, sample):
+    """the listed forward (gather -> net -> scatter by env) gives bit-identical action / log_prob / logits to the full-batch
+    call for the listed envs and leaves every other entry untouched -- below and above the fused-launch size"""
+    from brl_b200 import ops
+    from brl_b200.models import make_forward_pass
+    params = _params(6)
+    x = ops.obs_to_bf16(_real_obs(n))
+    g = torch.Generator(device=DEV).manual_seed(5)
+    mask = (torch.rand((n, 38), generator=g, device=DEV) < 0.5).to(torch.uint8)
+    mask[:, 0] = 1
+    fp = make_forward_pass(precision="tc")
+    packed = fp._packed(params)
+    a_full = torch.empty(n, dtype=torch.int32, device=DEV)
+    lp_full = torch.empty(n, dtype=torch.float32, device=DEV)
+    lg_full = torch.empty((n, 38), dtype=torch.float32, device=DEV)
+    ops.policy_act(x, packed, ops.mlp_scratch(n, DEV), mask, a_full, lp_full, None, lg_full, sample=sample, seed=77, env_offset=1000)
+    rows = torch.randperm(n, generator=g, device=DEV)[:n_rows].to(torch.int32).contiguous()
+    a = torch.full((n,), -5, dtype=torch.int32, device=DEV)
+    lp = torch.full((n,), 9.0, dtype=torch.float32, device=DEV)
+    lg = torch.full((n, 38), 7.0, dtype=torch.float32, device=DEV)
+    ops.policy_act_rows(x, packed, ops.mlp_rows_scratch(n_rows, DEV), mask, a, rows, lp, lg, sample=sample, seed=77, env_offset=1000)
+    sel = torch.zeros(n, dtype=torch.bool, device=DEV)
+    sel[rows.long()] = True
+    assert torch.equal(a[sel], a_full[sel]) and torch.equal(lp[sel], lp_full[sel]) and torch.equal(lg[sel], lg_full[sel])
+    assert bool((a[~sel] == -5).all()) and bool((lp[~sel] == 9.0).all()) and bool((lg[~sel] == 7.0).all())

@@ -54,7 +54,7 @@ def test_ppo_loss_and_gradient_match_autograd(value_clipping, reward_scaling, ma
     dlogits = torch.empty((B, 38), dtype=torch.float32, device=DEV)
     dvalue = torch.empty(B, dtype=torch.float32, device=DEV)
     stats = torch.zeros(8, dtype=torch.float32, device=DEV)
-    scratch = torch.zeros(16, dtype=torch.float64, device=DEV)
+    scratch = ops.ppo_scratch(DEV)
     ops.ppo_loss(f32(logits), f32(value), index.to(DEV), mask.to(torch.uint8).to(DEV).contiguous(), action.to(DEV), f32(old_lp),
                  f32(old_v), f32(adv), f32(tgt), dlogits, dvalue, stats, scratch, **cfg)
     got = stats.cpu().numpy()
@@ -179,7 +179,7 @@ def test_ppo_grad_matches_float64_autograd(B, total, obs_dtype, tune):
     scratch = ops.mlp_train_scratch(B, DEV)
     grads = torch.full_like(flat_p, float("nan"))
     stats = torch.zeros(8, dtype=torch.float32, device=DEV)
-    acc = torch.zeros(16, dtype=torch.float64, device=DEV)
+    acc = ops.ppo_scratch(DEV)
     ops.ppo_grad(obs.to(obs_dtype).to(DEV).contiguous(), blob, scratch, index.to(DEV), mask.to(torch.uint8).to(DEV).contiguous(),
                  action.to(DEV), f32(old_lp), f32(old_v), f32(adv), f32(tgt), grads, stats, acc, tune=tune, **cfg)
     got = stats.cpu().numpy()
@@ -265,6 +265,7 @@ def test_update_step_matches_float64_reference(precision):
     from brl_b200.update import make_update_step
     from brl_b200 import random as brandom
     from oracle import ppo_ref
+    from scripts.torch_baseline import TorchForwardPass, make_update_step_autograd
     T, n, mbs, epochs = 4, 64, 64, 2
     nmb = T * n // mbs
     config = dict(actor_illegal_action_mask=True, actor_illegal_action_penalty=False, clip_eps=0.2, ent_coef=0.001,
@@ -276,7 +277,7 @@ def test_update_step_matches_float64_reference(precision):
     mask[..., 0] = True
     action = torch.zeros((T, n), dtype=torch.int32)
     params = init_params(9, DEV)
-    fp = make_forward_pass("relu", "DeepMind", precision="fp32")
+    fp = TorchForwardPass("relu", "fp32")
     torch.manual_seed(3)  # the action sample below draws from the global CUDA generator
     with torch.no_grad():
         logits, value = fp.apply(params, obs.reshape(-1, 480).to(DEV))
@@ -294,8 +295,13 @@ def test_update_step_matches_float64_reference(precision):
     it = iter(perms)
     lr = 1e-3
     opt = AdamWithClip(lr, eps=1e-5, max_grad_norm=0.5)
-    update_step = make_update_step(config, make_forward_pass("relu", "DeepMind", precision=precision), opt,
-                                   permutation_fn=lambda rng, bs: next(it))
+    if precision == "fp32":   # cuBLAS + autograd cross-check (scripts/torch_baseline.py), not a product back end
+        update_step = make_update_step_autograd(config, fp, opt, permutation_fn=lambda rng, bs: next(it))
+        with pytest.raises(TypeError):
+            make_update_step(config, fp, opt)
+    else:
+        update_step = make_update_step(config, make_forward_pass("relu", "DeepMind", precision=precision), opt,
+                                       permutation_fn=lambda rng, bs: next(it))
     before = {k: v.copy() for k, v in params_to_numpy(params).items()}
     runner = (params, opt.init(params), None, None, 0, brandom.PRNGKey(0))
     runner2, (total_loss, aux) = update_step(runner, traj, adv.to(DEV), tgt.to(DEV))
@@ -352,3 +358,42 @@ def test_update_step_matches_float64_reference(precision):
         assert np.median(err) <= 0.01 * lr * count, float(np.median(err))
         assert np.quantile(err, 0.99) <= 0.1 * lr * count, [float(np.quantile(err, q)) for q in (0.5, 0.9, 0.99, 0.999, 1.0)]
     assert np.abs(delta_ref).max() > 0.5 * lr   # the update actually moved the parameters
+
+
+def test_illegal_action_statistic_is_opt_in_and_never_wrong():
+    """brl_ppo_grad with the default coefficient 0: the logged illegal_action_loss (spectral norm) is formed when asked for
+    (bit-identical to a run that asks for it) and is NaN -- not stale, not an approximation -- when not; nothing else moves."""
+    from brl_b200 import ops
+    from brl_b200.models import init_params
+    from brl_b200.optim import flatten_params
+    B, total = 512, 2000
+    logits, value, index, mask, action, old_lp, old_v, adv, tgt = _case(B, total, 11)
+    g = torch.Generator().manual_seed(2)
+    obs = (torch.rand((total, 480), generator=g) < 0.05).to(torch.float32)
+    f32 = lambda t: t.to(torch.float32).to(DEV).contiguous()  # noqa: E731
+    flat_p, _ = flatten_params(init_params(3, DEV))
+    blob = ops.mlp_pack_train(flat_p)
+    scratch = ops.mlp_train_scratch(B, DEV)
+    cfg = dict(clip_eps=0.2, ent_coef=0.01, vf_coef=0.5, illegal_l2_coef=0.0)
+    out = {}
+    for want in (True, False):
+        grads = torch.empty_like(flat_p)
+        stats = torch.full((8,), -3.0, dtype=torch.float32, device=DEV)
+        acc = ops.ppo_scratch(DEV)
+        ops.ppo_grad(obs.to(DEV), blob, scratch, index.to(DEV), mask.to(torch.uint8).to(DEV).contiguous(), action.to(DEV),
+                     f32(old_lp), f32(old_v), f32(adv), f32(tgt), grads, stats, acc, illegal_stat=want, **cfg)
+        torch.cuda.synchronize()
+        out[want] = (grads.clone(), stats.cpu().numpy())
+    assert torch.equal(out[True][0], out[False][0])
+    assert (out[True][1][:6] == out[False][1][:6]).all()
+    assert np.isnan(out[False][1][6]) and np.isfinite(out[True][1][6]) and out[True][1][6] > 0
+    # and the value is the matrix 2-norm of the illegal probabilities of THIS forward's logits
+    from scripts.torch_baseline import TorchForwardPass  # noqa: F401  (float64 check below needs no GEMM library)
+    from brl_b200.models import LAYERS, init_params as ip
+    p = ip(3, "cpu")
+    h = obs[index.long()].double()
+    for name in LAYERS[:4]:
+        h = torch.relu(h @ p[name]["w"].double() + p[name]["b"].double())
+    lg = h @ p[LAYERS[4]]["w"].double() + p[LAYERS[4]]["b"].double()
+    X = torch.softmax(lg, 1) * (~mask[index.long()])
+    np.testing.assert_allclose(out[True][1][6], float(torch.linalg.matrix_norm(X, 2)) / 2, rtol=5e-5)

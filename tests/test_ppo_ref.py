@@ -37,3 +37,33 @@ def test_adam_clip_first_step_is_sign_step():
     # below the threshold the gradient is untouched
     p2, m2, _ = ppo_ref.adam_clip_step(np.zeros(3), g / 100, np.zeros(3), np.zeros(3), 0, lr=0.1, max_grad_norm=0.5)
     np.testing.assert_allclose(m2, 0.1 * g / 100)
+
+
+def test_illegal_action_loss_is_the_spectral_norm_of_the_minibatch_matrix():
+    """src/update.py:141-142: `jnp.linalg.norm(X, ord=2)` of the 2-D [minibatch, 38] matrix X = probs * ~mask is its
+    largest singular value, NOT the Frobenius norm of the flattened matrix.  Known answer: two samples whose illegal mass
+    sits on DIFFERENT single actions give orthogonal rows, so sigma_max = max row norm while Frobenius = sqrt(sum)."""
+    B = 2
+    logits = torch.zeros((B, 38), dtype=torch.float64)
+    logits[0, 5], logits[1, 9] = 3.0, 1.0
+    mask = torch.ones((B, 38), dtype=torch.bool)
+    mask[0, 5] = False          # sample 0: action 5 illegal, sample 1: action 9 illegal
+    mask[1, 9] = False
+    z = torch.zeros(B, dtype=torch.float64)
+    _, aux = ppo_ref.loss_fn(logits, z, mask, torch.zeros(B, dtype=torch.long), z, z, z, z, clip_eps=0.2, ent_coef=0.0,
+                             vf_coef=0.5)
+    q0 = float(torch.softmax(logits[0], 0)[5])
+    q1 = float(torch.softmax(logits[1], 0)[9])
+    assert abs(float(aux[5]) - max(q0, q1) / 2) < 1e-12
+    assert abs(float(aux[5]) - np.sqrt(q0 * q0 + q1 * q1) / 2) > 1e-3      # and it is not the Frobenius value
+    # general case against NumPy's own matrix 2-norm (numpy.linalg.norm(x, 2) == what jnp.linalg.norm mirrors)
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn((64, 38), generator=g, dtype=torch.float64) * 2
+    mask = torch.rand((64, 38), generator=g) < 0.5
+    mask[:, 0] = True
+    z = torch.zeros(64, dtype=torch.float64)
+    _, aux = ppo_ref.loss_fn(logits, z, mask, torch.zeros(64, dtype=torch.long), z, z, z, z, clip_eps=0.2, ent_coef=0.0,
+                             vf_coef=0.5)
+    X = (torch.softmax(logits, 1) * (~mask)).numpy()
+    assert abs(float(aux[5]) - np.linalg.norm(X, 2) / 2) < 1e-12
+    assert abs(np.linalg.norm(X, 2) - np.linalg.svd(X, compute_uv=False)[0]) < 1e-12
