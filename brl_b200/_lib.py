@@ -39,6 +39,8 @@ F_EVAL_INDICATOR_BIDS = 0x0400
 F_HOST_STAGED = 0x0800
 F_RESULT_I16 = 0x1000
 F_UNIFORM_U16 = 0x2000
+F_SEED_SALT = 0x4000
+F_COUNT_DONE = 0x8000
 ABI_VERSION = 2  # include/brl_b200.h BRL_ABI_VERSION; load() refuses a library built from other headers
 EVAL_ACC_COLS = 76
 

@@ -193,11 +193,16 @@ __global__ void __launch_bounds__(256) k_match_stats(const float* __restrict__ x
 }
 
 // ---- roll_out bookkeeping -- src/roll_out.py:85-94: rewards[actor] / reward_scale -------------
+// With `done` / `count`: also terminated_count += sum(done) (src/roll_out.py:85), one atomic per block.
 __global__ void __launch_bounds__(256) k_gather_reward(const float* __restrict__ rewards, const int8_t* __restrict__ actor,
-                                                       float* __restrict__ out, int64_t n, float scale) {
+                                                       float* __restrict__ out, int64_t n, float scale,
+                                                       const uint8_t* __restrict__ done, unsigned long long* __restrict__ count) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    out[i] = rewards[4 * i + (actor[i] & 3)] / scale;
+    if (i < n) out[i] = rewards[4 * i + (actor[i] & 3)] / scale;
+    if (count != nullptr) {
+        const int c = __syncthreads_count(i < n && done[i] != 0);
+        if (threadIdx.x == 0 && c > 0) atomicAdd(count, (unsigned long long)c);
+    }
 }
 
 
@@ -294,9 +299,13 @@ int32_t brl_gather_reward(brl_stream_t stream, void** b, const void* opaque, siz
     if (!p) return rc;
     if (b[0] == nullptr || b[1] == nullptr || b[2] == nullptr) return fail(BRL_E_BUFFER, "brl_gather_reward: NULL buffer");
     if (p->n_envs == 0) return BRL_OK;
+    const bool counting = (p->flags & BRL_F_COUNT_DONE) != 0;
+    if (counting && (b[3] == nullptr || b[4] == nullptr || (reinterpret_cast<uintptr_t>(b[4]) & 7u)))
+        return fail(BRL_E_BUFFER, "brl_gather_reward: BRL_F_COUNT_DONE needs buffers [3] done and [4] count (8-byte aligned)");
     k_gather_reward<<<(unsigned)((p->n_envs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         static_cast<const float*>(b[0]), static_cast<const int8_t*>(b[1]), static_cast<float*>(b[2]), p->n_envs,
-        p->gamma);
+        p->gamma, counting ? static_cast<const uint8_t*>(b[3]) : nullptr,
+        counting ? static_cast<unsigned long long*>(b[4]) : nullptr);
     return check_launch("brl_gather_reward");
 }
 

@@ -266,22 +266,23 @@ __device__ __forceinline__ uint32_t load_uniform(const EnvArgs& a, int64_t idx) 
     return a.uniform16 ? (uint32_t)reinterpret_cast<const uint16_t*>(a.uniforms)[idx] << 16 : a.uniforms[idx];
 }
 
-// warp-specialised rollout: the writer warps fetch the caller's uniforms of steps [s0, s0 + kUChunk) for the block's envs
-// (row r of the chunk by warp r % n_writers; every load of a warp is issued before the first one is consumed)
+// warp-specialised rollout: the writer warps fetch the caller's uniforms of steps s0 + 1 .. s0 + kUChunk for the block's envs
+// (step r lives in ring slot [(r / kUChunk) & 1][r % kUChunk]; offset d of the burst by warp d % n_writers; every load of a
+// warp is issued before the first one is consumed)
 constexpr int kUChunk = 32;
-__device__ __forceinline__ void load_uniform_chunk(const EnvArgs& a, uint32_t (*buf)[32], int s0, int64_t i, bool active, int warp,
-                                                   int n_writers, int lane) {
+__device__ __forceinline__ void load_uniform_burst(const EnvArgs& a, uint32_t (*ring)[kUChunk][32], int s0, int64_t i, bool active,
+                                                   int warp, int n_writers, int lane) {
     for (int base = warp; base < kUChunk; base += 8 * n_writers) {
         uint32_t v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int r = base + j * n_writers;
-            v[j] = (active && r < kUChunk && s0 + r < a.k_steps) ? load_uniform(a, (int64_t)(s0 + r) * a.n + i) : 0u;
+            const int r = s0 + 1 + base + j * n_writers;
+            v[j] = (active && base + j * n_writers < kUChunk && r < a.k_steps) ? load_uniform(a, (int64_t)r * a.n + i) : 0u;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int r = base + j * n_writers;
-            if (r < kUChunk) buf[r][lane] = v[j];
+            const int r = s0 + 1 + base + j * n_writers;
+            if (base + j * n_writers < kUChunk) ring[(r / kUChunk) & 1][r % kUChunk][lane] = v[j];
         }
     }
 }
@@ -452,14 +453,9 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
             cache.prime(e, rs, lane, a.table, a.n_deals);
             mask = env_legal_mask(e);
         }
-    } else if (a.uniforms) {
-        // Caller-supplied uniforms are read in bursts of kUChunk steps (here: chunk 0), all warps' loads in flight at once
-        // and before the store stream starts: a 128-byte read per block per step, trickling into DRAM between the
-        // trajectory's writes, cost 6-13 % of the whole kernel (read/write turnarounds; the pool is evicted from L2
-        // by the 519 MB the launch writes), scripts/exp_e2e_gap.py.
-        load_uniform_chunk(a, uniforms[0], 0, i, active, warp, n_writers, lane);
     } else if (warp == 0) {
-        uniforms[0][0][lane] = action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step);
+        uniforms[0][0][lane] = a.uniforms ? (active ? load_uniform(a, i) : 0u)
+                                          : action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step);
     }
     __syncthreads();
     BRL_T0();
@@ -517,9 +513,13 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                 }
             }
             if (s + 1 < a.k_steps) {
-                if (a.uniforms) {  // next chunk: the env warp is still reading the other buffer
-                    if ((s + 1) % kUChunk == 0)
-                        load_uniform_chunk(a, uniforms[((s + 1) / kUChunk) & 1], s + 1, i, active, warp, n_writers, lane);
+                if (a.uniforms) {
+                    // Caller-supplied uniforms are read in bursts of kUChunk steps, every warp's loads in flight at once: a
+                    // 128-byte read per block per step, trickling into DRAM between the trajectory's writes, cost 6-13 % of
+                    // the whole kernel (read / write turnarounds; the pool is evicted from L2 by the 519 MB a launch
+                    // writes), scripts/exp_e2e_gap.py.  The burst for steps s+1 .. s+32 is issued at s = 0, 32, ...: at s = 0
+                    // the writers have nothing to store yet, so it hides under the env warp's first step.
+                    if (s % kUChunk == 0) load_uniform_burst(a, uniforms, s, i, active, warp, n_writers, lane);
                 } else if (warp == 0) {
                     uniforms[((s + 1) / kUChunk) & 1][(s + 1) % kUChunk][lane] =
                         action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)(s + 1));

@@ -105,6 +105,7 @@ struct ActArgs {
     uint32_t step;
     int sample;
     const int32_t* row_index;  // [n] or NULL: row r of the batch is env row_index[r] (mask / action / log_prob / value / RNG by env)
+    const uint64_t* seed_salt; // device u64 or NULL: XORed into `seed` (a captured CUDA graph replays with fresh noise)
 };
 
 __device__ __forceinline__ void epilogue_head_act_row(uint32_t t_row, const float* __restrict__ bias, bool row_ok, int64_t row,
@@ -138,6 +139,7 @@ __device__ __forceinline__ void epilogue_head_act_row(uint32_t t_row, const floa
         }
     }
     const uint64_t g = (uint64_t)(act.env_offset + row);
+    const uint64_t seed = act.seed_salt ? (act.seed ^ __ldg(act.seed_salt)) : act.seed;
     float best = -INFINITY, mx = -INFINITY, la = 0.0f;
     int best_a = kNumActions;
 #pragma unroll
@@ -145,7 +147,7 @@ __device__ __forceinline__ void epilogue_head_act_row(uint32_t t_row, const floa
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (act.sample) {
             const uint4 rr = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), kTagGum + (uint32_t)grp, act.step),
-                                        make_uint2((uint32_t)act.seed, (uint32_t)(act.seed >> 32)));
+                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
             w[0] = rr.x; w[1] = rr.y; w[2] = rr.z; w[3] = rr.w;
         }
 #pragma unroll
@@ -1002,6 +1004,11 @@ int32_t brl_policy_act(brl_stream_t stream, void** b, const void* opaque, size_t
     act.env_offset = p->env_offset;
     act.step = p->step;
     act.sample = (p->flags & BRL_F_SAMPLE) ? 1 : 0;
+    if (p->flags & BRL_F_SEED_SALT) {
+        act.seed_salt = static_cast<const uint64_t*>(b[8]);
+        if (act.seed_salt == nullptr || (reinterpret_cast<uintptr_t>(b[8]) & 7u)) return fail(BRL_E_BUFFER, "brl_policy_act: BRL_F_SEED_SALT needs an 8-byte aligned buffer [8]");
+        if (p->n_envs < kPairMinM) return fail(BRL_E_OPAQUE, "brl_policy_act: BRL_F_SEED_SALT is supported by the fused launch only (n_envs >= %d)", kPairMinM);
+    }
     return mlp_forward_impl("brl_policy_act", (cudaStream_t)stream, p, b[0], static_cast<const unsigned char*>(b[1]),
                             static_cast<__nv_bfloat16*>(b[2]), static_cast<float*>(b[7]), static_cast<float*>(b[6]), act);
 }

@@ -52,12 +52,12 @@
     X(brl_categorical, "iioo") \
     X(brl_match_stats, "ix") \
     X(brl_state_fields, "iooooooooooo") \
-    X(brl_gather_reward, "iio") \
+    X(brl_gather_reward, "iioix") \
     X(brl_team_rows, "iiooo") \
     X(brl_mlp_pack, "iiiiiiiiiiiio") \
     X(brl_obs_to_bf16, "io") \
     X(brl_mlp_forward, "iisoo") \
-    X(brl_policy_act, "iisioooo") \
+    X(brl_policy_act, "iisiooooi") \
     X(brl_policy_act_rows, "iisixixx") \
     X(brl_ppo_loss, "iiiiiiiiiooos") \
     X(brl_adam_clip, "xixxs") \

@@ -89,6 +89,7 @@ class ForwardPass:
         self._activation = torch.relu
         self.precision = precision
         self._scratch = None
+        self.seed_salt = None  # device int64[1] XORed into every sampling seed (set by a CUDA-graph rollout, see roll_out.py)
 
     @property
     def input_dtype(self):
@@ -97,6 +98,9 @@ class ForwardPass:
 
     def _packed(self, params):
         """bf16 hi/lo blob of `params`, re-packed when any tensor was replaced or updated in place."""
+        fixed = params.get("_brl_packed_fixed")  # a caller-owned blob at a fixed address (CUDA-graph rollout)
+        if fixed is not None:
+            return fixed
         ws = [params[name]["w"] for name in LAYERS]
         bs = [params[name]["b"] for name in LAYERS]
         stamp = tuple((t.data_ptr(), t._version) for t in ws + bs)
@@ -124,7 +128,8 @@ class ForwardPass:
         xb = ops.obs_to_bf16(x.contiguous())
         self._ensure_scratch(n, x.device)
         ops.policy_act(xb, self._packed(params), self._scratch, mask, action, log_prob, value, sample=sample, seed=seed,
-                       env_offset=env_offset, single_bf16=self.precision == "tc-bf16")
+                       env_offset=env_offset, single_bf16=self.precision == "tc-bf16",
+                       seed_salt=self.seed_salt if (sample and n >= 4096) else None)  # the salt lives in the fused launch
 
     def act_rows(self, params, obs_bf16: torch.Tensor, mask, action: torch.Tensor, rows: torch.Tensor, log_prob=None,
                  logits=None, *, sample: bool = False, seed: int = 0, env_offset: int = 0):
@@ -137,6 +142,10 @@ class ForwardPass:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=obs_bf16.device)
         ops.policy_act_rows(obs_bf16, self._packed(params), self._scratch, mask, action, rows, log_prob, logits, sample=sample, seed=seed,
                             env_offset=env_offset, single_bf16=self.precision == "tc-bf16")
+
+    def pack_into(self, params, blob: torch.Tensor) -> torch.Tensor:
+        """re-pack `params` into the caller's fixed-address blob"""
+        return ops.mlp_pack([params[name]["w"] for name in LAYERS], [params[name]["b"] for name in LAYERS], out=blob)
 
     def _ensure_scratch(self, n, device):
         if self._scratch is None or self._scratch.numel() < ops._lib.load().brl_mlp_scratch_bytes(n) or \

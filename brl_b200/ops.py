@@ -208,15 +208,20 @@ def match_stats(x: torch.Tensor, sums: torch.Tensor) -> None:
     _call("brl_match_stats", [_ptr(x), _ptr(sums)], _params(x.shape[0]))
 
 
-def gather_reward(rewards, actor, out, scale: float) -> None:
-    _call("brl_gather_reward", [_ptr(rewards), _ptr(actor), _ptr(out)],
-              _params(rewards.shape[0], gamma=scale))
+def gather_reward(rewards, actor, out, scale: float, done: Optional[torch.Tensor] = None,
+                  count: Optional[torch.Tensor] = None) -> None:
+    """reward = rewards[actor] / scale (src/roll_out.py:86-94); with `done` (u8) and `count` (int64[1]): count += sum(done)
+    in the same launch (src/roll_out.py:85)."""
+    counting = done is not None and count is not None
+    _call("brl_gather_reward", [_ptr(rewards), _ptr(actor), _ptr(out), _ptr(done) if counting else None,
+                                _ptr(count) if counting else None],
+          _params(rewards.shape[0], gamma=scale, flags=_lib.F_COUNT_DONE if counting else 0))
 
 
-def mlp_pack(weights, biases) -> torch.Tensor:
-    """Six haiku-layout fp32 (w[in,out], b[out]) pairs -> the packed bf16 hi/lo parameter blob."""
+def mlp_pack(weights, biases, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Six haiku-layout fp32 (w[in,out], b[out]) pairs -> the packed bf16 hi/lo parameter blob (`out`: re-pack in place)."""
     dev = weights[0].device
-    blob = torch.empty(_lib.load().brl_mlp_packed_bytes(), dtype=torch.uint8, device=dev)
+    blob = out if out is not None else torch.empty(_lib.load().brl_mlp_packed_bytes(), dtype=torch.uint8, device=dev)
     ws = [w.detach().to(torch.float32).contiguous() for w in weights]
     bs = [b.detach().to(torch.float32).contiguous() for b in biases]
     _call("brl_mlp_pack", [_ptr(t) for t in ws] + [_ptr(t) for t in bs] + [_ptr(blob)], _params(0))
@@ -256,7 +261,7 @@ def mlp_forward(obs_bf16: torch.Tensor, packed: torch.Tensor, scratch: torch.Ten
 def policy_act(obs_bf16: torch.Tensor, packed: torch.Tensor, scratch: torch.Tensor, mask: Optional[torch.Tensor],
                action: torch.Tensor, log_prob: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None,
                logits: Optional[torch.Tensor] = None, *, sample: bool = False, seed: int = 0, env_offset: int = 0,
-               step_index: int = 0, single_bf16: bool = False, tune: int = 0) -> None:
+               step_index: int = 0, single_bf16: bool = False, tune: int = 0, seed_salt: Optional[torch.Tensor] = None) -> None:
     """forward.apply + masked Categorical sample / mode (+ log_prob, value, logits on request) in one call
     (src/roll_out.py:73-81); same noise stream as `categorical`, so it equals mlp_forward followed by categorical."""
     n = obs_bf16.shape[0]
@@ -265,8 +270,9 @@ def policy_act(obs_bf16: torch.Tensor, packed: torch.Tensor, scratch: torch.Tens
     if scratch.numel() < _lib.load().brl_mlp_scratch_bytes(n):
         raise _lib.BrlError("policy_act: scratch too small (ops.mlp_scratch)")
     _call("brl_policy_act", [_ptr(obs_bf16), _ptr(packed), _ptr(scratch), _ptr(mask), _ptr(action), _ptr(log_prob), _ptr(value),
-                             _ptr(logits)],
-          _params(n, flags=(F_MLP_BF16 if single_bf16 else 0) | (F_SAMPLE if sample else 0) | tune, seed=seed,
+                             _ptr(logits), _ptr(seed_salt)],
+          _params(n, flags=(F_MLP_BF16 if single_bf16 else 0) | (F_SAMPLE if sample else 0) | tune |
+                  (_lib.F_SEED_SALT if seed_salt is not None else 0), seed=seed,
                   env_offset=env_offset, step=step_index))
 
 

@@ -91,6 +91,8 @@ typedef struct CUstream_st *brl_stream_t; /* == cudaStream_t */
 #define BRL_F_MLP_BF16      0x0200 /* brl_mlp_forward: one bf16 product per term instead of the 3-term split */
 #define BRL_F_RESULT_I16    0x1000 /* brl_rollout_random: also write the compact result i16[K,n] into buffers[10] */
 #define BRL_F_UNIFORM_U16   0x2000 /* brl_rollout_random / brl_env_rollout_host_compact*: caller-supplied uniforms are u16[K,n] */
+#define BRL_F_SEED_SALT     0x4000 /* brl_policy_act: buffers[8] = device u64 XORed into `seed` (replayed CUDA graphs draw fresh noise) */
+#define BRL_F_COUNT_DONE    0x8000 /* brl_gather_reward: buffers[3] u8 done[n], [4] inout u64 count += sum(done) (src/roll_out.py:85) */
 #define BRL_F_HOST_STAGED   0x0800 /* brl_env_create: never write results straight into pinned host buffers (always stage + copy) */
 
 /* tuning (0 = automatic): bits 16-17 envs per block of the one-launch kernels (1->8, 2->16, 3->32), bits 18-19 warps
@@ -206,6 +208,7 @@ int32_t brl_state_fields(brl_stream_t, void **buffers, const void *opaque, size_
 
 /* Transition bookkeeping of roll_out._env_step (src/roll_out.py:85-94):
  * buffers: [0] in f32 rewards[n,4]  [1] in i8 actor[n]  [2] out f32 reward[n] = rewards[actor] / scale
+ *          with BRL_F_COUNT_DONE: [3] in u8 done[n]  [4] inout u64 terminated_count[1] += sum(done)
  * scale passed in BrlParams.gamma. */
 int32_t brl_gather_reward(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 
@@ -230,7 +233,7 @@ int32_t brl_mlp_forward(brl_stream_t, void **buffers, const void *opaque, size_t
  * that drains a head-tile row holds its 38 logits and samples in place (same Philox noise as brl_categorical).
  * buffers: [0] in bf16 obs[n,480]  [1] in packed parameters  [2] scratch  [3] in u8 mask[n,38] (NULL -> unmasked)
  *          [4] out i32 action[n]  [5] out f32 log_prob[n] (NULL ok)  [6] out f32 value[n] (NULL ok)
- *          [7] out f32 logits[n,38] (NULL ok)
+ *          [7] out f32 logits[n,38] (NULL ok)  [8] in u64 seed_salt[1] -- read ONLY with BRL_F_SEED_SALT
  * params: flags BRL_F_SAMPLE / BRL_F_MLP_BF16, seed, env_offset, step as for brl_categorical. */
 int32_t brl_policy_act(brl_stream_t, void **buffers, const void *opaque, size_t opaque_len);
 /* brl_policy_act on a LIST of envs: n_envs = number of listed rows.  obs / mask / action / log_prob are the full per-env

@@ -101,7 +101,7 @@ def test_roll_out_and_gae_match_oracle_replay():
     ref = orc.OracleEnv(table, n)
     ref.init(keys.cpu().numpy().view(np.uint64))
     e0 = ref.export()
-    assert (traj.obs[0].cpu().numpy() == e0["observation"]).all()
+    assert (traj.obs[0].float().cpu().numpy() == e0["observation"]).all()   # recorded in the policy's input dtype (bf16 0/1)
     actor = e0["current_player"].copy()
     quads = _replay_quads(ref, trace, n)
     np_params = params_to_numpy(params)
@@ -112,11 +112,11 @@ def test_roll_out_and_gae_match_oracle_replay():
         want_r = rew[np.arange(n), actor] / np.float32(7600.0)
         assert (traj.reward[t].cpu().numpy() == want_r).all(), f"reward t={t}"
         obs_next = traj.obs[t + 1] if t + 1 < T else runner2[3]
-        assert (obs_next.cpu().numpy() == e["observation"]).all(), f"obs t={t}"
+        assert (obs_next.float().cpu().numpy() == e["observation"]).all(), f"obs t={t}"
         if t + 1 < T:
             assert (traj.legal_action_mask[t + 1].cpu().numpy() == e["legal_action_mask"].astype(bool)).all()
         # the recorded action was legal and its log-prob is the masked log-softmax of the actor's logits
-        logits, value = orc.mlp_forward(np_params, traj.obs[t].cpu().numpy())
+        logits, value = orc.mlp_forward(np_params, traj.obs[t].float().cpu().numpy())
         mask_t = traj.legal_action_mask[t].cpu().numpy()
         a = traj.action[t].cpu().numpy()
         assert mask_t[np.arange(n), a].all()
@@ -135,6 +135,56 @@ def test_roll_out_and_gae_match_oracle_replay():
                                last_val.cpu().numpy(), 1.0, 0.95)
     np.testing.assert_allclose(adv.cpu().numpy(), adv_ref, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(tgt.cpu().numpy(), tgt_ref, rtol=1e-6, atol=1e-7)
+
+
+def test_roll_out_cuda_graph_replay_equals_traced_launches():
+    """From 4096 envs on the T-step rollout is ONE CUDA graph replay.  With the same seeding scheme the plain-launch path
+    (traced and replayed through the oracle env) must give the bit-identical trajectory, and a second replay must draw
+    fresh noise (the per-rollout key is a device word, not a captured constant)."""
+    from brl_b200.models import init_params, make_forward_pass
+    from brl_b200.roll_out import make_roll_out
+    from brl_b200 import random as brandom
+    from oracle import oracle as orc
+    env, table = _mk_env()
+    n, T = 4096, 5
+    config = dict(actor_illegal_action_mask=True, actor_illegal_action_penalty=False, game_mode="competitive",
+                  num_steps=T, reward_scale=7600.0, gamma=1.0, gae_lambda=0.95)
+    params, opp_params = init_params(1, DEV), init_params(2, DEV)
+    keys = env.make_keys(78, n)
+
+    def fresh_runner():
+        state = env.init(keys)
+        return (params, None, state, state.observation, torch.zeros((), dtype=torch.int64, device=DEV), brandom.PRNGKey(9))
+
+    fp_g = make_forward_pass("relu", "DeepMind")
+    roll_g = make_roll_out(config, env, fp_g, fp_g)
+    runner_g, traj_g = roll_g(fresh_runner(), opp_params)                    # captures, then replays
+    got = {k: getattr(traj_g, k).clone() for k in traj_g._fields}
+    last_obs_g, count_g = runner_g[3].clone(), int(runner_g[4])
+    fp_e = make_forward_pass("relu", "DeepMind")
+    roll_e = make_roll_out(config, env, fp_e, fp_e)
+    trace = []
+    runner_e, traj_e = roll_e(fresh_runner(), opp_params, trace=trace, graph_seeding=True)
+    for k in traj_e._fields:
+        assert torch.equal(got[k], getattr(traj_e, k)), k
+    assert torch.equal(last_obs_g, runner_e[3]) and count_g == int(runner_e[4]) and runner_g[5] == runner_e[5]
+    # the traced run is a faithful rollout of the oracle env
+    ref = orc.OracleEnv(table, n)
+    ref.init(keys.cpu().numpy().view(np.uint64))
+    actor = ref.export()["current_player"].copy()
+    n_term = 0
+    for t, (rew, term, e) in enumerate(_replay_quads(ref, trace, n)):
+        assert (traj_e.done[t].cpu().numpy() == term.astype(bool)).all()
+        assert (traj_e.reward[t].cpu().numpy() == rew[np.arange(n), actor] / np.float32(7600.0)).all()
+        actor = e["current_player"].copy()
+        n_term += int(term.sum())
+    assert count_g == n_term
+    # second replay from the SAME start state: different per-rollout key -> different samples
+    _, traj_g2 = roll_g(fresh_runner()[:5] + (brandom.PRNGKey(10),), opp_params)
+    assert not torch.equal(traj_g2.action, got["action"])
+    # and continuing from the returned runner state works without copies going wrong (state aliases the graph's buffers)
+    runner_g3, traj_g3 = roll_g(runner_g, opp_params)
+    assert int(runner_g3[4]) >= count_g and torch.isfinite(traj_g3.value).all()
 
 
 @pytest.mark.parametrize("mode", ["deterministic", "free-run"])
