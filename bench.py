@@ -114,10 +114,10 @@ class ClockSampler:
 def _traffic(kernel_key):
     """per-launch DRAM bytes of the bench kernel from the committed `ncu --set full` capture (profiles/)"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
             doc = json.load(fh)
             e = doc[doc.get("_alias", {}).get(kernel_key, kernel_key)]
-        return e["traffic_bytes"], f"profiles/r01_traffic.json ({e['report']}: dram__bytes_read.sum + dram__bytes_write.sum, mean of {e['instances']} launches)"
+        return e["traffic_bytes"], f"profiles/r02_traffic.json ({e['report']}: dram__bytes_read.sum + dram__bytes_write.sum, mean of {e['instances']} launches)"
     except Exception:
         return None, "no ncu capture committed for this kernel"
 
@@ -212,7 +212,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         with _StdoutToStderr():
-            dist.init_process_group("nccl", device_id=dev)
+            import datetime
+            # a rank that dies or skips a collective must fail the run within minutes, not hold 8 GPUs for NCCL's default 10
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=150))
             dist.barrier()  # creates the communicator (and prints NCCL's banner) now
     _lib.load()  # fail loudly if the CUDA library is missing
 
@@ -577,9 +579,16 @@ def run_c1(torch, dev):
     gold = np.load(os.path.join(ROOT, "tests", "golden", "c1_eval_match.npz"))
     env = BridgeBidding(table=boards, device=dev)
     p1, p2 = load_params(w1, dev), load_params(w2, dev)
+    from brl_b200 import dist as bdist
     evaluate = make_simple_duplicate_evaluate(env, "relu", "DeepMind", "relu", "DeepMind", 100)
-    ms, res = _timed_match(torch, None, dev, 1, lambda: evaluate(p1, p2, brandom.PRNGKey(0)), reps=3)
-    (mean, se, win), _, _, cum = res
+
+    def match():  # rank 0 ONLY runs this leg: keep the statistics local (no collective the other ranks never join)
+        sums = torch.zeros(8, dtype=torch.float64, device=dev)
+        _, _, _, cum = evaluate(p1, p2, brandom.PRNGKey(0), local_sums=sums)
+        return bdist.stats_from_sums(sums.cpu()), cum
+
+    ms, res = _timed_match(torch, None, dev, 1, match, reps=3)
+    (mean, se, win), cum = res
     return {"workload": "configs[0]: eval.py model-pretrained-rl.pkl vs model-sl.pkl, num_eval_envs=100, 1000 real boards",
             "ms_per_match": ms, "imp_mean": mean, "imp_se": se, "win_rate": win,
             "golden_imp_mean": float(gold["stats"][0]), "golden_imp_se": float(gold["stats"][1]),
