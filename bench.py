@@ -149,6 +149,11 @@ def cpu_oracle_throughput(n_envs, t_steps, reps, n_threads, table):
     return n * k * len(times) / sum(times), times
 
 
+def _oracle_build():
+    from oracle import oracle as orc
+    return "gcc -O3 -march=" + ("x86-64-v3 (AVX2/BMI2/FMA)" if orc.so_path().endswith("_v3.so") else "x86-64-v2") + ", pthreads"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -167,8 +172,10 @@ def run_reference(args):
         "dtype": "u8/int32 state, f32 0/1 observation", "data": "synthetic",
         "config": _config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "build": _oracle_build(),
                          "note": "C restatement of pgx 1.4.0 bridge_bidding semantics (oracle/brl_oracle.c), not pgx: "
-                                 "jax/pgx are not installable in this image"},
+                                 "jax/pgx are not installable in this image.  It rebuilds the observation from the call "
+                                 "list every step, as the reference does; a reported baseline, not a tuned CPU port"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -312,7 +319,10 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{reps} x ({n} envs x {k} auto-reset random-legal steps), all outputs written, {cores} threads, "
                          f"{sum(times):.2f} s wall",
-               "note": "C restatement of pgx semantics (oracle/brl_oracle.c); pgx/JAX not installable here"}
+               "build": _oracle_build(),
+               "note": "C restatement of pgx semantics (oracle/brl_oracle.c); pgx/JAX not installable here.  It rebuilds the "
+                       "observation from the call list every step, as the reference does: a reported baseline, not a tuned "
+                       "CPU port -- the roofline fraction, not this ratio, says how good the kernel is"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -679,7 +679,8 @@ static int32_t launch_layer(cudaStream_t s, const void* a_hi, const void* a_lo, 
     if (ok && SPLIT_W) ok = make_map(&tw_lo, w_lo, (uint64_t)n_valid_rows, (uint64_t)k_in, (uint64_t)k_in, BN);
     if (!ok) return fail(BRL_E_LAUNCH, "brl_mlp_forward: cuTensorMapEncodeTiled failed");
     auto kern = k_mlp_layer<BN, SPLIT_A, SPLIT_W, HEAD>;
-    static bool attr_set = false;  // idempotent; a race only repeats the call
+    static bool attr_set_dev[kMaxDevices] = {};  // per device; idempotent, a race only repeats the call
+    bool& attr_set = attr_set_dev[device_slot()];
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
             return fail(BRL_E_LAUNCH, "brl_mlp_forward: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);
@@ -688,7 +689,8 @@ static int32_t launch_layer(cudaStream_t s, const void* a_hi, const void* a_lo, 
     LayerArgs la = args;
     la.n_tiles_n = (n_valid_rows + BN - 1) / BN;
     la.n_tiles = la.n_tiles_n * ((args.M + kBM - 1) / kBM);
-    static int n_sm = 0;
+    static int n_sm_dev[kMaxDevices] = {};
+    int& n_sm = n_sm_dev[device_slot()];
     if (n_sm == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -712,7 +714,8 @@ static int32_t launch_layer_pair(cudaStream_t s, const void* a_hi, const void* a
     if (ok && SPLIT_W) ok = make_map(&tw_lo, w_lo, (uint64_t)n_valid_rows, (uint64_t)k_in, (uint64_t)k_in, BN / 2);
     if (!ok) return fail(BRL_E_LAUNCH, "brl_mlp_forward: cuTensorMapEncodeTiled failed");
     auto kern = k_mlp_layer_pair<BN, SPLIT_A, SPLIT_W>;
-    static bool attr_set = false;
+    static bool attr_set_dev[kMaxDevices] = {};
+    bool& attr_set = attr_set_dev[device_slot()];
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
             return fail(BRL_E_LAUNCH, "brl_mlp_forward: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);
@@ -721,7 +724,8 @@ static int32_t launch_layer_pair(cudaStream_t s, const void* a_hi, const void* a
     LayerArgs la = args;
     la.n_tiles_n = n_valid_rows / BN;
     la.n_tiles = la.n_tiles_n * ((args.M + 2 * kBM - 1) / (2 * kBM));
-    static int n_sm = 0;
+    static int n_sm_dev[kMaxDevices] = {};
+    int& n_sm = n_sm_dev[device_slot()];
     if (n_sm == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -767,7 +771,8 @@ static int32_t launch_fused(cudaStream_t s, const void* obs, const unsigned char
     fa.tiles_per_layer = fa.nmb * kFusedTilesN;
     fa.n_tiles = 4 * fa.tiles_per_layer + fa.nmb;
     auto kern = k_mlp_fused<SPLIT>;
-    static int max_pairs = 0;  // co-resident CTA pairs: the dependency waits need every launched pair to be running
+    static int max_pairs_dev[kMaxDevices] = {};  // co-resident CTA pairs: the dependency waits need every launched pair to be running
+    int& max_pairs = max_pairs_dev[device_slot()];
     if (max_pairs == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
             return fail(BRL_E_LAUNCH, "brl_mlp_forward: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);

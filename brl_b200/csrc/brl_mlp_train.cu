@@ -708,7 +708,8 @@ static int32_t launch_fused_ops(cudaStream_t s, const OpSpec* ops, int n_ops, in
     fa.nmb = nmb;
     fa.ready = ready;
     fa.trace = trace;
-    static int n_sm = 0;
+    static int n_sm_dev[kMaxDevices] = {};
+    int& n_sm = n_sm_dev[device_slot()];
     if (n_sm == 0) {
         if (cudaFuncSetAttribute(k_train_fused<kFBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
             return fail(BRL_E_LAUNCH, "brl_ppo_grad: cannot reserve %u bytes of shared memory", Cfg::kSmemBytes);

@@ -38,6 +38,15 @@ inline const BrlParams* get_params(const void* opaque, size_t opaque_len, int32_
     return p;
 }
 
+// Per-device slot of a function-local cache (SM count, "kernel attribute already set", co-resident CTA count): these are
+// per-device facts, and a process may drive several GPUs.  Races only repeat idempotent driver calls.
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+
 // masked categorical over f32 logits[n,38] (brl_algo.cu); shared by brl_categorical and the unfused brl_policy_act path
 int32_t launch_categorical(cudaStream_t stream, const float* logits, const unsigned char* mask, int32_t* action, float* log_prob,
                            int64_t n, int sample, uint64_t seed, int64_t env_offset, uint32_t step, const int32_t* row_index = nullptr,

@@ -412,6 +412,12 @@ struct EpisodePrefetch {
     uint32_t slot;    // slot the NEXT episode's row is arriving in
     uint32_t parity;  // bit k = phase parity to wait for on slot k's mbarrier
 
+#ifdef BRL_PLAIN_EPISODE_LOAD
+    // Debug build (scripts/racecheck_prefetch.sh): no cp.async / mbarrier at all -- the next episode's row is read with plain
+    // loads when the episode starts.  Same results; compute-sanitizer racecheck then has nothing left to warn about, which
+    // shows that its four warnings on the prefetch slots come from not modelling mbarrier-tracked cp.async completion.
+    __device__ __forceinline__ void issue(const RowSlots&, int, const uint8_t* __restrict__) {}
+#else
     __device__ __forceinline__ void issue(const RowSlots& rs, int lane, const uint8_t* __restrict__ table) {
         const uint8_t* g = table + (size_t)next_draw.deal * kDealRowBytes;
         const uint32_t dst = smem_u32(rs.rows + ((size_t)slot * rs.epb + lane) * 3);
@@ -421,6 +427,7 @@ struct EpisodePrefetch {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 32u), "l"(g + 32) : "memory");
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
     }
+#endif
     __device__ __forceinline__ void prime(const Env& e, const RowSlots& rs, int lane, const uint8_t* __restrict__ table,
                                           uint32_t n_deals) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(rs.bar + lane)) : "memory");
@@ -434,6 +441,9 @@ struct EpisodePrefetch {
     // the episode ended: the prefetched row becomes current, start fetching the one after
     __device__ __forceinline__ void advance(const Env& e, const RowSlots& rs, int lane, const uint8_t* __restrict__ table,
                                             uint32_t n_deals) {
+#ifdef BRL_PLAIN_EPISODE_LOAD
+        cur.load(table, next_draw.deal);
+#else
         const uint32_t bar = smem_u32(rs.bar + (size_t)slot * rs.epb + lane);
         const uint32_t want = (parity >> slot) & 1u;
         uint32_t done = 0u;
@@ -448,6 +458,7 @@ struct EpisodePrefetch {
         cur.h01 = r[0];
         cur.h23 = r[1];
         cur.dd = r[2];
+#endif
         parity ^= 1u << slot;
         slot ^= 1u;
         next_draw = draw_episode(e.key_lo, e.key_hi, n_deals);

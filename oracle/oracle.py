@@ -17,6 +17,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libbrl_oracle.so")
+_SO_V3 = os.path.join(_HERE, "libbrl_oracle_v3.so")   # same source, -march=x86-64-v3 (AVX2 / BMI2 / FMA)
 
 NUM_ACTIONS = 38
 OBS_DIM = 480
@@ -27,12 +28,28 @@ def build(force: bool = False) -> str:
     """Compile the C restatement with the committed Makefile (gcc only)."""
     src = os.path.join(_HERE, "brl_oracle.c")
     hdr = os.path.join(_HERE, "brl_oracle.h")
-    stale = (not os.path.exists(_SO)) or any(
-        os.path.getmtime(f) > os.path.getmtime(_SO) for f in (src, hdr)
-    )
+    stale = any((not os.path.exists(so)) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in (src, hdr))
+                for so in (_SO, _SO_V3))
     if force or stale:
-        subprocess.run(["make", "-C", _HERE, "-B", "libbrl_oracle.so"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", _HERE, "-B", "all"], check=True, capture_output=True)
     return _SO
+
+
+def _host_has_avx2() -> bool:
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags"):
+                    f = line.split()
+                    return "avx2" in f and "bmi2" in f and "fma" in f
+    except OSError:
+        pass
+    return False
+
+
+def so_path() -> str:
+    """the build the host CPU can run fastest (x86-64-v3 when AVX2 / BMI2 / FMA are present)"""
+    return _SO_V3 if (_host_has_avx2() and os.path.exists(_SO_V3)) else _SO
 
 
 class _Params(C.Structure):
@@ -74,7 +91,7 @@ def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(_SO)
+        L = C.CDLL(so_path())
         L.orc_state_size.restype = C.c_size_t
         L.orc_score.restype = C.c_int32
         L.orc_score.argtypes = [C.c_int32] + [C.c_int] * 4

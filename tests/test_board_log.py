@@ -129,3 +129,67 @@ def test_reference_parser_and_analysis_accept_the_logs(tmp_path):
             s2 = -s2
         assert score_to_imp(s1, s2) == int(cum[i]), f"board {i}"
         assert [str(b) for b in d1.bid_history] == t1[i]["bid_history"]
+
+
+@pytest.mark.gpu
+def test_gpu_match_record_to_board_logs_and_reference_parser(tmp_path):
+    """SURVEY 8f-4 on the GPU path: a duplicate match played by the CUDA kernels (`record=` of
+    make_simple_duplicate_evaluate: per step the action and both tables' terminated flags), written as the reference's
+    JSON board logs.  The logs' own scores must give the GPU match's IMPs board by board; where the reference tree is
+    mounted its `JsonParser` + `calc_score` + `score_to_imp` (wb5/analyze_log.py:63-155) must agree too."""
+    import torch
+    from brl_b200 import BridgeBidding
+    from brl_b200 import random as brandom
+    from brl_b200.evaluation import make_simple_duplicate_evaluate
+    from brl_b200.models import init_params
+    dev = "cuda:0"
+    boards = H.load_boards()
+    env = BridgeBidding(table=boards["table"], device=dev)
+    n = 150
+    rng = brandom.PRNGKey(21)
+    _, sub = brandom.split(rng)
+    state0 = env.init(env.make_keys(sub, n))          # the same draws the evaluator makes: private fields of the start state
+    priv = {k: getattr(state0, "_" + k).cpu().numpy() for k in ("deal", "dealer", "shuffled_players")}
+    vul = np.stack([state0._vul_NS.cpu().numpy(), state0._vul_EW.cpu().numpy()], axis=1).astype(np.uint8)
+    evaluate = make_simple_duplicate_evaluate(env, "relu", "DeepMind", "relu", "DeepMind", n)
+    record = []
+    (mean, se, win), info_a, info_b, cum = evaluate(init_params(5, dev), init_params(6, dev), rng, record=record)
+    cum = cum.cpu().numpy()
+    t1, t2 = board_log.match_to_board_logs(boards["table"], priv["deal"], priv["dealer"], vul, priv["shuffled_players"], record,
+                                           team_names=("actor", "opp"), board_ids=[str(i) for i in range(n)])
+    assert len(t1) == len(t2) == n
+    for i, (e1, e2) in enumerate(zip(t1, t2)):
+        s1 = e1["scores"]["NS"] if e1["players"]["N"] == "actor" else e1["scores"]["EW"]
+        s2 = e2["scores"]["NS"] if e2["players"]["N"] == "actor" else e2["scores"]["EW"]
+        assert orc.imp(s1 + s2) == int(cum[i]), f"board {i}"
+        for e, info_bid in ((e1, int(info_a.last_bid[i])), (e2, int(info_b.last_bid[i]))):
+            if e["contract"] == "Passed_out":
+                assert info_bid == -1
+            else:
+                assert e["contract"].rstrip("X") == board_log.ACTION_STR[info_bid + 3]
+    assert abs(mean - float(cum.astype(np.float64).mean())) < 1e-9
+    if not os.path.isdir(REF_ENV):
+        return  # GPU box: the structural check above is all that can run
+    for name, entries in (("t1.json", t1), ("t2.json", t2)):
+        with open(tmp_path / name, "w") as fh:
+            board_log.write_logs(fh, entries)
+    sys.path.insert(0, REF_ENV)
+    try:
+        from bridge_env import Pair, Player
+        from bridge_env.data_handler.json_handler.parser import JsonParser
+        from bridge_env.score import calc_score, score_to_imp
+    finally:
+        sys.path.remove(REF_ENV)
+    parsed = []
+    for name in ("t1.json", "t2.json"):
+        with open(tmp_path / name) as fh:
+            parsed.append(JsonParser().parse_board_logs(fh))
+
+    def actor_score(d):
+        if d.contract.is_passed_out():
+            return 0
+        s = calc_score(d.contract, d.dda[d.declarer][d.contract.trump])
+        return s if d.declarer.pair is (Pair.NS if d.players[Player.N] == "actor" else Pair.EW) else -s
+
+    for i, (d1, d2) in enumerate(zip(*parsed)):
+        assert score_to_imp(actor_score(d1), actor_score(d2)) == int(cum[i]), f"board {i}"
