@@ -146,11 +146,14 @@ long long brl_xla_unreported_failures(void) { return g_unreported.load(std::memo
 
 // ---- (2) typed FFI handlers --------------------------------------------------------------
 #ifdef BRL_HAVE_XLA_FFI
+#include <string>
+
 #include "xla/ffi/api/ffi.h"
 namespace ffi = xla::ffi;
+// brl_stream_t is `struct CUstream_st*`, i.e. cudaStream_t: PlatformStream<brl_stream_t> needs no CUDA header here
 
 namespace {
-ffi::Error typed_call(brl_op_fn op, const char* name, const char* layout, cudaStream_t stream, ffi::RemainingArgs args,
+ffi::Error typed_call(brl_op_fn op, const char* name, const char* layout, brl_stream_t stream, ffi::RemainingArgs args,
                       ffi::RemainingRets rets, ffi::Span<const uint8_t> opaque) {
     void* xla[kMaxBuffers];
     size_t n = 0;
@@ -162,19 +165,19 @@ ffi::Error typed_call(brl_op_fn op, const char* name, const char* layout, cudaSt
     char msg[160];
     if (const char* err = reorder(layout, xla, b, msg, sizeof(msg)))
         return ffi::Error(ffi::ErrorCode::kInvalidArgument, std::string(name) + "_ffi: " + err);
-    if (op((brl_stream_t)stream, b, opaque.begin(), opaque.size()) != BRL_OK)
+    if (op(stream, b, opaque.begin(), opaque.size()) != BRL_OK)
         return ffi::Error(ffi::ErrorCode::kInvalidArgument, brl_last_error());
     return ffi::Error::Success();
 }
 }  // namespace
 
 #define BRL_TYPED_FFI(op, layout)                                                                                         \
-    static ffi::Error op##_ffi_impl(cudaStream_t stream, ffi::RemainingArgs args, ffi::RemainingRets rets,                \
+    static ffi::Error op##_ffi_impl(brl_stream_t stream, ffi::RemainingArgs args, ffi::RemainingRets rets,                \
                                     ffi::Span<const uint8_t> opaque) {                                                    \
         return typed_call(op, #op, layout, stream, args, rets, opaque);                                                   \
     }                                                                                                                     \
     XLA_FFI_DEFINE_HANDLER_SYMBOL(op##_ffi, op##_ffi_impl,                                                                \
-                                  ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().RemainingArgs().RemainingRets() \
+                                  ffi::Ffi::Bind().Ctx<ffi::PlatformStream<brl_stream_t>>().RemainingArgs().RemainingRets() \
                                       .Attr<ffi::Span<const uint8_t>>("opaque"));
 BRL_XLA_OPS(BRL_TYPED_FFI)
 #endif  // BRL_HAVE_XLA_FFI
