@@ -63,23 +63,40 @@ __global__ void __launch_bounds__(256) k_obs_to_bf16(const T* __restrict__ in, _
 
 // ---- epilogues: thread = one env row of the accumulator (TMEM lane), shared by all layer kernels ----------
 // hidden layer: + bias, ReLU, split into bf16 hi / lo for the next layer (128-bit stores)
+#ifdef BRL_MLP_TRACE
+__device__ unsigned long long g_mlp_epi[4];  // debug: SM clocks warp 2 spent in {tcgen05.ld + wait, arithmetic, stores, chunks}
+#define BRL_EPI_T0() long long _e0 = clock64()
+#define BRL_EPI_ACC(k) do { long long _e1 = clock64(); if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == 2 && blockIdx.x == 0) atomicAdd(&g_mlp_epi[k], (unsigned long long)(_e1 - _e0)); _e0 = _e1; } while (0)
+#else
+#define BRL_EPI_T0()
+#define BRL_EPI_ACC(k)
+#endif
+
+// SMEM_BIAS: `bias` points into shared memory (the fused forward stages every layer's bias once per CTA: with ~194 KB of the
+// SM given to the operand ring, what is left of L1 does not keep the 4 KB bias vector against the tile's own 131 KB of
+// stores, and 16 global loads per 32-column chunk each waited a full L2 round trip -- scripts/exp_mlp_trace.py)
+template <bool SMEM_BIAS = false>
 __device__ __forceinline__ void epilogue_hidden_row(uint32_t t_row, int n_cols, const float* __restrict__ bias, bool row_ok,
                                                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+    BRL_EPI_T0();
 #pragma unroll 1
     for (int c0 = 0; c0 < n_cols; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_row + (uint32_t)c0, r);
+        BRL_EPI_ACC(0);
         if (row_ok) {
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
-                const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + jj);  // warp-uniform
+                const float2 bb = SMEM_BIAS ? reinterpret_cast<const float2*>(bias + c0)[jj]
+                                            : __ldg(reinterpret_cast<const float2*>(bias + c0) + jj);  // warp-uniform
                 float x0 = fmaxf(__uint_as_float(r[2 * jj]) + bb.x, 0.0f);
                 float x1 = fmaxf(__uint_as_float(r[2 * jj + 1]) + bb.y, 0.0f);
                 __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
                 hi[jj] = *reinterpret_cast<uint32_t*>(&h);
                 lo[jj] = pack_bf16x2(x0 - __low2float(h), x1 - __high2float(h));
             }
+            BRL_EPI_ACC(1);
             uint4* ph = reinterpret_cast<uint4*>(out_hi + c0);
 #pragma unroll
             for (int v = 0; v < 4; ++v) ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
@@ -88,7 +105,59 @@ __device__ __forceinline__ void epilogue_hidden_row(uint32_t t_row, int n_cols, 
 #pragma unroll
                 for (int v = 0; v < 4; ++v) pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
             }
+            BRL_EPI_ACC(2);
         }
+    }
+}
+
+// Hidden-layer epilogue of the fused forward with TMA stores.  A thread owns one accumulator row; written straight to global
+// memory its 16-byte pieces land in 32 different rows per warp instruction (32 LSU wavefronts each, 8192 per 128 x 256
+// tile: ~4 us of the SM's load/store pipe -- the epilogue took 10-12 us per tile, longer than layer 0's 6 us main loop and on
+// every layer's dependency path, scripts/exp_mlp_trace.py).  Here each 32-column chunk is staged in shared memory as the
+// 32-row x 64-byte box of a 64B-swizzled tensor map (lane = row, conflict-free 128-bit stores) and one lane issues a bulk
+// tensor store for the hi and the lo block; rows past M are clipped by the map.  `stage` = this warp's 2 x 2 KB.
+__device__ __forceinline__ void epilogue_hidden_tma(uint32_t t_row, int n_cols, const float* __restrict__ bias, int lane,
+                                                    uint32_t stage, const CUtensorMap* st_hi, const CUtensorMap* st_lo,
+                                                    int col0, int row0) {
+    BRL_EPI_T0();
+    const uint32_t sw = (uint32_t)((lane >> 1) & 3);  // 64B swizzle: 16-byte chunk index ^= bits 7-8 of the byte offset
+#pragma unroll 1
+    for (int c0 = 0; c0 < n_cols; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + (uint32_t)c0, r);
+        BRL_EPI_ACC(0);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + jj);  // warp-uniform
+            float x0 = fmaxf(__uint_as_float(r[2 * jj]) + bb.x, 0.0f);
+            float x1 = fmaxf(__uint_as_float(r[2 * jj + 1]) + bb.y, 0.0f);
+            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+            hi[jj] = *reinterpret_cast<uint32_t*>(&h);
+            lo[jj] = pack_bf16x2(x0 - __low2float(h), x1 - __high2float(h));
+        }
+        BRL_EPI_ACC(1);
+        if (c0 > 0) {  // the previous chunk's stores have read the staging blocks
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+        }
+        const uint32_t row_hi = stage + (uint32_t)lane * 64u, row_lo = row_hi + 2048u;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const uint32_t off = ((uint32_t)v ^ sw) * 16u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + off), "r"(hi[4 * v]), "r"(hi[4 * v + 1]),
+                         "r"(hi[4 * v + 2]), "r"(hi[4 * v + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_lo + off), "r"(lo[4 * v]), "r"(lo[4 * v + 1]),
+                         "r"(lo[4 * v + 2]), "r"(lo[4 * v + 3]) : "memory");
+        }
+        fence_async_smem();  // generic-proxy writes -> async-proxy (TMA) reads
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(st_hi, stage, col0 + c0, row0);
+            tma_store_2d(st_lo, stage + 2048u, col0 + c0, row0);
+            bulk_commit();
+        }
+        BRL_EPI_ACC(2);
     }
 }
 
@@ -367,6 +436,7 @@ k_mlp_layer_pair(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
     auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
     auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
+    const uint32_t store_base = (bar_base + 256u + 1023u) & ~1023u;  // 8 epilogue warps x (hi, lo) x 2 KB store staging
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -482,6 +552,7 @@ k_mlp_layer_pair(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 // exceeds the co-resident cluster count, so the waits cannot deadlock (spins are bounded: a bug traps).
 struct FusedArgs {
     CUtensorMap a_hi[5], a_lo[5], w_hi[5], w_lo[5];
+    CUtensorMap st_hi[4], st_lo[4];  // the hidden layers' outputs as TMA-store destinations (32 x 32 boxes)
     const float* bias[5];
     __nv_bfloat16* out_hi[4];
     __nv_bfloat16* out_lo[4];
@@ -493,14 +564,21 @@ struct FusedArgs {
 };
 
 constexpr int kFusedBN = 256, kFusedTilesN = kHidden / kFusedBN;
-constexpr uint32_t kReadyPerBlock = kFusedTilesN * 4;  // n-tiles x epilogue warps
+// Epilogue warps of the fused forward: TWO per TMEM lane quadrant, each draining half of the tile's 256 columns.  One
+// warp per quadrant sits alone on its SM sub-partition and runs the bias / ReLU / bf16-split chain at ~7 clocks per
+// instruction (scripts/exp_mlp_trace.py: 10-12 us per tile, longer than layer 0's 6 us main loop and on every layer's
+// dependency path); two warps of a quadrant share a sub-partition and interleave.
+constexpr int kFusedEpiWarps = 8, kFusedThreads = 32 * (2 + kFusedEpiWarps);
+constexpr uint32_t kReadyPerBlock = kFusedTilesN * kFusedEpiWarps;  // n-tiles x epilogue warps
 
 template <bool SPLIT>
 struct FusedCfg {
     static constexpr uint32_t kABytes = kBM * kBK * 2, kWBytes = (kFusedBN / 2) * kBK * 2, kWHeadBytes = (kHeadPad / 2) * kBK * 2;
     static constexpr uint32_t kStageBytes = (kABytes + kWBytes) * (SPLIT ? 2 : 1);
     static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (int)(kSmemBudget / kStageBytes);
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr uint32_t kStoreStageBytes = 8 /*epilogue warps*/ * 2 /*hi, lo*/ * 2048;  // 32 rows x 64 B per warp and array
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*align*/ + kStoreStageBytes;
+    static_assert(kSmemBytes <= 227 * 1024, "operand ring + store staging exceed the SM's shared memory");
 };
 
 struct FusedTile { int layer, mb, nt; };
@@ -519,8 +597,23 @@ __device__ __forceinline__ FusedTile fused_tile(int t, int tiles_per_layer) {
     return f;
 }
 
+#ifdef BRL_MLP_TRACE
+// debug build (scripts/exp_mlp_trace.py): per-tile %globaltimer stamps of the fused forward, written by the leader CTA's role lanes
+// [0] dependency wait begins [1] dependency ready [2] last TMA issued [3] accumulator free, first MMA [4] last MMA committed
+// [5] accumulator seen by the epilogue [6] tile published [7] pair
+__device__ unsigned long long g_mlp_trace[1024][8];
+__device__ __forceinline__ unsigned long long mlp_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define BRL_MLP_STAMP(tile, k) do { if (leader && (tile) < 1024) g_mlp_trace[tile][k] = mlp_now(); } while (0)
+#else
+#define BRL_MLP_STAMP(tile, k)
+#endif
+
 template <bool SPLIT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_mlp_fused(const __grid_constant__ FusedArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1) k_mlp_fused(const __grid_constant__ FusedArgs a) {
     using Cfg = FusedCfg<SPLIT>;
     constexpr int S = Cfg::kStages;
     constexpr uint32_t kTmemCols = 2 * kFusedBN;
@@ -531,6 +624,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_ml
     auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
     auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
     auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
+    const uint32_t store_base = (bar_base + 256u + 1023u) & ~1023u;  // 8 epilogue warps x (hi, lo) x 2 KB store staging
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -541,7 +635,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_ml
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 2 * kFusedEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -570,6 +664,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_ml
                 const CUtensorMap* ma_lo = &a.a_lo[f.layer];
                 const CUtensorMap* mw_hi = &a.w_hi[f.layer];
                 const CUtensorMap* mw_lo = &a.w_lo[f.layer];
+                BRL_MLP_STAMP(tile, 0);
                 if (f.layer > 0) {  // the previous layer's rows [m0, m0 + 128) must be complete (all 4 n-tiles)
                     const uint32_t* flag = a.ready + (size_t)(f.layer - 1) * 2 * a.nmb + 2 * f.mb + rank;
                     uint32_t v = 0;
@@ -581,6 +676,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_ml
                     }
                     asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> async-proxy (TMA) reads
                 }
+                BRL_MLP_STAMP(tile, 1);
                 for (int kb = 0; kb < k_blocks; ++kb, ++it) {
                     const int s = (int)(it % S);
                     mbar_wait(empty_bar(s), ((it / S) & 1u) ^ 1u);
@@ -593,6 +689,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_ml
                     tma_load_2d_pair(sw, mw_hi, fb, kb * kBK, n0);
                     if (SPLIT) tma_load_2d_pair(sw + Cfg::kWBytes, mw_lo, fb, kb * kBK, n0);
                 }
+                BRL_MLP_STAMP(tile, 2);
             }
         }
     } else if (warp == 1) {
@@ -606,6 +703,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_ml
                 const uint32_t buf = j & 1u;
                 mbar_wait(tmem_empty_bar(buf), ((j >> 1) & 1u) ^ 1u);
                 tc_fence_after();
+                BRL_MLP_STAMP(tile, 3);
                 const uint32_t acc = tmem_acc + buf * kFusedBN;
                 for (int kb = 0; kb < k_blocks; ++kb, ++it) {
                     const int s = (int)(it % S);
@@ -626,10 +724,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_ml
                     umma_commit_pair(empty_bar(s));
                 }
                 umma_commit_pair(tmem_full_bar(buf));
+                BRL_MLP_STAMP(tile, 4);
             }
         }
-    } else {  // ===== epilogue =====
-        const int q = warp & 3;
+    } else {  // ===== epilogue: warp w drains TMEM lane quadrant w % 4, column half (w - 2) / 4 =====
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        constexpr int kHalfCols = kFusedBN / 2;
         const uint32_t lead_tmem_empty0 = tmem_empty_bar(0) & kPeerBitMask;
         uint32_t j = 0;
         for (int tile = pair; tile < n_tiles; tile += n_pairs, ++j) {
@@ -638,15 +738,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_ml
             const uint32_t buf = j & 1u;
             mbar_wait(tmem_full_bar(buf), (j >> 1) & 1u);
             tc_fence_after();
+            if (warp == 2 && lane == 0) { BRL_MLP_STAMP(tile, 5); }
             const int row = m0 + q * 32 + lane;
             const uint32_t t_row = tmem_acc + buf * kFusedBN + ((uint32_t)(q * 32) << 16);
             if (f.layer < 4) {
-                const int n0 = f.nt * kFusedBN;
-                __nv_bfloat16* oh = a.out_hi[f.layer];
-                __nv_bfloat16* ol = a.out_lo[f.layer];
-                epilogue_hidden_row(t_row, kFusedBN, a.bias[f.layer] + n0, row < a.M, oh + (size_t)row * kHidden + n0,
-                                    ol ? ol + (size_t)row * kHidden + n0 : nullptr);
-            } else {
+                const int n0 = f.nt * kFusedBN + half * kHalfCols;
+                if (SPLIT) {
+                    epilogue_hidden_tma(t_row + (uint32_t)(half * kHalfCols), kHalfCols, a.bias[f.layer] + n0, lane,
+                                        store_base + (uint32_t)(warp - 2) * 4096u, &a.st_hi[f.layer], &a.st_lo[f.layer], n0,
+                                        m0 + q * 32);
+                } else {
+                    __nv_bfloat16* oh = a.out_hi[f.layer];
+                    epilogue_hidden_row(t_row + (uint32_t)(half * kHalfCols), kHalfCols, a.bias[f.layer] + n0, row < a.M,
+                                        oh + (size_t)row * kHidden + n0, nullptr);
+                }
+            } else if (half == 0) {  // the 64-column head tile: one warp per quadrant
                 epilogue_head_act_row(t_row, a.bias[4], row < a.M, row, a.logits, a.value, a.act);
             }
             tc_fence_before();
@@ -654,9 +760,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) k_ml
             if (lane == 0) {
                 asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(lead_tmem_empty0 + 8u * buf) : "memory");
                 if (f.layer < 4) {
+                    if (SPLIT) {  // this warp's bulk tensor stores are performed (not just read) before the rows are published
+                        bulk_wait0();
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
                     __threadfence();  // cumulative: the warp's rows are visible GPU-wide before the count below
                     atomicAdd(a.ready + (size_t)f.layer * 2 * a.nmb + 2 * f.mb + rank, 1u);
                 }
+#ifdef BRL_MLP_TRACE
+                if (warp == 2 && leader && tile < 1024) { g_mlp_trace[tile][6] = mlp_now(); g_mlp_trace[tile][7] = (unsigned long long)pair; }
+#endif
             }
         }
     }
@@ -759,9 +872,13 @@ static int32_t launch_fused(cudaStream_t s, const void* obs, const unsigned char
         if (l < 4) {
             fa.out_hi[l] = buf_hi[l & 1];
             fa.out_lo[l] = SPLIT ? buf_lo[l & 1] : nullptr;
+            if (ok && SPLIT)
+                ok = make_map_store(&fa.st_hi[l], buf_hi[l & 1], (uint64_t)M, (uint64_t)kHidden, (uint64_t)kHidden) &&
+                     make_map_store(&fa.st_lo[l], buf_lo[l & 1], (uint64_t)M, (uint64_t)kHidden, (uint64_t)kHidden);
         }
     }
     if (!ok) return fail(BRL_E_LAUNCH, "brl_mlp_forward: cuTensorMapEncodeTiled failed");
+    static_assert(sizeof(FusedArgs) <= 4096, "kernel parameters");
     fa.logits = logits;
     fa.value = value;
     fa.act = act;
@@ -781,7 +898,7 @@ static int32_t launch_fused(cudaStream_t s, const void* obs, const unsigned char
         if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(n_sm & ~1));
-        cfg.blockDim = dim3(kMlpThreads);
+        cfg.blockDim = dim3(kFusedThreads);
         cfg.dynamicSmemBytes = Cfg::kSmemBytes;
         cudaLaunchAttribute at{};
         at.id = cudaLaunchAttributeClusterDimension;
@@ -799,7 +916,7 @@ static int32_t launch_fused(cudaStream_t s, const void* obs, const unsigned char
     }
     if (cudaMemsetAsync(ready, 0, fused_ready_bytes(M), s) != cudaSuccess) return check_launch("brl_mlp_forward (memset)");
     const int n_pairs = fa.n_tiles < max_pairs ? fa.n_tiles : max_pairs;
-    kern<<<(unsigned)(2 * n_pairs), kMlpThreads, Cfg::kSmemBytes, s>>>(fa);
+    kern<<<(unsigned)(2 * n_pairs), kFusedThreads, Cfg::kSmemBytes, s>>>(fa);
     return BRL_OK;
 }
 
@@ -947,6 +1064,17 @@ int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_
     return mlp_forward_impl("brl_mlp_forward", (cudaStream_t)stream, p, b[0], static_cast<const unsigned char*>(b[1]),
                             static_cast<__nv_bfloat16*>(b[2]), static_cast<float*>(b[3]), static_cast<float*>(b[4]), ActArgs{});
 }
+
+#ifdef BRL_MLP_TRACE
+int32_t brl_debug_mlp_trace(unsigned long long* out_1024x8) {
+    return cudaMemcpyFromSymbol(out_1024x8, g_mlp_trace, sizeof(g_mlp_trace)) == cudaSuccess ? 0 : -1;
+}
+int32_t brl_debug_mlp_epi(unsigned long long* out4, int reset) {
+    if (cudaMemcpyFromSymbol(out4, g_mlp_epi, sizeof(g_mlp_epi)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_mlp_epi, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int64_t brl_mlp_rows_scratch_bytes(int64_t n_rows) {  // brl_mlp_scratch_bytes + the gathered bf16 observation rows
     return brl_mlp_scratch_bytes(n_rows) + n_rows * (int64_t)kObsDimM * 2;
