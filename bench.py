@@ -296,33 +296,45 @@ def main():
                   warmup=args.warmup)
 
     extra = {}
+
+    def leg(name, fn):
+        """a secondary leg must never take the headline line down with it: its failure is recorded, not raised"""
+        try:
+            extra[name] = fn()
+        except Exception as exc:  # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- the north-star multi-GPU configs (all ranks take part; one all-reduce each) ----------------------------------
     if not args.no_matches:
-        extra["dup_selfplay_65536"] = run_dup_selfplay(torch, dist, dev, rank, world, table_np)
+        leg("dup_selfplay_65536", lambda: run_dup_selfplay(torch, dist, dev, rank, world, table_np))
         if world >= 8 or args.league:
-            extra["league_1M"] = run_league(torch, dist, dev, rank, world, table_np)
+            leg("league_1M", lambda: run_league(torch, dist, dev, rank, world, table_np))
         if rank == 0:
-            extra["c1_eval_match"] = run_c1(torch, dev)
+            leg("c1_eval_match", lambda: run_c1(torch, dev))
     if args.sweep and rank == 0:
-        extra["sweep"] = run_sweep(torch, ops, table, dev, peak)
-
+        leg("sweep", lambda: run_sweep(torch, ops, table, dev, peak))
     if rank == 0 and not args.no_policy:
-        extra["policy_rollout"] = run_policy_rollout(torch, table_np, dev)
+        leg("policy_rollout", lambda: run_policy_rollout(torch, table_np, dev))
     if rank == 0 and not args.no_update:
-        extra["ppo_update"] = run_ppo_update(torch, dev)
+        leg("ppo_update", lambda: run_ppo_update(torch, dev))
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        reps = 100  # ~1.2 s wall x all cores = 10-30 s of CPU work
-        v, times = cpu_oracle_throughput(n, k, reps, cores, table_np)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{reps} x ({n} envs x {k} auto-reset random-legal steps), all outputs written, {cores} threads, "
-                         f"{sum(times):.2f} s wall",
-               "build": _oracle_build(),
-               "note": "C restatement of pgx semantics (oracle/brl_oracle.c); pgx/JAX not installable here.  It rebuilds the "
-                       "observation from the call list every step, as the reference does: a reported baseline, not a tuned "
-                       "CPU port -- the roofline fraction, not this ratio, says how good the kernel is"}
+        try:
+            cores = os.cpu_count() or 1
+            reps = 100  # ~1.2 s wall x all cores = 10-30 s of CPU work
+            v, times = cpu_oracle_throughput(n, k, reps, cores, table_np)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{reps} x ({n} envs x {k} auto-reset random-legal steps), all outputs written, {cores} threads, "
+                             f"{sum(times):.2f} s wall",
+                   "build": _oracle_build(),
+                   "note": "C restatement of pgx semantics (oracle/brl_oracle.c); pgx/JAX not installable here.  It rebuilds the "
+                           "observation from the call list every step, as the reference does: a reported baseline, not a tuned "
+                           "CPU port -- the roofline fraction, not this ratio, says how good the kernel is"}
+        except Exception as exc:  # noqa: BLE001
+            cpu = {"error": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
