@@ -20,12 +20,13 @@ def _uniforms(orc, seed, n, k, offset=0, step0=0):
     return u
 
 
-@pytest.mark.parametrize("tune_kw", [{}, {"classic_rollout": True, "epw": 8}])
-def test_rollout_with_caller_supplied_uniforms_equals_philox_mode(tune_kw):
+@pytest.mark.parametrize("tune_kw,k", [({}, 12), ({"classic_rollout": True, "epw": 8}, 12), ({}, 100), ({"ring": 4}, 100),
+                                       ({"ring": 3, "writers": 1}, 70), ({"ring": 4}, 3)])
+def test_rollout_with_caller_supplied_uniforms_equals_philox_mode(tune_kw, k):
     from brl_b200 import _lib, ops
     from brl_b200.deals import synthetic_deal_table
     from oracle import oracle as orc
-    n, k, seed = 200, 12, 99
+    n, seed = 200, 99
     table = synthetic_deal_table(700, seed=2)
     table_t = torch.as_tensor(table, device=DEV)
     env = orc.OracleEnv(table, n)
