@@ -441,6 +441,8 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
     const size_t obs_row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
     const bool is_env_warp = warp == n_writers;
     const int mask_mode = a.balanced ? 2 : a.mask_vec;  // mode 2 copes with any alignment of the run
+    const bool env_philox = !a.uniforms && (a.flags & (1 << 27)) != 0;  // experiment: the env warp draws its own uniforms
+    const bool env_scalars = (a.flags & (1 << 28)) != 0;                // experiment: the env warp stores the per-env scalars
     Env e;
     EpisodePrefetch cache;
     uint64_t mask = 0ull;
@@ -464,7 +466,9 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
             if (s < a.k_steps) {
                 WsTile<EPB>& t = tiles[s & 1];
                 if (active) {
-                    int32_t act = kth_legal_action(mask, uniforms[(s / kUChunk) & 1][s % kUChunk][lane]);
+                    const uint32_t u = env_philox ? action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)s)
+                                                  : uniforms[(s / kUChunk) & 1][s % kUChunk][lane];
+                    int32_t act = kth_legal_action(mask, u);
                     float4 rew = env_step_autoreset_prefetch(e, cache, rs, lane, act, a.table, a.n_deals, a.illegal_penalty,
                                                              a.illegal_bonus);
                     n_term += f_terminated(e);
@@ -482,11 +486,20 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                         R[14] = (uint32_t)(hand >> 20);
                     }
                     t.M[lane] = mask;
-                    t.rew[lane] = rew;
-                    t.act[lane] = (uint32_t)act;
                     t.q[lane] = (uint8_t)q;
-                    t.term[lane] = (uint8_t)f_terminated(e);
-                    t.cur[lane] = (uint8_t)f_player_at(e, q);
+                    if (env_scalars) {  // per-env scalars straight from the env warp's registers
+                        const int64_t row = (int64_t)s * a.n + i;
+                        if (a.rewards) a.rewards[row] = rew;
+                        if (a.terminated) a.terminated[row] = (uint8_t)f_terminated(e);
+                        if (a.result16) a.result16[row] = pack_result16(rew.x, f_terminated(e));
+                        if (a.current_player) a.current_player[row] = (int8_t)f_player_at(e, q);
+                        if (a.action_out) a.action_out[row] = act;
+                    } else {
+                        t.rew[lane] = rew;
+                        t.act[lane] = (uint32_t)act;
+                        t.term[lane] = (uint8_t)f_terminated(e);
+                        t.cur[lane] = (uint8_t)f_player_at(e, q);
+                    }
                 } else if (lane < EPB) {
                     t.M[lane] = 0ull;
                 }
@@ -503,7 +516,7 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                 if (a.mask)
                     emit_mask_run(t.M, (int)threadIdx.x, n_writers * 32, a.mask + (size_t)(row0 + env_base) * kNumActions,
                                   n_valid * kNumActions, mask_mode);
-                if (warp == n_writers - 1 && active) {  // per-env scalars, coalesced over the tile
+                if (!env_scalars && warp == n_writers - 1 && active) {  // per-env scalars, coalesced over the tile
                     const int64_t row = row0 + i;
                     if (a.rewards) a.rewards[row] = t.rew[lane];
                     if (a.terminated) a.terminated[row] = t.term[lane];
@@ -520,7 +533,7 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                     // writes), scripts/exp_e2e_gap.py.  The burst for steps s+1 .. s+32 is issued at s = 0, 32, ...: at s = 0
                     // the writers have nothing to store yet, so it hides under the env warp's first step.
                     if (s % kUChunk == 0) load_uniform_burst(a, uniforms, s, i, active, warp, n_writers, lane);
-                } else if (warp == 0) {
+                } else if (warp == 0 && !env_philox) {
                     uniforms[((s + 1) / kUChunk) & 1][(s + 1) % kUChunk][lane] =
                         action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)(s + 1));
                 }
@@ -544,166 +557,6 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                 atomicAdd(&a.stats[1], (unsigned long long)rew0);
                 atomicAdd(&a.stats[2], (unsigned long long)n_valid * (unsigned long long)a.k_steps);
             }
-        }
-    }
-}
-
-// ---- the same roles over a RING of K hand-over tiles -------------------------------------
-// k_rollout_ws hands tiles over with one __syncthreads per step: every step costs max(env warp, slowest writer warp) and any
-// jitter of either role stalls the other (scripts/exp_role_cycles.py: the writers work 5,000-5,700 clocks per step and still
-// wait 300-1,000 at the barrier).  Here step s lives in slot s % K with two mbarriers: `full` (the env warp arrives once the
-// tile is staged) and `empty` (every writer warp arrives once it has stored the tile), so the env warp runs up to K - 1 steps
-// ahead, and each writer warp advances on its own.  Uniforms: ring position r % 64; the writers produce step s + K (Philox) or
-// the burst s + 32 .. s + 63 (caller-supplied, at s % 32 == 0) BEFORE they arrive on `empty` of iteration s, and the env warp's
-// wait for that arrival (step s + K) is what makes them visible.
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0u;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    }
-}
-
-template <int EPB, int OBS, int K>
-__global__ void __launch_bounds__(256) k_rollout_ring(const EnvArgs a) {
-    static_assert(K >= 2 && K <= kUChunk, "ring depth");
-    __shared__ WsTile<EPB> tiles[K];
-    __shared__ uint32_t uniforms[2][kUChunk][32];  // ring of 2 * kUChunk steps
-    __shared__ uint4 row_slots[2 * EPB * 3];
-    __shared__ unsigned long long row_bars[2 * EPB];
-    __shared__ unsigned long long full_bar[K], empty_bar[K];
-    const RowSlots rs{row_slots, row_bars, EPB};
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_writers = (int)(blockDim.x >> 5) - 1;
-    const int64_t env_base = a.balanced ? ((int64_t)blockIdx.x * a.n) / gridDim.x : (int64_t)blockIdx.x * EPB;
-    const int64_t env_end = a.balanced ? ((int64_t)(blockIdx.x + 1) * a.n) / gridDim.x : env_base + EPB;
-    const int n_valid = (int)((a.n < env_end ? a.n : env_end) - env_base);
-    const bool active = lane < n_valid;
-    const int64_t i = env_base + lane;
-    const size_t obs_row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
-    const bool is_env_warp = warp == n_writers;
-    const int mask_mode = a.balanced ? 2 : a.mask_vec;
-    if (is_env_warp) {
-        if (lane < K) {
-            mbar_init(&full_bar[lane], 1u);
-            mbar_init(&empty_bar[lane], (uint32_t)n_writers);
-        }
-        if (lane < 2)
-            for (int k = 0; k < K; ++k) tiles[k].M[EPB + lane] = 0ull;
-    } else if (a.uniforms) {
-        load_uniform_burst(a, uniforms, -1, i, active, warp, n_writers, lane);  // steps 0 .. 31
-    } else {
-        for (int r = warp; r < K && r < a.k_steps; r += n_writers)
-            uniforms[0][r][lane] = action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)r);
-    }
-    if (is_env_warp) {
-        Env e;
-        EpisodePrefetch cache;
-        uint64_t mask = 0ull;
-        unsigned long long n_term = 0;
-        long long rew0 = 0;
-        if (active) {
-            load_env(a.state_in, a.stride, i, e);
-            cache.prime(e, rs, lane, a.table, a.n_deals);
-            mask = env_legal_mask(e);
-        }
-        __syncthreads();
-        BRL_T0();
-        for (int s = 0; s < a.k_steps; ++s) {
-            const int slot = s % K;
-            if (s >= K) mbar_wait(&empty_bar[slot], (uint32_t)((s / K) - 1) & 1u);
-            BRL_ACC(1);
-            WsTile<EPB>& t = tiles[slot];
-            if (active) {
-                int32_t act = kth_legal_action(mask, uniforms[(s / kUChunk) & 1][s % kUChunk][lane]);
-                float4 rew = env_step_autoreset_prefetch(e, cache, rs, lane, act, a.table, a.n_deals, a.illegal_penalty,
-                                                         a.illegal_bonus);
-                n_term += f_terminated(e);
-                rew0 += (long long)rew.x;
-                mask = env_legal_mask(e);
-                const uint32_t q = f_cur_seat(e);
-                uint32_t* R = &t.R[lane * kRowStride];
-                if (a.obs) {
-                    const uint32_t us = (q & 1u) ? f_vul_ew(e) : f_vul_ns(e), them = (q & 1u) ? f_vul_ns(e) : f_vul_ew(e);
-                    const uint64_t hand = cache.cur.hand(e.deal, q);
-                    R[0] = e.H[0] | (us ? 2u : 1u) | (them ? 8u : 4u);
-#pragma unroll
-                    for (int w = 1; w < 13; ++w) R[w] = e.H[w];
-                    R[13] = e.H[13] | (uint32_t)(hand << 12);
-                    R[14] = (uint32_t)(hand >> 20);
-                }
-                t.M[lane] = mask;
-                t.rew[lane] = rew;
-                t.act[lane] = (uint32_t)act;
-                t.q[lane] = (uint8_t)q;
-                t.term[lane] = (uint8_t)f_terminated(e);
-                t.cur[lane] = (uint8_t)f_player_at(e, q);
-            } else if (lane < EPB) {
-                t.M[lane] = 0ull;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[slot]);
-            BRL_ACC(0);
-        }
-        if (active) store_env(a.state_out, a.stride, i, e);
-        asm volatile("cp.async.wait_all;" ::: "memory");  // the last prefetch must land before the block's smem is released
-        if (a.stats) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                n_term += __shfl_xor_sync(0xffffffffu, n_term, o);
-                rew0 += __shfl_xor_sync(0xffffffffu, rew0, o);
-            }
-            if (lane == 0) {
-                atomicAdd(&a.stats[0], n_term);
-                atomicAdd(&a.stats[1], (unsigned long long)rew0);
-                atomicAdd(&a.stats[2], (unsigned long long)n_valid * (unsigned long long)a.k_steps);
-            }
-        }
-    } else {
-        __syncthreads();
-        BRL_T0();
-        for (int s = 0; s < a.k_steps; ++s) {
-            const int slot = s % K;
-            mbar_wait(&full_bar[slot], (uint32_t)(s / K) & 1u);
-            BRL_ACC(warp == 0 ? 3 : 5);
-            const WsTile<EPB>& t = tiles[slot];
-            const int64_t row0 = (int64_t)s * a.n;
-            if (a.obs) {
-                unsigned char* obs = static_cast<unsigned char*>(a.obs) + (size_t)row0 * obs_row_bytes;
-                for (int r = warp; r < n_valid; r += n_writers)
-                    emit_obs_row_rot<OBS>(&t.R[r * kRowStride], t.q[r], lane, obs, env_base + r);
-            }
-            if (a.mask)
-                emit_mask_run(t.M, (int)threadIdx.x, n_writers * 32, a.mask + (size_t)(row0 + env_base) * kNumActions,
-                              n_valid * kNumActions, mask_mode);
-            if (warp == n_writers - 1 && active) {  // per-env scalars, coalesced over the tile
-                const int64_t row = row0 + i;
-                if (a.rewards) a.rewards[row] = t.rew[lane];
-                if (a.terminated) a.terminated[row] = t.term[lane];
-                if (a.result16) a.result16[row] = pack_result16(t.rew[lane].x, t.term[lane]);
-                if (a.current_player) a.current_player[row] = (int8_t)t.cur[lane];
-                if (a.action_out) a.action_out[row] = (int32_t)t.act[lane];
-            }
-            if (a.uniforms) {
-                if (s % kUChunk == 0 && s + kUChunk < a.k_steps)
-                    load_uniform_burst(a, uniforms, s + kUChunk - 1, i, active, warp, n_writers, lane);
-            } else if (warp == 0 && s + K < a.k_steps) {
-                uniforms[((s + K) / kUChunk) & 1][(s + K) % kUChunk][lane] =
-                    action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)(s + K));
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[slot]);
-            BRL_ACC(warp == 0 ? 2 : 4);
         }
     }
 }
@@ -944,10 +797,7 @@ template <int EPB, int OBS>
 static void launch_ws_inst(const EnvArgs& a, int writers, cudaStream_t s) {
     unsigned grid = (unsigned)((a.n + EPB - 1) / EPB);
     if (a.balanced) grid = ((grid + 147u) / 148u) * 148u;  // 148 SMs: same number of blocks on every SM
-    const int ring = (a.flags >> 27) & 3;  // experiment: 0/1 = barrier hand-over, 2 = ring of 3 tiles, 3 = ring of 4
-    if (ring == 2) k_rollout_ring<EPB, OBS, 3><<<grid, 32 * (1 + writers), 0, s>>>(a);
-    else if (ring == 3) k_rollout_ring<EPB, OBS, 4><<<grid, 32 * (1 + writers), 0, s>>>(a);
-    else k_rollout_ws<EPB, OBS><<<grid, 32 * (1 + writers), 0, s>>>(a);
+    k_rollout_ws<EPB, OBS><<<grid, 32 * (1 + writers), 0, s>>>(a);
 }
 template <int OBS>
 static void launch_ws_obs(const EnvArgs& a, int epb, int writers, cudaStream_t s) {

@@ -1,6 +1,6 @@
-"""Interleaved A/B of the rollout kernel's hand-over: __syncthreads + two tiles (ring=0) against the mbarrier ring of 3 / 4
-tiles, by writer-warp count, Philox mode and caller-supplied uniforms (bench shape: 8192 envs x 32 steps, f32 observations).
-Median over rounds; configurations alternate inside one process."""
+"""Interleaved A/B of role-balance variants of the rollout kernel (bench shape: 8192 envs x 32 steps, f32 observations):
+who draws the Philox uniforms (writer warp 0 / the env warp) and who stores the per-env scalars (last writer warp / the env
+warp), by writer-warp count; Philox mode and caller-supplied uniforms.  Median over rounds; configurations alternate."""
 import json
 import os
 import statistics
@@ -29,12 +29,14 @@ def main():
     traj = ops.EnvOutputs(n, dev, rows=k)
     u = torch.randint(0, 2 ** 31 - 1, (k, n), dtype=torch.int32, device=dev)
     cfgs = {}
-    for ring in (0, 3, 4):
-        for w in (3, 4, 5, 6):
-            for uni in (False, True):
-                if uni and w not in (4, 5):
-                    continue
-                cfgs[f"ring{ring} w{w} {'caller-u' if uni else 'philox'}"] = (_lib.tune(writers=w, ring=ring), uni)
+    for ep in (False, True):
+        for es in (False, True):
+            for w in (3, 4, 5):
+                for uni in (False, True):
+                    if uni and (ep or w != 4):
+                        continue
+                    cfgs[f"philox@{'env' if ep else 'w0 '} scalars@{'env ' if es else 'last'} w{w} {'caller-u' if uni else 'philox'}"] = \
+                        (_lib.tune(writers=w, env_philox=ep, env_scalars=es), uni)
     res = {name: [] for name in cfgs}
     step = 0
     for r in range(rounds):
@@ -52,7 +54,7 @@ def main():
             res[name].append(e0.elapsed_time(e1) / reps)
     for name, v in sorted(res.items(), key=lambda kv: statistics.median(kv[1])):
         med = statistics.median(v)
-        print(f"{name:24s} n={n} median={med*1e3:7.2f} us  min={min(v)*1e3:7.2f}  max={max(v)*1e3:7.2f}  "
+        print(f"{name:44s} n={n} median={med*1e3:7.2f} us  min={min(v)*1e3:7.2f}  max={max(v)*1e3:7.2f}  "
               f"frac(median)={1980*n*k/med/1e6/peak:.3f}")
 
 

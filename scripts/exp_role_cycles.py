@@ -8,8 +8,8 @@ L = _lib.load()
 dev = "cuda:0"
 table = torch.as_tensor(synthetic_deal_table(100000, 0), device=dev)
 n, k = 8192, 32
-ring = int(sys.argv[1]) if len(sys.argv) > 1 else 0   # 0 = __syncthreads hand-over, 3 / 4 = mbarrier ring of that many tiles
-tune = _lib.tune(ring=ring)
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 0   # bit 0: env warp draws the uniforms, bit 1: env warp stores the scalars
+tune = _lib.tune(env_philox=bool(variant & 1), env_scalars=bool(variant & 2))
 state, out0 = ops.new_state(n, dev), ops.EnvOutputs(n, dev)
 ops.init(ops.make_keys(1, n, dev), table, state, out0)
 traj = ops.EnvOutputs(n, dev, rows=k)
@@ -27,6 +27,6 @@ e1.record(); torch.cuda.synchronize()
 L.brl_debug_role_cycles(out, 1)
 blocks = 296
 per = lambda v: v / (reps * blocks * (k + 1))
-print("ring", ring, "ms per launch (timing build)", e0.elapsed_time(e1) / reps)
+print("variant", variant, "ms per launch (timing build)", e0.elapsed_time(e1) / reps)
 print("env warp: work %.0f  barrier %.0f | warp 0: work %.0f barrier %.0f | other warps (sum): work %.0f barrier %.0f  [SM clocks per step]" %
       tuple(per(out[i]) for i in range(6)))
