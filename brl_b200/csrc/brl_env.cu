@@ -441,8 +441,6 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
     const size_t obs_row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
     const bool is_env_warp = warp == n_writers;
     const int mask_mode = a.balanced ? 2 : a.mask_vec;  // mode 2 copes with any alignment of the run
-    const bool env_philox = !a.uniforms && (a.flags & (1 << 27)) != 0;  // experiment: the env warp draws its own uniforms
-    const bool env_scalars = (a.flags & (1 << 28)) != 0;                // experiment: the env warp stores the per-env scalars
     Env e;
     EpisodePrefetch cache;
     uint64_t mask = 0ull;
@@ -466,9 +464,7 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
             if (s < a.k_steps) {
                 WsTile<EPB>& t = tiles[s & 1];
                 if (active) {
-                    const uint32_t u = env_philox ? action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)s)
-                                                  : uniforms[(s / kUChunk) & 1][s % kUChunk][lane];
-                    int32_t act = kth_legal_action(mask, u);
+                    int32_t act = kth_legal_action(mask, uniforms[(s / kUChunk) & 1][s % kUChunk][lane]);
                     float4 rew = env_step_autoreset_prefetch(e, cache, rs, lane, act, a.table, a.n_deals, a.illegal_penalty,
                                                              a.illegal_bonus);
                     n_term += f_terminated(e);
@@ -486,20 +482,11 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                         R[14] = (uint32_t)(hand >> 20);
                     }
                     t.M[lane] = mask;
+                    t.rew[lane] = rew;
+                    t.act[lane] = (uint32_t)act;
                     t.q[lane] = (uint8_t)q;
-                    if (env_scalars) {  // per-env scalars straight from the env warp's registers
-                        const int64_t row = (int64_t)s * a.n + i;
-                        if (a.rewards) a.rewards[row] = rew;
-                        if (a.terminated) a.terminated[row] = (uint8_t)f_terminated(e);
-                        if (a.result16) a.result16[row] = pack_result16(rew.x, f_terminated(e));
-                        if (a.current_player) a.current_player[row] = (int8_t)f_player_at(e, q);
-                        if (a.action_out) a.action_out[row] = act;
-                    } else {
-                        t.rew[lane] = rew;
-                        t.act[lane] = (uint32_t)act;
-                        t.term[lane] = (uint8_t)f_terminated(e);
-                        t.cur[lane] = (uint8_t)f_player_at(e, q);
-                    }
+                    t.term[lane] = (uint8_t)f_terminated(e);
+                    t.cur[lane] = (uint8_t)f_player_at(e, q);
                 } else if (lane < EPB) {
                     t.M[lane] = 0ull;
                 }
@@ -516,7 +503,7 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                 if (a.mask)
                     emit_mask_run(t.M, (int)threadIdx.x, n_writers * 32, a.mask + (size_t)(row0 + env_base) * kNumActions,
                                   n_valid * kNumActions, mask_mode);
-                if (!env_scalars && warp == n_writers - 1 && active) {  // per-env scalars, coalesced over the tile
+                if (warp == n_writers - 1 && active) {  // per-env scalars, coalesced over the tile
                     const int64_t row = row0 + i;
                     if (a.rewards) a.rewards[row] = t.rew[lane];
                     if (a.terminated) a.terminated[row] = t.term[lane];
@@ -533,7 +520,7 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                     // writes), scripts/exp_e2e_gap.py.  The burst for steps s+1 .. s+32 is issued at s = 0, 32, ...: at s = 0
                     // the writers have nothing to store yet, so it hides under the env warp's first step.
                     if (s % kUChunk == 0) load_uniform_burst(a, uniforms, s, i, active, warp, n_writers, lane);
-                } else if (warp == 0 && !env_philox) {
+                } else if (warp == 0) {
                     uniforms[((s + 1) / kUChunk) & 1][(s + 1) % kUChunk][lane] =
                         action_uniform(a.seed, (uint64_t)(a.env_offset + i), a.step + (uint32_t)(s + 1));
                 }

@@ -8,13 +8,11 @@ L = _lib.load()
 dev = "cuda:0"
 table = torch.as_tensor(synthetic_deal_table(100000, 0), device=dev)
 n, k = 8192, 32
-variant = int(sys.argv[1]) if len(sys.argv) > 1 else 0   # bit 0: env warp draws the uniforms, bit 1: env warp stores the scalars
-tune = _lib.tune(env_philox=bool(variant & 1), env_scalars=bool(variant & 2))
 state, out0 = ops.new_state(n, dev), ops.EnvOutputs(n, dev)
 ops.init(ops.make_keys(1, n, dev), table, state, out0)
 traj = ops.EnvOutputs(n, dev, rows=k)
 for i in range(3):
-    ops.rollout_random(state, table, k, traj, seed=1, step0=i * k, tune=tune)
+    ops.rollout_random(state, table, k, traj, seed=1, step0=i * k)
 torch.cuda.synchronize()
 out = (C.c_ulonglong * 8)()
 L.brl_debug_role_cycles(out, 1)
@@ -22,11 +20,11 @@ reps = 10
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for i in range(reps):
-    ops.rollout_random(state, table, k, traj, seed=1, step0=(3 + i) * k, tune=tune)
+    ops.rollout_random(state, table, k, traj, seed=1, step0=(3 + i) * k)
 e1.record(); torch.cuda.synchronize()
 L.brl_debug_role_cycles(out, 1)
 blocks = 296
 per = lambda v: v / (reps * blocks * (k + 1))
-print("variant", variant, "ms per launch (timing build)", e0.elapsed_time(e1) / reps)
+print("ms per launch (timing build)", e0.elapsed_time(e1) / reps)
 print("env warp: work %.0f  barrier %.0f | warp 0: work %.0f barrier %.0f | other warps (sum): work %.0f barrier %.0f  [SM clocks per step]" %
       tuple(per(out[i]) for i in range(6)))

@@ -20,8 +20,7 @@ def _uniforms(orc, seed, n, k, offset=0, step0=0):
     return u
 
 
-@pytest.mark.parametrize("tune_kw,k", [({}, 12), ({"classic_rollout": True, "epw": 8}, 12), ({}, 100), ({"env_scalars": True}, 100),
-                                       ({"env_philox": True, "env_scalars": True, "writers": 1}, 70)])
+@pytest.mark.parametrize("tune_kw,k", [({}, 12), ({"classic_rollout": True, "epw": 8}, 12), ({}, 100), ({"writers": 1}, 70)])
 def test_rollout_with_caller_supplied_uniforms_equals_philox_mode(tune_kw, k):
     from brl_b200 import _lib, ops
     from brl_b200.deals import synthetic_deal_table
