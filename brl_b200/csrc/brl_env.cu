@@ -72,7 +72,6 @@ struct EnvArgs {
     int32_t flags, k_steps, mode;
     float illegal_penalty, illegal_bonus;
     int mask_vec;  // mask rows may be written with 128-bit stores
-    int obs32;     // observation rows may be written with 256-bit stores (buffer 32-byte aligned; every row size is a multiple of 32)
     int balanced;  // warp-specialised rollout: envs split evenly over a grid that is a multiple of the SM count
 };
 
@@ -89,56 +88,8 @@ __device__ __forceinline__ uint32_t pair_to_bf16x2(uint32_t two) {
     return ((two & 1u) ? 0x00003F80u : 0u) | ((two & 2u) ? 0x3F800000u : 0u);
 }
 
-// one 256-bit store (sm_100: STG.E.256); `p` must be 32-byte aligned
-__device__ __forceinline__ void st_global_v8(void* p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
-                                             uint32_t w5, uint32_t w6, uint32_t w7) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2), "r"(w3),
-                 "r"(w4), "r"(w5), "r"(w6), "r"(w7)
-                 : "memory");
-}
-
-// 32 bytes of one observation row from the bits they encode: f32 -- 8 bits -> 8 floats; bf16 -- 16 bits -> 16 values;
-// u8 -- 32 bits -> 32 bytes.  Half the store instructions of the 128-bit form and ~40 % fewer instructions per row.
-template <int OBS>
-__device__ __forceinline__ void st_obs32(void* p, uint32_t bits) {
-    if (OBS == kObsF32) {
-        // bit i -> 1.0f: (bits & 2^i) * (0x3F800000 >> i), one logic op + one integer multiply per value
-        const uint32_t one = 0x3F800000u;
-        st_global_v8(p, (bits & 1u) * one, (bits & 2u) * (one >> 1), (bits & 4u) * (one >> 2), (bits & 8u) * (one >> 3),
-                     (bits & 16u) * (one >> 4), (bits & 32u) * (one >> 5), (bits & 64u) * (one >> 6), (bits & 128u) * (one >> 7));
-    } else if (OBS == kObsU8) {
-        st_global_v8(p, spread4(bits & 15u), spread4((bits >> 4) & 15u), spread4((bits >> 8) & 15u), spread4((bits >> 12) & 15u),
-                     spread4((bits >> 16) & 15u), spread4((bits >> 20) & 15u), spread4((bits >> 24) & 15u), spread4(bits >> 28));
-    } else {
-        st_global_v8(p, pair_to_bf16x2(bits), pair_to_bf16x2(bits >> 2), pair_to_bf16x2(bits >> 4), pair_to_bf16x2(bits >> 6),
-                     pair_to_bf16x2(bits >> 8), pair_to_bf16x2(bits >> 10), pair_to_bf16x2(bits >> 12), pair_to_bf16x2(bits >> 14));
-    }
-}
-
-// 32-byte piece `c` of a row covers these bits of the 15 words W[] (W = a callable word index -> word)
-//   f32: byte c of the bits (c < 60); bf16: half-word c (c < 30); u8: word c (c < 15)
-template <int OBS>
-struct ObsChunk {
-    static constexpr int kChunks = OBS == kObsF32 ? kObsDim / 8 : (OBS == kObsU8 ? kObsDim / 32 : kObsDim / 16);
-    static __device__ __forceinline__ int word(int c) { return OBS == kObsF32 ? c >> 2 : (OBS == kObsU8 ? c : c >> 1); }
-    static __device__ __forceinline__ uint32_t take(uint32_t w, int c) {
-        return OBS == kObsF32 ? (w >> ((c & 3) * 8)) & 0xFFu : (OBS == kObsU8 ? w : (w >> ((c & 1) * 16)) & 0xFFFFu);
-    }
-};
-
 // phase 2 building blocks: cooperative, fully coalesced expansion.
 // One warp writes one observation row (480 values) from its 15 words of bits.
-template <int OBS>
-__device__ __forceinline__ void emit_obs_row32(const uint32_t* R, int lane, void* obs, int64_t env) {
-    const size_t row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
-    unsigned char* row = static_cast<unsigned char*>(obs) + (size_t)env * row_bytes;
-#pragma unroll
-    for (int k = 0; k < (ObsChunk<OBS>::kChunks + 31) / 32; ++k) {
-        const int c = lane + 32 * k;
-        if (c < ObsChunk<OBS>::kChunks) st_obs32<OBS>(row + 32 * c, ObsChunk<OBS>::take(R[ObsChunk<OBS>::word(c)], c));
-    }
-}
-
 template <int OBS>
 __device__ __forceinline__ void emit_obs_row(const uint32_t* R, int lane, void* obs, int64_t env) {
     if (OBS == kObsF32) {
@@ -211,13 +162,9 @@ __device__ __forceinline__ void emit_mask_run(const uint64_t* M, int tid, int nt
 
 template <int EPW, int OBS>
 __device__ __forceinline__ void emit_tile(const WarpTile<EPW>& t, int lane, int64_t env_base, int n_valid,
-                                          void* obs, uint8_t* mask, int mask_vec, int obs32) {
-    if (obs != nullptr) {
-        if (obs32)
-            for (int e = 0; e < n_valid; ++e) emit_obs_row32<OBS>(&t.R[e * kRowStride], lane, obs, env_base + e);
-        else
-            for (int e = 0; e < n_valid; ++e) emit_obs_row<OBS>(&t.R[e * kRowStride], lane, obs, env_base + e);
-    }
+                                          void* obs, uint8_t* mask, int mask_vec) {
+    if (obs != nullptr)
+        for (int e = 0; e < n_valid; ++e) emit_obs_row<OBS>(&t.R[e * kRowStride], lane, obs, env_base + e);
     if (mask != nullptr) emit_mask_run(t.M, lane, 32, mask + env_base * kNumActions, n_valid * kNumActions, mask_vec);
 }
 
@@ -226,13 +173,10 @@ __device__ __forceinline__ void emit_tile(const WarpTile<EPW>& t, int lane, int6
 // pure-write kernel gains 10-15 % when the window of rows in flight per block shrinks from 128 to <= 32)
 template <int EPW, int OBS>
 __device__ __forceinline__ void emit_block(const WarpTile<EPW>& t, int tid, int nthreads, int64_t env_base, int n_valid,
-                                           void* obs, uint8_t* mask, int mask_vec, int obs32) {
+                                           void* obs, uint8_t* mask, int mask_vec) {
     if (obs != nullptr) {
         const int warp = tid >> 5, lane = tid & 31, nw = nthreads >> 5;
-        if (obs32)
-            for (int e = warp; e < n_valid; e += nw) emit_obs_row32<OBS>(&t.R[e * kRowStride], lane, obs, env_base + e);
-        else
-            for (int e = warp; e < n_valid; e += nw) emit_obs_row<OBS>(&t.R[e * kRowStride], lane, obs, env_base + e);
+        for (int e = warp; e < n_valid; e += nw) emit_obs_row<OBS>(&t.R[e * kRowStride], lane, obs, env_base + e);
     }
     if (mask != nullptr) emit_mask_run(t.M, tid, nthreads, mask + env_base * kNumActions, n_valid * kNumActions, mask_vec);
 }
@@ -313,7 +257,7 @@ __global__ void __launch_bounds__(256) k_step(const EnvArgs a) {
         }
     }
     __syncthreads();
-    emit_block<EPW, OBS>(t, (int)threadIdx.x, (int)blockDim.x, env_base, n_valid, a.obs, a.mask, a.mask_vec, a.obs32);
+    emit_block<EPW, OBS>(t, (int)threadIdx.x, (int)blockDim.x, env_base, n_valid, a.obs, a.mask, a.mask_vec);
 }
 
 // caller-supplied action uniform of trajectory row `idx`: u32, or u16 widened to the top half of a u32 (the k-th
@@ -383,7 +327,7 @@ __global__ void __launch_bounds__(128) k_rollout(const EnvArgs a) {
         __syncwarp();
         emit_tile<EPW, OBS>(t, lane, env_base, n_valid,
                             a.obs ? static_cast<unsigned char*>(a.obs) + (size_t)row0 * obs_row_bytes : nullptr,
-                            a.mask ? a.mask + (size_t)row0 * kNumActions : nullptr, a.mask_vec, a.obs32);
+                            a.mask ? a.mask + (size_t)row0 * kNumActions : nullptr, a.mask_vec);
         __syncwarp();
     }
     if (active) store_env(a.state_out, a.stride, i, e);
@@ -432,24 +376,6 @@ __device__ __forceinline__ uint32_t obs_word_rot(const uint32_t* R, int w, uint3
     if (w == 13) return rotr_nibbles(v & 0xFFFu, q) | (v & 0xFFFFF000u);
     if (w == 14) return v;
     return rotr_nibbles(v, q);
-}
-
-// 256-bit form of emit_obs_row_rot: history bits rotate, vulnerability (word 0 bits 0-3) and hand bits (word 13 bits 12+,
-// word 14) do not -- `hist` is the per-word mask of rotating bits, a per-lane constant the compiler hoists out of the row loop
-template <int OBS>
-__device__ __forceinline__ void emit_obs_row_rot32(const uint32_t* R, uint32_t q, int lane, void* obs, int64_t env) {
-    const size_t row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
-    unsigned char* row = static_cast<unsigned char*>(obs) + (size_t)env * row_bytes;
-#pragma unroll
-    for (int k = 0; k < (ObsChunk<OBS>::kChunks + 31) / 32; ++k) {
-        const int c = lane + 32 * k;
-        if (c < ObsChunk<OBS>::kChunks) {
-            const int w = ObsChunk<OBS>::word(c);
-            const uint32_t hist = w == 0 ? ~15u : (w == 13 ? 0xFFFu : (w == 14 ? 0u : ~0u));
-            const uint32_t v = R[w];
-            st_obs32<OBS>(row + 32 * c, ObsChunk<OBS>::take((rotr_nibbles(v, q) & hist) | (v & ~hist), c));
-        }
-    }
 }
 
 template <int OBS>
@@ -571,12 +497,8 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                 const int64_t row0 = (int64_t)(s - 1) * a.n;
                 if (a.obs) {
                     unsigned char* obs = static_cast<unsigned char*>(a.obs) + (size_t)row0 * obs_row_bytes;
-                    if (a.obs32)
-                        for (int r = warp; r < n_valid; r += n_writers)
-                            emit_obs_row_rot32<OBS>(&t.R[r * kRowStride], t.q[r], lane, obs, env_base + r);
-                    else
-                        for (int r = warp; r < n_valid; r += n_writers)
-                            emit_obs_row_rot<OBS>(&t.R[r * kRowStride], t.q[r], lane, obs, env_base + r);
+                    for (int r = warp; r < n_valid; r += n_writers)
+                        emit_obs_row_rot<OBS>(&t.R[r * kRowStride], t.q[r], lane, obs, env_base + r);
                 }
                 if (a.mask)
                     emit_mask_run(t.M, (int)threadIdx.x, n_writers * 32, a.mask + (size_t)(row0 + env_base) * kNumActions,
@@ -665,7 +587,7 @@ __global__ void __launch_bounds__(256) k_produce(const EnvArgs a) {
         }
     }
     __syncthreads();
-    emit_block<EPW, OBS>(t, (int)threadIdx.x, (int)blockDim.x, env_base, n_valid, a.obs, a.mask, a.mask_vec, a.obs32);
+    emit_block<EPW, OBS>(t, (int)threadIdx.x, (int)blockDim.x, env_base, n_valid, a.obs, a.mask, a.mask_vec);
 }
 
 // ---- legal_action_mask alone -------------------------------------------------------------
@@ -734,7 +656,7 @@ __global__ void __launch_bounds__(256) k_dup_step(const EnvArgs a) {
         }
     }
     __syncthreads();
-    emit_block<EPW, OBS>(t, (int)threadIdx.x, (int)blockDim.x, env_base, n_valid, a.obs, a.mask, a.mask_vec, a.obs32);
+    emit_block<EPW, OBS>(t, (int)threadIdx.x, (int)blockDim.x, env_base, n_valid, a.obs, a.mask, a.mask_vec);
 }
 
 // ---- private field export ----------------------------------------------------------------
@@ -917,7 +839,6 @@ static void set_outputs(EnvArgs& a, void** b, int first, int rows) {
     a.terminated = static_cast<uint8_t*>(b[first + 3]);
     a.current_player = static_cast<int8_t*>(b[first + 4]);
     a.mask_vec = mask_vec_ok(a.mask, a.n, rows);
-    a.obs32 = a.obs != nullptr && (reinterpret_cast<uintptr_t>(a.obs) & 31u) == 0 && !(a.flags & (1 << 27));  // bit 27: experiment, force 128-bit
 }
 
 static int32_t check_outputs(const EnvArgs& a, const char* fn) {
@@ -1081,7 +1002,6 @@ int32_t brl_observe(brl_stream_t stream, void** b, const void* opaque, size_t le
     a.in_player_id = static_cast<const int8_t*>(b[1]);
     a.table = static_cast<const uint8_t*>(b[2]);
     a.obs = b[3];
-    a.obs32 = (reinterpret_cast<uintptr_t>(a.obs) & 31u) == 0 && !(a.flags & (1 << 27));
     launch_produce(a, (cudaStream_t)stream);
     return check_launch("brl_observe");
 }
