@@ -22,7 +22,7 @@ def main():
     traj = ops.EnvOutputs(n, dev, rows=k)
     cfgs = {}
     for epb in (32, 16):
-        for w in ((2, 3, 4, 5) if epb == 32 else (1, 2, 3)):
+        for w in ((2, 3, 4, 5) if epb == 32 else (1, 2, 3, 4)):
             for bal in (False, True):
                 cfgs[f"epb{epb} w{w} {'bal' if bal else 'plain'}"] = _lib.tune(epw=epb, writers=w, balanced=bal)
     res = {name: [] for name in cfgs}
