@@ -45,14 +45,14 @@ ABI_VERSION = 2  # include/brl_b200.h BRL_ABI_VERSION; load() refuses a library 
 EVAL_ACC_COLS = 76
 
 
-def tune(epw: int = 0, wpb: int = 0, classic_rollout: bool = False, writers: int = 0, balanced=None, direct_stores: bool = False) -> int:
+def tune(epw: int = 0, wpb: int = 0, classic_rollout: bool = False, writers: int = 0, balanced=None) -> int:
     """flag bits: envs-per-warp of the tile kernels / envs-per-block of the warp-specialised
     rollout (8/16/32), warps-per-block of the tile kernels (1/2/4/8), classic_rollout = the
     tile-per-warp rollout instead of the warp-specialised one, writers = writer warps of the
     warp-specialised rollout (1..7).  0 = automatic everywhere."""
     return (({0: 0, 8: 1, 16: 2, 32: 3}[epw] << 16) | ({0: 0, 1: 1, 2: 2, 4: 3, 8: 3 | (1 << 8)}[wpb] << 18) |
             ((1 << 20) if classic_rollout else 0) | ((writers & 7) << 21) |
-            (0 if balanced is None else ((1 << 24) if balanced else (1 << 25))) | ((1 << 27) if direct_stores else 0))
+            (0 if balanced is None else ((1 << 24) if balanced else (1 << 25))))
 
 
 class BrlParams(C.Structure):

@@ -73,8 +73,6 @@ struct EnvArgs {
     float illegal_penalty, illegal_bonus;
     int mask_vec;  // mask rows may be written with 128-bit stores
     int balanced;  // warp-specialised rollout: envs split evenly over a grid that is a multiple of the SM count
-    int bulk_rows; // warp-specialised rollout: > 0 = observation rows leave through per-warp shared staging + one bulk copy per
-                   // step (this many staging rows per writer warp); 0 = direct 128-bit stores
 };
 
 // 4 bits -> 4 bytes of 0/1
@@ -424,11 +422,6 @@ __device__ unsigned long long g_role_cycles[8];
 #define BRL_ACC(slot)
 #endif
 
-#ifndef BRL_ROW_UNROLL
-#define BRL_ROW_UNROLL 1
-#endif
-constexpr int kRowUnroll = BRL_ROW_UNROLL;
-
 template <int EPB, int OBS>
 __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
     __shared__ WsTile<EPB> tiles[2];
@@ -448,13 +441,6 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
     const size_t obs_row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
     const bool is_env_warp = warp == n_writers;
     const int mask_mode = a.balanced ? 2 : a.mask_vec;  // mode 2 copes with any alignment of the run
-    // bulk mode: writer warp w owns the CONTIGUOUS rows [w * rpw, (w + 1) * rpw) of the block, expands them into its own shared
-    // staging buffer and hands the whole run (rpw * row bytes, ~13 KB) to the TMA as one cp.async.bulk per step
-    extern __shared__ __align__(128) unsigned char ws_stage[];
-    const int rpw = (n_valid + n_writers - 1) / n_writers;
-    const int r_lo = warp * rpw < n_valid ? warp * rpw : n_valid;
-    const int r_hi = r_lo + rpw < n_valid ? r_lo + rpw : n_valid;
-    unsigned char* const stage = ws_stage + (size_t)warp * a.bulk_rows * obs_row_bytes;
     Env e;
     EpisodePrefetch cache;
     uint64_t mask = 0ull;
@@ -511,28 +497,8 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                 const int64_t row0 = (int64_t)(s - 1) * a.n;
                 if (a.obs) {
                     unsigned char* obs = static_cast<unsigned char*>(a.obs) + (size_t)row0 * obs_row_bytes;
-                    if (a.bulk_rows) {
-                        if (r_hi > r_lo) {
-                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // last step's copy has left the buffer
-                            __syncwarp();
-#pragma unroll(kRowUnroll)
-                            for (int r = r_lo; r < r_hi; ++r)
-                                emit_obs_row_rot<OBS>(&t.R[r * kRowStride], t.q[r], lane, stage, r - r_lo);
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            __syncwarp();
-                            if (lane == 0) {
-                                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
-                                                 obs + (size_t)(env_base + r_lo) * obs_row_bytes),
-                                             "r"(smem_u32(stage)), "r"((uint32_t)((r_hi - r_lo) * obs_row_bytes))
-                                             : "memory");
-                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                            }
-                        }
-                    } else {
-#pragma unroll(kRowUnroll)
-                        for (int r = warp; r < n_valid; r += n_writers)
-                            emit_obs_row_rot<OBS>(&t.R[r * kRowStride], t.q[r], lane, obs, env_base + r);
-                    }
+                    for (int r = warp; r < n_valid; r += n_writers)
+                        emit_obs_row_rot<OBS>(&t.R[r * kRowStride], t.q[r], lane, obs, env_base + r);
                 }
                 if (a.mask)
                     emit_mask_run(t.M, (int)threadIdx.x, n_writers * 32, a.mask + (size_t)(row0 + env_base) * kNumActions,
@@ -564,7 +530,6 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
         __syncthreads();
         BRL_ACC(is_env_warp ? 1 : (warp == 0 ? 3 : 5));
     }
-    if (!is_env_warp && a.bulk_rows && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (is_env_warp) {
         if (active) store_env(a.state_out, a.stride, i, e);
         asm volatile("cp.async.wait_all;" ::: "memory");  // the last prefetch must land before the block's smem is released
@@ -819,23 +784,7 @@ template <int EPB, int OBS>
 static void launch_ws_inst(const EnvArgs& a, int writers, cudaStream_t s) {
     unsigned grid = (unsigned)((a.n + EPB - 1) / EPB);
     if (a.balanced) grid = ((grid + 147u) / 148u) * 148u;  // 148 SMs: same number of blocks on every SM
-    const size_t row_bytes = OBS == kObsF32 ? kObsDim * 4 : (OBS == kObsU8 ? kObsDim : kObsDim * 2);
-    EnvArgs b = a;
-    b.bulk_rows = (a.obs != nullptr && !(a.flags & (1 << 27))) ? (EPB + writers - 1) / writers : 0;  // bit 27: experiment, direct stores
-    const size_t smem = (size_t)b.bulk_rows * writers * row_bytes;
-    if (smem > 0) {  // static + dynamic exceeds the 48 KB default for most shapes: (EPB + writers - 1) rows at most
-        static bool attr_set_dev[kMaxDevices] = {};  // per device; idempotent, a race only repeats the call
-        bool& attr_set = attr_set_dev[device_slot()];
-        if (!attr_set) {
-            if (cudaFuncSetAttribute(k_rollout_ws<EPB, OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024) != cudaSuccess) {
-                (void)cudaGetLastError();
-                b.bulk_rows = 0;  // cannot reserve the staging buffers: direct stores
-            } else {
-                attr_set = true;
-            }
-        }
-    }
-    k_rollout_ws<EPB, OBS><<<grid, 32 * (1 + writers), b.bulk_rows ? smem : 0, s>>>(b);
+    k_rollout_ws<EPB, OBS><<<grid, 32 * (1 + writers), 0, s>>>(a);
 }
 template <int OBS>
 static void launch_ws_obs(const EnvArgs& a, int epb, int writers, cudaStream_t s) {

@@ -177,10 +177,7 @@ def test_plain_step_terminal_is_absorbing_and_noop():
     (8, 7, {"classic_rollout": True, "epw": 8}),
     # balanced env split (grid = multiple of 148 SMs, ragged 27/28-env blocks, unaligned mask runs)
     (8192, 6, {}), (8192, 4, {"balanced": False}), (5000, 7, {"balanced": True}), (1001, 5, {"balanced": True, "epw": 16}),
-    (37, 4, {"balanced": True}),
-    # observation rows by direct stores instead of shared staging + one bulk copy per writer warp and step
-    (2048, 24, {"direct_stores": True}), (8192, 6, {"direct_stores": True}), (100, 40, {"writers": 1, "direct_stores": True}),
-    (8192, 40, {"writers": 7}), (70000, 3, {"writers": 5, "epw": 16})])
+    (37, 4, {"balanced": True}), (8192, 40, {"writers": 7}), (70000, 3, {"writers": 5, "epw": 16})])
 def test_fused_rollout_kernel_matches_oracle(n, k, tune_kw):
     """brl_rollout_random (K steps in one launch, in-kernel random-legal policy) against
     the oracle's rollout: whole [K, n, ...] trajectories bit-exact."""
