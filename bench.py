@@ -343,7 +343,9 @@ def main():
             "e2e": e2e, "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": "brl::k_rollout_ws<f32> (296 blocks = 2 per SM, 27-28 envs each: 1 env warp + 4 writer warps)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * k, "avg_launch_ms": avg_kernel_ms},
+                         "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * k, "avg_launch_ms": avg_kernel_ms,
+                         "note": "write-only stream; at 8192 envs per GPU the limiter is the SM-side store path, not DRAM "
+                                 "(profiles/r02_n_rollout_decomposition.txt); the same kernel reaches 0.92 at 65,536 envs"},
             "cpu_baseline": cpu, "clocks": clocks,
             "episode_stats": {"finished_auctions": float(sums[0]), "sum_reward_player0": float(sums[1]),
                               "env_steps": float(sums[2]), "collective": "1 NCCL all-reduce of i64[4], in place on the kernel's statistics buffer" if world > 1 else "none (1 rank)"},
