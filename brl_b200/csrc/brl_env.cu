@@ -497,6 +497,9 @@ __global__ void __launch_bounds__(256) k_rollout_ws(const EnvArgs a) {
                 const int64_t row0 = (int64_t)(s - 1) * a.n;
                 if (a.obs) {
                     unsigned char* obs = static_cast<unsigned char*>(a.obs) + (size_t)row0 * obs_row_bytes;
+                    // two rows in flight per warp: the second row's shared loads and expansion fill the first row's store / dependency
+                    // stalls (measured 91.6 -> 89.4 us per launch at the bench shape; four rows: 94.2, scripts/exp_lib_variants.py)
+#pragma unroll 2
                     for (int r = warp; r < n_valid; r += n_writers)
                         emit_obs_row_rot<OBS>(&t.R[r * kRowStride], t.q[r], lane, obs, env_base + r);
                 }
