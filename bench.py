@@ -362,11 +362,12 @@ def run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps, warmu
     `e2e` (headline): one `brl_env_rollout_host_compact_async` call per bench step = the same 32 x 8192 env-steps as
     `value`, three calls in flight.  HOST in: the randomness of the action choice from pinned memory (the `action` input
     of the algorithmic byte count; the host owns the PRNG stream the way the reference's host owns the jax key) as
-    u16[32, 8192] (2 B per env-step; the k-th legal action is (u16 * #legal) >> 16).  HOST out: the step's result as
+    u32[32, 8192] (4 B per env-step; the k-th legal action is (u * #legal) >> 32).  HOST out: the step's result as
     i16[32, 8192] = 2 * rewards[player 0] + terminated -- lossless for rewards f32[.., 4] + terminated u8, which is what
     roll_out's consumer reads (src/roll_out.py:86-94) -- + the statistics vector.  The observation / mask / f32 reward
     trajectories stay in HBM for the device-resident consumer, exactly as `traj_batch` does in the reference
-    (src/roll_out.py:105-108).  Sub-entries: `u32_uniforms` (compact result, 4 B/env-step in), `f32_payload` (round 1's
+    (src/roll_out.py:105-108).  Sub-entries: `u16_uniforms` (2 B/env-step in: half the H2D bytes, but its kernel is 2 %
+    slower and at 1-8 GPUs of this pool it never wins -- profiles/r02_*bench*), `f32_payload` (round 1's
     payload: u32 in, rewards f32[4] + terminated u8 out = 17 B/env-step), `sync_per_call` (f32 payload, blocking).
     `full_io`: the other extreme -- one env.step per call with EVERY Env-surface output copied to the host (PCIe-bound
     by construction: 536 B per env-step in pgx's bool observation dtype)."""
@@ -446,20 +447,20 @@ def run_e2e(torch, np, _lib, table_np, n, offset, dev, world, dist, steps, warmu
         L.brl_env_destroy(h)
         return dt, finished, dt_sync
 
-    dt16, finished, _ = leg("compact16")
-    dt32, _, _ = leg("compact32")
+    dt32, finished, _ = leg("compact32")
+    dt16, _, _ = leg("compact16")
     dtf, _, dt_sync = leg("f32")
     tot = n * k * steps * world
-    res = {"value": tot / dt16, "unit": UNIT, "h2d_bytes_per_step": n * k * 2, "d2h_bytes_per_step": n * k * 2 + 32,
-           "steps": steps, "ms_per_step": 1e3 * dt16 / steps,
+    res = {"value": tot / dt32, "unit": UNIT, "h2d_bytes_per_step": n * k * 4, "d2h_bytes_per_step": n * k * 2 + 32,
+           "steps": steps, "ms_per_step": 1e3 * dt32 / steps,
            "api": "brl_env_rollout_host_compact_async + brl_env_wait (C ABI, host buffers), three calls in flight: per bench "
-                  "step H2D u16[32,8192] action randomness from pinned memory, one fused rollout launch writing the full "
+                  "step H2D u32[32,8192] action randomness from pinned memory, one fused rollout launch writing the full "
                   "trajectory (incl. f32 rewards / u8 terminated) to HBM, D2H result i16[32,8192] = 2*rewards[player 0] + "
                   "terminated (lossless: rewards are s*[+,+,-,-]) + stats into pinned memory, read by the host while the next "
                   "steps compute; obs/mask trajectories stay in HBM for the device-resident learner (as traj_batch does "
                   "in the reference)",
            "timed_with": "host wall clock around the whole loop, max over ranks", "finished_auctions_read_on_host": finished,
-           "u32_uniforms": {"value": tot / dt32, "ms_per_step": 1e3 * dt32 / steps, "h2d_bytes_per_step": n * k * 4,
+           "u16_uniforms": {"value": tot / dt16, "ms_per_step": 1e3 * dt16 / steps, "h2d_bytes_per_step": n * k * 2,
                             "d2h_bytes_per_step": n * k * 2 + 32},
            "f32_payload": {"value": tot / dtf, "ms_per_step": 1e3 * dtf / steps, "h2d_bytes_per_step": n * k * 4,
                            "d2h_bytes_per_step": n * k * 17 + 32,

@@ -11,6 +11,6 @@ d=json.loads(open("gpurun_out/$TAG/bench_n$N.json").read().strip().splitlines()[
 e=d["e2e"]
 print("value",d["value"],"ms",d["ms_per_step"])
 print("e2e",e["value"],e["ms_per_step"])
-for k in ("u32_uniforms","f32_payload","sync_per_call"): print(k,e[k]["value"],e[k]["ms_per_step"])
+for k in ("u16_uniforms","f32_payload","sync_per_call"): print(k,e[k]["value"],e[k]["ms_per_step"])
 PY
 cat gpurun_out/$TAG/pcie_n$N.jsonl
