@@ -162,18 +162,22 @@ def make_roll_out(config, env, actor_forward_pass, opp_forward_pass):
         actor_forward_pass.pack_into(params, c["blobs"][0])
         (opp_forward_pass if opp_params is not params else actor_forward_pass).pack_into(opp_params, c["blobs"][1])
         if c["graph"] is None:
-            actor_forward_pass.seed_salt = opp_forward_pass.seed_salt = c["salt"]
+            prev = (getattr(actor_forward_pass, "seed_salt", None), getattr(opp_forward_pass, "seed_salt", None))
+            actor_forward_pass.seed_salt = opp_forward_pass.seed_salt = c["salt"]  # baked into the captured launches only
             saved = (buf.packed.clone(), buf.obs[0].clone(), buf.mask[0].clone(), buf.player[0].clone())
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                body(buf, fixed_a, fixed_o, _CAPTURE_KEY, None)  # warm-up: lazy allocations (scratch), attribute calls
-                buf.packed.copy_(saved[0]); buf.obs[0].copy_(saved[1]); buf.mask[0].copy_(saved[2]); buf.player[0].copy_(saved[3])
-                buf.count.zero_()
-                side.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    body(buf, fixed_a, fixed_o, _CAPTURE_KEY, None)
+            try:
+                with torch.cuda.stream(side):
+                    body(buf, fixed_a, fixed_o, _CAPTURE_KEY, None)  # warm-up: lazy allocations (scratch), attribute calls
+                    buf.packed.copy_(saved[0]); buf.obs[0].copy_(saved[1]); buf.mask[0].copy_(saved[2]); buf.player[0].copy_(saved[3])
+                    buf.count.zero_()
+                    side.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        body(buf, fixed_a, fixed_o, _CAPTURE_KEY, None)
+            finally:
+                actor_forward_pass.seed_salt, opp_forward_pass.seed_salt = prev
             torch.cuda.current_stream(dev).wait_stream(side)
             c["graph"] = g
             buf.packed.copy_(saved[0]); buf.obs[0].copy_(saved[1]); buf.mask[0].copy_(saved[2]); buf.player[0].copy_(saved[3])

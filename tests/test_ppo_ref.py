@@ -67,3 +67,95 @@ def test_illegal_action_loss_is_the_spectral_norm_of_the_minibatch_matrix():
     X = (torch.softmax(logits, 1) * (~mask)).numpy()
     assert abs(float(aux[5]) - np.linalg.norm(X, 2) / 2) < 1e-12
     assert abs(np.linalg.norm(X, 2) - np.linalg.svd(X, compute_uv=False)[0]) < 1e-12
+
+
+def _loss(logits, value, mask, action, old_lp, old_v, gae, tgt, **kw):
+    f = lambda x: torch.tensor(x, dtype=torch.float64)  # noqa: E731
+    cfg = dict(clip_eps=0.2, ent_coef=0.0, vf_coef=0.5)
+    cfg.update(kw)
+    return ppo_ref.loss_fn(f(logits), f(value), torch.tensor(mask, dtype=torch.bool), torch.tensor(action), f(old_lp), f(old_v),
+                           f(gae), f(tgt), **cfg)
+
+
+def test_actor_loss_clipping_by_hand_both_signs_of_the_advantage():
+    """src/update.py:116-131: -min(ratio * gae, clip(ratio, 1 - eps, 1 + eps) * gae), averaged over the minibatch.
+    Four samples, all with p(action) = 0.5 under the new policy (two legal actions, equal logits):
+      ratio 2,   gae +1 -> min(2, 1.2)    = 1.2   (clipped: no more reward for moving further)
+      ratio 2,   gae -1 -> min(-2, -1.2)  = -2    (NOT clipped: the pessimistic bound)
+      ratio 0.5, gae +1 -> min(.5, .8)    = 0.5   (not clipped)
+      ratio 0.5, gae -1 -> min(-.5, -.8)  = -0.8  (clipped)"""
+    logits = [[0.0, 0.0] + [9.0] * 36] * 4
+    mask = [[True, True] + [False] * 36] * 4
+    old_lp = [np.log(0.25), np.log(0.25), np.log(1.0), np.log(1.0)]
+    total, (vl, la, ent, kl, cf, _) = _loss(logits, [0.0] * 4, mask, [0, 1, 0, 1], old_lp, [0.0] * 4, [1.0, -1.0, 1.0, -1.0], [0.0] * 4)
+    assert abs(float(la) - (-(1.2 - 2.0 + 0.5 - 0.8) / 4)) < 1e-12
+    assert float(cf) == 1.0                                            # |ratio - 1| = 1 and .5, both > .2
+    r = np.array([2.0, 2.0, 0.5, 0.5])
+    assert abs(float(kl) - float(((r - 1) - np.log(r)).mean())) < 1e-12   # :153
+    assert abs(float(ent) - np.log(2)) < 1e-12 and float(vl) == 0.0
+    assert abs(float(total) - float(la)) < 1e-12
+
+
+def test_value_loss_with_and_without_clipping_by_hand():
+    """src/update.py:49-68.  old value 0, eps .2.  Sample A: v = .5, target 1: clipped prediction .2 is FURTHER from the
+    target, max picks it: (.8)^2.  Sample B: v = .5, target 0: clipped prediction .2 is closer, max picks the unclipped
+    (.5)^2.  value_loss = 0.5 * mean."""
+    logits = [[0.0] * 38] * 2
+    mask = [[True] * 38] * 2
+    lp = [np.log(1 / 38)] * 2
+    _, aux = _loss(logits, [0.5, 0.5], mask, [0, 0], lp, [0.0, 0.0], [0.0, 0.0], [1.0, 0.0])
+    assert abs(float(aux[0]) - 0.5 * (0.64 + 0.25) / 2) < 1e-12
+    _, aux = _loss(logits, [0.5, 0.5], mask, [0, 0], lp, [0.0, 0.0], [0.0, 0.0], [1.0, 0.0], value_clipping=False)
+    assert abs(float(aux[0]) - 0.5 * (0.25 + 0.25) / 2) < 1e-12
+
+
+def test_reward_scaling_uses_the_population_std_plus_eps():
+    """src/update.py:35-36: (gae - mean) / (std + 1e-8) with jnp's default ddof = 0.  gae = (1, 3): mean 2, std 1 ->
+    (-1, +1); with ratio 1 everywhere the actor loss is -mean(scaled gae) = 0, and with ratios (1.1, 1) it is
+    -(1.1 * -1 + 1 * 1) / 2 = 0.05."""
+    logits = [[0.0, 0.0] + [0.0] * 36] * 2
+    mask = [[True, True] + [False] * 36] * 2
+    _, aux = _loss(logits, [0.0] * 2, mask, [0, 0], [np.log(0.5 / 1.1), np.log(0.5)], [0.0] * 2, [1.0, 3.0], [0.0] * 2,
+                   reward_scaling=True)
+    assert abs(float(aux[1]) - 0.05) < 1e-7                              # 1e-8 in the denominator
+    _, aux = _loss(logits, [0.0] * 2, mask, [0, 0], [np.log(0.5 / 1.1), np.log(0.5)], [0.0] * 2, [1.0, 3.0], [0.0] * 2)
+    assert abs(float(aux[1]) - (-(1.1 * 1.0 + 1.0 * 3.0) / 2)) < 1e-12  # unscaled
+
+
+def test_unmasked_policy_takes_log_prob_from_all_38_logits_but_entropy_from_the_legal_ones():
+    """src/update.py:12-24 (no_masked_policy) vs :133-137 (the entropy always masks)."""
+    logits = [[np.log(2.0), 0.0, 0.0] + [-50.0] * 35]
+    mask = [[True, True, False] + [False] * 35]
+    # unmasked p(action 0) = 2 / 4; masked distribution over the two legal actions = (2/3, 1/3)
+    _, aux = _loss(logits, [0.0], mask, [0], [np.log(0.5)], [0.0], [1.0], [0.0], masked_policy=False)
+    assert abs(float(aux[1]) - (-1.0)) < 1e-9                            # ratio 1 -> -gae
+    h = -(2 / 3 * np.log(2 / 3) + 1 / 3 * np.log(1 / 3))
+    assert abs(float(aux[2]) - h) < 1e-9
+    _, aux = _loss(logits, [0.0], mask, [0], [np.log(0.5)], [0.0], [1.0], [0.0], masked_policy=True)
+    assert abs(float(aux[1]) - (-min(4 / 3, 1.2))) < 1e-9                # masked p = 2/3 -> ratio 4/3, clipped at 1.2
+
+
+def test_adam_second_step_by_hand():
+    """optax.adam(lr, eps=1e-5): m, v moments, bias correction by 1 - b^t with t counted from 1, eps OUTSIDE the root
+    (eps_root = 0).  Two steps with g = 1 then g = -1 on one parameter, no clipping."""
+    p, m, v = ppo_ref.adam_clip_step(np.zeros(1), np.array([1.0]), np.zeros(1), np.zeros(1), 0, lr=0.1, max_grad_norm=0)
+    assert abs(p[0] - (-0.1 / (1 + 1e-5))) < 1e-15
+    p, m, v = ppo_ref.adam_clip_step(p, np.array([-1.0]), m, v, 1, lr=0.1, max_grad_norm=0)
+    m2 = 0.9 * 0.1 - 0.1                                                 # = -0.01
+    v2 = 0.999 * 0.001 + 0.001
+    step = 0.1 * (m2 / (1 - 0.9 ** 2)) / (np.sqrt(v2 / (1 - 0.999 ** 2)) + 1e-5)
+    assert abs(m[0] - m2) < 1e-15 and abs(v[0] - v2) < 1e-15
+    assert abs(p[0] - (-0.1 / (1 + 1e-5) - step)) < 1e-15
+
+
+def test_linear_learning_rate_schedule_matches_ppo_py():
+    """ppo.py:186-192: lr * (1 - (count // (num_minibatches * update_epochs)) / num_updates), evaluated by optax at the
+    count BEFORE the increment; and global_gradient_clipping = False drops the clip (ppo.py:203, 210)."""
+    from brl_b200.optim import make_optimizer
+    cfg = dict(lr=1e-3, anneal_lr=True, num_minibatches=4, update_epochs=2, num_updates=10, max_grad_norm=0.5)
+    opt = make_optimizer(cfg)
+    assert opt.lr_at(0) == 1e-3 and opt.lr_at(7) == 1e-3               # the whole first update (8 optimizer steps)
+    assert abs(opt.lr_at(8) - 1e-3 * 0.9) < 1e-18 and abs(opt.lr_at(79) - 1e-3 * 0.1) < 1e-18
+    assert opt.max_grad_norm == 0.5
+    opt = make_optimizer(dict(cfg, anneal_lr=False, global_gradient_clipping=False))
+    assert opt.lr_at(123) == 1e-3 and opt.max_grad_norm == 0.0
