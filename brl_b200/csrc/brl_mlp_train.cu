@@ -857,7 +857,7 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
     }
     int nb = 0;
     int dgrad_op[5] = {-1, -1, -1, -1, -1};  // op index (in bwd) that produced dz of layer l (1..4)
-    {   // head wgrad: [1024, 39] = h4^T . dz5 -> w4 grads (38 columns) + w5 grads (the value column)
+    auto add_head_wgrad = [&] {  // [1024, 39] = h4^T . dz5 -> w4 grads (38 columns) + w5 grads (the value column)
         OpSpec& o = bwd[nb++];
         o = OpSpec{};
         o.a_hi = sc + S.h_hi[3]; o.a_lo = sc + S.h_lo[3]; o.m_rows = kHidden; o.lda = kHidden; o.a_mn = 1;
@@ -865,34 +865,47 @@ int32_t brl_ppo_grad(brl_stream_t stream, void** b, const void* opaque, size_t l
         o.epi = kEpiWgrad;
         o.g.c = grads + F.w[4]; o.g.ld_c = 38; o.g.n_c = 38; o.g.c2 = grads + F.w[5]; o.g.sumsq = grad_sumsq;
         o.dep = -1;
-    }
-    for (int l = 4; l >= 1; --l) {
-        {   // dgrad into layer l
-            OpSpec& o = bwd[nb];
-            o = OpSpec{};
-            const int k_out = l == 4 ? kHeadPad : kHidden;  // width of dz_{l+1}
-            o.a_hi = l == 4 ? sc + S.dz5_hi : sc + S.dz_hi[l];
-            o.a_lo = l == 4 ? sc + S.dz5_lo : sc + S.dz_lo[l];
-            o.m_rows = B; o.lda = k_out;
-            o.w_hi = blob + T.wn_hi[l]; o.w_lo = blob + T.wn_lo[l]; o.n_rows = kHidden; o.ldb = k_out; o.k_cols = k_out;
-            o.epi = kEpiDgrad;
-            o.g.out_hi = bf(S.dz_hi[l - 1]); o.g.out_lo = bf(S.dz_lo[l - 1]);
-            o.g.ld_out = kHidden;
-            o.g.relu_src = bf(S.h_hi[l - 1]);
-            o.dep = l == 4 ? -1 : dgrad_op[l + 1]; o.dep_all = 0;
-            dgrad_op[l] = nb++;
-        }
-        {   // wgrad of layer l (0-based parameter index l - 1): dW = h_{l-1}^T . dz_l
-            OpSpec& o = bwd[nb++];
-            o = OpSpec{};
-            o.a_hi = l == 1 ? sc + S.obs : sc + S.h_hi[l - 2];
-            o.a_lo = l == 1 ? nullptr : sc + S.h_lo[l - 2];
-            o.m_rows = l == 1 ? kObsDimM : kHidden; o.lda = o.m_rows; o.a_mn = 1;
-            o.w_hi = sc + S.dz_hi[l - 1]; o.w_lo = sc + S.dz_lo[l - 1]; o.n_rows = kHidden; o.ldb = kHidden; o.w_mn = 1; o.k_cols = B;
-            o.epi = kEpiWgrad;
-            o.g.c = grads + F.w[l - 1]; o.g.ld_c = kHidden; o.g.n_c = kHidden; o.g.sumsq = grad_sumsq;
-            o.dep = dgrad_op[l]; o.dep_all = 1;
-        }
+    };
+    auto add_dgrad = [&](int l) {  // dz_{l+1} -> dz_l (the layer-to-layer chain of the backward)
+        OpSpec& o = bwd[nb];
+        o = OpSpec{};
+        const int k_out = l == 4 ? kHeadPad : kHidden;  // width of dz_{l+1}
+        o.a_hi = l == 4 ? sc + S.dz5_hi : sc + S.dz_hi[l];
+        o.a_lo = l == 4 ? sc + S.dz5_lo : sc + S.dz_lo[l];
+        o.m_rows = B; o.lda = k_out;
+        o.w_hi = blob + T.wn_hi[l]; o.w_lo = blob + T.wn_lo[l]; o.n_rows = kHidden; o.ldb = k_out; o.k_cols = k_out;
+        o.epi = kEpiDgrad;
+        o.g.out_hi = bf(S.dz_hi[l - 1]); o.g.out_lo = bf(S.dz_lo[l - 1]);
+        o.g.ld_out = kHidden;
+        o.g.relu_src = bf(S.h_hi[l - 1]);
+        o.dep = l == 4 ? -1 : dgrad_op[l + 1]; o.dep_all = 0;
+        dgrad_op[l] = nb++;
+    };
+    auto add_wgrad = [&](int l) {  // wgrad of layer l (0-based parameter index l - 1): dW = h_{l-1}^T . dz_l
+        OpSpec& o = bwd[nb++];
+        o = OpSpec{};
+        o.a_hi = l == 1 ? sc + S.obs : sc + S.h_hi[l - 2];
+        o.a_lo = l == 1 ? nullptr : sc + S.h_lo[l - 2];
+        o.m_rows = l == 1 ? kObsDimM : kHidden; o.lda = o.m_rows; o.a_mn = 1;
+        o.w_hi = sc + S.dz_hi[l - 1]; o.w_lo = sc + S.dz_lo[l - 1]; o.n_rows = kHidden; o.ldb = kHidden; o.w_mn = 1; o.k_cols = B;
+        o.epi = kEpiWgrad;
+        o.g.c = grads + F.w[l - 1]; o.g.ld_c = kHidden; o.g.n_c = kHidden; o.g.sumsq = grad_sumsq;
+        o.dep = dgrad_op[l]; o.dep_all = 1;
+    };
+    {
+        // The dgrad chain dz5 -> dz4 -> ... -> dz1 is the critical path; the weight gradients only have to come after the dz they
+        // contract.  Tiles are dealt round-robin in list order, so the chain goes first and every wgrad one layer behind it: no
+        // CTA holds a chain tile behind a full-K wgrad tile that could have run later (0.1695 -> 0.1688 ms per step against
+        // "head wgrad first, then dgrad_l / wgrad_l per layer": the chain's own latency, not queueing, is what bounds it).
+        add_dgrad(4);
+        add_dgrad(3);
+        add_head_wgrad();
+        add_wgrad(4);
+        add_dgrad(2);
+        add_wgrad(3);
+        add_dgrad(1);
+        add_wgrad(2);
+        add_wgrad(1);
     }
     const int nmb = ready_blocks(B);
     uint32_t* ready = reinterpret_cast<uint32_t*>(sc + S.ready);
