@@ -1,6 +1,6 @@
 #!/bin/bash
 # end-of-round check on one GPU: the whole GPU suite, smoke(), the default bench and the reference arm
-O=gpurun_out/r2B; mkdir -p $O
+O=gpurun_out/r2F; mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/smoke.log
 timeout 900 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"
