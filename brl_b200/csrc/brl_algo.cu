@@ -227,6 +227,7 @@ int32_t brl_gae(brl_stream_t stream, void** b, const void* opaque, size_t len) {
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     static const char* names[] = {"done", "value", "reward", "last_val", "advantages", "targets"};
     for (int k = 0; k < 6; ++k)
         if (b[k] == nullptr) return fail(BRL_E_BUFFER, "brl_gae: buffer '%s' is NULL", names[k]);
@@ -243,6 +244,7 @@ int32_t brl_categorical(brl_stream_t stream, void** b, const void* opaque, size_
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     if (b[0] == nullptr) return fail(BRL_E_BUFFER, "brl_categorical: buffer 'logits' is NULL");
     if (p->n_envs == 0) return BRL_OK;
     return launch_categorical((cudaStream_t)stream, static_cast<const float*>(b[0]), static_cast<const uint8_t*>(b[1]),
@@ -254,6 +256,10 @@ int32_t brl_team_rows(brl_stream_t stream, void** b, const void* opaque, size_t 
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) {  // an empty batch: both lists are empty
+        if (b[4] != nullptr) cudaMemsetAsync(b[4], 0, 2 * sizeof(int32_t), (cudaStream_t)stream);
+        return check_launch("brl_team_rows");
+    }
     BRL_REQUIRE(b[0], "current_player");
     BRL_REQUIRE(b[2], "rows_team1");
     BRL_REQUIRE(b[3], "rows_team2");
@@ -271,6 +277,7 @@ int32_t brl_imp_reward(brl_stream_t stream, void** b, const void* opaque, size_t
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "a_rewards");
     BRL_REQUIRE(b[1], "b_rewards");
     BRL_REQUIRE(b[2], "imp");
@@ -284,6 +291,7 @@ int32_t brl_match_stats(brl_stream_t stream, void** b, const void* opaque, size_
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     if (b[0] == nullptr || b[1] == nullptr) return fail(BRL_E_BUFFER, "brl_match_stats: NULL buffer");
     if (p->n_envs == 0) return BRL_OK;
     unsigned grid = (unsigned)((p->n_envs + 255) / 256);
@@ -297,6 +305,7 @@ int32_t brl_gather_reward(brl_stream_t stream, void** b, const void* opaque, siz
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     if (b[0] == nullptr || b[1] == nullptr || b[2] == nullptr) return fail(BRL_E_BUFFER, "brl_gather_reward: NULL buffer");
     if (p->n_envs == 0) return BRL_OK;
     const bool counting = (p->flags & BRL_F_COUNT_DONE) != 0;

@@ -871,6 +871,7 @@ int32_t brl_make_keys(brl_stream_t stream, void** b, const void* opaque, size_t 
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "keys");
     if (p->n_envs == 0) return BRL_OK;
     k_make_keys<<<(unsigned)((p->n_envs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
@@ -882,6 +883,7 @@ int32_t brl_init(brl_stream_t stream, void** b, const void* opaque, size_t len) 
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "keys");
     BRL_REQUIRE(b[1], "deal_table");
     BRL_REQUIRE(b[2], "state_out");
@@ -902,6 +904,7 @@ int32_t brl_reset_fields(brl_stream_t stream, void** b, const void* opaque, size
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     static const char* names[] = {"deal", "dealer", "vul_ns", "vul_ew", "shuffled_players"};
     for (int k = 0; k < 5; ++k)
         if (b[k] == nullptr) return fail(BRL_E_BUFFER, "brl_reset_fields: buffer '%s' is NULL", names[k]);
@@ -928,6 +931,7 @@ int32_t brl_step(brl_stream_t stream, void** b, const void* opaque, size_t len) 
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "state_in");
     if (!(p->flags & BRL_F_RANDOM_ACTION) && b[1] == nullptr) return fail(BRL_E_BUFFER, "brl_step: buffer 'action' is NULL");
     BRL_REQUIRE(b[2], "deal_table");
@@ -950,6 +954,7 @@ int32_t brl_duplicate_step(brl_stream_t stream, void** b, const void* opaque, si
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "state_in");
     if (b[1] == nullptr) return fail(BRL_E_BUFFER, "brl_duplicate_step: buffer 'action' is NULL");
     BRL_REQUIRE(b[2], "deal_table");
@@ -976,6 +981,7 @@ int32_t brl_duplicate_init(brl_stream_t stream, void** b, const void* opaque, si
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "state_in");
     BRL_REQUIRE(b[1], "deal_table");
     BRL_REQUIRE(b[2], "state_out");
@@ -995,6 +1001,7 @@ int32_t brl_observe(brl_stream_t stream, void** b, const void* opaque, size_t le
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "state");
     BRL_REQUIRE(b[2], "deal_table");
     BRL_REQUIRE(b[3], "obs");
@@ -1013,6 +1020,7 @@ int32_t brl_legal_mask(brl_stream_t stream, void** b, const void* opaque, size_t
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "state");
     if (b[1] == nullptr) return fail(BRL_E_BUFFER, "brl_legal_mask: buffer 'mask' is NULL");
     EnvArgs a = {};
@@ -1030,6 +1038,7 @@ int32_t brl_rollout_random(brl_stream_t stream, void** b, const void* opaque, si
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "state");
     BRL_REQUIRE(b[1], "deal_table");
     if (p->k_steps <= 0) return fail(BRL_E_OPAQUE, "brl_rollout_random: k_steps must be > 0");
@@ -1061,6 +1070,7 @@ int32_t brl_state_fields(brl_stream_t stream, void** b, const void* opaque, size
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "state");
     if (p->n_envs == 0) return BRL_OK;
     FieldArgs a;

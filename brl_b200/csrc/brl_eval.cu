@@ -167,6 +167,7 @@ int32_t brl_eval_act_log(brl_stream_t stream, void** b, const void* opaque, size
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     static const char* names[] = {"logits_actor", "logits_opp", "mask", "current_player", "terminated", "action", "acc"};
     for (int k = 0; k < 7; ++k)
         if (b[k] == nullptr && k != 1) return fail(BRL_E_BUFFER, "brl_eval_act_log: buffer '%s' is NULL", names[k]);
@@ -191,6 +192,7 @@ int32_t brl_eval_summary(brl_stream_t stream, void** b, const void* opaque, size
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     static const char* names[] = {"acc", "cum_return", "step_count", "a.last_bid", "a.last_bidder", "a.call_x", "a.call_xx"};
     for (int k = 0; k < 7; ++k)
         if (b[k] == nullptr) return fail(BRL_E_BUFFER, "brl_eval_summary: buffer '%s' is NULL", names[k]);

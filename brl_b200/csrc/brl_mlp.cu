@@ -965,6 +965,7 @@ int32_t brl_obs_to_bf16(brl_stream_t stream, void** b, const void* opaque, size_
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "obs");
     BRL_REQUIRE(b[1], "obs_bf16");
     if (p->n_envs == 0) return BRL_OK;
@@ -1055,6 +1056,7 @@ int32_t brl_mlp_forward(brl_stream_t stream, void** b, const void* opaque, size_
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "obs_bf16");
     BRL_REQUIRE(b[1], "packed");
     BRL_REQUIRE(b[2], "scratch");
@@ -1087,6 +1089,7 @@ int32_t brl_policy_act_rows(brl_stream_t stream, void** b, const void* opaque, s
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "obs_bf16");
     BRL_REQUIRE(b[1], "packed");
     BRL_REQUIRE(b[2], "scratch");
@@ -1121,6 +1124,7 @@ int32_t brl_policy_act(brl_stream_t stream, void** b, const void* opaque, size_t
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "obs_bf16");
     BRL_REQUIRE(b[1], "packed");
     BRL_REQUIRE(b[2], "scratch");

@@ -473,6 +473,7 @@ int32_t brl_gather_rows(brl_stream_t stream, void** b, const void* opaque, size_
     int32_t rc;
     const BrlParams* p = get_params(opaque, len, &rc);
     if (!p) return rc;
+    if (p->n_envs == 0) return BRL_OK;  // an empty batch is a no-op; its buffers may be NULL (zero-size XLA / torch buffers)
     BRL_REQUIRE(b[0], "src");
     if (b[1] == nullptr) return fail(BRL_E_BUFFER, "brl_gather_rows: buffer 'index' is NULL");
     BRL_REQUIRE(b[2], "dst");

@@ -111,7 +111,8 @@ typedef struct CUstream_st *brl_stream_t; /* == cudaStream_t */
 #define BRL_E_HANDLE (-4)   /* bad BrlEnv handle */
 
 typedef struct BrlParams {
-    int64_t n_envs;        /* envs in this call (this rank's shard)                    */
+    int64_t n_envs;        /* envs in this call (this rank's shard); 0 = an empty batch: every batched op returns BRL_OK
+                              without touching (or requiring) its buffers -- brl_team_rows still zeroes its counts */
     int64_t env_offset;    /* global index of env 0 (RNG counters use global indices)  */
     int64_t state_stride;  /* envs per plane of the packed state buffers (>= n_envs)   */
     uint64_t seed;         /* key of the counter-based action / Gumbel RNG             */

@@ -377,3 +377,28 @@ def test_c1_eval_match_with_bundled_weights_reproduces_golden():
         assert (info.last_bid.cpu().numpy() == g[k + "_last_bid"]).all()
         assert (info.last_bidder.cpu().numpy() == g[k + "_last_bidder"]).all()
         assert (info.rewards.cpu().numpy() == g[k + "_rewards"]).all()
+
+
+def test_empty_batch_is_a_no_op_for_every_batched_op():
+    """n_envs = 0 (an empty shard, a zero-size XLA / torch buffer whose pointer is NULL): every batched op returns BRL_OK
+    without requiring or touching its buffers; brl_team_rows still reports two empty lists."""
+    import ctypes as C
+    from brl_b200 import _lib
+    L = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    nulls = (C.c_void_p * 24)()
+    p0 = _lib.BrlParams(0, 0, 0, 1, 10, _lib.F_AUTORESET, 0, 4, -1.0, 1.0, 0.99, 0.95)
+    for name in ("brl_make_keys", "brl_init", "brl_reset_fields", "brl_step", "brl_duplicate_init", "brl_duplicate_step", "brl_observe",
+                 "brl_legal_mask", "brl_rollout_random", "brl_state_fields", "brl_gae", "brl_categorical", "brl_imp_reward",
+                 "brl_match_stats", "brl_gather_reward", "brl_obs_to_bf16", "brl_mlp_forward", "brl_policy_act", "brl_policy_act_rows",
+                 "brl_gather_rows", "brl_eval_act_log", "brl_eval_summary"):
+        rc = getattr(L, name)(C.c_void_p(stream), nulls, C.byref(p0), C.sizeof(p0))
+        assert rc == 0, (name, L.brl_last_error())
+    counts = torch.full((2,), 7, dtype=torch.int32, device=DEV)
+    bufs = (C.c_void_p * 5)(None, None, None, None, counts.data_ptr())
+    assert L.brl_team_rows(C.c_void_p(stream), bufs, C.byref(p0), C.sizeof(p0)) == 0
+    assert counts.tolist() == [0, 0]
+    # ... and a non-empty call with a NULL required buffer is still an error, not a crash
+    p1 = _lib.BrlParams(8, 0, 8, 1, 10, 0, 0, 0, -1.0, 1.0, 0.0, 0.0)
+    assert L.brl_step(C.c_void_p(stream), nulls, C.byref(p1), C.sizeof(p1)) == -2
+    assert b"NULL" in L.brl_last_error()
